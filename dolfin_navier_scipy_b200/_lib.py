@@ -1,0 +1,437 @@
+"""ctypes binding of ``libdnsb200.so`` (C ABI declared in ``include/dnsb.h``).
+
+There is no CPU fallback: if the library is missing or no CUDA device is
+available, every entry point raises ``RuntimeError``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, 'libdnsb200.so')
+
+c_int_p = ctypes.POINTER(ctypes.c_int32)
+c_dbl_p = ctypes.POINTER(ctypes.c_double)
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+
+_lib = None
+
+# name: (restype, argtypes) -- mirrors include/dnsb.h one to one
+_vp, _i, _d, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong
+SIGNATURES = {
+    'dnsb_ctx_create': (_i, [_i, c_void_pp]),
+    'dnsb_ctx_destroy': (None, [_vp]),
+    'dnsb_last_error': (ctypes.c_char_p, [_vp]),
+    'dnsb_version': (_i, []),
+    'dnsb_device_info': (_i, [_vp, ctypes.POINTER(_i),
+                              ctypes.POINTER(ctypes.c_size_t),
+                              ctypes.POINTER(_i)]),
+    'dnsb_sync': (_i, [_vp]),
+    'dnsb_launch_count': (_ll, [_vp]),
+    'dnsb_launch_count_reset': (None, [_vp]),
+    'dnsb_set_mesh': (_i, [_vp, _i, _i, c_int_p, c_dbl_p, _i, c_int_p]),
+    'dnsb_set_conv_pattern': (_i, [_vp, c_int_p, c_int_p, c_int_p]),
+    'dnsb_convvec': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, _i]),
+    'dnsb_convmats': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),
+    'dnsb_csr_create': (_i, [_vp, _i, _i, c_int_p, c_int_p, c_dbl_p, c_dbl_p,
+                             c_void_pp]),
+    'dnsb_csr_destroy': (None, [_vp]),
+    'dnsb_spmm': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, _i, _d, _d]),
+    'dnsb_spmm_dev': (_i, [_vp, _vp, _vp, _vp, _i, _d, _d]),
+    'dnsb_solver_create': (_i, [_vp, _vp, _vp, _vp, c_dbl_p, _i, _i, _i, _d,
+                                _d, c_void_pp]),
+    'dnsb_solver_destroy': (None, [_vp]),
+    'dnsb_solver_add_schur_level': (_i, [_vp, _vp, _vp, _vp, _i, _d, _d,
+                                         c_dbl_p]),
+    'dnsb_solver_set_velocity_transfer': (_i, [_vp, _vp, _vp]),
+    'dnsb_solver_add_velocity_level': (_i, [_vp, _vp, _vp, _vp, _i, _d, _d,
+                                            c_dbl_p]),
+    'dnsb_solver_set_schur_mass': (_i, [_vp, c_dbl_p, c_dbl_p]),
+    'dnsb_solver_solve': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, _d, _i,
+                               c_int_p, c_dbl_p]),
+    'dnsb_imex_create': (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, c_dbl_p,
+                              c_int_p, _i, _i, c_int_p, c_dbl_p, c_dbl_p,
+                              c_dbl_p, c_void_pp]),
+    'dnsb_imex_destroy': (None, [_vp]),
+    'dnsb_imex_set_solvers': (_i, [_vp, _vp, _vp, _vp]),
+    'dnsb_imex_set_forcing': (_i, [_vp, _i, c_dbl_p, _i, c_dbl_p]),
+    'dnsb_imex_set_state': (_i, [_vp, c_dbl_p, c_dbl_p]),
+    'dnsb_imex_run': (_i, [_vp, _i, _i, _d, _i, _i, _d, _i,
+                           ctypes.POINTER(_i)]),
+    'dnsb_imex_get_state': (_i, [_vp, c_dbl_p, c_dbl_p]),
+    'dnsb_imex_num_snapshots': (_i, [_vp]),
+    'dnsb_imex_get_snapshots': (_i, [_vp, c_dbl_p]),
+    'dnsb_imex_stats': (_i, [_vp, ctypes.POINTER(_ll), ctypes.POINTER(_ll),
+                             c_dbl_p]),
+    'dnsb_imex_gram_dev': (_i, [_vp, _vp]),
+}
+
+
+def load(path=None):
+    """load the shared library and declare every symbol of ``dnsb.h``"""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = LIBPATH if path is None else path
+    if not os.path.isfile(path):
+        raise RuntimeError(
+            'libdnsb200.so not found at {0}: build it with '
+            '`python -c "import __graft_entry__ as g; g.build()"` -- there is '
+            'no CPU fallback for the device path'.format(path))
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if a symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(c_dbl_p)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(c_int_p)
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else a.reshape(shape)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class DnsbError(RuntimeError):
+    pass
+
+
+class Context(object):
+    """one device + one stream (``dnsb_ctx``)"""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = ctypes.c_void_p()
+        rc = self.lib.dnsb_ctx_create(int(device), ctypes.byref(h))
+        self.h = h
+        self.device = int(device)
+        if rc != 0:
+            msg = self.lib.dnsb_last_error(h).decode() if h else 'no context'
+            raise DnsbError('dnsb_ctx_create(device={0}) failed: {1}'.
+                            format(device, msg))
+        self._keep = []
+
+    def check(self, rc):
+        if rc != 0:
+            raise DnsbError(self.lib.dnsb_last_error(self.h).decode())
+
+    def info(self):
+        sm, mem, cc = ctypes.c_int(), ctypes.c_size_t(), ctypes.c_int()
+        self.check(self.lib.dnsb_device_info(self.h, ctypes.byref(sm),
+                                             ctypes.byref(mem),
+                                             ctypes.byref(cc)))
+        return dict(sm_count=sm.value, mem_bytes=mem.value, cc=cc.value)
+
+    def sync(self):
+        self.check(self.lib.dnsb_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.dnsb_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.lib.dnsb_launch_count_reset(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.dnsb_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    # -- CSR ----------------------------------------------------------------
+    def csr(self, mat, vals2=None):
+        return Csr(self, mat, vals2)
+
+
+_CTX = {}
+
+
+def default_context(device=None):
+    if device is None:
+        device = int(os.environ.get('LOCAL_RANK', '0'))
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]
+
+
+class Csr(object):
+    """device CSR matrix (``dnsb_csr``); ``vals2`` shares the pattern"""
+
+    def __init__(self, ctx, mat, vals2=None):
+        import scipy.sparse as sps
+        mat = sps.csr_matrix(mat)
+        mat.sort_indices()
+        self.ctx = ctx
+        self.shape = mat.shape
+        self.nnz = mat.nnz
+        indptr, indices = _i32(mat.indptr), _i32(mat.indices)
+        v1 = _f64(mat.data)
+        v2 = _f64(vals2)
+        if v2 is not None and v2.size != v1.size:
+            raise ValueError('vals2 must match the pattern of the matrix')
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.dnsb_csr_create(ctx.h, mat.shape[0], mat.shape[1],
+                                          _ip(indptr), _ip(indices), _dp(v1),
+                                          _dp(v2), ctypes.byref(h)))
+        self.h = h
+        self.has2 = v2 is not None
+
+    def spmm(self, x, coef=None, alpha=1.0, beta=0.0, y=None):
+        """``alpha*A@x + beta*y`` for x of shape (ncols,) or (ncols, nb)"""
+        x = _f64(x)
+        nb = 1 if x.ndim == 1 else x.shape[1]
+        out = np.zeros((self.shape[0],) + x.shape[1:]) if y is None \
+            else _f64(y).copy()
+        coef = _f64(coef)
+        self.ctx.check(self.ctx.lib.dnsb_spmm(self.h, _dp(coef), _dp(x),
+                                              _dp(out), nb, alpha, beta))
+        return out
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dnsb_csr_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+
+class ConvDevice(object):
+    """mesh + convection kernels (K1a/K1b) bound to a P2 vector space"""
+
+    def __init__(self, V, ctx=None):
+        self.ctx = default_context() if ctx is None else ctx
+        self.V = V
+        mesh = V.mesh()
+        gl, detj = V.geometry()
+        geom = np.stack([gl[:, 1, 0], gl[:, 1, 1], gl[:, 2, 0], gl[:, 2, 1],
+                         detj], axis=1)
+        ncol, colour = V.colouring()
+        cn = _i32(V.cell_nodes)
+        geom = _f64(geom)
+        colour = _i32(colour)
+        self.ncolours = ncol
+        self.nvf = V.dim()
+        self.ctx.check(self.ctx.lib.dnsb_set_mesh(
+            self.ctx.h, mesh.num_cells, V.num_nodes, _ip(cn), _dp(geom), ncol,
+            _ip(colour)))
+        self._pattern = None
+
+    @property
+    def pattern(self):
+        """(indptr, indices) of the P2 vector space; uploads the cell slots"""
+        if self._pattern is None:
+            cn = self.V.cell_nodes.astype(np.int64)
+            nc = cn.shape[0]
+            NV = self.nvf
+            vd = np.stack([2*cn, 2*cn + 1], axis=2).reshape(nc, 12)
+            keys = (vd[:, :, None]*NV + vd[:, None, :]).reshape(-1)
+            ukeys = np.unique(keys)
+            rows = ukeys // NV
+            indices = (ukeys % NV).astype(np.int32)
+            indptr = np.zeros(NV + 1, dtype=np.int64)
+            np.add.at(indptr, rows + 1, 1)
+            indptr = np.cumsum(indptr).astype(np.int32)
+            slots = np.searchsorted(ukeys, keys).astype(np.int32)
+            self.ctx.check(self.ctx.lib.dnsb_set_conv_pattern(
+                self.ctx.h, _ip(indptr), _ip(indices), _ip(slots)))
+            self._pattern = (indptr, indices)
+        return self._pattern
+
+    def convvec(self, u1, u2=None):
+        u1 = _f64(u1)
+        nb = 1 if u1.ndim == 1 else u1.shape[1]
+        if u1.shape[0] != self.nvf:
+            raise ValueError('convvec needs full vectors of size V.dim()')
+        u2 = _f64(u2)
+        out = np.empty_like(u1)
+        self.ctx.check(self.ctx.lib.dnsb_convvec(self.ctx.h, _dp(u1), _dp(u2),
+                                                 _dp(out), nb))
+        return out
+
+    def convmats(self, u0):
+        indptr, indices = self.pattern
+        u0 = _f64(u0).reshape(-1)
+        n1 = np.empty(indices.size)
+        n2 = np.empty(indices.size)
+        f3 = np.empty(self.nvf)
+        self.ctx.check(self.ctx.lib.dnsb_convmats(self.ctx.h, _dp(u0), _dp(n1),
+                                                  _dp(n2), _dp(f3)))
+        return n1, n2, f3
+
+
+def device_for(V, ctx=None):
+    """the (cached) device object of a function space"""
+    dev = getattr(V, '_dnsb_dev', None)
+    if dev is None or (ctx is not None and dev.ctx is not ctx):
+        dev = ConvDevice(V, ctx)
+        V._dnsb_dev = dev
+    return dev
+
+
+class SaddleSolver(object):
+    """``dnsb_solver``: FGMRES for [[F_m, JT], [J, 0]] (see ``dnsb.h``)"""
+
+    def __init__(self, ctx, fmat, jmat, jtmat, coef=None, nb=1, restart=40,
+                 cheb_steps=3, lmin=None, lmax=None):
+        self.ctx = ctx
+        self.fmat, self.jmat, self.jtmat = fmat, jmat, jtmat
+        self.nb = nb
+        self.nv, self.np_ = fmat.shape[0], jmat.shape[0]
+        coef = _f64(coef)
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.dnsb_solver_create(
+            ctx.h, fmat.h, jmat.h, jtmat.h, _dp(coef), nb, restart, cheb_steps,
+            float(lmin), float(lmax), ctypes.byref(h)))
+        self.h = h
+        self._levels = []
+
+    def add_schur_level(self, amat=None, pmat=None, rmat=None, nsmooth=2,
+                        lmin=0.0, lmax=0.0, dense_inv=None):
+        dense_inv = _f64(dense_inv)
+        self._levels.append((amat, pmat, rmat))
+        self.ctx.check(self.ctx.lib.dnsb_solver_add_schur_level(
+            self.h, amat.h if amat is not None else None,
+            pmat.h if pmat is not None else None,
+            rmat.h if rmat is not None else None, nsmooth, float(lmin),
+            float(lmax), _dp(dense_inv)))
+
+    def set_velocity_transfer(self, pmat, rmat):
+        self._levels.append((pmat, rmat))
+        self.ctx.check(self.ctx.lib.dnsb_solver_set_velocity_transfer(
+            self.h, pmat.h, rmat.h))
+
+    def add_velocity_level(self, amat=None, pmat=None, rmat=None, nsmooth=2,
+                           lmin=0.0, lmax=0.0, dense_inv=None):
+        dense_inv = _f64(dense_inv)
+        self._levels.append((amat, pmat, rmat))
+        self.ctx.check(self.ctx.lib.dnsb_solver_add_velocity_level(
+            self.h, amat.h if amat is not None else None,
+            pmat.h if pmat is not None else None,
+            rmat.h if rmat is not None else None, nsmooth, float(lmin),
+            float(lmax), _dp(dense_inv)))
+
+    def set_schur_mass(self, mp_dinv, mp_scale):
+        mp_dinv, mp_scale = _f64(mp_dinv), _f64(mp_scale)
+        self.ctx.check(self.ctx.lib.dnsb_solver_set_schur_mass(
+            self.h, _dp(mp_dinv), _dp(mp_scale)))
+
+    def solve(self, rhsv, rhsp=None, x0=None, tol=1e-11, maxit=400):
+        """returns ``(vp, iters, relres)``; arrays are (n, nb) or (n,)"""
+        rhsv = _f64(rhsv)
+        flat = rhsv.ndim == 1
+        rhsv = rhsv.reshape(self.nv, self.nb)
+        rhsp = _f64(rhsp, (self.np_, self.nb)) if rhsp is not None else None
+        x0 = _f64(x0, (self.nv + self.np_, self.nb)) if x0 is not None \
+            else None
+        vp = np.empty((self.nv + self.np_, self.nb))
+        iters = np.zeros(self.nb, dtype=np.int32)
+        relres = np.zeros(self.nb)
+        self.ctx.check(self.ctx.lib.dnsb_solver_solve(
+            self.h, _dp(rhsv), _dp(rhsp), _dp(x0), _dp(vp), float(tol),
+            int(maxit), _ip(iters), _dp(relres)))
+        return (vp.reshape(-1) if flat else vp), iters, relres
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dnsb_solver_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+
+class ImexEngine(object):
+    """``dnsb_imex``: device-resident CNAB / SBDF2 / IMEX-Euler loop"""
+    SCHEMES = dict(cnab=0, sbdf2=1, imexeuler=2)
+
+    def __init__(self, ctx, scheme, nb, dt, mmat, amat, jmat, jtmat, nu,
+                 invinds, bcinds, bcvals, fv=None, fp=None):
+        self.ctx = ctx
+        self.nb = nb
+        self.nv, self.np_ = mmat.shape[0], jmat.shape[0]
+        self._keep = (mmat, amat, jmat, jtmat)
+        nu = _f64(np.broadcast_to(np.asarray(nu, dtype=float), (nb,)))
+        invinds, bcinds = _i32(invinds), _i32(bcinds)
+        bcvals = _f64(bcvals)
+        fv = _f64(fv, (-1,)) if fv is not None else None
+        fp = _f64(fp, (-1,)) if fp is not None else None
+        h = ctypes.c_void_p()
+        ctx.check(ctx.lib.dnsb_imex_create(
+            ctx.h, self.SCHEMES[scheme], nb, float(dt), mmat.h, amat.h, jmat.h,
+            jtmat.h, _dp(nu), _ip(invinds), invinds.size, bcinds.size,
+            _ip(bcinds), _dp(bcvals), _dp(fv), _dp(fp), ctypes.byref(h)))
+        self.h = h
+
+    def set_solvers(self, loop, pred=None, corr=None):
+        self._solvers = (loop, pred, corr)
+        self.ctx.check(self.ctx.lib.dnsb_imex_set_solvers(
+            self.h, loop.h, pred.h if pred else None, corr.h if corr else None))
+
+    def set_forcing(self, bvecs, useries):
+        """``f(t_n) = sum_k useries[n, k, m]*bvecs[:, k]``"""
+        bvecs = _f64(bvecs).reshape(self.nv, -1)
+        nk = bvecs.shape[1]
+        useries = np.asarray(useries, dtype=float)
+        if useries.ndim == 2:       # (ntimes, nk): shared by all members
+            useries = useries[:, :, None]
+        useries = _f64(np.broadcast_to(useries,
+                                       (useries.shape[0], nk, self.nb)))
+        self.ctx.check(self.ctx.lib.dnsb_imex_set_forcing(
+            self.h, nk, _dp(bvecs), useries.shape[0], _dp(useries)))
+
+    def set_state(self, v0, p0=None):
+        v0 = _f64(np.broadcast_to(np.asarray(v0, dtype=float).
+                                  reshape(self.nv, -1), (self.nv, self.nb)))
+        if p0 is not None:
+            p0 = _f64(np.broadcast_to(np.asarray(p0, dtype=float).
+                                      reshape(self.np_, -1),
+                                      (self.np_, self.nb)))
+        self.ctx.check(self.ctx.lib.dnsb_imex_set_state(self.h, _dp(v0),
+                                                        _dp(p0)))
+
+    def run(self, nsteps, snap_stride=0, tol=1e-11, maxit=400, guess=8,
+            check_ff_maxv=1e8, ntimeslices=10):
+        ff = ctypes.c_int(0)
+        self.ctx.check(self.ctx.lib.dnsb_imex_run(
+            self.h, int(nsteps), int(snap_stride), float(tol), int(maxit),
+            int(guess), float(check_ff_maxv), int(ntimeslices),
+            ctypes.byref(ff)))
+        return ff.value
+
+    def state(self):
+        v = np.empty((self.nv, self.nb))
+        p = np.empty((self.np_, self.nb))
+        self.ctx.check(self.ctx.lib.dnsb_imex_get_state(self.h, _dp(v),
+                                                        _dp(p)))
+        return v, p
+
+    def snapshots(self):
+        ns = self.ctx.lib.dnsb_imex_num_snapshots(self.h)
+        out = np.empty((ns, self.nv + self.np_, self.nb))
+        if ns > 0:
+            self.ctx.check(self.ctx.lib.dnsb_imex_get_snapshots(self.h,
+                                                                _dp(out)))
+        return out
+
+    def stats(self):
+        it, ns, rr = _ll(), _ll(), ctypes.c_double()
+        self.ctx.check(self.ctx.lib.dnsb_imex_stats(
+            self.h, ctypes.byref(it), ctypes.byref(ns), ctypes.byref(rr)))
+        return dict(iters=it.value, solves=ns.value, last_relres=rr.value)
+
+    def gram_dev(self, g_dev_ptr):
+        self.ctx.check(self.ctx.lib.dnsb_imex_gram_dev(
+            self.h, ctypes.c_void_p(int(g_dev_ptr))))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dnsb_imex_destroy(self.h)
+            self.h = ctypes.c_void_p()

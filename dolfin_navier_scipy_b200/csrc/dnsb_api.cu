@@ -1,0 +1,1528 @@
+// dnsb_api.cu -- C ABI of libdnsb200.so (see include/dnsb.h)
+//
+// Build:  nvcc -shared -Xcompiler -fPIC -O3 -lineinfo
+//              -gencode arch=compute_100a,code=sm_100a  dnsb_api.cu -o libdnsb200.so
+#include "../../include/dnsb.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "dnsb_common.cuh"
+#include "dnsb_kernels.cuh"
+
+#define DNSB_VERSION 100
+
+// ===========================================================================
+// launch helpers
+// ===========================================================================
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                              \
+  do {                                                                         \
+    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+    (ctx)->launches++;                                                         \
+  } while (0)
+
+static inline int pow2_floor(int x) {
+  int p = 1;
+  while (2 * p <= x) p *= 2;
+  return p;
+}
+
+struct RedCfg {   // launch shape of the batched reductions
+  int nblocks, rpb, threads;
+  size_t smem;
+};
+
+static RedCfg red_cfg(dnsb_ctx *ctx, int n, int nb) {
+  RedCfg c;
+  c.rpb = pow2_floor(std::max(1, 256 / nb));
+  c.threads = c.rpb * nb;
+  int want = std::max(1, std::min(2 * ctx->sm_count, (n + c.rpb - 1) / c.rpb));
+  c.nblocks = want;
+  c.smem = (size_t)c.threads * sizeof(double);
+  return c;
+}
+
+// ===========================================================================
+// CSR handle
+// ===========================================================================
+struct dnsb_csr {
+  dnsb_ctx *ctx = nullptr;
+  int nrows = 0, ncols = 0, nnz = 0;
+  DBuf<int> indptr, indices;
+  DBuf<double> v1, v2;
+  bool has2 = false;
+  // host copies (setup only: assembling the block matrix K, diagonal positions)
+  std::vector<int> h_indptr, h_indices;
+  std::vector<double> h_v1, h_v2;
+  CsrDev view() const {
+    CsrDev a;
+    a.nrows = nrows; a.ncols = ncols; a.nnz = nnz;
+    a.indptr = indptr.p; a.indices = indices.p;
+    a.v1 = v1.p; a.v2 = has2 ? v2.p : nullptr;
+    return a;
+  }
+};
+
+static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
+                     const int32_t *indices, const double *vals1,
+                     const double *vals2, dnsb_csr **out) {
+  DNSB_REQUIRE(ctx, nrows >= 0 && ncols >= 0 && indptr && out, "bad csr args");
+  const int nnz = indptr[nrows];
+  DNSB_REQUIRE(ctx, nnz >= 0 && (nnz == 0 || (indices && vals1)), "bad csr data");
+  for (int i = 0; i < nrows; ++i)
+    DNSB_REQUIRE(ctx, indptr[i] <= indptr[i + 1], "indptr not monotone");
+  for (int k = 0; k < nnz; ++k)
+    DNSB_REQUIRE(ctx, indices[k] >= 0 && indices[k] < ncols, "column index out of range");
+  dnsb_csr *m = new (std::nothrow) dnsb_csr();
+  DNSB_REQUIRE(ctx, m != nullptr, "out of host memory");
+  m->ctx = ctx; m->nrows = nrows; m->ncols = ncols; m->nnz = nnz;
+  m->has2 = vals2 != nullptr;
+  m->h_indptr.assign(indptr, indptr + nrows + 1);
+  m->h_indices.assign(indices, indices + nnz);
+  m->h_v1.assign(vals1, vals1 + nnz);
+  if (vals2) m->h_v2.assign(vals2, vals2 + nnz);
+  cudaError_t e;
+  if ((e = m->indptr.upload(indptr, nrows + 1, ctx->stream)) != cudaSuccess ||
+      (e = m->indices.upload(indices, nnz, ctx->stream)) != cudaSuccess ||
+      (e = m->v1.upload(vals1, nnz, ctx->stream)) != cudaSuccess ||
+      (vals2 && (e = m->v2.upload(vals2, nnz, ctx->stream)) != cudaSuccess)) {
+    ctx->fail(std::string("csr upload: ") + cudaGetErrorString(e), __FILE__, __LINE__);
+    m->indptr.release(); m->indices.release(); m->v1.release(); m->v2.release();
+    delete m;
+    return -1;
+  }
+  *out = m;
+  return 0;
+}
+
+static void csr_free(dnsb_csr *m) {
+  if (!m) return;
+  m->indptr.release(); m->indices.release(); m->v1.release(); m->v2.release();
+  delete m;
+}
+
+// y = alpha*A*x + beta*z  on device pointers
+static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
+                     const double *x, const double *z, double *y, int nb,
+                     double alpha, double beta) {
+  if (A->nrows == 0) return;
+  if (nb == 1) {
+    const size_t threads = (size_t)A->nrows * 8;
+    LAUNCH(ctx, k_spmm<8>, cdiv(threads, 256), 256, 0, A->view(), coef, x, z, y,
+           nb, alpha, beta);
+  } else {
+    const size_t threads = (size_t)A->nrows * nb;
+    LAUNCH(ctx, k_spmm<1>, cdiv(threads, 256), 256, 0, A->view(), coef, x, z, y,
+           nb, alpha, beta);
+  }
+}
+
+// ===========================================================================
+// context
+// ===========================================================================
+static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7]) {
+  const double s15 = std::sqrt(15.0);
+  const double a1 = (6.0 - s15) / 21.0, a2 = (6.0 + s15) / 21.0;
+  const double w1 = (155.0 - s15) / 1200.0, w2 = (155.0 + s15) / 1200.0;
+  const double qp[7][3] = {{1. / 3, 1. / 3, 1. / 3},
+                           {1 - 2 * a1, a1, a1}, {a1, 1 - 2 * a1, a1}, {a1, a1, 1 - 2 * a1},
+                           {1 - 2 * a2, a2, a2}, {a2, 1 - 2 * a2, a2}, {a2, a2, 1 - 2 * a2}};
+  const double w[7] = {9. / 40, w1, w1, w1, w2, w2, w2};
+  for (int q = 0; q < 7; ++q) {
+    const double l0 = qp[q][0], l1 = qp[q][1], l2 = qp[q][2];
+    qw[q] = w[q];
+    phi[q][0] = l0 * (2 * l0 - 1); phi[q][1] = l1 * (2 * l1 - 1);
+    phi[q][2] = l2 * (2 * l2 - 1); phi[q][3] = 4 * l1 * l2;
+    phi[q][4] = 4 * l0 * l2;       phi[q][5] = 4 * l0 * l1;
+    for (int a = 0; a < 6; ++a)
+      for (int i = 0; i < 3; ++i) dphi[q][a][i] = 0.0;
+    dphi[q][0][0] = 4 * l0 - 1; dphi[q][1][1] = 4 * l1 - 1; dphi[q][2][2] = 4 * l2 - 1;
+    dphi[q][3][1] = 4 * l2; dphi[q][3][2] = 4 * l1;
+    dphi[q][4][0] = 4 * l2; dphi[q][4][2] = 4 * l0;
+    dphi[q][5][0] = 4 * l1; dphi[q][5][1] = 4 * l0;
+  }
+}
+
+extern "C" int dnsb_version(void) { return DNSB_VERSION; }
+
+extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
+  if (!out) return -2;
+  *out = nullptr;
+  dnsb_ctx *ctx = new (std::nothrow) dnsb_ctx();
+  if (!ctx) return -3;
+  ctx->device = device;
+  *out = ctx;   // returned even on failure so that the message can be read
+  DNSB_CK(ctx, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DNSB_CK(ctx, cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc = prop.major * 10 + prop.minor;
+  ctx->mem_bytes = prop.totalGlobalMem;
+  DNSB_CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  double phi[7][6], dphi[7][6][3], qw[7];
+  fill_tabulation(phi, dphi, qw);
+  DNSB_CK(ctx, cudaMemcpyToSymbol(c_phi, phi, sizeof phi));
+  DNSB_CK(ctx, cudaMemcpyToSymbol(c_dphi, dphi, sizeof dphi));
+  DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
+  return 0;
+}
+
+extern "C" void dnsb_ctx_destroy(dnsb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->cn.release(); ctx->geom.release();
+  ctx->cindptr.release(); ctx->cindices.release(); ctx->cslots.release();
+  ctx->stage_a.release(); ctx->stage_b.release();
+  ctx->stage_c.release(); ctx->stage_d.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *dnsb_last_error(dnsb_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : "null context";
+}
+
+extern "C" int dnsb_device_info(dnsb_ctx *ctx, int *sm_count, size_t *mem_bytes, int *cc) {
+  if (!ctx) return -2;
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+  if (cc) *cc = ctx->cc;
+  return 0;
+}
+
+extern "C" int dnsb_sync(dnsb_ctx *ctx) {
+  if (!ctx) return -2;
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" long long dnsb_launch_count(dnsb_ctx *ctx) { return ctx ? ctx->launches : -1; }
+extern "C" void dnsb_launch_count_reset(dnsb_ctx *ctx) { if (ctx) ctx->launches = 0; }
+
+// ===========================================================================
+// mesh + convection
+// ===========================================================================
+extern "C" int dnsb_set_mesh(dnsb_ctx *ctx, int ncell, int nnodes,
+                             const int32_t *cell_nodes, const double *geom,
+                             int ncolours, const int32_t *cell_colour) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, ncell > 0 && nnodes > 0 && cell_nodes && geom && cell_colour &&
+               ncolours > 0, "bad mesh arguments");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  // counting sort of the cells by colour (stable: keeps the mesh order inside
+  // a colour); verify the colouring on the way (no shared node per colour)
+  std::vector<int> count(ncolours + 1, 0);
+  for (int c = 0; c < ncell; ++c) {
+    DNSB_REQUIRE(ctx, cell_colour[c] >= 0 && cell_colour[c] < ncolours, "colour out of range");
+    count[cell_colour[c] + 1]++;
+  }
+  for (int k = 0; k < ncolours; ++k) count[k + 1] += count[k];
+  ctx->colour_ptr = count;
+  std::vector<int> pos(count.begin(), count.end() - 1);
+  ctx->perm.assign(ncell, 0);
+  for (int c = 0; c < ncell; ++c) ctx->perm[pos[cell_colour[c]]++] = c;
+  {
+    std::vector<int> stamp(nnodes, -1);
+    for (int k = 0; k < ncolours; ++k)
+      for (int q = ctx->colour_ptr[k]; q < ctx->colour_ptr[k + 1]; ++q) {
+        const int c = ctx->perm[q];
+        for (int a = 0; a < 6; ++a) {
+          const int nd = cell_nodes[c * 6 + a];
+          DNSB_REQUIRE(ctx, nd >= 0 && nd < nnodes, "cell node out of range");
+          DNSB_REQUIRE(ctx, stamp[nd] != k, "invalid colouring: node shared within a colour");
+          stamp[nd] = k;
+        }
+      }
+  }
+  std::vector<int> cn((size_t)6 * ncell);
+  std::vector<double> gm((size_t)5 * ncell);
+  for (int q = 0; q < ncell; ++q) {
+    const int c = ctx->perm[q];
+    for (int a = 0; a < 6; ++a) cn[(size_t)a * ncell + q] = cell_nodes[c * 6 + a];
+    for (int a = 0; a < 5; ++a) gm[(size_t)a * ncell + q] = geom[c * 5 + a];
+  }
+  DNSB_CK(ctx, ctx->cn.upload(cn.data(), cn.size(), ctx->stream));
+  DNSB_CK(ctx, ctx->geom.upload(gm.data(), gm.size(), ctx->stream));
+  ctx->ncell = ncell; ctx->nnodes = nnodes; ctx->ncolours = ncolours;
+  ctx->cnnz = 0;
+  return 0;
+}
+
+extern "C" int dnsb_set_conv_pattern(dnsb_ctx *ctx, const int32_t *indptr,
+                                     const int32_t *indices, const int32_t *cell_slots) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, ctx->ncell > 0, "set the mesh first");
+  DNSB_REQUIRE(ctx, indptr && indices && cell_slots, "null pattern");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const int nrows = 2 * ctx->nnodes;
+  const int nnz = indptr[nrows];
+  const int ncell = ctx->ncell;
+  std::vector<int> sl((size_t)144 * ncell);
+  for (int q = 0; q < ncell; ++q) {
+    const int c = ctx->perm[q];
+    for (int e = 0; e < 144; ++e) {
+      const int s = cell_slots[(size_t)c * 144 + e];
+      DNSB_REQUIRE(ctx, s >= 0 && s < nnz, "cell slot out of range");
+      sl[(size_t)e * ncell + q] = s;
+    }
+  }
+  DNSB_CK(ctx, ctx->cindptr.upload(indptr, nrows + 1, ctx->stream));
+  DNSB_CK(ctx, ctx->cindices.upload(indices, nnz, ctx->stream));
+  DNSB_CK(ctx, ctx->cslots.upload(sl.data(), sl.size(), ctx->stream));
+  ctx->cnnz = nnz;
+  return 0;
+}
+
+// out = c(u1,u2) on device vectors (2*nnodes*nb), out is overwritten
+static int convvec_dev(dnsb_ctx *ctx, const double *u1, const double *u2,
+                       double *out, int nb) {
+  const size_t nfull = (size_t)2 * ctx->nnodes * nb;
+  DNSB_CK(ctx, cudaMemsetAsync(out, 0, nfull * sizeof(double), ctx->stream));
+  for (int k = 0; k < ctx->ncolours; ++k) {
+    const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
+    if (c1 <= c0) continue;
+    const size_t threads = (size_t)(c1 - c0) * nb;
+    if (u2 == nullptr || u2 == u1)
+      LAUNCH(ctx, k_convvec<true>, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell,
+             ctx->cn.p, ctx->geom.p, u1, u1, out, nb);
+    else
+      LAUNCH(ctx, k_convvec<false>, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell,
+             ctx->cn.p, ctx->geom.p, u1, u2, out, nb);
+  }
+  return 0;
+}
+
+extern "C" int dnsb_convvec(dnsb_ctx *ctx, const double *u1, const double *u2,
+                            double *out, int nb) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, ctx->ncell > 0, "set the mesh first");
+  DNSB_REQUIRE(ctx, u1 && out && nb >= 1, "bad arguments");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const size_t nfull = (size_t)2 * ctx->nnodes * nb;
+  DNSB_CK(ctx, ctx->stage_a.upload(u1, nfull, ctx->stream));
+  if (u2) DNSB_CK(ctx, ctx->stage_b.upload(u2, nfull, ctx->stream));
+  DNSB_CK(ctx, ctx->stage_c.alloc(nfull));
+  int rc = convvec_dev(ctx, ctx->stage_a.p, u2 ? ctx->stage_b.p : nullptr,
+                       ctx->stage_c.p, nb);
+  if (rc) return rc;
+  DNSB_CK(ctx, cudaMemcpyAsync(out, ctx->stage_c.p, nfull * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dnsb_convmats(dnsb_ctx *ctx, const double *u0, double *n1_data,
+                             double *n2_data, double *f3) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, ctx->ncell > 0 && ctx->cnnz > 0, "set mesh and pattern first");
+  DNSB_REQUIRE(ctx, u0 != nullptr, "null u0");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const size_t nfull = (size_t)2 * ctx->nnodes;
+  const size_t nnz = ctx->cnnz;
+  DNSB_CK(ctx, ctx->stage_a.upload(u0, nfull, ctx->stream));
+  DNSB_CK(ctx, ctx->stage_b.alloc(nnz));
+  DNSB_CK(ctx, ctx->stage_c.alloc(nnz));
+  DNSB_CK(ctx, ctx->stage_d.alloc(nfull));
+  DNSB_CK(ctx, ctx->stage_b.zero(ctx->stream));
+  DNSB_CK(ctx, ctx->stage_c.zero(ctx->stream));
+  DNSB_CK(ctx, ctx->stage_d.zero(ctx->stream));
+  for (int k = 0; k < ctx->ncolours; ++k) {
+    const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
+    if (c1 <= c0) continue;
+    const size_t threads = (size_t)(c1 - c0) * 6;
+    LAUNCH(ctx, k_convmats, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell, ctx->cn.p,
+           ctx->geom.p, ctx->cslots.p, ctx->stage_a.p,
+           n1_data ? ctx->stage_b.p : nullptr, n2_data ? ctx->stage_c.p : nullptr,
+           f3 ? ctx->stage_d.p : nullptr);
+  }
+  if (n1_data) DNSB_CK(ctx, cudaMemcpyAsync(n1_data, ctx->stage_b.p, nnz * sizeof(double),
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+  if (n2_data) DNSB_CK(ctx, cudaMemcpyAsync(n2_data, ctx->stage_c.p, nnz * sizeof(double),
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+  if (f3) DNSB_CK(ctx, cudaMemcpyAsync(f3, ctx->stage_d.p, nfull * sizeof(double),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ===========================================================================
+// CSR API
+// ===========================================================================
+extern "C" int dnsb_csr_create(dnsb_ctx *ctx, int nrows, int ncols,
+                               const int32_t *indptr, const int32_t *indices,
+                               const double *vals1, const double *vals2,
+                               dnsb_csr **out) {
+  if (!ctx) return -2;
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  return csr_build(ctx, nrows, ncols, indptr, indices, vals1, vals2, out);
+}
+
+extern "C" void dnsb_csr_destroy(dnsb_csr *mat) {
+  if (mat) cudaSetDevice(mat->ctx->device);
+  csr_free(mat);
+}
+
+extern "C" int dnsb_spmm_dev(dnsb_csr *mat, const double *coef_dev,
+                             const double *x_dev, double *y_dev, int nb,
+                             double alpha, double beta) {
+  if (!mat) return -2;
+  dnsb_ctx *ctx = mat->ctx;
+  DNSB_REQUIRE(ctx, x_dev && y_dev && nb >= 1, "bad arguments");
+  DNSB_REQUIRE(ctx, !(mat->has2 && coef_dev == nullptr), "matrix has a second value array: coef required");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  spmm_dev(ctx, mat, coef_dev, x_dev, y_dev, y_dev, nb, alpha, beta);
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dnsb_spmm(dnsb_csr *mat, const double *coef, const double *x,
+                         double *y, int nb, double alpha, double beta) {
+  if (!mat) return -2;
+  dnsb_ctx *ctx = mat->ctx;
+  DNSB_REQUIRE(ctx, x && y && nb >= 1, "bad arguments");
+  DNSB_REQUIRE(ctx, !(mat->has2 && coef == nullptr), "matrix has a second value array: coef required");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, ctx->stage_a.upload(x, (size_t)mat->ncols * nb, ctx->stream));
+  if (beta != 0.0)
+    DNSB_CK(ctx, ctx->stage_b.upload(y, (size_t)mat->nrows * nb, ctx->stream));
+  else
+    DNSB_CK(ctx, ctx->stage_b.alloc((size_t)mat->nrows * nb));
+  if (coef) DNSB_CK(ctx, ctx->stage_c.upload(coef, nb, ctx->stream));
+  spmm_dev(ctx, mat, coef ? ctx->stage_c.p : nullptr, ctx->stage_a.p, ctx->stage_b.p,
+           ctx->stage_b.p, nb, alpha, beta);
+  DNSB_CK(ctx, cudaMemcpyAsync(y, ctx->stage_b.p, (size_t)mat->nrows * nb * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ===========================================================================
+// saddle-point solver
+// ===========================================================================
+// one level of a multigrid hierarchy (pressure/Schur block or velocity block)
+enum { MG_MULTI = 0, MG_DENSE = 1, MG_SMOOTH = 2 };
+struct MgLevel {
+  dnsb_csr *A = nullptr, *P = nullptr, *R = nullptr;
+  const double *coef = nullptr;   // per-member coefficient of A.v2 (level 0 of the velocity block)
+  int n = 0, nsmooth = 1, kind = MG_MULTI;
+  double lmin = 0, lmax = 0;
+  DBuf<double> dinv_dense;   // n*n (MG_DENSE)
+  DBuf<double> dinv_own;     // n*nb Jacobi (owned)
+  const double *dinv = nullptr;
+  DBuf<double> b, x, r, d0, d1, t;   // n*nb work vectors
+};
+
+struct dnsb_solver {
+  dnsb_ctx *ctx = nullptr;
+  int nv = 0, np = 0, ntot = 0, nb = 1, mr = 30, kF = 3;
+  double lmin = 0, lmax = 0;
+  dnsb_csr *F = nullptr, *J = nullptr, *JT = nullptr;
+  dnsb_csr *K = nullptr;   // owned: [F JT; J 0]
+  DBuf<double> coef;       // nb (device copy)
+  bool has_coef = false;
+  DBuf<double> dinv;       // nv*nb
+  DBuf<int> diagpos;
+  DBuf<double> Vb, Zb, w;  // Krylov bases
+  DBuf<double> cres, cd0, cd1;   // Chebyshev work (nv*nb)
+  DBuf<double> partial, partial2;
+  RedCfg rc;
+  // GMRES scalars
+  DBuf<double> gR, gcs, gsn, gg, gh, ginvh, gbnorm, gresid;
+  DBuf<int> gdone, gits, gittot, gflags;
+  GmresState gs;
+  int *h_flags = nullptr;   // pinned
+  std::vector<MgLevel *> levels;    // Schur (pressure) hierarchy
+  std::vector<MgLevel *> vlevels;   // velocity hierarchy; [0] = F itself
+  DBuf<double> mp_dinv, mp_scale;
+  bool has_mass = false;
+  int expect_its = 0;
+  bool save_v0 = false;        // keep r0/beta and 1/beta of the first cycle
+  DBuf<double> v0save, ibeta0;
+  // user-facing staging
+  DBuf<double> sb, sx;
+  long long stat_iters = 0, stat_solves = 0, stat_launched = 0;
+  double stat_max_relres = 0;
+};
+
+static int find_diagpos(dnsb_ctx *ctx, const dnsb_csr *A, std::vector<int> &dp) {
+  dp.assign(A->nrows, -1);
+  for (int i = 0; i < A->nrows; ++i) {
+    for (int k = A->h_indptr[i]; k < A->h_indptr[i + 1]; ++k)
+      if (A->h_indices[k] == i) { dp[i] = k; break; }
+    DNSB_REQUIRE(ctx, dp[i] >= 0, "matrix has a structurally zero diagonal entry");
+  }
+  return 0;
+}
+
+extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
+                                  dnsb_csr *jtmat, const double *coef, int nb,
+                                  int restart, int cheb_steps, double lmin,
+                                  double lmax, dnsb_solver **out) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, fmat && jmat && jtmat && out, "null matrices");
+  DNSB_REQUIRE(ctx, nb >= 1 && nb <= 1024, "nb must be in 1..1024");
+  DNSB_REQUIRE(ctx, restart >= 2 && restart <= 200, "restart must be in 2..200");
+  DNSB_REQUIRE(ctx, cheb_steps >= 1, "cheb_steps >= 1");
+  DNSB_REQUIRE(ctx, lmax > lmin && lmin > 0, "need 0 < lmin < lmax");
+  const int nv = fmat->nrows, np = jmat->nrows;
+  DNSB_REQUIRE(ctx, fmat->ncols == nv && jmat->ncols == nv && jtmat->nrows == nv &&
+               jtmat->ncols == np, "inconsistent block shapes");
+  DNSB_REQUIRE(ctx, !(fmat->has2 && !coef), "fmat has two value arrays: coef required");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  dnsb_solver *s = new (std::nothrow) dnsb_solver();
+  DNSB_REQUIRE(ctx, s != nullptr, "out of host memory");
+  s->ctx = ctx; s->nv = nv; s->np = np; s->ntot = nv + np; s->nb = nb;
+  s->mr = restart; s->kF = cheb_steps; s->lmin = lmin; s->lmax = lmax;
+  s->F = fmat; s->J = jmat; s->JT = jtmat;
+  *out = s;
+  // ---- block matrix K = [F JT; J 0] on the host, then upload -------------
+  {
+    const int ntot = s->ntot;
+    std::vector<int> ip(ntot + 1, 0), ix;
+    std::vector<double> a1, a2;
+    const size_t nnz = (size_t)fmat->nnz + jtmat->nnz + jmat->nnz;
+    ix.reserve(nnz); a1.reserve(nnz);
+    if (fmat->has2) a2.reserve(nnz);
+    for (int i = 0; i < nv; ++i) {
+      for (int k = fmat->h_indptr[i]; k < fmat->h_indptr[i + 1]; ++k) {
+        ix.push_back(fmat->h_indices[k]);
+        a1.push_back(fmat->h_v1[k]);
+        if (fmat->has2) a2.push_back(fmat->h_v2[k]);
+      }
+      for (int k = jtmat->h_indptr[i]; k < jtmat->h_indptr[i + 1]; ++k) {
+        ix.push_back(nv + jtmat->h_indices[k]);
+        a1.push_back(jtmat->h_v1[k]);
+        if (fmat->has2) a2.push_back(0.0);
+      }
+      ip[i + 1] = (int)ix.size();
+    }
+    for (int j = 0; j < np; ++j) {
+      for (int k = jmat->h_indptr[j]; k < jmat->h_indptr[j + 1]; ++k) {
+        ix.push_back(jmat->h_indices[k]);
+        a1.push_back(jmat->h_v1[k]);
+        if (fmat->has2) a2.push_back(0.0);
+      }
+      ip[nv + j + 1] = (int)ix.size();
+    }
+    int rc = csr_build(ctx, ntot, ntot, ip.data(), ix.data(), a1.data(),
+                       fmat->has2 ? a2.data() : nullptr, &s->K);
+    if (rc) return rc;
+    // the block matrix is only needed on the device
+    std::vector<int>().swap(s->K->h_indptr); std::vector<int>().swap(s->K->h_indices);
+    std::vector<double>().swap(s->K->h_v1); std::vector<double>().swap(s->K->h_v2);
+  }
+  if (coef) {
+    DNSB_CK(ctx, s->coef.upload(coef, nb, ctx->stream));
+    s->has_coef = true;
+  }
+  std::vector<int> dp;
+  { int rc = find_diagpos(ctx, fmat, dp); if (rc) return rc; }
+  DNSB_CK(ctx, s->diagpos.upload(dp.data(), dp.size(), ctx->stream));
+  const size_t nvb = (size_t)nv * nb, ntb = (size_t)s->ntot * nb;
+  DNSB_CK(ctx, s->dinv.alloc(nvb));
+  LAUNCH(ctx, k_diag_inv, cdiv(nvb, 256), 256, 0, fmat->view(), s->diagpos.p,
+         s->has_coef ? s->coef.p : nullptr, s->dinv.p, nb);
+  {
+    MgLevel *V0 = new (std::nothrow) MgLevel();
+    DNSB_REQUIRE(ctx, V0 != nullptr, "out of host memory");
+    V0->A = fmat; V0->coef = s->has_coef ? s->coef.p : nullptr;
+    V0->n = nv; V0->nsmooth = s->kF; V0->kind = MG_SMOOTH;
+    V0->lmin = lmin; V0->lmax = lmax; V0->dinv = s->dinv.p;
+    s->vlevels.push_back(V0);
+    DNSB_CK(ctx, V0->b.alloc(nvb)); DNSB_CK(ctx, V0->r.alloc(nvb));
+    DNSB_CK(ctx, V0->d0.alloc(nvb)); DNSB_CK(ctx, V0->d1.alloc(nvb));
+    DNSB_CK(ctx, V0->t.alloc(nvb));
+  }
+  DNSB_CK(ctx, s->Vb.alloc(ntb * (s->mr + 1)));
+  DNSB_CK(ctx, s->Zb.alloc(ntb * s->mr));
+  DNSB_CK(ctx, s->w.alloc(ntb));
+  DNSB_CK(ctx, s->cres.alloc(nvb));
+  DNSB_CK(ctx, s->cd0.alloc(nvb));
+  DNSB_CK(ctx, s->cd1.alloc(nvb));
+  s->rc = red_cfg(ctx, s->ntot, nb);
+  DNSB_CK(ctx, s->partial.alloc((size_t)s->rc.nblocks * (s->mr + 1) * nb));
+  DNSB_CK(ctx, s->partial2.alloc((size_t)s->rc.nblocks * nb));
+  const int mr = s->mr;
+  DNSB_CK(ctx, s->gR.alloc((size_t)(mr + 1) * mr * nb));
+  DNSB_CK(ctx, s->gcs.alloc((size_t)mr * nb));
+  DNSB_CK(ctx, s->gsn.alloc((size_t)mr * nb));
+  DNSB_CK(ctx, s->gg.alloc((size_t)(mr + 1) * nb));
+  DNSB_CK(ctx, s->gh.alloc((size_t)(mr + 1) * nb));
+  DNSB_CK(ctx, s->ginvh.alloc(nb));
+  DNSB_CK(ctx, s->gbnorm.alloc(nb));
+  DNSB_CK(ctx, s->gresid.alloc(nb));
+  DNSB_CK(ctx, s->gdone.alloc(nb));
+  DNSB_CK(ctx, s->gits.alloc(nb));
+  DNSB_CK(ctx, s->gittot.alloc(nb));
+  DNSB_CK(ctx, s->gflags.alloc(4));
+  DNSB_CK(ctx, s->ibeta0.alloc(nb));
+  s->gs.R = s->gR.p; s->gs.cs = s->gcs.p; s->gs.sn = s->gsn.p; s->gs.g = s->gg.p;
+  s->gs.h = s->gh.p; s->gs.invh = s->ginvh.p; s->gs.bnorm = s->gbnorm.p;
+  s->gs.resid = s->gresid.p; s->gs.done = s->gdone.p; s->gs.its = s->gits.p;
+  s->gs.ittot = s->gittot.p; s->gs.flags = s->gflags.p; s->gs.mr = mr;
+  DNSB_CK(ctx, cudaMallocHost((void **)&s->h_flags, 4 * sizeof(int)));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+static void level_free(MgLevel *L) {
+  if (!L) return;
+  L->dinv_dense.release(); L->dinv_own.release(); L->b.release(); L->x.release();
+  L->r.release(); L->d0.release(); L->d1.release(); L->t.release();
+  delete L;
+}
+
+extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  csr_free(s->K);
+  s->coef.release(); s->dinv.release(); s->diagpos.release();
+  s->Vb.release(); s->Zb.release(); s->w.release();
+  s->cres.release(); s->cd0.release(); s->cd1.release();
+  s->partial.release(); s->partial2.release();
+  s->gR.release(); s->gcs.release(); s->gsn.release(); s->gg.release(); s->gh.release();
+  s->ginvh.release(); s->gbnorm.release(); s->gresid.release();
+  s->gdone.release(); s->gits.release(); s->gittot.release(); s->gflags.release();
+  s->mp_dinv.release(); s->mp_scale.release(); s->sb.release(); s->sx.release();
+  s->v0save.release(); s->ibeta0.release();
+  for (MgLevel *L : s->levels) level_free(L);
+  for (MgLevel *L : s->vlevels) level_free(L);
+  if (s->h_flags) cudaFreeHost(s->h_flags);
+  delete s;
+}
+
+// append a level to the pressure (block 0) or velocity (block 1) hierarchy
+static int solver_add_level(dnsb_solver *s, int block, dnsb_csr *amat, dnsb_csr *pmat,
+                            dnsb_csr *rmat, int nsmooth, double lmin, double lmax,
+                            const double *dense_inv) {
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  std::vector<MgLevel *> &lv = block == 0 ? s->levels : s->vlevels;
+  int nexpect;
+  if (lv.empty()) {
+    DNSB_REQUIRE(ctx, block == 0, "velocity level 0 is the matrix F itself");
+    nexpect = s->np;
+  } else {
+    MgLevel *up = lv.back();
+    DNSB_REQUIRE(ctx, up->kind == MG_MULTI && up->P, "previous level is terminal");
+    nexpect = up->P->ncols;
+  }
+  MgLevel *L = new (std::nothrow) MgLevel();
+  DNSB_REQUIRE(ctx, L != nullptr, "out of host memory");
+  L->n = nexpect;
+  cudaError_t e = cudaSuccess;
+  if (dense_inv) {
+    L->kind = MG_DENSE;
+    e = L->dinv_dense.upload(dense_inv, (size_t)nexpect * nexpect, ctx->stream);
+    if (e != cudaSuccess) { level_free(L); DNSB_CK(ctx, e); }
+  } else {
+    bool ok = amat && amat->nrows == nexpect && amat->ncols == nexpect && lmax > lmin &&
+              lmin > 0 && nsmooth >= 1 && !amat->has2;
+    if (ok && (pmat || rmat))
+      ok = pmat && rmat && pmat->nrows == nexpect && rmat->ncols == nexpect &&
+           rmat->nrows == pmat->ncols;
+    if (!ok) { delete L; DNSB_REQUIRE(ctx, false, "inconsistent multigrid level"); }
+    L->kind = pmat ? MG_MULTI : MG_SMOOTH;
+    L->A = amat; L->P = pmat; L->R = rmat;
+    L->nsmooth = nsmooth; L->lmin = lmin; L->lmax = lmax;
+    std::vector<int> dp;
+    if (find_diagpos(ctx, amat, dp)) { delete L; return -2; }
+    DBuf<int> dpd;
+    e = dpd.upload(dp.data(), dp.size(), ctx->stream);
+    if (e != cudaSuccess) { level_free(L); DNSB_CK(ctx, e); }
+    const size_t nn = (size_t)nexpect * s->nb;
+    if ((e = L->dinv_own.alloc(nn)) != cudaSuccess) { level_free(L); dpd.release(); DNSB_CK(ctx, e); }
+    LAUNCH(ctx, k_diag_inv, cdiv(nn, 256), 256, 0, amat->view(), dpd.p,
+           (const double *)nullptr, L->dinv_own.p, s->nb);
+    cudaStreamSynchronize(ctx->stream);
+    dpd.release();
+    L->dinv = L->dinv_own.p;
+  }
+  const size_t nn = (size_t)L->n * s->nb;
+  if ((e = L->b.alloc(nn)) != cudaSuccess || (e = L->x.alloc(nn)) != cudaSuccess ||
+      (e = L->r.alloc(nn)) != cudaSuccess || (e = L->d0.alloc(nn)) != cudaSuccess ||
+      (e = L->d1.alloc(nn)) != cudaSuccess || (e = L->t.alloc(nn)) != cudaSuccess) {
+    level_free(L);
+    DNSB_CK(ctx, e);
+  }
+  lv.push_back(L);
+  return 0;
+}
+
+extern "C" int dnsb_solver_add_schur_level(dnsb_solver *s, dnsb_csr *amat,
+                                           dnsb_csr *pmat, dnsb_csr *rmat,
+                                           int nsmooth, double lmin, double lmax,
+                                           const double *dense_inv) {
+  if (!s) return -2;
+  return solver_add_level(s, 0, amat, pmat, rmat, nsmooth, lmin, lmax, dense_inv);
+}
+
+extern "C" int dnsb_solver_set_velocity_transfer(dnsb_solver *s, dnsb_csr *pmat,
+                                                 dnsb_csr *rmat) {
+  if (!s) return -2;
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_REQUIRE(ctx, pmat && rmat && pmat->nrows == s->nv && rmat->ncols == s->nv &&
+               rmat->nrows == pmat->ncols, "inconsistent velocity transfer operators");
+  DNSB_REQUIRE(ctx, s->vlevels.size() == 1, "velocity hierarchy already built");
+  s->vlevels[0]->P = pmat; s->vlevels[0]->R = rmat;
+  s->vlevels[0]->kind = MG_MULTI;
+  return 0;
+}
+
+extern "C" int dnsb_solver_add_velocity_level(dnsb_solver *s, dnsb_csr *amat,
+                                              dnsb_csr *pmat, dnsb_csr *rmat,
+                                              int nsmooth, double lmin, double lmax,
+                                              const double *dense_inv) {
+  if (!s) return -2;
+  return solver_add_level(s, 1, amat, pmat, rmat, nsmooth, lmin, lmax, dense_inv);
+}
+
+extern "C" int dnsb_solver_set_schur_mass(dnsb_solver *s, const double *mp_dinv,
+                                          const double *mp_scale) {
+  if (!s) return -2;
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_REQUIRE(ctx, mp_dinv && mp_scale, "null arguments");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, s->mp_dinv.upload(mp_dinv, s->np, ctx->stream));
+  DNSB_CK(ctx, s->mp_scale.upload(mp_scale, s->nb, ctx->stream));
+  s->has_mass = true;
+  return 0;
+}
+
+// dense coarse solve  y = alpha*(Dinv x [+ scale_m*mp_dinv*x])
+static void dense_apply(dnsb_solver *s, const MgLevel *L, const double *x,
+                        double *y, double alpha, bool with_mass) {
+  dnsb_ctx *ctx = s->ctx;
+  const int n = L->n, nb = s->nb;
+  const double *ad = with_mass ? s->mp_dinv.p : nullptr;
+  const double *as = with_mass ? s->mp_scale.p : nullptr;
+  if (nb <= 1)
+    LAUNCH(ctx, k_dense_gemv<1>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else if (nb <= 2)
+    LAUNCH(ctx, k_dense_gemv<2>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else if (nb <= 4)
+    LAUNCH(ctx, k_dense_gemv<4>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else if (nb <= 8)
+    LAUNCH(ctx, k_dense_gemv<8>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else if (nb <= 16)
+    LAUNCH(ctx, k_dense_gemm<16>, dim3(cdiv(n, DG_TM), cdiv(nb, 16)), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else if (nb <= 32)
+    LAUNCH(ctx, k_dense_gemm<32>, dim3(cdiv(n, DG_TM), cdiv(nb, 32)), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else
+    LAUNCH(ctx, k_dense_gemm<64>, dim3(cdiv(n, DG_TM), cdiv(nb, 64)), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+}
+
+// z = (k-step Jacobi-Chebyshev)(A) r  with zero initial guess; `res` may alias r
+static void cheb_plain(dnsb_solver *s, const dnsb_csr *A, const double *coef,
+                       const double *dinv, const double *r, double *z, double *res,
+                       double *d0, double *d1, int k, double lmin, double lmax) {
+  dnsb_ctx *ctx = s->ctx;
+  const int nb = s->nb;
+  const size_t nn = (size_t)A->nrows * nb;
+  const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+  const double sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  LAUNCH(ctx, k_cheb_init_plain, cdiv(nn, 256), 256, 0, r, dinv, res, d0, z, nn, 1.0 / theta);
+  double *dc = d0, *dn = d1;
+  for (int i = 0; i + 1 < k; ++i) {
+    const double rho_n = 1.0 / (2.0 * sigma - rho);
+    const double c1 = rho_n * rho, c2 = 2.0 * rho_n / delta;
+    if (nb == 1)
+      LAUNCH(ctx, k_cheb_step<8>, cdiv((size_t)A->nrows * 8, 256), 256, 0, A->view(), coef, dc, dinv, res, dn, z, nb, c1, c2);
+    else
+      LAUNCH(ctx, k_cheb_step<1>, cdiv(nn, 256), 256, 0, A->view(), coef, dc, dinv, res, dn, z, nb, c1, c2);
+    std::swap(dc, dn);
+    rho = rho_n;
+  }
+}
+
+// out[i,m] = alpha*(a[i,m] + b[i,m]*rowscale[i])
+__global__ void k_rowscale_add(const double *a, const double *b, const double *rowscale,
+                               double *out, int n, int nb, double alpha) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * nb) return;
+  out[t] = alpha * (a[t] + b[t] * rowscale[t / nb]);
+}
+
+// out[i,m] = alpha*a[i,m]*rowscale[i]
+__global__ void k_rowscale_mul(const double *a, const double *rowscale, double *out, int n,
+                               int nb, double alpha) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * nb) return;
+  out[t] = alpha * a[t] * rowscale[t / nb];
+}
+
+// x = Vcycle(b) on level l of hierarchy `lv` (b, x: n_l*nb device vectors,
+// b is not modified)
+static void mg_vcycle(dnsb_solver *s, std::vector<MgLevel *> &lv, size_t l,
+                      const double *b, double *x) {
+  dnsb_ctx *ctx = s->ctx;
+  MgLevel *L = lv[l];
+  const int nb = s->nb;
+  if (L->kind == MG_DENSE) {
+    dense_apply(s, L, b, x, 1.0, false);
+    return;
+  }
+  if (L->kind == MG_SMOOTH) {
+    cheb_plain(s, L->A, L->coef, L->dinv, b, x, L->r.p, L->d0.p, L->d1.p, L->nsmooth, L->lmin, L->lmax);
+    return;
+  }
+  const size_t nn = (size_t)L->n * nb;
+  MgLevel *C = lv[l + 1];
+  // pre-smoothing from a zero guess
+  cheb_plain(s, L->A, L->coef, L->dinv, b, x, L->r.p, L->d0.p, L->d1.p, L->nsmooth, L->lmin, L->lmax);
+  // residual and restriction
+  spmm_dev(ctx, L->A, L->coef, x, b, L->r.p, nb, -1.0, 1.0);
+  spmm_dev(ctx, L->R, nullptr, L->r.p, nullptr, C->b.p, nb, 1.0, 0.0);
+  mg_vcycle(s, lv, l + 1, C->b.p, C->x.p);
+  // prolongation and correction
+  spmm_dev(ctx, L->P, nullptr, C->x.p, x, x, nb, 1.0, 1.0);
+  // post-smoothing:  x += cheb(b - A x)
+  spmm_dev(ctx, L->A, L->coef, x, b, L->r.p, nb, -1.0, 1.0);
+  cheb_plain(s, L->A, L->coef, L->dinv, L->r.p, L->t.p, L->r.p, L->d0.p, L->d1.p,
+             L->nsmooth, L->lmin, L->lmax);
+  LAUNCH(ctx, k_axpby, cdiv(nn, 256), 256, 0, 1.0, (const double *)x, 1.0, (const double *)L->t.p, x, nn);
+}
+
+// z = P^-1 r   (block upper-triangular preconditioner)
+static int apply_prec(dnsb_solver *s, const double *r, double *z) {
+  dnsb_ctx *ctx = s->ctx;
+  const int nb = s->nb, nv = s->nv, np = s->np;
+  const size_t nvb = (size_t)nv * nb, npb = (size_t)np * nb;
+  const double *rv = r, *rp = r + nvb;
+  double *zv = z, *zp = z + nvb;
+  DNSB_REQUIRE(ctx, !s->levels.empty() || s->has_mass, "no Schur approximation set");
+  // ---- zp = -Sh^-1 rp ------------------------------------------------------
+  if (s->levels.empty()) {
+    // scaled (lumped) pressure mass matrix only:  zp = -scale_m * mp_dinv_i * rp
+    LAUNCH(ctx, k_scale_member, cdiv(npb, 256), 256, 0, rp, s->mp_scale.p, zp, (size_t)np, nb);
+    LAUNCH(ctx, k_rowscale_mul, cdiv(npb, 256), 256, 0, zp, s->mp_dinv.p, zp, np, nb, -1.0);
+  } else {
+    MgLevel *L0 = s->levels[0];
+    if (L0->kind == MG_DENSE) {
+      dense_apply(s, L0, rp, zp, -1.0, s->has_mass);
+    } else {
+      mg_vcycle(s, s->levels, 0, rp, L0->x.p);
+      if (s->has_mass) {
+        // t = scale_m*rp ;  zp = -(x + mp_dinv_i*t)
+        LAUNCH(ctx, k_scale_member, cdiv(npb, 256), 256, 0, rp, s->mp_scale.p, L0->t.p, (size_t)np, nb);
+        LAUNCH(ctx, k_rowscale_add, cdiv(npb, 256), 256, 0, L0->x.p, L0->t.p, s->mp_dinv.p, zp, np, nb, -1.0);
+      } else {
+        LAUNCH(ctx, k_axpby, cdiv(npb, 256), 256, 0, -1.0, (const double *)L0->x.p, 0.0,
+               (const double *)nullptr, zp, npb);
+      }
+    }
+  }
+  // ---- zv = Fh^-1 (rv - JT zp) ---------------------------------------------
+  MgLevel *V0 = s->vlevels[0];
+  if (V0->kind != MG_SMOOTH) {
+    spmm_dev(ctx, s->JT, nullptr, zp, rv, V0->b.p, nb, -1.0, 1.0);
+    mg_vcycle(s, s->vlevels, 0, V0->b.p, zv);
+    return 0;
+  }
+  // single level: Chebyshev only, fused with the gradient coupling
+  const double theta = 0.5 * (s->lmax + s->lmin), delta = 0.5 * (s->lmax - s->lmin);
+  const double sigma = theta / delta;
+  double rho = 1.0 / sigma;
+  if (nb == 1)
+    LAUNCH(ctx, k_cheb_init<8>, cdiv((size_t)nv * 8, 256), 256, 0, s->JT->view(), zp, rv,
+           s->dinv.p, s->cres.p, s->cd0.p, zv, nb, 1.0 / theta);
+  else
+    LAUNCH(ctx, k_cheb_init<1>, cdiv(nvb, 256), 256, 0, s->JT->view(), zp, rv, s->dinv.p,
+           s->cres.p, s->cd0.p, zv, nb, 1.0 / theta);
+  double *dc = s->cd0.p, *dn = s->cd1.p;
+  const double *coef = s->has_coef ? s->coef.p : nullptr;
+  for (int i = 0; i + 1 < s->kF; ++i) {
+    const double rho_n = 1.0 / (2.0 * sigma - rho);
+    const double c1 = rho_n * rho, c2 = 2.0 * rho_n / delta;
+    if (nb == 1)
+      LAUNCH(ctx, k_cheb_step<8>, cdiv((size_t)nv * 8, 256), 256, 0, s->F->view(), coef, dc,
+             s->dinv.p, s->cres.p, dn, zv, nb, c1, c2);
+    else
+      LAUNCH(ctx, k_cheb_step<1>, cdiv(nvb, 256), 256, 0, s->F->view(), coef, dc, s->dinv.p,
+             s->cres.p, dn, zv, nb, c1, c2);
+    std::swap(dc, dn);
+    rho = rho_n;
+  }
+  return 0;
+}
+
+static int read_flags(dnsb_solver *s) {
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_CK(ctx, cudaMemcpyAsync(s->h_flags, s->gs.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// FGMRES on device vectors: b (ntot*nb), x (in: initial guess, out: solution)
+static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double tol,
+                            int maxit, bool zero_guess) {
+  dnsb_ctx *ctx = s->ctx;
+  const int nb = s->nb, ntot = s->ntot, mr = s->mr;
+  const size_t ntb = (size_t)ntot * nb;
+  const RedCfg &rc = s->rc;
+  const double *coef = s->has_coef ? s->coef.p : nullptr;
+  // |b|
+  LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, b, b, ntot, nb, rc.rpb, s->partial2.p);
+  LAUNCH(ctx, k_set_bnorm, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, s->partial2.p, rc.nblocks, nb);
+  if (zero_guess) DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
+  int total = 0;
+  bool first = true;
+  int expect = s->expect_its;
+  while (true) {
+    double *V0 = s->Vb.p;
+    if (zero_guess && first)
+      DNSB_CK(ctx, cudaMemcpyAsync(V0, b, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+      spmm_dev(ctx, s->K, coef, x, b, V0, nb, -1.0, 1.0);
+    LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, V0, V0, ntot, nb, rc.rpb, s->partial2.p);
+    LAUNCH(ctx, k_gmres_begin, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, s->partial2.p,
+           rc.nblocks, nb, tol, first ? 1 : 0);
+    LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, V0, s->gs.invh, V0, (size_t)ntot, nb);
+    if (first && s->save_v0) {
+      DNSB_CK(ctx, cudaMemcpyAsync(s->v0save.p, V0, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      DNSB_CK(ctx, cudaMemcpyAsync(s->ibeta0.p, s->gs.invh, nb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    first = false;
+    if (read_flags(s)) return -1;
+    if (s->h_flags[0] == 0) break;
+    int j = 0;
+    bool alldone = false;
+    for (; j < mr && total < maxit; ++j, ++total) {
+      double *Vj = s->Vb.p + (size_t)j * ntb;
+      double *Zj = s->Zb.p + (size_t)j * ntb;
+      if (apply_prec(s, Vj, Zj)) return -1;
+      spmm_dev(ctx, s->K, coef, Zj, nullptr, s->w.p, nb, 1.0, 0.0);
+      LAUNCH(ctx, k_mdot, rc.nblocks, rc.threads, rc.smem, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb,
+             rc.rpb, s->partial.p);
+      LAUNCH(ctx, k_reduce_partials, cdiv((size_t)(j + 1) * nb, 128), 128, 0, s->partial.p,
+             rc.nblocks, (j + 1) * nb, s->gs.h);
+      LAUNCH(ctx, k_gs_update, rc.nblocks, rc.threads, rc.smem, s->Vb.p, ntb, j + 1, s->gs.h,
+             s->w.p, ntot, nb, rc.rpb, s->partial2.p);
+      LAUNCH(ctx, k_gmres_givens, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, s->partial2.p,
+             rc.nblocks, nb, j, tol);
+      LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, s->w.p, s->gs.invh,
+             s->Vb.p + (size_t)(j + 1) * ntb, (size_t)ntot, nb);
+      // convergence poll: skipped while far from the expected iteration count
+      if (total + 1 >= expect - 1 || j + 1 == mr || total + 1 == maxit) {
+        if (read_flags(s)) return -1;
+        if (s->h_flags[0] == 0) { alldone = true; ++j; ++total; break; }
+      }
+    }
+    const int ncols = j;
+    if (ncols > 0) {
+      LAUNCH(ctx, k_gmres_solve_y, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, nb, ncols);
+      LAUNCH(ctx, k_gmres_update_x, cdiv(ntb, 256), 256, 0, s->Zb.p, ntb, ncols, s->gs.h, x,
+             (size_t)ntot, nb);
+    }
+    if (alldone || total >= maxit) break;
+  }
+  // h_flags[1]: iteration at which the last member converged (<= total; the
+  // difference are iterations launched between two convergence polls)
+  const int needed = std::min(total, std::max(0, s->h_flags[1]));
+  s->expect_its = needed;
+  s->stat_iters += needed;
+  s->stat_launched += total;
+  s->stat_solves += 1;
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dnsb_solver_solve(dnsb_solver *s, const double *rhsv, const double *rhsp,
+                                 const double *x0, double *vp, double tol, int maxit,
+                                 int *iters, double *relres) {
+  if (!s) return -2;
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_REQUIRE(ctx, rhsv && vp && maxit >= 1 && tol > 0, "bad arguments");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const int nb = s->nb;
+  const size_t nvb = (size_t)s->nv * nb, npb = (size_t)s->np * nb, ntb = nvb + npb;
+  DNSB_CK(ctx, s->sb.alloc(ntb));
+  DNSB_CK(ctx, s->sx.alloc(ntb));
+  DNSB_CK(ctx, cudaMemcpyAsync(s->sb.p, rhsv, nvb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (rhsp)
+    DNSB_CK(ctx, cudaMemcpyAsync(s->sb.p + nvb, rhsp, npb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  else
+    DNSB_CK(ctx, cudaMemsetAsync(s->sb.p + nvb, 0, npb * sizeof(double), ctx->stream));
+  if (x0)
+    DNSB_CK(ctx, cudaMemcpyAsync(s->sx.p, x0, ntb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  s->expect_its = 0;
+  int rc = solver_solve_dev(s, s->sb.p, s->sx.p, tol, maxit, x0 == nullptr);
+  if (rc) return rc;
+  DNSB_CK(ctx, cudaMemcpyAsync(vp, s->sx.p, ntb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> res(nb), bn(nb);
+  std::vector<int> it(nb);
+  DNSB_CK(ctx, cudaMemcpyAsync(res.data(), s->gs.resid, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaMemcpyAsync(bn.data(), s->gs.bnorm, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaMemcpyAsync(it.data(), s->gs.ittot, nb * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int m = 0; m < nb; ++m) {
+    if (iters) iters[m] = it[m];
+    if (relres) relres[m] = bn[m] > 0 ? res[m] / bn[m] : 0.0;
+  }
+  return 0;
+}
+
+// ===========================================================================
+// IMEX time stepper
+// ===========================================================================
+struct dnsb_imex {
+  dnsb_ctx *ctx = nullptr;
+  int scheme = 0, nb = 1, nv = 0, np = 0, nvf = 0, nbc = 0;
+  double dt = 0;
+  dnsb_csr *M = nullptr, *A = nullptr, *J = nullptr, *JT = nullptr;
+  dnsb_csr *Rm = nullptr;   // owned: CNAB rhs operator  M - dt/2*A_m
+  dnsb_solver *sl = nullptr, *sp = nullptr, *sc = nullptr;
+  DBuf<double> nu, coefR, coefA;   // nb
+  DBuf<int> inv, bcinds;
+  DBuf<double> bcvals, fv, fp;
+  // forcing
+  int nk = 0, ntimes = 0;
+  DBuf<double> Bk, useries;
+  // state
+  DBuf<double> v, vprev, p, vfull, cfull, nfc_c, nfc_o, nfc_t, tmp, b, x;
+  // solution / rhs history for the initial guesses
+  int hist_len = 0, hist_cnt = 0, hist_pos = 0, hist_mode = 0;
+  DBuf<double> xh, bh, gr, partialh, x0, normpart, normout;
+  double last_relres = 0;
+  long long run_iters = 0, run_solves = 0;
+  // snapshots
+  DBuf<double> snaps;
+  int nsnap = 0, snap_cap = 0;
+  long long step = 0;   // steps done so far
+  bool have_state = false;
+  bool p_stale = false;
+};
+
+extern "C" int dnsb_imex_create(dnsb_ctx *ctx, int scheme, int nb, double dt,
+                                dnsb_csr *mmat, dnsb_csr *amat, dnsb_csr *jmat,
+                                dnsb_csr *jtmat, const double *nu,
+                                const int32_t *invinds, int nv, int nbc,
+                                const int32_t *bcinds, const double *bcvals,
+                                const double *fv, const double *fp, dnsb_imex **out) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, out && mmat && amat && jmat && jtmat && nu && invinds, "null arguments");
+  DNSB_REQUIRE(ctx, scheme >= 0 && scheme <= 2, "scheme must be 0 (CNAB), 1 (SBDF2) or 2 (IMEX Euler)");
+  DNSB_REQUIRE(ctx, ctx->ncell > 0, "set the mesh first");
+  DNSB_REQUIRE(ctx, nb >= 1 && dt > 0, "bad nb/dt");
+  DNSB_REQUIRE(ctx, mmat->nrows == nv && amat->nrows == nv && jmat->ncols == nv, "matrix sizes vs nv");
+  DNSB_REQUIRE(ctx, mmat->nnz == amat->nnz, "M and A must share one pattern");
+  DNSB_REQUIRE(ctx, amat->has2, "amat needs vals2 = a0 (nu-independent stiffness)");
+  for (int k = 0; k < mmat->nnz; ++k)
+    DNSB_REQUIRE(ctx, mmat->h_indices[k] == amat->h_indices[k], "M and A must share one pattern");
+  const int nvf = 2 * ctx->nnodes;
+  for (int i = 0; i < nv; ++i)
+    DNSB_REQUIRE(ctx, invinds[i] >= 0 && invinds[i] < nvf, "invinds out of range");
+  for (int i = 0; i < nbc; ++i)
+    DNSB_REQUIRE(ctx, bcinds[i] >= 0 && bcinds[i] < nvf, "bcinds out of range");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  dnsb_imex *e = new (std::nothrow) dnsb_imex();
+  DNSB_REQUIRE(ctx, e != nullptr, "out of host memory");
+  *out = e;
+  e->ctx = ctx; e->scheme = scheme; e->nb = nb; e->dt = dt;
+  e->nv = nv; e->np = jmat->nrows; e->nvf = nvf; e->nbc = nbc;
+  e->M = mmat; e->A = amat; e->J = jmat; e->JT = jtmat;
+  DNSB_CK(ctx, e->nu.upload(nu, nb, ctx->stream));
+  std::vector<double> cr(nb);
+  for (int m = 0; m < nb; ++m) cr[m] = -0.5 * dt * nu[m];
+  DNSB_CK(ctx, e->coefR.upload(cr.data(), nb, ctx->stream));
+  DNSB_CK(ctx, e->inv.upload(invinds, nv, ctx->stream));
+  if (nbc > 0) {
+    DNSB_CK(ctx, e->bcinds.upload(bcinds, nbc, ctx->stream));
+    DNSB_CK(ctx, e->bcvals.upload(bcvals, nbc, ctx->stream));
+  }
+  std::vector<double> zero(std::max(nv, e->np), 0.0);
+  DNSB_CK(ctx, e->fv.upload(fv ? fv : zero.data(), nv, ctx->stream));
+  DNSB_CK(ctx, e->fp.upload(fp ? fp : zero.data(), e->np, ctx->stream));
+  if (scheme == 0) {
+    // R = M - dt/2*arob  (vals1),  a0 (vals2) with coef -dt/2*nu_m
+    std::vector<double> r1(mmat->nnz);
+    for (int k = 0; k < mmat->nnz; ++k) r1[k] = mmat->h_v1[k] - 0.5 * dt * amat->h_v1[k];
+    int rc = csr_build(ctx, nv, nv, mmat->h_indptr.data(), mmat->h_indices.data(), r1.data(),
+                       amat->h_v2.data(), &e->Rm);
+    if (rc) return rc;
+  }
+  const size_t nvb = (size_t)nv * nb, npb = (size_t)e->np * nb, nfb = (size_t)nvf * nb;
+  DNSB_CK(ctx, e->v.alloc(nvb)); DNSB_CK(ctx, e->vprev.alloc(nvb));
+  DNSB_CK(ctx, e->p.alloc(npb));
+  DNSB_CK(ctx, e->vfull.alloc(nfb)); DNSB_CK(ctx, e->cfull.alloc(nfb));
+  DNSB_CK(ctx, e->nfc_c.alloc(nvb)); DNSB_CK(ctx, e->nfc_o.alloc(nvb));
+  DNSB_CK(ctx, e->nfc_t.alloc(nvb)); DNSB_CK(ctx, e->tmp.alloc(nvb));
+  DNSB_CK(ctx, e->b.alloc(nvb + npb)); DNSB_CK(ctx, e->x.alloc(nvb + npb));
+  DNSB_CK(ctx, e->vfull.zero(ctx->stream));
+  if (nbc > 0)
+    LAUNCH(ctx, k_set_bcs, cdiv((size_t)nbc * nb, 256), 256, 0, e->bcinds.p, e->bcvals.p,
+           e->vfull.p, nbc, nb);
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" void dnsb_imex_destroy(dnsb_imex *e) {
+  if (!e) return;
+  cudaSetDevice(e->ctx->device);
+  cudaStreamSynchronize(e->ctx->stream);
+  csr_free(e->Rm);
+  e->nu.release(); e->coefR.release(); e->coefA.release(); e->inv.release();
+  e->bcinds.release(); e->bcvals.release(); e->fv.release(); e->fp.release();
+  e->Bk.release(); e->useries.release();
+  e->v.release(); e->vprev.release(); e->p.release(); e->vfull.release(); e->cfull.release();
+  e->nfc_c.release(); e->nfc_o.release(); e->nfc_t.release(); e->tmp.release();
+  e->b.release(); e->x.release(); e->xh.release(); e->bh.release(); e->x0.release();
+  e->gr.release(); e->partialh.release(); e->snaps.release();
+  e->normpart.release(); e->normout.release();
+  delete e;
+}
+
+extern "C" int dnsb_imex_set_solvers(dnsb_imex *e, dnsb_solver *loop, dnsb_solver *pred,
+                                     dnsb_solver *corr) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, loop != nullptr, "loop solver required");
+  for (dnsb_solver *s : {loop, pred, corr})
+    if (s) DNSB_REQUIRE(ctx, s->nv == e->nv && s->np == e->np && s->nb == e->nb, "solver shape mismatch");
+  if (e->scheme != 2) DNSB_REQUIRE(ctx, pred && corr, "CNAB/SBDF2 need the Heun solvers");
+  e->sl = loop; e->sp = pred; e->sc = corr;
+  return 0;
+}
+
+extern "C" int dnsb_imex_set_forcing(dnsb_imex *e, int nk, const double *bvecs,
+                                     int ntimes, const double *useries) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, nk >= 0 && (nk == 0 || (bvecs && useries && ntimes >= 1)), "bad forcing");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  e->nk = nk; e->ntimes = ntimes;
+  if (nk > 0) {
+    DNSB_CK(ctx, e->Bk.upload(bvecs, (size_t)e->nv * nk, ctx->stream));
+    DNSB_CK(ctx, e->useries.upload(useries, (size_t)ntimes * nk * e->nb, ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int dnsb_imex_set_state(dnsb_imex *e, const double *v0, const double *p0) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, v0 != nullptr, "null v0");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const size_t nvb = (size_t)e->nv * e->nb, npb = (size_t)e->np * e->nb;
+  DNSB_CK(ctx, cudaMemcpyAsync(e->v.p, v0, nvb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (p0)
+    DNSB_CK(ctx, cudaMemcpyAsync(e->p.p, p0, npb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  else
+    DNSB_CK(ctx, e->p.zero(ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  e->step = 0; e->hist_cnt = 0; e->hist_pos = 0; e->nsnap = 0;
+  e->have_state = true;
+  e->p_stale = false;
+  return 0;
+}
+
+// nfc = -c(vfull)[inv] for the current inner velocity `v`
+static int imex_nonl(dnsb_imex *e, const double *v, double *nfc) {
+  dnsb_ctx *ctx = e->ctx;
+  const size_t nvb = (size_t)e->nv * e->nb;
+  LAUNCH(ctx, k_scatter_inner, cdiv(nvb, 256), 256, 0, v, e->inv.p, e->vfull.p, e->nv, e->nb);
+  int rc = convvec_dev(ctx, e->vfull.p, nullptr, e->cfull.p, e->nb);
+  if (rc) return rc;
+  LAUNCH(ctx, k_gather_neg, cdiv(nvb, 256), 256, 0, e->cfull.p, e->inv.p, nfc, e->nv, e->nb);
+  return 0;
+}
+
+static const double *useries_at(dnsb_imex *e, long long n) {
+  if (e->nk == 0) return nullptr;
+  long long k = std::min<long long>(std::max<long long>(n, 0), e->ntimes - 1);
+  return e->useries.p + (size_t)k * e->nk * e->nb;
+}
+
+// p = -q/dt from the last saddle solution, if it is newer than e->p
+static void imex_refresh_p(dnsb_imex *e) {
+  if (!e->p_stale) return;
+  const size_t npb = (size_t)e->np * e->nb;
+  LAUNCH(e->ctx, k_extract_p, cdiv(npb, 256), 256, 0, e->x.p, e->p.p, e->nv, e->np, e->nb,
+         -1.0 / e->dt);
+  e->p_stale = false;
+}
+
+// snapshot = [v (nv*nb); p (np*nb)]
+static int imex_snapshot(dnsb_imex *e) {
+  dnsb_ctx *ctx = e->ctx;
+  if (e->nsnap >= e->snap_cap) return 0;
+  const size_t nvb = (size_t)e->nv * e->nb, npb = (size_t)e->np * e->nb;
+  imex_refresh_p(e);
+  double *dst = e->snaps.p + (size_t)e->nsnap * (nvb + npb);
+  DNSB_CK(ctx, cudaMemcpyAsync(dst, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DNSB_CK(ctx, cudaMemcpyAsync(dst + nvb, e->p.p, npb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  e->nsnap++;
+  return 0;
+}
+
+// ---- initial guesses ------------------------------------------------------
+// guess 0: previous solution; 1: linear extrapolation 2x_n - x_{n-1};
+// k >= 2: projection onto the span of the last k solution increments
+// (Fischer 1998): the history holds pairs (xt_i, bt_i) with K xt_i = bt_i and
+// orthonormal bt_i, so  x0 = sum_i <bt_i, b> xt_i  minimises |b - K x0| over
+// the span.  After the solve the new pair is ((x - x0)/beta, r0/beta) with
+// r0 = b - K x0, beta = |r0| -- exactly FGMRES' first basis vector.
+static int imex_guess(dnsb_imex *e, int guess, double *x) {
+  dnsb_ctx *ctx = e->ctx;
+  const int nb = e->nb;
+  const int ntot = e->nv + e->np;
+  const size_t ntb = (size_t)ntot * nb;
+  const int L = e->hist_len;
+  if (e->hist_cnt == 0) return 1;   // caller supplies the default guess
+  if (guess <= 1) {
+    const int last = (e->hist_pos + L - 1) % L;
+    const double *xl = e->xh.p + (size_t)last * ntb;
+    if (guess == 0 || e->hist_cnt == 1) {
+      DNSB_CK(ctx, cudaMemcpyAsync(x, xl, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      const int prev = (e->hist_pos + L - 2) % L;
+      LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 2.0, xl, -1.0,
+             (const double *)(e->xh.p + (size_t)prev * ntb), x, ntb);
+    }
+    return 0;
+  }
+  RedCfg rc = red_cfg(ctx, ntot, nb);
+  LAUNCH(ctx, k_mdot, rc.nblocks, rc.threads, rc.smem, e->bh.p, ntb, L, e->b.p, ntot, nb,
+         rc.rpb, e->partialh.p);
+  LAUNCH(ctx, k_reduce_partials, cdiv((size_t)L * nb, 128), 128, 0, e->partialh.p, rc.nblocks,
+         L * nb, e->gr.p);
+  DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
+  LAUNCH(ctx, k_gmres_update_x, cdiv(ntb, 256), 256, 0, e->xh.p, ntb, L, e->gr.p, x,
+         (size_t)ntot, nb);
+  return 0;
+}
+
+// xt = (x - x0) * scale[m]
+__global__ void k_diff_scale(const double *__restrict__ x, const double *__restrict__ x0,
+                             const double *__restrict__ scale, double *__restrict__ out,
+                             size_t n, int nb) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * nb) return;
+  out[idx] = (x[idx] - x0[idx]) * scale[idx % nb];
+}
+
+static int imex_push_history(dnsb_imex *e, int guess) {
+  dnsb_ctx *ctx = e->ctx;
+  if (e->hist_len == 0) return 0;
+  const int nb = e->nb, L = e->hist_len;
+  const int ntot = e->nv + e->np;
+  const size_t ntb = (size_t)ntot * nb;
+  const int s = e->hist_pos;
+  if (guess <= 1) {
+    DNSB_CK(ctx, cudaMemcpyAsync(e->xh.p + (size_t)s * ntb, e->x.p, ntb * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    // (x - x0)/beta and r0/beta (saved by the solver at its first cycle)
+    LAUNCH(ctx, k_diff_scale, cdiv(ntb, 256), 256, 0, e->x.p, e->x0.p, e->sl->ibeta0.p,
+           e->xh.p + (size_t)s * ntb, (size_t)ntot, nb);
+    DNSB_CK(ctx, cudaMemcpyAsync(e->bh.p + (size_t)s * ntb, e->sl->v0save.p, ntb * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  e->hist_pos = (s + 1) % L;
+  e->hist_cnt++;
+  return 0;
+}
+
+// |v_m| > maxv or NaN for any member?  (time_int_utils.py:94-103)
+static int imex_blowup(dnsb_imex *e, const double *vc, double maxv, bool *bad) {
+  dnsb_ctx *ctx = e->ctx;
+  const int nb = e->nb;
+  RedCfg rcn = red_cfg(ctx, e->nv, nb);
+  LAUNCH(ctx, k_dot1, rcn.nblocks, rcn.threads, rcn.smem, vc, vc, e->nv, nb, rcn.rpb, e->normpart.p);
+  LAUNCH(ctx, k_reduce_partials, cdiv(nb, 128), 128, 0, e->normpart.p, rcn.nblocks, nb, e->normout.p);
+  std::vector<double> hn(nb);
+  DNSB_CK(ctx, cudaMemcpyAsync(hn.data(), e->normout.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  *bad = false;
+  for (int m = 0; m < nb; ++m)
+    if (!(std::sqrt(hn[m]) <= maxv)) *bad = true;   // also catches NaN
+  return 0;
+}
+
+extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double tol,
+                             int maxit, int guess, double check_ff_maxv,
+                             int ntimeslices, int *ffflag) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, e->have_state, "set the initial state first");
+  DNSB_REQUIRE(ctx, e->sl != nullptr, "set the solvers first");
+  DNSB_REQUIRE(ctx, nsteps >= 1 && tol > 0 && maxit >= 1 && guess >= 0 && guess <= 64, "bad run arguments");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const int nb = e->nb, nv = e->nv, np = e->np;
+  const size_t nvb = (size_t)nv * nb, npb = (size_t)np * nb, ntb = nvb + npb;
+  const double dt = e->dt;
+  if (ffflag) *ffflag = 0;
+  // ---- history buffers -----------------------------------------------------
+  const int L = guess >= 2 ? guess : 2;
+  if (e->hist_len != L || e->hist_mode != (guess >= 2 ? 2 : 1)) {
+    e->hist_len = L; e->hist_cnt = 0; e->hist_pos = 0;
+    e->hist_mode = guess >= 2 ? 2 : 1;
+    DNSB_CK(ctx, e->xh.alloc(ntb * L));
+    DNSB_CK(ctx, e->xh.zero(ctx->stream));
+    if (guess >= 2) {
+      RedCfg rc = red_cfg(ctx, nv + np, nb);
+      DNSB_CK(ctx, e->bh.alloc(ntb * L));
+      DNSB_CK(ctx, e->bh.zero(ctx->stream));
+      DNSB_CK(ctx, e->gr.alloc((size_t)L * nb));
+      DNSB_CK(ctx, e->partialh.alloc((size_t)rc.nblocks * L * nb));
+      DNSB_CK(ctx, e->x0.alloc(ntb));
+    }
+  }
+  if (guess >= 2) {
+    DNSB_CK(ctx, e->sl->v0save.alloc(ntb));
+    e->sl->save_v0 = true;
+  } else {
+    e->sl->save_v0 = false;
+  }
+  {
+    RedCfg rcn = red_cfg(ctx, nv, nb);
+    DNSB_CK(ctx, e->normpart.alloc((size_t)rcn.nblocks * nb));
+    DNSB_CK(ctx, e->normout.alloc(nb));
+  }
+  // ---- snapshots -----------------------------------------------------------
+  if (snap_stride > 0) {
+    const int need = e->nsnap + nsteps / snap_stride + 2;
+    if (need > e->snap_cap) {
+      DBuf<double> ns;
+      DNSB_CK(ctx, ns.alloc((size_t)need * ntb));
+      if (e->nsnap > 0)
+        DNSB_CK(ctx, cudaMemcpyAsync(ns.p, e->snaps.p, (size_t)e->nsnap * ntb * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+      e->snaps.release();
+      e->snaps = ns;
+      e->snap_cap = need;
+    }
+    if (e->step == 0) { int rc = imex_snapshot(e); if (rc) return rc; }
+  }
+  const long long it0 = e->sl->stat_iters, ns0 = e->sl->stat_solves;
+  bool solved = false;
+  int done = 0;
+  // ======================= start-up (Heun) step =============================
+  if (e->step == 0 && e->scheme != 2) {
+    const double *u0 = useries_at(e, 0), *u1 = useries_at(e, 1);
+    int rc = imex_nonl(e, e->v.p, e->nfc_c.p);                 // nfc(v0)
+    if (rc) return rc;
+    // predictor (IMEX Euler):  (M + dt A) tv = M v + dt f(t1) + dt nfc(v0)
+    spmm_dev(ctx, e->M, nullptr, e->v.p, nullptr, e->b.p, nb, 1.0, 0.0);
+    LAUNCH(ctx, k_rhs_combine, cdiv(nvb, 256), 256, 0, e->b.p, (const double *)e->nfc_c.p, dt,
+           (const double *)nullptr, 0.0, (const double *)e->fv.p, dt, (const double *)e->Bk.p, e->nk,
+           (const double *)nullptr, 0.0, u1, dt, nv, nb);
+    LAUNCH(ctx, k_fill_rhsp, cdiv(npb, 256), 256, 0, e->b.p, e->fp.p, nv, np, nb);
+    DNSB_CK(ctx, cudaMemcpyAsync(e->x.p, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    DNSB_CK(ctx, cudaMemsetAsync(e->x.p + nvb, 0, npb * sizeof(double), ctx->stream));
+    e->sp->expect_its = 0;
+    e->sp->save_v0 = false;
+    rc = solver_solve_dev(e->sp, e->b.p, e->x.p, tol, maxit, false);
+    if (rc) return rc;
+    // corrector:  M v1 = M v - dt/2 A (v + tv) + dt/2 (f0 + f1 + nfc(v0) + nfc(tv))
+    rc = imex_nonl(e, e->x.p, e->nfc_t.p);                      // nfc(tv)
+    if (rc) return rc;
+    LAUNCH(ctx, k_axpby, cdiv(nvb, 256), 256, 0, 1.0, (const double *)e->v.p, 1.0,
+           (const double *)e->x.p, e->tmp.p, nvb);
+    spmm_dev(ctx, e->M, nullptr, e->v.p, nullptr, e->b.p, nb, 1.0, 0.0);
+    spmm_dev(ctx, e->A, e->nu.p, e->tmp.p, e->b.p, e->b.p, nb, -0.5 * dt, 1.0);
+    LAUNCH(ctx, k_rhs_combine, cdiv(nvb, 256), 256, 0, e->b.p, (const double *)e->nfc_c.p, 0.5 * dt,
+           (const double *)e->nfc_t.p, 0.5 * dt, (const double *)e->fv.p, dt,
+           (const double *)e->Bk.p, e->nk, u0, 0.5 * dt, u1, 0.5 * dt, nv, nb);
+    LAUNCH(ctx, k_fill_rhsp, cdiv(npb, 256), 256, 0, e->b.p, e->fp.p, nv, np, nb);
+    e->sc->expect_its = 0;
+    e->sc->save_v0 = false;
+    rc = solver_solve_dev(e->sc, e->b.p, e->x.p, tol, maxit, false);
+    if (rc) return rc;
+    if (e->scheme == 1)
+      DNSB_CK(ctx, cudaMemcpyAsync(e->vprev.p, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    DNSB_CK(ctx, cudaMemcpyAsync(e->v.p, e->x.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    e->p_stale = true;
+    imex_refresh_p(e);
+    e->step = 1;
+    done = 1;
+    if (snap_stride > 0 && e->step % snap_stride == 0) { rc = imex_snapshot(e); if (rc) return rc; }
+    // nfc_c holds nfc(v0): it becomes nfc_o in the first loop step
+  }
+  // ======================= the time loop ====================================
+  // blow-up guard at the start of each of the `ntimeslices` slices and of the
+  // remainder slice (time_int_utils.py:94-103, 480-489)
+  const int loopsteps = nsteps - done;
+  const int lenofts = ntimeslices > 0 ? loopsteps / ntimeslices : 0;
+  bool blown = false;
+  for (int it = 0; it < loopsteps; ++it) {
+    if (ntimeslices > 0) {
+      bool check = false;
+      for (int k = 0; k <= ntimeslices; ++k)
+        if (it == k * lenofts) check = true;
+      if (check) {
+        bool bad = false;
+        int rcb = imex_blowup(e, e->scheme == 1 ? e->vprev.p : e->v.p, check_ff_maxv, &bad);
+        if (rcb) return rcb;
+        if (bad) { blown = true; break; }
+      }
+    }
+    const long long n = e->step + 1;   // index of the new time level
+    const double *uc = useries_at(e, n - 1), *un = useries_at(e, n);
+    int rc;
+    if (e->scheme == 0) {
+      std::swap(e->nfc_o.p, e->nfc_c.p);
+      rc = imex_nonl(e, e->v.p, e->nfc_c.p);
+      if (rc) return rc;
+      spmm_dev(ctx, e->Rm, e->coefR.p, e->v.p, nullptr, e->b.p, nb, 1.0, 0.0);
+      LAUNCH(ctx, k_rhs_combine, cdiv(nvb, 256), 256, 0, e->b.p, (const double *)e->nfc_c.p, 1.5 * dt,
+             (const double *)e->nfc_o.p, -0.5 * dt, (const double *)e->fv.p, dt,
+             (const double *)e->Bk.p, e->nk, uc, 0.5 * dt, un, 0.5 * dt, nv, nb);
+    } else if (e->scheme == 1) {
+      std::swap(e->nfc_o.p, e->nfc_c.p);
+      rc = imex_nonl(e, e->v.p, e->nfc_c.p);
+      if (rc) return rc;
+      // rhs = 1/3 M (4 v_c - v_p) + 2/3 dt (2 nfc_c - nfc_p) + 2/3 dt f_n
+      LAUNCH(ctx, k_axpby, cdiv(nvb, 256), 256, 0, 4.0 / 3.0, (const double *)e->v.p, -1.0 / 3.0,
+             (const double *)e->vprev.p, e->tmp.p, nvb);
+      spmm_dev(ctx, e->M, nullptr, e->tmp.p, nullptr, e->b.p, nb, 1.0, 0.0);
+      LAUNCH(ctx, k_rhs_combine, cdiv(nvb, 256), 256, 0, e->b.p, (const double *)e->nfc_c.p,
+             4.0 / 3.0 * dt, (const double *)e->nfc_o.p, -2.0 / 3.0 * dt, (const double *)e->fv.p,
+             2.0 / 3.0 * dt, (const double *)e->Bk.p, e->nk, (const double *)nullptr, 0.0, un,
+             2.0 / 3.0 * dt, nv, nb);
+    } else {
+      // IMEX Euler: (M + dt A) v+ = M v + dt (f(t+) + nfc(v))
+      rc = imex_nonl(e, e->v.p, e->nfc_c.p);
+      if (rc) return rc;
+      spmm_dev(ctx, e->M, nullptr, e->v.p, nullptr, e->b.p, nb, 1.0, 0.0);
+      LAUNCH(ctx, k_rhs_combine, cdiv(nvb, 256), 256, 0, e->b.p, (const double *)e->nfc_c.p, dt,
+             (const double *)nullptr, 0.0, (const double *)e->fv.p, dt, (const double *)e->Bk.p,
+             e->nk, (const double *)nullptr, 0.0, un, dt, nv, nb);
+    }
+    LAUNCH(ctx, k_fill_rhsp, cdiv(npb, 256), 256, 0, e->b.p, e->fp.p, nv, np, nb);
+    rc = imex_guess(e, guess, e->x.p);
+    if (rc < 0) return rc;
+    if (rc == 1) {   // no history yet: [v; q = -dt p]
+      DNSB_CK(ctx, cudaMemcpyAsync(e->x.p, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      LAUNCH(ctx, k_axpby, cdiv(npb, 256), 256, 0, -dt, (const double *)e->p.p, 0.0,
+             (const double *)nullptr, e->x.p + nvb, npb);
+    }
+    if (guess >= 2)
+      DNSB_CK(ctx, cudaMemcpyAsync(e->x0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    rc = solver_solve_dev(e->sl, e->b.p, e->x.p, tol, maxit, false);
+    if (rc) return rc;
+    solved = true;
+    e->p_stale = true;
+    rc = imex_push_history(e, guess);
+    if (rc) return rc;
+    if (e->scheme == 1)
+      DNSB_CK(ctx, cudaMemcpyAsync(e->vprev.p, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    DNSB_CK(ctx, cudaMemcpyAsync(e->v.p, e->x.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    e->step = n;
+    if (snap_stride > 0 && e->step % snap_stride == 0) { rc = imex_snapshot(e); if (rc) return rc; }
+  }
+  if (!blown && ntimeslices > 0 && ntimeslices * lenofts == loopsteps) {
+    // the (empty) remainder slice still runs the guard once
+    bool bad = false;
+    int rcb = imex_blowup(e, e->scheme == 1 ? e->vprev.p : e->v.p, check_ff_maxv, &bad);
+    if (rcb) return rcb;
+    if (bad) blown = true;
+  }
+  if (blown && ffflag) *ffflag = 1;
+  imex_refresh_p(e);
+  // relative residual of the last solve (max over members)
+  {
+    std::vector<double> res(nb), bn(nb);
+    DNSB_CK(ctx, cudaMemcpyAsync(res.data(), e->sl->gs.resid, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DNSB_CK(ctx, cudaMemcpyAsync(bn.data(), e->sl->gs.bnorm, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    double mx = 0;
+    if (solved)
+      for (int m = 0; m < nb; ++m) mx = std::max(mx, bn[m] > 0 ? res[m] / bn[m] : 0.0);
+    e->last_relres = mx;
+  }
+  e->run_iters = e->sl->stat_iters - it0;
+  e->run_solves = e->sl->stat_solves - ns0;
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dnsb_imex_get_state(dnsb_imex *e, double *v, double *p) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const size_t nvb = (size_t)e->nv * e->nb, npb = (size_t)e->np * e->nb;
+  if (v) DNSB_CK(ctx, cudaMemcpyAsync(v, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (p) DNSB_CK(ctx, cudaMemcpyAsync(p, e->p.p, npb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int dnsb_imex_num_snapshots(dnsb_imex *e) { return e ? e->nsnap : -2; }
+
+extern "C" int dnsb_imex_get_snapshots(dnsb_imex *e, double *out) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, out != nullptr, "null output");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const size_t ntb = (size_t)(e->nv + e->np) * e->nb;
+  if (e->nsnap > 0)
+    DNSB_CK(ctx, cudaMemcpyAsync(out, e->snaps.p, (size_t)e->nsnap * ntb * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" int dnsb_imex_stats(dnsb_imex *e, long long *total_iters, long long *nsolves,
+                               double *max_relres) {
+  if (!e || !e->sl) return -2;
+  if (total_iters) *total_iters = e->run_iters;
+  if (nsolves) *nsolves = e->run_solves;
+  if (max_relres) *max_relres = e->last_relres;
+  return 0;
+}
+
+// G[a,b] = sum_m sum_i X_a[i,m] * (M X_b)[i,m]
+__global__ void k_gram_partial(const double *__restrict__ X, size_t xstride,
+                               const double *__restrict__ MX,
+                               int ns, size_t nvb, double *__restrict__ partial) {
+  // block (a, b) pair over blockIdx.y; grid-stride chunks over blockIdx.x
+  extern __shared__ double sred[];
+  const int pair = blockIdx.y;
+  const int a = pair / ns, b = pair % ns;
+  const double *xa = X + (size_t)a * xstride, *mb = MX + (size_t)b * nvb;
+  const size_t chunk = (nvb + gridDim.x - 1) / gridDim.x;
+  const size_t i0 = (size_t)blockIdx.x * chunk, i1 = min(nvb, i0 + chunk);
+  double acc = 0.0;
+  for (size_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) acc += xa[i] * mb[i];
+  sred[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sred[threadIdx.x] += sred[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * ns * ns + pair] = sred[0];
+}
+
+extern "C" int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, g_dev != nullptr && e->nsnap > 0, "no snapshots / null output");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const int ns = e->nsnap, nb = e->nb;
+  const size_t nvb = (size_t)e->nv * nb, ntb = (size_t)(e->nv + e->np) * nb;
+  DBuf<double> MX, part;
+  DNSB_CK(ctx, MX.alloc((size_t)ns * nvb));
+  for (int a = 0; a < ns; ++a)
+    spmm_dev(ctx, e->M, nullptr, e->snaps.p + (size_t)a * ntb, nullptr, MX.p + (size_t)a * nvb, nb, 1.0, 0.0);
+  const int nchunks = 32;
+  DNSB_CK(ctx, part.alloc((size_t)nchunks * ns * ns));
+  LAUNCH(ctx, k_gram_partial, dim3(nchunks, ns * ns), 256, 256 * sizeof(double), e->snaps.p, ntb, MX.p, ns, nvb, part.p);
+  LAUNCH(ctx, k_reduce_partials, cdiv((size_t)ns * ns, 128), 128, 0, part.p, nchunks, ns * ns, g_dev);
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  MX.release(); part.release();
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,91 @@
+// dnsb_common.cuh -- context, device buffers, error handling (host side)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+struct dnsb_ctx;
+
+#define DNSB_CK(ctx, call)                                                    \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      (ctx)->fail(std::string(#call) + ": " + cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                  \
+      return -1;                                                              \
+    }                                                                         \
+  } while (0)
+
+#define DNSB_REQUIRE(ctx, cond, msg)                                          \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      (ctx)->fail(std::string(msg) + " [" #cond "]", __FILE__, __LINE__);     \
+      return -2;                                                              \
+    }                                                                         \
+  } while (0)
+
+// plain device buffer; freed explicitly (no exceptions across the ABI)
+template <class T>
+struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    if (p && n == count) return cudaSuccess;   // reuse
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+    if (e != cudaSuccess) { p = nullptr; n = 0; }
+    return e;
+  }
+  cudaError_t upload(const T *h, size_t count, cudaStream_t s) {
+    cudaError_t e = alloc(count);
+    if (e != cudaSuccess || count == 0) return e;
+    e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);   // host buffer is borrowed: finish now
+  }
+  cudaError_t zero(cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    return cudaMemsetAsync(p, 0, n * sizeof(T), s);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct dnsb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int cc = 0;
+  size_t mem_bytes = 0;
+  std::string err;
+  long long launches = 0;
+
+  // ---- mesh / convection data (cells permuted into colour order) ----------
+  int ncell = 0, nnodes = 0, ncolours = 0;
+  DBuf<int> cn;          // 6*ncell, SoA: cn[k*ncell + c]
+  DBuf<double> geom;     // 5*ncell, SoA
+  std::vector<int> colour_ptr;   // ncolours+1 offsets into the permuted cells
+  std::vector<int> perm;         // permuted position -> original cell
+  // fixed pattern of the P2 vector space + per-cell slots (144*ncell SoA)
+  int cnnz = 0;
+  DBuf<int> cindptr, cindices, cslots;
+  // staging buffers for the host-pointer entry points
+  DBuf<double> stage_a, stage_b, stage_c, stage_d;
+
+  void fail(const std::string &what, const char *file, int line) {
+    char buf[64];
+    snprintf(buf, sizeof buf, " (%s:%d)", file, line);
+    err = what + buf;
+  }
+};
+
+static inline unsigned int cdiv(size_t a, size_t b) {
+  return (unsigned int)((a + b - 1) / b);
+}

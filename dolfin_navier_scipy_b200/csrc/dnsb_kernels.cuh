@@ -1,0 +1,780 @@
+// dnsb_kernels.cuh -- device kernels of libdnsb200 (sm_100a, fp64, int32 idx)
+//
+// All vectors are batched member-fastest: x[i*nb + m].  Every kernel is
+// memory/latency bound: no tensor-core work on this path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+// ---------------------------------------------------------------------------
+// P2 tabulation on the 7-point degree-5 rule (filled by dnsb_ctx_create)
+// ---------------------------------------------------------------------------
+__constant__ double c_phi[7][6];       // phi_a(q)
+__constant__ double c_dphi[7][6][3];   // d phi_a / d lambda_i (q)
+__constant__ double c_qw[7];           // weights, sum = 1 (times area)
+
+struct CsrDev {
+  int nrows, ncols, nnz;
+  const int *__restrict__ indptr;
+  const int *__restrict__ indices;
+  const double *__restrict__ v1;
+  const double *__restrict__ v2;   // may be null
+};
+
+// ---------------------------------------------------------------------------
+// K1a: convection vector  c_(n,a) += int (grad(u1) u2)_a phi_n   per cell.
+// thread <-> (cell, member); cells [c0,c1) share one colour => plain RMW.
+// Algorithmic bytes per (cell, member): 24 (ids, amortised over members)
+// + 40 (geometry, amortised) + 96 gather + 192 RMW = 352 B  (SURVEY 8d).
+// ---------------------------------------------------------------------------
+template <bool SAME>
+__global__ void __launch_bounds__(128)
+k_convvec(int c0, int c1, int ncell, const int *__restrict__ cn,
+          const double *__restrict__ geom, const double *__restrict__ u1,
+          const double *__restrict__ u2, double *__restrict__ out, int nb) {
+  long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = c0 + (int)(tid / nb);
+  int m = (int)(tid % nb);
+  if (cell >= c1) return;
+  int n[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) n[k] = cn[k * ncell + cell];
+  const double g1x = geom[0 * ncell + cell], g1y = geom[1 * ncell + cell];
+  const double g2x = geom[2 * ncell + cell], g2y = geom[3 * ncell + cell];
+  const double detj = geom[4 * ncell + cell];
+  const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+  double U1[6][2], U2[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    U1[k][0] = u1[(size_t)(2 * n[k]) * nb + m];
+    U1[k][1] = u1[(size_t)(2 * n[k] + 1) * nb + m];
+    if (SAME) {
+      U2[k][0] = U1[k][0];
+      U2[k][1] = U1[k][1];
+    } else {
+      U2[k][0] = u2[(size_t)(2 * n[k]) * nb + m];
+      U2[k][1] = u2[(size_t)(2 * n[k] + 1) * nb + m];
+    }
+  }
+  double acc[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k][0] = acc[k][1] = 0.0;
+  const double wdet = 0.5 * fabs(detj);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    double ux = 0, uy = 0, dxx = 0, dxy = 0, dyx = 0, dyy = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double gx = c_dphi[q][a][0] * g0x + c_dphi[q][a][1] * g1x +
+                        c_dphi[q][a][2] * g2x;
+      const double gy = c_dphi[q][a][0] * g0y + c_dphi[q][a][1] * g1y +
+                        c_dphi[q][a][2] * g2y;
+      ux += U2[a][0] * c_phi[q][a];
+      uy += U2[a][1] * c_phi[q][a];
+      dxx += U1[a][0] * gx;   // d_x u_x
+      dxy += U1[a][0] * gy;   // d_y u_x
+      dyx += U1[a][1] * gx;   // d_x u_y
+      dyy += U1[a][1] * gy;   // d_y u_y
+    }
+    const double w = c_qw[q] * wdet;
+    const double ax = w * (dxx * ux + dxy * uy);
+    const double ay = w * (dyx * ux + dyy * uy);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      acc[a][0] += ax * c_phi[q][a];
+      acc[a][1] += ay * c_phi[q][a];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    out[(size_t)(2 * n[k]) * nb + m] += acc[k][0];
+    out[(size_t)(2 * n[k] + 1) * nb + m] += acc[k][1];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K1b: convection matrices into the fixed CSR pattern.  thread <-> (cell,
+// local row n): 6 N1 entries (block diagonal, written for both components),
+// 24 N2 entries, 2 f3 entries.  Cells of one colour own disjoint slots.
+//   N1[(n,a),(m,a)] = int (u0.grad phi_m) phi_n
+//   N2[(n,a),(m,b)] = int d_b u0_a phi_m phi_n
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_convmats(int c0, int c1, int ncell, const int *__restrict__ cn,
+           const double *__restrict__ geom, const int *__restrict__ slots,
+           const double *__restrict__ u0, double *__restrict__ n1,
+           double *__restrict__ n2, double *__restrict__ f3) {
+  long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = c0 + (int)(tid / 6);
+  int n = (int)(tid % 6);
+  if (cell >= c1) return;
+  int nd[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) nd[k] = cn[k * ncell + cell];
+  const double g1x = geom[0 * ncell + cell], g1y = geom[1 * ncell + cell];
+  const double g2x = geom[2 * ncell + cell], g2y = geom[3 * ncell + cell];
+  const double detj = geom[4 * ncell + cell];
+  const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+  double U[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    U[k][0] = u0[2 * nd[k]];
+    U[k][1] = u0[2 * nd[k] + 1];
+  }
+  double a1[6], a2[2][6][2], fx = 0, fy = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    a1[k] = 0;
+    a2[0][k][0] = a2[0][k][1] = a2[1][k][0] = a2[1][k][1] = 0;
+  }
+  const double wdet = 0.5 * fabs(detj);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    double gx[6], gy[6];
+    double ux = 0, uy = 0, dxx = 0, dxy = 0, dyx = 0, dyy = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      gx[a] = c_dphi[q][a][0] * g0x + c_dphi[q][a][1] * g1x +
+              c_dphi[q][a][2] * g2x;
+      gy[a] = c_dphi[q][a][0] * g0y + c_dphi[q][a][1] * g1y +
+              c_dphi[q][a][2] * g2y;
+      ux += U[a][0] * c_phi[q][a];
+      uy += U[a][1] * c_phi[q][a];
+      dxx += U[a][0] * gx[a];
+      dxy += U[a][0] * gy[a];
+      dyx += U[a][1] * gx[a];
+      dyy += U[a][1] * gy[a];
+    }
+    // phi_n(q) for this thread's row (n is not a compile-time constant)
+    const double pn = c_phi[q][n];
+    const double w = c_qw[q] * wdet * pn;
+    fx += w * (dxx * ux + dxy * uy);
+    fy += w * (dyx * ux + dyy * uy);
+#pragma unroll
+    for (int mm = 0; mm < 6; ++mm) {
+      a1[mm] += w * (ux * gx[mm] + uy * gy[mm]);
+      const double wp = w * c_phi[q][mm];
+      a2[0][mm][0] += wp * dxx;   // (a=x, b=x): d_x u_x
+      a2[0][mm][1] += wp * dxy;   // (a=x, b=y): d_y u_x
+      a2[1][mm][0] += wp * dyx;   // (a=y, b=x): d_x u_y
+      a2[1][mm][1] += wp * dyy;   // (a=y, b=y): d_y u_y
+    }
+  }
+  // slots[(r*12 + c)*ncell + cell], r = 2n+a, c = 2m+b
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+#pragma unroll
+    for (int mm = 0; mm < 6; ++mm) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int s = slots[(size_t)((2 * n + a) * 12 + 2 * mm + b) * ncell + cell];
+        if (n2) n2[s] += a2[a][mm][b];
+        if (n1 && a == b) n1[s] += a1[mm];
+      }
+    }
+  }
+  if (f3) {
+    f3[2 * nd[n]] += fx;
+    f3[2 * nd[n] + 1] += fy;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: CSR SpMV / SpMM.  LPR lanes cooperate on one (row, member) pair; LPR=1
+// is thread per (row, member) -- the batched case, where the nb lanes of a row
+// read one matrix entry (broadcast) and nb contiguous x values (coalesced).
+// Algorithmic bytes: 12*nnz (+8*nnz with v2) + 4(nrows+1) + 8*nb*(ncols+nrows).
+// ---------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ double csr_rowdot(const CsrDev &A, double coefm,
+                                             const double *__restrict__ x,
+                                             int nb, int row, int m, int lane,
+                                             bool valid) {
+  double acc = 0.0;
+  if (valid) {
+    const int k0 = A.indptr[row], k1 = A.indptr[row + 1];
+    if (A.v2) {
+      for (int k = k0 + lane; k < k1; k += LPR)
+        acc += (A.v1[k] + coefm * A.v2[k]) * x[(size_t)A.indices[k] * nb + m];
+    } else {
+      for (int k = k0 + lane; k < k1; k += LPR)
+        acc += A.v1[k] * x[(size_t)A.indices[k] * nb + m];
+    }
+  }
+  if (LPR > 1) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1)
+      acc += __shfl_down_sync(0xffffffffu, acc, o, LPR);
+  }
+  return acc;
+}
+
+#define DNSB_ROWMAP(LPR)                                                      \
+  const long tid_ = (long)blockIdx.x * blockDim.x + threadIdx.x;              \
+  const long grp_ = tid_ / LPR;                                               \
+  const int lane = (int)(tid_ % LPR);                                         \
+  const int row = (int)(grp_ / nb);                                           \
+  const int m = (int)(grp_ % nb);                                             \
+  const bool valid = row < A.nrows;
+
+// y = alpha*A*x + beta*z   (z may alias y; z ignored when beta == 0)
+template <int LPR>
+__global__ void
+k_spmm(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
+       const double *z, double *y, int nb, double alpha, double beta) {
+  DNSB_ROWMAP(LPR)
+  const double cm = (valid && coef) ? coef[m] : 0.0;
+  const double acc = csr_rowdot<LPR>(A, cm, x, nb, row, m, lane, valid);
+  if (valid && lane == 0) {
+    const size_t i = (size_t)row * nb + m;
+    y[i] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[i];
+  }
+}
+
+// Chebyshev start, fused with the gradient coupling:
+//   res = rv - JT*zp ;  d = dinv*res/theta ;  z = d
+template <int LPR>
+__global__ void
+k_cheb_init(CsrDev A /*JT*/, const double *__restrict__ zp,
+            const double *__restrict__ rv, const double *__restrict__ dinv,
+            double *__restrict__ res, double *__restrict__ d,
+            double *__restrict__ z, int nb, double inv_theta) {
+  DNSB_ROWMAP(LPR)
+  const double acc = csr_rowdot<LPR>(A, 0.0, zp, nb, row, m, lane, valid);
+  if (valid && lane == 0) {
+    const size_t i = (size_t)row * nb + m;
+    const double r = rv[i] - acc;
+    const double dd = dinv[i] * r * inv_theta;
+    res[i] = r;
+    d[i] = dd;
+    z[i] = dd;
+  }
+}
+
+// plain variant (no coupling): res = r ; d = dinv*r/theta ; z = d
+__global__ void k_cheb_init_plain(const double *__restrict__ r,
+                                  const double *__restrict__ dinv,
+                                  double *__restrict__ res,
+                                  double *__restrict__ d, double *__restrict__ z,
+                                  size_t n, double inv_theta) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double rr = r[i];
+  const double dd = dinv[i] * rr * inv_theta;
+  res[i] = rr;
+  d[i] = dd;
+  z[i] = dd;
+}
+
+// Chebyshev step:  res -= F*d ;  dn = c1*d + c2*dinv*res ;  z += dn
+template <int LPR>
+__global__ void
+k_cheb_step(CsrDev A /*F*/, const double *__restrict__ coef,
+            const double *__restrict__ d, const double *__restrict__ dinv,
+            double *__restrict__ res, double *__restrict__ dn,
+            double *__restrict__ z, int nb, double c1, double c2) {
+  DNSB_ROWMAP(LPR)
+  const double cm = (valid && coef) ? coef[m] : 0.0;
+  const double acc = csr_rowdot<LPR>(A, cm, d, nb, row, m, lane, valid);
+  if (valid && lane == 0) {
+    const size_t i = (size_t)row * nb + m;
+    const double r = res[i] - acc;
+    const double dd = c1 * d[i] + c2 * dinv[i] * r;
+    res[i] = r;
+    dn[i] = dd;
+    z[i] += dd;
+  }
+}
+
+// dinv[i,m] = 1/(v1[dp_i] + coef[m]*v2[dp_i])
+__global__ void k_diag_inv(CsrDev A, const int *__restrict__ diagpos,
+                           const double *__restrict__ coef,
+                           double *__restrict__ dinv, int nb) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)A.nrows * nb) return;
+  const int row = (int)(t / nb), m = (int)(t % nb);
+  const int k = diagpos[row];
+  double dv = A.v1[k];
+  if (A.v2 && coef) dv += coef[m] * A.v2[k];
+  dinv[t] = 1.0 / dv;
+}
+
+// ---------------------------------------------------------------------------
+// dense  Y = alpha * D * X   (D: n x n row-major, X: n x nb)
+// small nb: one warp per row, lanes split the columns (GEMV-like, D-bandwidth
+// bound: 8*n*n bytes).
+// ---------------------------------------------------------------------------
+template <int NBMAX>
+__global__ void
+k_dense_gemv(const double *__restrict__ D, const double *__restrict__ X,
+             double *__restrict__ Y, int n, int nb, double alpha,
+             const double *__restrict__ add_dinv,
+             const double *__restrict__ add_scale) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  double acc[NBMAX];
+#pragma unroll
+  for (int m = 0; m < NBMAX; ++m) acc[m] = 0.0;
+  const double *drow = D + (size_t)warp * n;
+  for (int j = lane; j < n; j += 32) {
+    const double dv = drow[j];
+#pragma unroll
+    for (int m = 0; m < NBMAX; ++m)
+      if (m < nb) acc[m] += dv * X[(size_t)j * nb + m];
+  }
+#pragma unroll
+  for (int m = 0; m < NBMAX; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      acc[m] += __shfl_down_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m < NBMAX; ++m)
+      if (m < nb) {
+        double v = acc[m];
+        if (add_dinv)
+          v += add_scale[m] * add_dinv[warp] * X[(size_t)warp * nb + m];
+        Y[(size_t)warp * nb + m] = alpha * v;
+      }
+  }
+}
+
+// larger nb: shared-memory tiled GEMM; block = 256 threads computes a
+// TM x nb tile of Y; thread (tr, tc) accumulates rows tr+{0,16} x members
+// tc + 16*k.
+#define DG_TM 32
+#define DG_TK 32
+template <int NBT>   // members per block tile: 16, 32 or 64
+__global__ void
+k_dense_gemm(const double *__restrict__ D, const double *__restrict__ X,
+             double *__restrict__ Y, int n, int nb, double alpha,
+             const double *__restrict__ add_dinv,
+             const double *__restrict__ add_scale) {
+  __shared__ double sD[DG_TM][DG_TK + 1];
+  __shared__ double sX[DG_TK][NBT];
+  const int tr = threadIdx.x / 16;       // 0..15
+  const int tc = threadIdx.x % 16;       // 0..15
+  const int row0 = blockIdx.x * DG_TM;
+  const int m0 = blockIdx.y * NBT;
+  constexpr int MC = NBT / 16;           // member columns per thread
+  double acc[2][MC];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < MC; ++c) acc[r][c] = 0.0;
+  for (int j0 = 0; j0 < n; j0 += DG_TK) {
+    // stage D tile (TM x TK): 1024 elements / 256 threads
+    for (int e = threadIdx.x; e < DG_TM * DG_TK; e += 256) {
+      const int r = e / DG_TK, c = e % DG_TK;
+      const int gi = row0 + r, gj = j0 + c;
+      sD[r][c] = (gi < n && gj < n) ? D[(size_t)gi * n + gj] : 0.0;
+    }
+    for (int e = threadIdx.x; e < DG_TK * NBT; e += 256) {
+      const int r = e / NBT, c = e % NBT;
+      const int gj = j0 + r, gm = m0 + c;
+      sX[r][c] = (gj < n && gm < nb) ? X[(size_t)gj * nb + gm] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < DG_TK; ++k) {
+      const double d0 = sD[tr][k], d1 = sD[tr + 16][k];
+#pragma unroll
+      for (int c = 0; c < MC; ++c) {
+        const double xv = sX[k][tc + 16 * c];
+        acc[0][c] += d0 * xv;
+        acc[1][c] += d1 * xv;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int gi = row0 + tr + 16 * r;
+    if (gi >= n) continue;
+#pragma unroll
+    for (int c = 0; c < MC; ++c) {
+      const int gm = m0 + tc + 16 * c;
+      if (gm >= nb) continue;
+      double v = acc[r][c];
+      if (add_dinv) v += add_scale[gm] * add_dinv[gi] * X[(size_t)gi * nb + gm];
+      Y[(size_t)gi * nb + gm] = alpha * v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// batched reductions (deterministic two-stage: block partials, then a serial
+// sum over blocks in fixed order).  Block = RPB x nb threads (RPB power of 2).
+// ---------------------------------------------------------------------------
+// partial[(b*nvec + i)*nb + m] = sum_{rows in chunk b} V_i[row,m]*w[row,m]
+__global__ void k_mdot(const double *__restrict__ V, size_t vstride, int nvec,
+                       const double *__restrict__ w, int n, int nb, int rpb,
+                       double *__restrict__ partial) {
+  extern __shared__ double sred[];
+  const int m = threadIdx.x % nb;
+  const int rr = threadIdx.x / nb;
+  const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  for (int i = 0; i < nvec; ++i) {
+    const double *vi = V + (size_t)i * vstride;
+    double acc = 0.0;
+    for (int r = r0 + rr; r < r1; r += rpb) {
+      const size_t idx = (size_t)r * nb + m;
+      acc += vi[idx] * w[idx];
+    }
+    sred[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = rpb >> 1; s > 0; s >>= 1) {
+      if (rr < s) sred[threadIdx.x] += sred[threadIdx.x + s * nb];
+      __syncthreads();
+    }
+    if (rr == 0) partial[((size_t)blockIdx.x * nvec + i) * nb + m] = sred[m];
+    __syncthreads();
+  }
+}
+
+// out[c] = sum_b partial[b*count + c]
+__global__ void k_reduce_partials(const double *__restrict__ partial,
+                                  int nblocks, int count,
+                                  double *__restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= count) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * count + c];
+  out[c] = s;
+}
+
+// w -= sum_i h[i*nb+m]*V_i ;  partial2[b*nb+m] = sum |w|^2 over the chunk
+__global__ void k_gs_update(const double *__restrict__ V, size_t vstride,
+                            int nvec, const double *__restrict__ h,
+                            double *__restrict__ w, int n, int nb, int rpb,
+                            double *__restrict__ partial2) {
+  extern __shared__ double sred[];
+  const int m = threadIdx.x % nb;
+  const int rr = threadIdx.x / nb;
+  const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  double nrm = 0.0;
+  for (int r = r0 + rr; r < r1; r += rpb) {
+    const size_t idx = (size_t)r * nb + m;
+    double wv = w[idx];
+    for (int i = 0; i < nvec; ++i)
+      wv -= h[(size_t)i * nb + m] * V[(size_t)i * vstride + idx];
+    w[idx] = wv;
+    nrm += wv * wv;
+  }
+  sred[threadIdx.x] = nrm;
+  __syncthreads();
+  for (int s = rpb >> 1; s > 0; s >>= 1) {
+    if (rr < s) sred[threadIdx.x] += sred[threadIdx.x + s * nb];
+    __syncthreads();
+  }
+  if (rr == 0) partial2[(size_t)blockIdx.x * nb + m] = sred[m];
+}
+
+// partial[b*nb+m] = sum over chunk of x*y  (norms / single dots)
+__global__ void k_dot1(const double *__restrict__ x, const double *__restrict__ y,
+                       int n, int nb, int rpb, double *__restrict__ partial) {
+  extern __shared__ double sred[];
+  const int m = threadIdx.x % nb;
+  const int rr = threadIdx.x / nb;
+  const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  double acc = 0.0;
+  for (int r = r0 + rr; r < r1; r += rpb) {
+    const size_t idx = (size_t)r * nb + m;
+    acc += x[idx] * y[idx];
+  }
+  sred[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = rpb >> 1; s > 0; s >>= 1) {
+    if (rr < s) sred[threadIdx.x] += sred[threadIdx.x + s * nb];
+    __syncthreads();
+  }
+  if (rr == 0) partial[(size_t)blockIdx.x * nb + m] = sred[m];
+}
+
+// ---------------------------------------------------------------------------
+// FGMRES scalar work, one thread per member.  Hessenberg columns are stored
+// rotated (R factor): R[(i*(mr) + j)*nb + m] for i <= j.
+// ---------------------------------------------------------------------------
+struct GmresState {
+  double *R;        // (mr+1)*mr*nb
+  double *cs, *sn;  // mr*nb
+  double *g;        // (mr+1)*nb
+  double *h;        // (mr+1)*nb  -- CGS coefficients of the current column
+  double *invh;     // nb         -- 1/h_{j+1,j} (0 for finished members)
+  double *bnorm;    // nb
+  double *resid;    // nb         -- current |residual|
+  int *done;        // nb
+  int *its;         // nb  iterations in the current cycle
+  int *ittot;       // nb  total iterations of the solve
+  int *flags;       // [0]: number of members not yet done
+  int mr;
+};
+
+// start of a cycle: beta = |r| from partials; V0 scale = 1/beta
+__global__ void k_gmres_begin(GmresState S, const double *__restrict__ partial,
+                              int nblocks, int nb, double tol, int first_cycle) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;   // single block launch
+  if (m < nb) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nb + m];
+    const double beta = sqrt(s);
+    if (first_cycle) S.ittot[m] = 0;
+    S.its[m] = 0;
+    S.resid[m] = beta;
+    S.g[m] = beta;
+    const bool fin = !(beta > tol * S.bnorm[m]);   // also catches NaN -> done
+    S.done[m] = fin ? 1 : 0;
+    S.invh[m] = fin ? 0.0 : 1.0 / beta;
+  }
+  __syncthreads();
+  if (m == 0) {
+    int cnt = 0, mx = 0;
+    for (int k = 0; k < nb; ++k) {
+      cnt += S.done[k] ? 0 : 1;
+      mx = max(mx, S.ittot[k]);
+    }
+    S.flags[0] = cnt;
+    S.flags[1] = mx;
+  }
+}
+
+// bnorm[m] = |b_m| from partials
+__global__ void k_set_bnorm(GmresState S, const double *__restrict__ partial,
+                            int nblocks, int nb) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nb + m];
+  S.bnorm[m] = sqrt(s);
+}
+
+// after CGS of column j: h[0..j] known, |w|^2 in partial2.  Apply the old
+// rotations, build the new one, update g, test convergence.
+__global__ void k_gmres_givens(GmresState S, const double *__restrict__ partial2,
+                               int nblocks, int nb, int j, double tol) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < nb) {
+    if (S.done[m]) {
+      S.invh[m] = 0.0;
+    } else {
+      double s = 0.0;
+      for (int b = 0; b < nblocks; ++b) s += partial2[(size_t)b * nb + m];
+      const double hn = sqrt(s);
+      const int mr = S.mr;
+      double hprev = S.h[m];   // h[0]
+      for (int i = 0; i < j; ++i) {
+        const double c = S.cs[(size_t)i * nb + m], sn = S.sn[(size_t)i * nb + m];
+        const double hnext = S.h[(size_t)(i + 1) * nb + m];
+        const double t = c * hprev + sn * hnext;
+        hprev = -sn * hprev + c * hnext;
+        S.R[((size_t)i * mr + j) * nb + m] = t;
+      }
+      const double dd = hypot(hprev, hn);
+      double c = 1.0, sn = 0.0;
+      if (dd > 0.0) { c = hprev / dd; sn = hn / dd; }
+      S.cs[(size_t)j * nb + m] = c;
+      S.sn[(size_t)j * nb + m] = sn;
+      S.R[((size_t)j * mr + j) * nb + m] = dd;
+      const double gj = S.g[(size_t)j * nb + m];
+      S.g[(size_t)(j + 1) * nb + m] = -sn * gj;
+      S.g[(size_t)j * nb + m] = c * gj;
+      const double res = fabs(sn * gj);
+      S.resid[m] = res;
+      S.its[m] = j + 1;
+      S.ittot[m] += 1;
+      const bool fin = !(res > tol * S.bnorm[m]) || !(hn > 0.0);
+      S.done[m] = fin ? 1 : 0;
+      S.invh[m] = fin ? 0.0 : 1.0 / hn;
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int cnt = 0, mx = 0;
+    for (int k = 0; k < nb; ++k) {
+      cnt += S.done[k] ? 0 : 1;
+      mx = max(mx, S.ittot[k]);
+    }
+    S.flags[0] = cnt;
+    S.flags[1] = mx;   // iterations actually needed so far (max over members)
+  }
+}
+
+// y = R^-1 g (per member, using its[m] columns); stored in S.h[i*nb+m]
+__global__ void k_gmres_solve_y(GmresState S, int nb, int jmax) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  const int k = S.its[m];
+  const int mr = S.mr;
+  for (int i = jmax - 1; i >= 0; --i) {
+    if (i >= k) {
+      S.h[(size_t)i * nb + m] = 0.0;
+      continue;
+    }
+    double s = S.g[(size_t)i * nb + m];
+    for (int l = i + 1; l < k; ++l)
+      s -= S.R[((size_t)i * mr + l) * nb + m] * S.h[(size_t)l * nb + m];
+    S.h[(size_t)i * nb + m] = s / S.R[((size_t)i * mr + i) * nb + m];
+  }
+}
+
+// x += sum_i y[i*nb+m] * Z_i
+__global__ void k_gmres_update_x(const double *__restrict__ Z, size_t zstride,
+                                 int nvec, const double *__restrict__ y,
+                                 double *__restrict__ x, size_t n, int nb) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * nb) return;
+  const int m = (int)(idx % nb);
+  double s = x[idx];
+  for (int i = 0; i < nvec; ++i)
+    s += y[(size_t)i * nb + m] * Z[(size_t)i * zstride + idx];
+  x[idx] = s;
+}
+
+// out = x * scale[m]
+__global__ void k_scale_member(const double *__restrict__ x,
+                               const double *__restrict__ scale,
+                               double *__restrict__ out, size_t n, int nb) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * nb) return;
+  out[idx] = x[idx] * scale[idx % nb];
+}
+
+// ---------------------------------------------------------------------------
+// elementwise helpers of the time stepper
+// ---------------------------------------------------------------------------
+// z = a*x + b*y  (y may be null)
+__global__ void k_axpby(double a, const double *__restrict__ x, double b,
+                        const double *__restrict__ y, double *__restrict__ z,
+                        size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  z[i] = y ? a * x[i] + b * y[i] : a * x[i];
+}
+
+// vfull[inv[i], m] = v[i, m]
+__global__ void k_scatter_inner(const double *__restrict__ v,
+                                const int *__restrict__ inv,
+                                double *__restrict__ vfull, int nv, int nb) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nv * nb) return;
+  const int i = (int)(t / nb), m = (int)(t % nb);
+  vfull[(size_t)inv[i] * nb + m] = v[t];
+}
+
+// vfull[bcinds[k], m] = bcvals[k]   (later entries win: serial per index list
+// is resolved on the host, which passes unique indices)
+__global__ void k_set_bcs(const int *__restrict__ bcinds,
+                          const double *__restrict__ bcvals,
+                          double *__restrict__ vfull, int nbc, int nb) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nbc * nb) return;
+  const int k = (int)(t / nb), m = (int)(t % nb);
+  vfull[(size_t)bcinds[k] * nb + m] = bcvals[k];
+}
+
+// nfc[i,m] = -cfull[inv[i], m]
+__global__ void k_gather_neg(const double *__restrict__ cfull,
+                             const int *__restrict__ inv,
+                             double *__restrict__ nfc, int nv, int nb) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nv * nb) return;
+  const int i = (int)(t / nb), m = (int)(t % nb);
+  nfc[t] = -cfull[(size_t)inv[i] * nb + m];
+}
+
+// rhs[i,m] += ca*na[i,m] + cb*nb_[i,m] + cf*fv[i] + sum_k (wa*ua[k,m] + wb*ub[k,m])*B[i,k]
+//   na/nb_: convection terms; fv: constant forcing (shared by members);
+//   ua/ub: input samples at two time levels (nk x nb), B: nv x nk (row-major)
+__global__ void k_rhs_combine(double *__restrict__ rhs,
+                              const double *__restrict__ na, double ca,
+                              const double *__restrict__ nbv, double cb,
+                              const double *__restrict__ fv, double cf,
+                              const double *__restrict__ B, int nk,
+                              const double *__restrict__ ua, double wa,
+                              const double *__restrict__ ub, double wb,
+                              int nv, int nb) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nv * nb) return;
+  const int i = (int)(t / nb), m = (int)(t % nb);
+  double r = rhs[t];
+  if (na) r += ca * na[t];
+  if (nbv) r += cb * nbv[t];
+  if (fv) r += cf * fv[i];
+  for (int k = 0; k < nk; ++k) {
+    double u = 0.0;
+    if (ua) u += wa * ua[(size_t)k * nb + m];
+    if (ub) u += wb * ub[(size_t)k * nb + m];
+    r += u * B[(size_t)i * nk + k];
+  }
+  rhs[t] = r;
+}
+
+// b[(nv+j), m] = fp[j]  (pressure part of the saddle rhs, shared by members)
+__global__ void k_fill_rhsp(double *__restrict__ b, const double *__restrict__ fp,
+                            int nv, int np, int nb) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)np * nb) return;
+  const int j = (int)(t / nb);
+  b[(size_t)nv * nb + t] = fp[j];
+}
+
+// p[j,m] = scale * x[(nv+j), m]
+__global__ void k_extract_p(const double *__restrict__ x, double *__restrict__ p,
+                            int nv, int np, int nb, double scale) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)np * nb) return;
+  p[t] = scale * x[(size_t)nv * nb + t];
+}
+
+// small dense per-member least squares for the projection guess:
+// solves (G + eps I) c = r for each member, G: L x L (row-major, nb batched)
+__global__ void k_small_spd_solve(double *__restrict__ G, double *__restrict__ r,
+                                  int L, int nb, int last) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= nb) return;
+  // Cholesky in place (lower), tiny L (<= 16)
+  double tr = 0.0;
+  for (int i = 0; i < L; ++i) tr += G[((size_t)i * L + i) * nb + m];
+  const double eps = 1e-14 * tr / L;
+  bool ok = true;
+  for (int j = 0; j < L && ok; ++j) {
+    double s = G[((size_t)j * L + j) * nb + m] + eps;
+    for (int k = 0; k < j; ++k) {
+      const double l = G[((size_t)j * L + k) * nb + m];
+      s -= l * l;
+    }
+    if (!(s > 0.0)) { ok = false; break; }
+    const double ljj = sqrt(s);
+    G[((size_t)j * L + j) * nb + m] = ljj;
+    for (int i = j + 1; i < L; ++i) {
+      double t = G[((size_t)i * L + j) * nb + m];
+      for (int k = 0; k < j; ++k)
+        t -= G[((size_t)i * L + k) * nb + m] * G[((size_t)j * L + k) * nb + m];
+      G[((size_t)i * L + j) * nb + m] = t / ljj;
+    }
+  }
+  if (!ok) {   // fall back to "previous solution" as the guess
+    for (int i = 0; i < L; ++i) r[(size_t)i * nb + m] = (i == last) ? 1.0 : 0.0;
+    return;
+  }
+  for (int i = 0; i < L; ++i) {
+    double t = r[(size_t)i * nb + m];
+    for (int k = 0; k < i; ++k)
+      t -= G[((size_t)i * L + k) * nb + m] * r[(size_t)k * nb + m];
+    r[(size_t)i * nb + m] = t / G[((size_t)i * L + i) * nb + m];
+  }
+  for (int i = L - 1; i >= 0; --i) {
+    double t = r[(size_t)i * nb + m];
+    for (int k = i + 1; k < L; ++k)
+      t -= G[((size_t)k * L + i) * nb + m] * r[(size_t)k * nb + m];
+    r[(size_t)i * nb + m] = t / G[((size_t)i * L + i) * nb + m];
+  }
+}

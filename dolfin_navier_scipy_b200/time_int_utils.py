@@ -1,0 +1,268 @@
+"""IMEX time integration on the device.
+
+Mirrors `dolfin_navier_scipy/time_int_utils.py`: `cnab` (`tiu:23-145`),
+`sbdftwo` (`tiu:260-355`), `semi_implicit_euler` (`tiu:566-635`).  The whole
+loop body of `tiu:104-143` -- convection re-evaluation, right-hand side, saddle
+point solve, blow-up guard -- runs inside ``libdnsb200`` (``dnsb_imex_run``);
+the host only sets up operators and preconditioners once.
+
+The reference passes the convection term as an opaque Python callback
+(``f_vdp``).  The device loop needs to know what that callback does, so the
+integrators take the function space and boundary data instead (``V``,
+``invinds``, ``dbcinds``, ``dbcvals``), which is what `snu.solve_nse` has at
+hand when it builds the callback (`stokes_navier_utils.py:1136-1140`).
+"""
+import numpy as np
+import scipy.sparse as sps
+
+from . import _lib
+from . import hostsetup
+
+__all__ = ['cnab', 'sbdftwo', 'semi_implicit_euler', 'DeviceImex',
+           'lowrank_forcing']
+
+_THETA = dict(cnab=.5, sbdf2=2./3, imexeuler=1.)
+
+
+def _on_pattern(X, pat):
+    """values of ``X`` on the (larger) CSR pattern of ``pat`` (explicit zeros)"""
+    pat = sps.csr_matrix(pat)
+    X = sps.coo_matrix(X)
+    pc = pat.tocoo()
+    rows = np.concatenate([pc.row, X.row])
+    cols = np.concatenate([pc.col, X.col])
+    vals = np.concatenate([np.zeros(pc.nnz), X.data])
+    out = sps.coo_matrix((vals, (rows, cols)), shape=pat.shape).tocsr()
+    out.sum_duplicates()
+    out.sort_indices()
+    if out.nnz != pat.nnz:
+        raise ValueError('matrix does not fit the given pattern')
+    return out
+
+
+def _union_pattern(mats):
+    acc = None
+    for m in mats:
+        m = sps.csr_matrix(m)
+        p = sps.csr_matrix((np.ones(m.nnz), m.indices, m.indptr),
+                           shape=m.shape)
+        acc = p if acc is None else acc + p
+    acc = acc.tocsr()
+    acc.sort_indices()
+    return acc
+
+
+def lowrank_forcing(fvtd, trange, nv, maxrank=64, tol=1e-13):
+    """sample ``fvtd(t)`` on ``trange`` and factor it as ``B @ U``
+
+    The device loop evaluates ``f(t_n) = sum_k U[k, n] B[:, k]``; separable
+    forcings such as ``sin(t)*b`` (`tests/time_dep_nse_bcrob.py:33-34`) have
+    rank 1.  Raises if the sampled forcing has rank > ``maxrank``.
+    """
+    Fs = np.hstack([np.asarray(fvtd(t), dtype=float).reshape(nv, 1)
+                    for t in trange])
+    nrm = np.linalg.norm(Fs)
+    if nrm == 0.:
+        return np.zeros((nv, 1)), np.zeros((len(trange), 1))
+    rng = np.random.default_rng(0)
+    k = min(maxrank + 8, Fs.shape[1])
+    Q, _ = np.linalg.qr(Fs@rng.standard_normal((Fs.shape[1], k)))
+    U = Q.T@Fs
+    # compress to the numerical rank
+    uu, ss, vv = np.linalg.svd(U, full_matrices=False)
+    r = int(np.sum(ss > tol*ss[0]))
+    B = Q@uu[:, :r]
+    U = (ss[:r, None]*vv[:r, :])
+    if r > maxrank or np.linalg.norm(Fs - B@U) > 1e-12*nrm:
+        raise NotImplementedError('time dependent forcing of rank > {0}'.
+                                  format(maxrank))
+    return B, U.T.copy()
+
+
+class DeviceImex(object):
+    """device-resident IMEX integrator for ``nb`` trajectories on one mesh
+
+    ``A_m = nus[m]*A0 + Arob``; all members share M, J, the mesh, the pattern
+    and the boundary data.  For a single trajectory pass ``A0=A, nus=[1.]``.
+    """
+
+    def __init__(self, M, A0, J, V, invinds, dbcinds, dbcvals, dt,
+                 scheme='cnab', nus=(1.,), Arob=None, fv=None, fp=None,
+                 ctx=None, cheb_steps=3, restart=40, coarse_max=4096,
+                 mp_diag=None):
+        self.ctx = _lib.default_context() if ctx is None else ctx
+        self.scheme = scheme
+        self.dt = float(dt)
+        self.nus = np.atleast_1d(np.asarray(nus, dtype=float))
+        self.nb = self.nus.size
+        self.V = V
+        self.invinds = np.asarray(invinds, dtype=np.int32)
+        M, A0, J = sps.csr_matrix(M), sps.csr_matrix(A0), sps.csr_matrix(J)
+        self.NP, self.NV = J.shape
+        mats = [M, A0] + ([] if Arob is None else [sps.csr_matrix(Arob)])
+        pat = _union_pattern(mats)
+        Mp, A0p = _on_pattern(M, pat), _on_pattern(A0, pat)
+        Arp = _on_pattern(sps.csr_matrix(pat.shape) if Arob is None else Arob,
+                          pat)
+        self._host = dict(M=Mp, A0=A0p, Arob=Arp, J=J)
+        # Dirichlet data: unique indices, last write wins (`dts:534-535`)
+        aux = {}
+        for i, v in zip(dbcinds, dbcvals):
+            aux[int(i)] = float(v)
+        bci = np.array(sorted(aux.keys()), dtype=np.int32)
+        bcv = np.array([aux[i] for i in bci], dtype=float)
+        self.dev = _lib.device_for(V, self.ctx)
+        ctx = self.ctx
+        self.mmat = ctx.csr(Mp)
+        self.amat = ctx.csr(Arp, A0p.data)
+        JT = J.T.tocsr()
+        JT.sort_indices()
+        self.jmat, self.jtmat = ctx.csr(J), ctx.csr(JT)
+        self.engine = _lib.ImexEngine(ctx, scheme, self.nb, self.dt,
+                                      self.mmat, self.amat, self.jmat,
+                                      self.jtmat, self.nus, self.invinds, bci,
+                                      bcv, fv=fv, fp=fp)
+        # ---- solvers: loop (tau = theta*dt), Heun predictor (dt), corr (0) --
+        theta = _THETA[scheme]
+        taus = [theta*self.dt] if scheme == 'imexeuler' \
+            else [theta*self.dt, self.dt, 0.]
+        self.solvers, self.infos = [], []
+        hierarchy = None
+        numean = float(np.mean(self.nus))
+        for tau in taus:
+            F1 = sps.csr_matrix((Mp.data + tau*Arp.data, Mp.indices,
+                                 Mp.indptr), shape=Mp.shape)
+            mpd = None if mp_diag is None or tau == 0. else mp_diag
+            if hierarchy is None:
+                sd = F1.diagonal() + tau*numean*A0p.diagonal()
+                S = hostsetup.lumped_schur(sd, J)
+                hierarchy = hostsetup.sa_amg_hierarchy(S,
+                                                       coarse_max=coarse_max)
+            s, info = hostsetup.make_saddle_solver(
+                ctx, F1, J, JT, F2=A0p, coef=tau*self.nus, nb=self.nb,
+                restart=restart, cheb_steps=cheb_steps, hierarchy=hierarchy,
+                mp_diag=mpd,
+                mp_scale=None if mpd is None else tau*self.nus)
+            self.solvers.append(s)
+            self.infos.append(info)
+        self.engine.set_solvers(*self.solvers)
+
+    def set_forcing(self, B, U):
+        self.engine.set_forcing(B, U)
+
+    def set_state(self, v0, p0=None):
+        self.engine.set_state(v0, p0)
+
+    def run(self, nsteps, **kw):
+        return self.engine.run(nsteps, **kw)
+
+    def state(self):
+        return self.engine.state()
+
+    def snapshots(self):
+        """(nsnap, NV, nb) velocities and (nsnap, NP, nb) pressures"""
+        s = self.engine.snapshots()
+        return s[:, :self.NV, :], s[:, self.NV:, :]
+
+    def stats(self):
+        return self.engine.stats()
+
+    def close(self):
+        self.engine.close()
+        for s in self.solvers:
+            s.close()
+
+
+def _run_imex(scheme, trange=None, inivel=None, inip=None, M=None, A=None,
+              J=None, f_tdp=None, g_tdp=None, scalep=-1., V=None,
+              invinds=None, dbcinds=None, dbcvals=None, savevp=None,
+              check_ff_maxv=1e8, ntimeslices=10, tol=1e-11, maxit=400,
+              guess=8, cheb_steps=3, f_vdp='convection', ctx=None,
+              return_engine=False, **kw):
+    if f_vdp != 'convection' and f_vdp is not None:
+        raise NotImplementedError(
+            'the device loop assembles the P2 convection itself; a foreign '
+            '`f_vdp` callback cannot run on the device')
+    if scalep != -1.:
+        raise NotImplementedError('scalep != -1')
+    trange = np.asarray(trange, dtype=float)
+    dtv = np.diff(trange)
+    if not np.allclose(np.linalg.norm(np.diff(dtv)), 0):
+        raise NotImplementedError()                      # `tiu:358-363`
+    dt = trange[1] - trange[0]
+    NP, NV = J.shape
+    fv0 = np.zeros((NV, 1)) if f_tdp is None else None
+    B = U = None
+    if f_tdp is not None:
+        B, U = lowrank_forcing(f_tdp, trange, NV)
+    fp = np.zeros((NP, 1)) if g_tdp is None else np.asarray(g_tdp(trange[0]))
+    integ = DeviceImex(M, A, J, V, invinds, dbcinds, dbcvals, dt,
+                       scheme=scheme, nus=(1.,), fv=fv0, fp=fp, ctx=ctx,
+                       cheb_steps=cheb_steps)
+    if B is not None:
+        integ.set_forcing(B, U)
+    integ.set_state(inivel, inip)
+    nsteps = trange.size - 1
+    stride = 1 if savevp is not None else 0
+    ffflag = integ.run(nsteps, snap_stride=stride, tol=tol, maxit=maxit,
+                       guess=guess, check_ff_maxv=check_ff_maxv,
+                       ntimeslices=ntimeslices)
+    v_n, p_n = integ.state()
+    if savevp is not None:
+        from .dolfin_to_sparrays import append_bcs_vec
+        vs, ps = integ.snapshots()
+        for k in range(vs.shape[0]):
+            vfull = append_bcs_vec(vs[k, :, :1], V=V, invinds=invinds,
+                                   bcinds=dbcinds, bcvals=dbcvals)
+            savevp(vfull, ps[k, :, :1], time=trange[k])
+    if return_engine:
+        return v_n, p_n, ffflag, integ
+    integ.close()
+    return v_n, p_n, ffflag
+
+
+def cnab(**kw):
+    """Crank-Nicolson/Adams-Bashforth on the device -- `tiu:23-145`
+
+    ``cnab(trange=, inivel=, inip=, M=, A=, J=, f_tdp=, g_tdp=, V=, invinds=,
+    dbcinds=, dbcvals=, savevp=, check_ff_maxv=, ntimeslices=)`` returns
+    ``(v_n, p_n, ffflag)`` like the reference.
+    """
+    return _run_imex('cnab', **kw)
+
+
+def sbdftwo(**kw):
+    """SBDF2 on the device -- `tiu:260-355`"""
+    return _run_imex('sbdf2', **kw)
+
+
+def semi_implicit_euler(iniv=None, jmat=None, mmat=None, amat=None, rhsv=None,
+                        trange=None, data_trange=None, fp=None, V=None,
+                        invinds=None, dbcinds=None, dbcvals=None, fv=None,
+                        fvtd=None, **kw):
+    """IMEX Euler with the P2 convection treated explicitly -- `tiu:566-635`
+
+    The reference takes an opaque ``rhsv(t, v)``; on the device the right hand
+    side is ``fv + fvtd(t) - N(v)v`` (pass ``fv``/``fvtd``), the use the
+    reference's scripts make of it.  Returns the list of velocities at
+    ``data_trange``.
+    """
+    if rhsv is not None:
+        raise NotImplementedError('opaque `rhsv(t, v)` callbacks cannot run '
+                                  'on the device; pass `fv`/`fvtd`')
+    trange = np.asarray(trange, dtype=float)
+    NP, NV = jmat.shape
+    integ = DeviceImex(mmat, amat, jmat, V, invinds, dbcinds, dbcvals,
+                       trange[1] - trange[0], scheme='imexeuler', nus=(1.,),
+                       fv=np.zeros((NV, 1)) if fv is None else fv,
+                       fp=np.zeros((NP, 1)) if fp is None else fp)
+    if fvtd is not None:
+        integ.set_forcing(*lowrank_forcing(fvtd, trange, NV))
+    integ.set_state(iniv)
+    integ.run(trange.size - 1, snap_stride=1, ntimeslices=0,
+              **{k: v for k, v in kw.items() if k in ('tol', 'maxit', 'guess')})
+    vs, _ = integ.snapshots()
+    integ.close()
+    dtr = trange if data_trange is None else np.asarray(data_trange)
+    idx = [int(np.argmin(np.abs(trange - t))) for t in dtr]
+    return [vs[k, :, :1] for k in idx]

@@ -1,0 +1,120 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every
+symbol `include/dnsb.h` declares; host-side setup logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import scipy.sparse as sps
+
+import __graft_entry__ as ge
+from dolfin_navier_scipy_b200 import _lib, fem, hostsetup
+from dolfin_navier_scipy_b200 import time_int_utils as tiu
+from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    with open(os.path.join(ROOT, 'include', 'dnsb.h')) as f:
+        txt = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    return sorted(set(re.findall(r'\b(dnsb_[a-z0-9_]+)\s*\(', txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    lib = ge.build()
+    dll = ctypes.CDLL(lib)
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(dll, n), n
+    # the ctypes table mirrors the header one to one
+    assert sorted(_lib.SIGNATURES.keys()) == names
+    assert dll.dnsb_version() >= 100
+
+
+def test_colouring_is_valid_and_balanced():
+    for lvl in (1, 2):
+        m = fem.load_mesh('cylinder_%d' % lvl)
+        ncol, col = fem.colour_cells(m)
+        for c in range(ncol):
+            verts = m.cells[col == c].ravel()
+            assert verts.size == np.unique(verts).size   # no shared vertex
+        counts = np.bincount(col, minlength=ncol)
+        assert counts.max() <= 2.5*counts.mean()
+
+
+def test_lowrank_forcing_is_exact_for_separable_inputs():
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal((50, 2))
+    tr = np.linspace(0, 1, 17)
+    B, U = tiu.lowrank_forcing(
+        lambda t: np.sin(t)*b[:, :1] + t*t*b[:, 1:], tr, 50)
+    assert B.shape[1] == 2 and U.shape == (17, 2)
+    for k, t in enumerate(tr):
+        assert np.allclose(B@U[k], np.sin(t)*b[:, 0] + t*t*b[:, 1], atol=1e-12)
+
+
+def test_pattern_embedding_keeps_explicit_zeros():
+    A = sps.random(20, 20, .3, random_state=1, format='csr') + sps.identity(20)
+    M = sps.identity(20, format='csr')
+    pat = tiu._union_pattern([M, A])
+    Mp = tiu._on_pattern(M, pat)
+    assert Mp.nnz == pat.nnz and abs(Mp - M).max() == 0
+    assert np.array_equal(Mp.indices, pat.indices)
+
+
+def test_sa_amg_two_grid_converges_on_lumped_schur(cyl1):
+    # host set-up sanity: V-cycle (numpy emulation of the device cycle) as a
+    # stationary iteration contracts the error of the pressure operator
+    femp, sm, rhsd = cyl1
+    F = sm['M'] + .5/512*sm['A']
+    S = hostsetup.lumped_schur(F.diagonal(), sm['J'])
+    levels, dense = hostsetup.sa_amg_hierarchy(S, coarse_max=200)
+    assert len(levels) >= 1 and dense.shape[0] <= 200
+
+    def cheb(A, dinv, r, k, lmin, lmax):
+        th, de = .5*(lmax + lmin), .5*(lmax - lmin)
+        sg = th/de
+        rho = 1/sg
+        z, res = np.zeros_like(r), r.copy()
+        d = dinv*res/th
+        for i in range(k):
+            z += d
+            if i == k - 1:
+                break
+            res -= A@d
+            rn = 1/(2*sg - rho)
+            d = rn*rho*d + 2*rn/de*(dinv*res)
+            rho = rn
+        return z
+
+    def vcyc(l, b):
+        if l == len(levels):
+            return dense@b
+        lv = levels[l]
+        dinv = 1/lv['A'].diagonal()
+        x = cheb(lv['A'], dinv, b, 2, lv['lmin'], lv['lmax'])
+        x = x + lv['P']@vcyc(l + 1, lv['R']@(b - lv['A']@x))
+        return x + cheb(lv['A'], dinv, b - lv['A']@x, 2, lv['lmin'], lv['lmax'])
+    rng = np.random.default_rng(0)
+    xex = rng.standard_normal(S.shape[0])
+    b = S@xex
+    x = np.zeros_like(b)
+    for _ in range(12):
+        x = x + vcyc(0, b - S@x)
+    assert np.linalg.norm(x - xex) < 1e-3*np.linalg.norm(xex)
+
+
+def test_condense_and_append_roundtrip(cyl1):
+    femp, sm, rhsd = cyl1
+    V, inv = femp['V'], femp['invinds']
+    v = np.arange(inv.size, dtype=float).reshape(-1, 1)
+    vf = dts.append_bcs_vec(v, V=V, invinds=inv, bcinds=femp['dbcinds'],
+                            bcvals=femp['dbcvals'])
+    assert vf.shape == (V.dim(), 1) and not np.any(np.isnan(vf))
+    assert np.array_equal(vf[inv], v)
+    Ac, fvbc = dts.condense_velmatsbybcs(sm['Afull'], invinds=inv,
+                                         dbcinds=femp['dbcinds'],
+                                         dbcvals=femp['dbcvals'])
+    assert abs(Ac - sm['A']).max() < 1e-15

@@ -1,0 +1,184 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle
+on the same inputs.  Tolerances follow BASELINE.json: relative L2 error of
+velocity and pressure <= 1e-8 per step in fp64."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from conftest import soldict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from dolfin_navier_scipy_b200 import _lib
+    return _lib.default_context(0)
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b))/np.linalg.norm(b)
+
+
+def test_device_is_b200_class(ctx):
+    info = ctx.info()
+    assert info['cc'] >= 100, info
+    assert info['sm_count'] >= 100
+
+
+def test_convvec_matches_oracle(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    from oracle import convection as oconv
+    femp, sm, rhsd = cyl1
+    V = femp['V']
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(V.dim())
+    w = rng.standard_normal(V.dim())
+    c = dts.get_convvec(V=V, u0_vec=u)
+    assert c.shape == (V.dim(), 1)
+    assert _rel(c.ravel(), oconv.convvec(V, u)) < 1e-13
+    c2 = dts.get_convvec(V=V, u0_vec=u, uone_utwo_same=False, utwo_vec=w)
+    assert _rel(c2.ravel(), oconv.convvec(V, u, w)) < 1e-13
+    # inner-node interface (`dts:466-467`)
+    inv = femp['invinds']
+    ci = dts.get_convvec(V=V, u0_vec=u, invinds=inv)
+    assert np.array_equal(ci, c[inv])
+
+
+def test_convvec_batched_and_deterministic(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import _lib
+    from oracle import convection as oconv
+    femp = cyl1[0]
+    V = femp['V']
+    dev = _lib.device_for(V)
+    rng = np.random.default_rng(1)
+    U = rng.standard_normal((V.dim(), 5))
+    C = dev.convvec(U)
+    for m in range(5):
+        assert _rel(C[:, m], oconv.convvec(V, U[:, m])) < 1e-13
+    assert np.array_equal(C, dev.convvec(U))       # bit-reproducible
+
+
+def test_convmats_match_oracle(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    from oracle import convection as oconv
+    femp = cyl1[0]
+    V = femp['V']
+    rng = np.random.default_rng(2)
+    u = rng.standard_normal(V.dim())
+    N1, N2, f3 = dts.get_convmats(u0_vec=u, V=V)
+    O1, O2, o3 = oconv.convmats(V, u)
+    assert abs(N1 - O1).max() < 1e-13*abs(O1).max()
+    assert abs(N2 - O2).max() < 1e-13*abs(O2).max()
+    assert _rel(f3, o3) < 1e-13
+    # `tests/test_units_fenicsci.py:84-85`
+    assert _rel(N1@u, f3.ravel()) < 1e-12 and _rel(N2@u, f3.ravel()) < 1e-12
+
+
+def test_spmm_matches_scipy(cyl1, ctx):
+    femp, sm, rhsd = cyl1
+    A = sps.csr_matrix(sm['A'])
+    rng = np.random.default_rng(3)
+    mat = ctx.csr(A)
+    x = rng.standard_normal(A.shape[1])
+    assert _rel(mat.spmm(x), A@x) < 1e-14
+    X = rng.standard_normal((A.shape[1], 7))
+    Y0 = rng.standard_normal((A.shape[0], 7))
+    Y = mat.spmm(X, alpha=-.5, beta=2., y=Y0)
+    assert _rel(Y, -.5*(A@X) + 2*Y0) < 1e-14
+    # two value arrays with per-member coefficients
+    M = sps.csr_matrix(sm['M'])
+    from dolfin_navier_scipy_b200.time_int_utils import _on_pattern, _union_pattern
+    pat = _union_pattern([M, A])
+    Mp, Ap = _on_pattern(M, pat), _on_pattern(A, pat)
+    m2 = ctx.csr(Mp, Ap.data)
+    coef = np.array([0., 1., .25, -2., 3., .5, 7.])
+    Y = m2.spmm(X, coef=coef)
+    for k in range(7):
+        assert _rel(Y[:, k], M@X[:, k] + coef[k]*(A@X[:, k])) < 1e-13
+    # rectangular
+    J = sps.csr_matrix(sm['J'])
+    assert _rel(ctx.csr(J).spmm(x), J@x) < 1e-14
+
+
+def test_saddle_solver_matches_lu(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from oracle.lau import solve_sadpnt_smw as olu
+    femp, sm, rhsd = cyl1
+    dt = 1./512
+    F = (sm['M'] + .5*dt*sm['A']).tocsr()
+    rng = np.random.default_rng(4)
+    b = sm['M']@rng.standard_normal((F.shape[0], 2))
+    g = np.zeros((sm['J'].shape[0], 2))
+    stats = []
+    vp = lau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b,
+                              rhsp=g, krylov='gmres',
+                              krpslvprms=dict(tol=1e-12, maxiter=200,
+                                              convstatsl=stats))
+    ref = olu(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b, rhsp=g)
+    NV = F.shape[0]
+    assert vp.shape == ref.shape
+    assert _rel(vp[:NV], ref[:NV]) < 1e-9
+    assert _rel(vp[NV:], ref[NV:]) < 1e-8
+    assert 0 < stats[0] < 80
+
+
+def test_imex_cnab_parity_per_step(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    sd = soldict(femp, sm, rhsd, t0=0., tE=24./512, Nts=24,
+                 start_ssstokes=True, return_vp_dict=True)
+    got = snu.solve_nse(**sd)
+    ref = osnu.solve_nse(**sd)
+    assert sorted(got.keys()) == sorted(float(t) for t in ref.keys())
+    tr = sorted(ref.keys())
+    for t in tr[1:]:
+        assert _rel(got[float(t)]['v'], ref[t]['v']) < 1e-8, t
+        assert _rel(got[float(t)]['p'], ref[t]['p']) < 1e-8, t
+
+
+def test_imex_sbdf2_final_state(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    sd = soldict(femp, sm, rhsd, t0=0., tE=20./512, Nts=20,
+                 start_ssstokes=True, return_final_vp=True,
+                 time_int_scheme='sbdf2')
+    v, p = snu.solve_nse(**sd)
+    vo, po = osnu.solve_nse(**sd)
+    assert _rel(v, vo) < 1e-8 and _rel(p, po) < 1e-8
+
+
+def test_ensemble_members_equal_single_runs(cyl1, ctx):
+    """batched trajectories (shared pattern, different nu) == individual runs"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    nu0 = femp['nu']
+    A0 = sm['A']/nu0
+    nus = np.array([nu0, .5*nu0, 2*nu0])
+    dt, nsteps = 1./512, 10
+    # boundary contribution of A scales with nu: fv_m = nu_m/nu0 * fv
+    inv = femp['invinds']
+    v0 = osnu.solve_nse(t0=0, tE=dt, Nts=1, start_ssstokes=True,
+                        return_vp_dict=True, **soldict(femp, sm, rhsd))
+    v_ini = v0[0.0]['v'][inv]
+    # per-member forcing through the input interface: fv_m = (nu_m/nu0) fv
+    integ = tiu.DeviceImex(sm['M'], A0, sm['J'], femp['V'], inv,
+                           femp['dbcinds'], femp['dbcvals'], dt, nus=nus,
+                           fp=rhsd['fp'])
+    U = np.broadcast_to((nus/nu0)[None, None, :], (nsteps + 1, 1, 3))
+    integ.set_forcing(rhsd['fv'], U)
+    integ.set_state(v_ini, v0[0.0]['p'])
+    integ.run(nsteps, tol=1e-12)
+    V, P = integ.state()
+    integ.close()
+    for m, nu in enumerate(nus):
+        sd = soldict(femp, sm, rhsd)
+        sd.update(A=nu*A0, fv=nu/nu0*rhsd['fv'])
+        ref = osnu.solve_nse(t0=0, tE=nsteps*dt, Nts=nsteps, iniv=v0[0.0]['v'],
+                             inip=v0[0.0]['p'], return_final_vp=True, **sd)
+        assert _rel(V[:, m:m+1], ref[0]) < 1e-8, m
+        assert _rel(P[:, m:m+1], ref[1]) < 1e-7, m

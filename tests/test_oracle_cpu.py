@@ -1,0 +1,207 @@
+"""CPU tests: the oracle against the reference's own identities / known answers
+ and the host-side FEM shim."""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from dolfin_navier_scipy_b200 import fem
+from dolfin_navier_scipy_b200 import problem_setups as dnsps
+from oracle import convection as oconv
+from oracle import snu as osnu
+from oracle import tiu as otiu
+from oracle.lau import solve_sadpnt_smw
+
+from conftest import soldict
+
+
+def test_mesh_fixture_counts():
+    # sizes and cylinder-facet counts of the fixtures
+    expect = {1: (806, 1501, 2307, 18), 2: (1289, 2413, 3702, 31),
+              4: (3836, 7364, 11200, 94)}
+    for lvl, (nv, nc, ne, ncyl) in expect.items():
+        f = dnsps.cyl_fems(refinement_level=lvl)
+        m = f['mesh']
+        assert (m.num_vertices, m.num_cells, m.num_edges) == (nv, nc, ne)
+        assert int(f['facetmasks']['cylinder'].sum()) == ncyl
+        masks = f['facetmasks']
+        tot = sum(int(masks[k].sum()) for k in
+                  ('inflow', 'walls', 'cylinder', 'outflow'))
+        assert tot == m.bnd_edge.size          # 0 unclassified
+
+
+def test_rotcyl_facet_classification_matches_marker_histogram():
+    # marker histogram of karman2D-rotcyl_lvl1_facet_region: 18/7/49+49/134
+    f = dnsps.gen_bccont_fems(
+        scheme='TH', bccontrol=False,
+        strtomeshfile='mesh/karman2D-rotcyl_lvl1.xml.gz',
+        strtobcsobs='mesh/karman2D-rotcyl-bm_geo_cntrlbc.json',
+        inflowvel=.2)
+    fm = f['facetmasks']
+    assert int(fm['pe1'].sum()) == 18 and int(fm['pe2'].sum()) == 7
+    assert int(fm['walls'].sum()) == 98 and int(fm['pe5'].sum()) == 134
+    d = np.load(fem._MESHDIR + '/karman2D-rotcyl_lvl1.npz')
+    assert list(d['facet_hist'][1:]) == [18, 7, 49, 49, 134]
+
+
+def test_operator_identities_unit_square():
+    m = fem.unit_square_mesh(6)
+    V, Q = fem.VectorP2Space(m), fem.P1Space(m)
+    ops = fem.assemble_stokes_operators(V, Q, nu=1.)
+    M, A, J, MP = ops['M'], ops['A'], ops['J'], ops['MP']
+    xn = V.node_coords()
+    one = np.ones(V.num_nodes)
+    assert abs(one@M[::2, :][:, ::2]@one - 1.) < 1e-13
+    assert abs(MP.sum() - 1.) < 1e-13
+    rot = np.zeros(V.dim())
+    rot[0::2], rot[1::2] = -xn[:, 1], xn[:, 0]
+    assert np.abs(A@rot).max() < 1e-12          # rigid rotation: eps(u) = 0
+    u = np.zeros(V.dim())
+    u[0::2], u[1::2] = xn[:, 0]**2, xn[:, 1]
+    assert abs((J@u).sum() - 2.) < 1e-13        # int div u = int 2x+1
+    assert abs(u@A@u - 14./3) < 1e-12           # int 2 eps:grad = 2(4x^2+1)
+    assert abs(JTnorm(ops)) < 1e-14
+
+
+def JTnorm(ops):
+    return abs(ops['JT'] - ops['J'].T).max()
+
+
+def test_convection_identities_test_units_fenicsci():
+    # `tests/test_units_fenicsci.py:69-85`: convvec(u) == N1(u) u == N2(u) u
+    m = fem.unit_square_mesh(8)
+    V = fem.VectorP2Space(m)
+    xn = V.node_coords()
+    x, y = xn[:, 0], xn[:, 1]
+    u = np.zeros(V.dim())            # the div-free field of the reference test
+    u[0::2] = x*x*(1 - x)*(1 - x)*2*y*(1 - y)*(2*y - 1)
+    u[1::2] = y*y*(1 - y)*(1 - y)*2*x*(1 - x)*(1 - 2*x)
+    N1, N2, f3 = oconv.convmats(V, u)
+    cv = oconv.convvec(V, u)
+    assert np.linalg.norm(N1@u - cv) < 1e-14
+    assert np.linalg.norm(N2@u - cv) < 1e-14
+    assert np.linalg.norm(f3.ravel() - cv) < 1e-14
+
+
+def test_convection_exact_polynomial_integral():
+    # sum_i w_i c_i = int (grad(u) u) . w  for P2 fields u, w: exact value by
+    # sympy on the unit square (independent of any quadrature rule)
+    import sympy as sp
+    xs, ys = sp.symbols('x y')
+    ue = sp.Matrix([xs**2 + xs*ys - ys, 1 + xs - 2*ys**2 + xs*ys])
+    we = sp.Matrix([ys**2 - xs, xs*ys + 1])
+    gu = ue.jacobian([xs, ys])
+    integrand = ((gu*ue).T*we)[0, 0]
+    exact = float(sp.integrate(sp.integrate(integrand, (xs, 0, 1)), (ys, 0, 1)))
+    m = fem.unit_square_mesh(3)
+    V = fem.VectorP2Space(m)
+    fu = sp.lambdify((xs, ys), ue, 'numpy')
+    fw = sp.lambdify((xs, ys), we, 'numpy')
+    xn = V.node_coords()
+    u = np.zeros(V.dim())
+    w = np.zeros(V.dim())
+    for k, (a, b) in enumerate(xn):
+        uu, ww = np.asarray(fu(a, b)).ravel(), np.asarray(fw(a, b)).ravel()
+        u[2*k:2*k+2], w[2*k:2*k+2] = uu, ww
+    assert abs(w@oconv.convvec(V, u) - exact) < 1e-12*max(1., abs(exact))
+
+
+def test_pfromv_identity_test_units_pfromv(cyl1):
+    # `tests/test_units_pfromv.py:17-45`: get_pfromv(v_ss) == p_ss
+    femp, sm, rhsd = cyl1
+    sd = soldict(femp, sm, rhsd)
+    sd.pop('JT')
+    v, p = osnu.solve_steadystate_nse(return_vp=True, JT=sm['JT'], **sd)
+    inv = femp['invinds']
+    pfv = osnu.get_pfromv(v=v[inv, :], V=femp['V'], M=sm['M'], A=sm['A'],
+                          J=sm['J'], fv=rhsd['fv'], invinds=inv,
+                          dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'])
+    assert np.allclose(pfv, p, rtol=1e-8, atol=1e-10)
+
+
+def test_step_residuals_test_units_residuals(cyl1):
+    # `tests/test_units_residuals.py:93-124`: scipy residuals of the Heun and
+    # AB2 steps vanish (projected onto the divergence-free space via J)
+    femp, sm, rhsd = cyl1
+    M, A, J = sm['M'], sm['A'], sm['J']
+    V, inv = femp['V'], femp['invinds']
+    trange = np.linspace(0., 3./256, 4)
+    dt = trange[1] - trange[0]
+    vpd = osnu.solve_nse(trange=trange, start_ssstokes=True,
+                         return_vp_dict=True, **soldict(femp, sm, rhsd))
+    ts = sorted(vpd.keys())
+
+    def nfc(vfull):
+        return -oconv.convvec(V, vfull.ravel())[inv].reshape(-1, 1)
+    v = [vpd[t]['v'][inv] for t in ts]
+    p = [vpd[t]['p'] for t in ts]
+    n = [nfc(vpd[t]['v']) for t in ts]
+    fv = rhsd['fv']
+    # AB2 step 1 -> 2 and 2 -> 3 (`test_units_residuals.py:121-124`)
+    for k in (2, 3):
+        res = 1./dt*M@(v[k] - v[k-1]) + .5*A@(v[k] + v[k-1]) \
+            - (1.5*n[k-1] - .5*n[k-2]) - J.T@p[k] - fv
+        assert np.linalg.norm(res) < 1e-9*np.linalg.norm(fv)
+        assert np.linalg.norm(J@v[k] - rhsd['fp']) < 1e-10
+
+
+def test_cnab_second_order_in_time(cyl1):
+    # `tests/tdp_convcheck.py:115-138`: halving dt quarters the error
+    femp, sm, rhsd = cyl1
+    sd = soldict(femp, sm, rhsd)
+    tE = 0.05
+    ref = osnu.solve_nse(t0=0., tE=tE, Nts=128, start_ssstokes=True,
+                         return_final_vp=True, **sd)[0]
+    errs = []
+    for nts in (8, 16, 32):
+        v = osnu.solve_nse(t0=0., tE=tE, Nts=nts, start_ssstokes=True,
+                           return_final_vp=True, **sd)[0]
+        errs.append(np.linalg.norm(v - ref))
+    rates = np.log2(np.array(errs[:-1])/np.array(errs[1:]))
+    assert np.all(rates > 1.7), rates
+
+
+def test_sbdf2_and_imex_euler_run(cyl1):
+    femp, sm, rhsd = cyl1
+    sd = soldict(femp, sm, rhsd)
+    v1 = osnu.solve_nse(t0=0., tE=.02, Nts=16, start_ssstokes=True,
+                        return_final_vp=True, time_int_scheme='sbdf2', **sd)[0]
+    v2 = osnu.solve_nse(t0=0., tE=.02, Nts=16, start_ssstokes=True,
+                        return_final_vp=True, time_int_scheme='cnab', **sd)[0]
+    assert np.linalg.norm(v1 - v2) < 2e-3*np.linalg.norm(v2)
+    inv = femp['invinds']
+    vs = otiu.semi_implicit_euler(
+        iniv=v2, jmat=sm['J'], mmat=sm['M'], amat=sm['A'],
+        rhsv=lambda t, v: rhsd['fv'], trange=np.linspace(0, .01, 5))
+    assert len(vs) == 5 and np.all(np.isfinite(vs[-1]))
+
+
+def test_solve_sadpnt_smw_contract():
+    rng = np.random.default_rng(1)
+    A = sps.random(30, 30, .2, random_state=2) + 30*sps.identity(30)
+    J = sps.random(6, 30, .5, random_state=3)
+    b, g = rng.standard_normal((30, 2)), rng.standard_normal((6, 2))
+    vp = solve_sadpnt_smw(amat=A.tocsr(), jmat=J.tocsr(), rhsv=b, rhsp=g)
+    assert vp.shape == (36, 2)
+    assert np.allclose(A@vp[:30] + J.T@vp[30:], b)
+    assert np.allclose(J@vp[:30], g)
+
+
+@pytest.mark.parametrize('lvl', [1])
+def test_schaefer_turek_dfg_2d1(lvl):
+    # `tests/steadystate_schaefer-turek_2D-1.py:112-114`: Cd, Cl, dP of DFG 2D-1
+    femp, sm, rhsd = dnsps.get_sysmats(
+        problem='gen_bccont', nu=1e-3, charvel=.2, scheme='TH', mergerhs=True,
+        meshparams=dict(strtomeshfile='mesh/karman2D-rotcyl_lvl%d.xml.gz' % lvl,
+                        movingwallcntrl=False,
+                        strtophysicalregions='mesh/karman2D-rotcyl_lvl%d_'
+                        'facet_region.xml.gz' % lvl,
+                        strtobcsobs='mesh/karman2D-rotcyl-bm_geo_cntrlbc.json'))
+    v, p = osnu.solve_steadystate_nse(return_vp=True,
+                                      **soldict(femp, sm, rhsd))
+    cd, cl = osnu.drag_lift(sm['Afull'], sm['JTfull'], femp['V'], v, p,
+                            femp['ldsbcinds'])
+    dp = femp['Q'].eval_at(p, (.15, .2)) - femp['Q'].eval_at(p, (.25, .2))
+    # the tested residual is the force of the cylinder on the fluid (sign)
+    assert abs(-cd - 5.57953523384) < 2e-3
+    assert abs(-cl - 0.010618948146) < 2e-5
+    assert abs(dp - 0.11752016697) < 5e-5
