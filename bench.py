@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- cylinder-wake DoF.steps/s on N B200 vs. the host CPU.
+
+Workload (BASELINE.json config 5 on the finest `cylinderwake` mesh, the
+configuration the headline metric is quoted on): an ensemble of Robin
+boundary-control trajectories of the cylinder wake, Reynolds numbers swept over
+[60, 150], Taylor-Hood P2-P1 on `cylinder_4` (28 970 + 3 836 condensed DoFs per
+member), CNAB (Crank-Nicolson / Adams-Bashforth-2) with dt = 1/2048, members
+sharded over the GPUs (`--members` per GPU, weak scaling, no collective on the
+step path).  One "step" = one time step of all members of the batch:
+convection re-evaluation (K1a), right-hand side (K2), saddle-point solve (K3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--members B]
+                    [--mesh 4] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of
+the reference's scipy path (oracle/: SuperLU + compiled cell loop) on the box's
+host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'cylinder-wake DoF*steps/s'
+UNIT = 'DoF*steps/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--warmup', type=int, default=6)
+    ap.add_argument('--members', type=int, default=64,
+                    help='ensemble members per GPU')
+    ap.add_argument('--mesh', type=int, default=4)
+    ap.add_argument('--nts', type=int, default=2048, help='steps per time unit')
+    ap.add_argument('--tol', type=float, default=1e-12)
+    ap.add_argument('--guess', type=int, default=8)
+    ap.add_argument('--cheb', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-seconds', type=float, default=12.)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-profile', action='store_true')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# --------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,'
+         'clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith('active'):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None,
+                    sm_max_mhz=max(smax) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# --------------------------------------------------------------------------
+# CPU restatement of the reference (oracle) -- baseline / reference arm
+# --------------------------------------------------------------------------
+def _cpu_member_worker(args):
+    """CNAB steps of ONE member with the oracle (SuperLU + compiled cell loop);
+    returns (steps done, seconds in the step loop)."""
+    (N, Re, nts, palpha, seconds, maxsteps) = args
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spsla
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from oracle.cconv import CConv
+    from oracle.snu import append_bcs_vec
+    from oracle.lau import solve_sadpnt_smw
+    femp, sm, rv, rb = dnsps.get_sysmats(
+        problem='cylinderwake', Re=Re, bccontrol=True, scheme='TH',
+        meshparams=dict(refinement_level=N))
+    M, J = sm['M'], sm['J']
+    A = sm['A'] + sm['Arob']/palpha                # `time_dep_nse_bcrob.py:27`
+    Brob = sm['Brob']/palpha
+    bdiff = Brob[:, :1] - Brob[:, 1:]
+    fv = rb['fv'] + rv['fv']
+    fp = rb['fp'] + rv['fp']
+    NP, NV = J.shape
+    V, inv = femp['V'], femp['invinds']
+    cc = CConv(V)
+    dt = 1./nts
+
+    def nfc(v):
+        vf = append_bcs_vec(v, V.dim(), inv, femp['dbcinds'], femp['dbcvals'])
+        return -cc.convvec(vf)[inv].reshape(-1, 1)
+    # set-up (not timed): Stokes start, factorisation (`tiu:89-91`)
+    v = solve_sadpnt_smw(amat=A, jmat=J, rhsv=fv, rhsp=fp)[:NV]
+    K = sps.vstack([sps.hstack([M + .5*dt*A, J.T]),
+                    sps.hstack([J, sps.csr_matrix((NP, NP))])], format='csc')
+    lu = spsla.factorized(K)
+    nfc_c = nfc(v)
+    t, n = 0., 0
+    tic = time.perf_counter()
+    while n < maxsteps and time.perf_counter() - tic < seconds:
+        # loop body of `time_int_utils.py:104-143`
+        nfc_o, nfc_c = nfc_c, nfc(v)
+        rhs = M@v - .5*dt*(A@v) + .5*dt*(3*nfc_c - nfc_o) \
+            + .5*dt*(2*fv + (np.sin(t) + np.sin(t + dt))*bdiff)
+        vp = lu(np.vstack([rhs, fp]).flatten())
+        v = vp[:NV].reshape((NV, 1))
+        t += dt
+        n += 1
+    return n, time.perf_counter() - tic
+
+
+def cpu_reference(args, nworkers, seconds, maxsteps=10**9):
+    """all host cores: one member per worker process, Re spread over [60,150]"""
+    import multiprocessing as mp
+    Res = np.linspace(60., 150., max(nworkers, 2))[:nworkers]
+    jobs = [(args.mesh, float(Re), args.nts, 1e-5, seconds, maxsteps)
+            for Re in Res]
+    if nworkers == 1:
+        res = [_cpu_member_worker(jobs[0])]
+    else:
+        with mp.get_context('spawn').Pool(nworkers) as pool:
+            res = pool.map(_cpu_member_worker, jobs)
+    return res
+
+
+def dofs_of(mesh_level):
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    femp, sm, rv, rb = dnsps.get_sysmats(
+        problem='cylinderwake', Re=100., bccontrol=True, scheme='TH',
+        meshparams=dict(refinement_level=mesh_level))
+    NP, NV = sm['J'].shape
+    return NV, NP
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    ncores = os.cpu_count() or 1
+    NV, NP = dofs_of(args.mesh)
+    # warm-up + K timed "steps": each step is a bounded sample (one CNAB step
+    # of one member per core); the LU factorisation is set-up, not timed
+    per_step_budget = 30.
+    res = cpu_reference(args, ncores, seconds=per_step_budget,
+                        maxsteps=args.warmup + args.steps)
+    nsteps = min(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    members = len(res)
+    value = members*(NV + NP)*nsteps/tmax
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference',
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3*tmax/max(nsteps, 1), higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f64',
+                data='synthetic',
+                config=workload_config(args, members, 1),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=ncores,
+                                  kind='port',
+                                  sample='{0} members (one per core) x {1} CNAB '
+                                  'steps incl. warm-up, SuperLU solve + compiled '
+                                  'cell loop; factorisation excluded'.
+                                  format(members, nsteps)),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0,
+                         d2h_bytes_per_step=0))
+    return line
+
+
+def workload_config(args, members_total, world):
+    return dict(workload='cylinderwake Robin-control ensemble, Re in [60,150], '
+                'mesh cylinder_%d, Taylor-Hood P2-P1, CNAB dt=1/%d, '
+                '%d members per GPU' % (args.mesh, args.nts, args.members),
+                members_total=members_total, members_per_gpu=args.members,
+                mesh='cylinder_%d' % args.mesh, scheme='cnab',
+                parallelism='ensemble-sharded x%d, no step-path collective'
+                % world,
+                tol=args.tol, guess=args.guess, cheb_steps=args.cheb,
+                l2_note='ensemble working set (vectors %d members) exceeds L2'
+                % args.members)
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from dolfin_navier_scipy_b200 import _lib
+    from dolfin_navier_scipy_b200 import ensemble as ens
+
+    torch.cuda.set_device(local_rank)
+    ctx = _lib.default_context(local_rank)
+    nmembers = args.members*world
+    ntimes = args.warmup + 3*args.steps + 8
+    integ, info = ens.cylinder_ensemble(
+        N=args.mesh, nmembers=nmembers, rank=rank, world=world,
+        dt=1./args.nts, ntimes=ntimes, ctx=ctx, cheb_steps=args.cheb)
+    NV, NP, nb = info['NV'], info['NP'], integ.nb
+    # initial state: steady Stokes solution (`start_ssstokes`, snu:903-908) for
+    # the mean viscosity, shared by the members of the shard; solved on the
+    # device (velocity AMG + lumped Schur FGMRES)
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    sm, inv = info['sm'], np.asarray(info['femp']['invinds'])
+    numean = float(np.mean(info['nus']))
+    Ast = numean*sm['A'] if info['Arob'] is None else \
+        numean*sm['A'] + info['Arob']
+    vp = lau.solve_sadpnt_smw(amat=Ast, jmat=sm['J'], jmatT=sm['JT'],
+                              rhsv=numean*info['B'][:, :1], rhsp=info['fp'],
+                              krylov='gmres', vgroups=(inv//2, inv % 2),
+                              krpslvprms=dict(tol=1e-10, maxiter=1500))
+    v0 = np.repeat(vp[:NV], nb, axis=1)
+    p0 = np.repeat(-vp[NV:], nb, axis=1)
+    runkw = dict(tol=args.tol, guess=args.guess, ntimeslices=0, maxit=400)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    # ---- warm-up ------------------------------------------------------------
+    integ.set_state(v0, p0)
+    nwarm = max(args.warmup, 3)
+    integ.run(nwarm, **runkw)
+    # ---- timed: device-resident steps (inputs already in HBM) ---------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ctx.reset_launch_count()
+    t0 = time.perf_counter()
+    integ.run(args.steps, **runkw)
+    dev_ms = integ.engine.last_run_ms()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = ctx.launch_count()
+    clocks = sampler.stop()
+    st = integ.stats()
+    tt = torch.tensor([dev_ms, wall*1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(tt[0]), float(tt[1])
+    units = (NV + NP)*args.members*world*args.steps
+    value = units/(dev_ms_max*1e-3)
+
+    # ---- e2e: through the public API with host buffers ----------------------
+    # per step the host supplies the boundary-control signal (H2D, host numpy
+    # buffers) and receives the (v, p) state of every member (D2H): the
+    # running integration is fed the next chunk of the control series and the
+    # full trajectory is read back
+    B = info['B']
+    U = np.ascontiguousarray(info['U'][nwarm + args.steps:
+                                       nwarm + 2*args.steps + 1])
+    integ.engine.reset_snapshots()
+    barrier()
+    t0 = time.perf_counter()
+    integ.set_forcing(B, U)
+    integ.run(args.steps, snap_stride=1, **runkw)
+    vs, ps = integ.snapshots()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = units/float(te[0])
+    h2d = (B.nbytes + U.nbytes)/float(args.steps)
+    d2h = (vs.nbytes + ps.nbytes)/float(max(vs.shape[0], 1))
+    finite = bool(np.all(np.isfinite(vs[-1])))
+
+    # ---- per-kernel device times (CUDA events on the library's stream) ------
+    roofline = None
+    kern = {}
+    if not args.no_profile:
+        ctx.profile_begin(400000)
+        integ.run(args.steps, **runkw)
+        kern = ctx.profile_end()
+        roofline = roofline_of(kern, info, integ, args)
+
+    # ---- POD Gram matrix: the one collective (not on the step path) ---------
+    G = ens.gram_allreduce(integ)
+    gram = dict(ns=int(G.shape[0]), trace=float(torch.trace(G)),
+                symmetric=bool(torch.allclose(G, G.T, rtol=1e-10, atol=0)))
+
+    if rank != 0:
+        return None
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world,
+                steps=args.steps, warmup=args.warmup,
+                ms_per_step=dev_ms_max/args.steps, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f64',
+                data='synthetic', impl='ours',
+                config=workload_config(args, args.members*world, world),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT,
+                         h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         note='control-signal chunk H2D, K steps, (v,p) of every '
+                         'step D2H through DeviceImex (host numpy buffers)'),
+                gpu_launches=int(launches),
+                wall_ms_per_step=wall_ms_max/args.steps,
+                solver=dict(fgmres_iters_per_step=st['iters']/max(st['solves'], 1),
+                            last_relres=st['last_relres'], finite=finite),
+                dofs_per_member=NV + NP, gram=gram)
+    if roofline is not None:
+        line['roofline'] = roofline
+        tot = sum(v[1] for v in kern.values())
+        line['kernel_share'] = {k: round(v[1]/tot, 4) for k, v in
+                                sorted(kern.items(), key=lambda kv: -kv[1][1])[:8]}
+    return line
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured'
+    return 6650., 'fallback'
+
+
+def roofline_of(kern, info, integ, args):
+    """algorithmic bytes of the dominant kernel / its mean CUDA-event duration
+
+    Byte counts: fused Chebyshev step on F (k_cheb_step):
+    20 B/nnz (fp64 value x2 arrays + int32 column) + 4(n+1) + 56 B per
+    (row, member); plain SpMM (k_spmm): (12|20) B/nnz + 4(n+1) + 8 B per
+    (column, member) + 8 B per (row, member).
+    """
+    peak, which = measured_peak()
+    name = max(kern.items(), key=lambda kv: kv[1][1])[0]
+    cnt, ms = kern[name]
+    nb = integ.nb
+    host = integ._host
+    nnzF, n = host['M'].nnz, host['M'].shape[0]
+    J = host['J']
+    if name.startswith('k_cheb_step'):
+        bytes_ = 20.*nnzF + 4.*(n + 1) + 56.*n*nb
+    elif name.startswith('k_spmm'):
+        # dominated by the block matrix K = [F JT; J 0] (two value arrays)
+        nnzK = nnzF + 2*J.nnz
+        nt = n + J.shape[0]
+        bytes_ = 20.*nnzK + 4.*(nt + 1) + 16.*nt*nb
+    elif name.startswith('k_cheb_init'):
+        bytes_ = 12.*J.nnz + 4.*(n + 1) + 8.*J.shape[0]*nb + 40.*n*nb
+    elif name.startswith('k_dense_gem'):
+        npp = J.shape[0]
+        bytes_ = 8.*npp*npp + 16.*npp*nb
+    else:
+        bytes_ = float('nan')
+    dur = ms*1e-3/cnt
+    ach = bytes_/dur/1e9
+    return dict(bound='hbm', kernel=name, achieved=ach, peak=peak,
+                peak_source=which, unit='GB/s', frac=ach/peak, traffic=None,
+                launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line))
+        return
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', rank=rank, world_size=world,
+                                device_id=torch.device('cuda', local_rank))
+    line = run_ours(args, rank, world, local_rank)
+    if rank == 0 and not args.no_cpu_baseline:
+        NV, NP = line['dofs_per_member'] - 0, 0
+        res = cpu_reference(args, 1, seconds=args.cpu_seconds)
+        n, t = res[0]
+        line['cpu_baseline'] = dict(
+            value=line['dofs_per_member']*n/t, unit=UNIT, cores=1,
+            kind='port',
+            sample='1 member (Re=60), {0} CNAB steps in {1:.1f} s: SuperLU '
+            'solve + compiled cell loop, factorisation excluded'.format(n, t))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -30,6 +30,8 @@ SIGNATURES = {
     'dnsb_sync': (_i, [_vp]),
     'dnsb_launch_count': (_ll, [_vp]),
     'dnsb_launch_count_reset': (None, [_vp]),
+    'dnsb_profile_begin': (_i, [_vp, _i]),
+    'dnsb_profile_end': (_i, [_vp, ctypes.c_char_p, _i]),
     'dnsb_set_mesh': (_i, [_vp, _i, _i, c_int_p, c_dbl_p, _i, c_int_p]),
     'dnsb_set_conv_pattern': (_i, [_vp, c_int_p, c_int_p, c_int_p]),
     'dnsb_convvec': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, _i]),
@@ -59,8 +61,10 @@ SIGNATURES = {
     'dnsb_imex_set_state': (_i, [_vp, c_dbl_p, c_dbl_p]),
     'dnsb_imex_run': (_i, [_vp, _i, _i, _d, _i, _i, _d, _i,
                            ctypes.POINTER(_i)]),
+    'dnsb_imex_last_run_ms': (_d, [_vp]),
     'dnsb_imex_get_state': (_i, [_vp, c_dbl_p, c_dbl_p]),
     'dnsb_imex_num_snapshots': (_i, [_vp]),
+    'dnsb_imex_reset_snapshots': (_i, [_vp]),
     'dnsb_imex_get_snapshots': (_i, [_vp, c_dbl_p]),
     'dnsb_imex_stats': (_i, [_vp, ctypes.POINTER(_ll), ctypes.POINTER(_ll),
                              c_dbl_p]),
@@ -145,6 +149,21 @@ class Context(object):
 
     def reset_launch_count(self):
         self.lib.dnsb_launch_count_reset(self.h)
+
+    def profile_begin(self, max_records=200000):
+        self.check(self.lib.dnsb_profile_begin(self.h, int(max_records)))
+
+    def profile_end(self):
+        """{kernel: (count, total_ms)} measured with CUDA events"""
+        buf = ctypes.create_string_buffer(1 << 16)
+        n = self.lib.dnsb_profile_end(self.h, buf, len(buf))
+        if n < 0:
+            self.check(n)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(' ', 2)
+            out[name] = (int(cnt), float(ms))
+        return out
 
     def close(self):
         if self.h:
@@ -397,7 +416,7 @@ class ImexEngine(object):
         self.ctx.check(self.ctx.lib.dnsb_imex_set_state(self.h, _dp(v0),
                                                         _dp(p0)))
 
-    def run(self, nsteps, snap_stride=0, tol=1e-11, maxit=400, guess=8,
+    def run(self, nsteps, snap_stride=0, tol=1e-12, maxit=400, guess=8,
             check_ff_maxv=1e8, ntimeslices=10):
         ff = ctypes.c_int(0)
         self.ctx.check(self.ctx.lib.dnsb_imex_run(
@@ -405,6 +424,9 @@ class ImexEngine(object):
             int(guess), float(check_ff_maxv), int(ntimeslices),
             ctypes.byref(ff)))
         return ff.value
+
+    def last_run_ms(self):
+        return float(self.ctx.lib.dnsb_imex_last_run_ms(self.h))
 
     def state(self):
         v = np.empty((self.nv, self.nb))
@@ -420,6 +442,9 @@ class ImexEngine(object):
             self.ctx.check(self.ctx.lib.dnsb_imex_get_snapshots(self.h,
                                                                 _dp(out)))
         return out
+
+    def reset_snapshots(self):
+        self.ctx.check(self.ctx.lib.dnsb_imex_reset_snapshots(self.h))
 
     def stats(self):
         it, ns, rr = _ll(), _ll(), ctypes.c_double()

@@ -19,8 +19,20 @@
 // ===========================================================================
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                              \
   do {                                                                         \
-    kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
-    (ctx)->launches++;                                                         \
+    dnsb_ctx *c_ = (ctx);                                                      \
+    const bool pr_ = c_->prof && c_->recs.size() < c_->prof_cap;               \
+    cudaEvent_t pe0_ = nullptr, pe1_ = nullptr;                                \
+    if (pr_) {                                                                 \
+      cudaEventCreate(&pe0_);                                                  \
+      cudaEventCreate(&pe1_);                                                  \
+      cudaEventRecord(pe0_, c_->stream);                                       \
+    }                                                                          \
+    kern<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__);                \
+    if (pr_) {                                                                 \
+      cudaEventRecord(pe1_, c_->stream);                                       \
+      c_->recs.push_back(ProfRec{#kern, pe0_, pe1_});                          \
+    }                                                                          \
+    c_->launches++;                                                            \
   } while (0)
 
 static inline int pow2_floor(int x) {
@@ -197,6 +209,53 @@ extern "C" int dnsb_sync(dnsb_ctx *ctx) {
   if (!ctx) return -2;
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+extern "C" int dnsb_profile_begin(dnsb_ctx *ctx, int max_records) {
+  if (!ctx) return -2;
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  for (ProfRec &r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  ctx->recs.clear();
+  ctx->prof_cap = max_records > 0 ? (size_t)max_records : 0;
+  ctx->prof = max_records > 0;
+  return 0;
+}
+
+// "name count total_ms\n" per kernel, sorted by total time; returns the
+// number of bytes needed (incl. the terminating 0) or < 0 on error
+extern "C" int dnsb_profile_end(dnsb_ctx *ctx, char *buf, int buflen) {
+  if (!ctx) return -2;
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->prof = false;
+  std::vector<std::string> names;
+  std::vector<double> tot;
+  std::vector<long long> cnt;
+  for (ProfRec &r : ctx->recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    size_t k = 0;
+    for (; k < names.size(); ++k) if (names[k] == r.name) break;
+    if (k == names.size()) { names.push_back(r.name); tot.push_back(0.0); cnt.push_back(0); }
+    tot[k] += ms; cnt[k] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  ctx->recs.clear();
+  std::vector<size_t> order(names.size());
+  for (size_t k = 0; k < order.size(); ++k) order[k] = k;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tot[a] > tot[b]; });
+  std::string out;
+  char line[256];
+  for (size_t k : order) {
+    snprintf(line, sizeof line, "%s %lld %.6f\n", names[k].c_str(), cnt[k], tot[k]);
+    out += line;
+  }
+  if (buf && buflen > 0) {
+    const size_t ncopy = std::min((size_t)buflen - 1, out.size());
+    memcpy(buf, out.data(), ncopy);
+    buf[ncopy] = 0;
+  }
+  return (int)out.size() + 1;
 }
 
 extern "C" long long dnsb_launch_count(dnsb_ctx *ctx) { return ctx ? ctx->launches : -1; }
@@ -987,6 +1046,7 @@ struct dnsb_imex {
   DBuf<double> bcvals, fv, fp;
   // forcing
   int nk = 0, ntimes = 0;
+  long long force_t0 = 0;   // time level of useries[0]
   DBuf<double> Bk, useries;
   // state
   DBuf<double> v, vprev, p, vfull, cfull, nfc_c, nfc_o, nfc_t, tmp, b, x;
@@ -999,6 +1059,8 @@ struct dnsb_imex {
   DBuf<double> snaps;
   int nsnap = 0, snap_cap = 0;
   long long step = 0;   // steps done so far
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the last run
+  float last_run_ms = 0.f;
   bool have_state = false;
   bool p_stale = false;
 };
@@ -1058,6 +1120,8 @@ extern "C" int dnsb_imex_create(dnsb_ctx *ctx, int scheme, int nb, double dt,
   DNSB_CK(ctx, e->nfc_c.alloc(nvb)); DNSB_CK(ctx, e->nfc_o.alloc(nvb));
   DNSB_CK(ctx, e->nfc_t.alloc(nvb)); DNSB_CK(ctx, e->tmp.alloc(nvb));
   DNSB_CK(ctx, e->b.alloc(nvb + npb)); DNSB_CK(ctx, e->x.alloc(nvb + npb));
+  DNSB_CK(ctx, cudaEventCreate(&e->ev0));
+  DNSB_CK(ctx, cudaEventCreate(&e->ev1));
   DNSB_CK(ctx, e->vfull.zero(ctx->stream));
   if (nbc > 0)
     LAUNCH(ctx, k_set_bcs, cdiv((size_t)nbc * nb, 256), 256, 0, e->bcinds.p, e->bcvals.p,
@@ -1072,6 +1136,8 @@ extern "C" void dnsb_imex_destroy(dnsb_imex *e) {
   cudaSetDevice(e->ctx->device);
   cudaStreamSynchronize(e->ctx->stream);
   csr_free(e->Rm);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
   e->nu.release(); e->coefR.release(); e->coefA.release(); e->inv.release();
   e->bcinds.release(); e->bcvals.release(); e->fv.release(); e->fp.release();
   e->Bk.release(); e->useries.release();
@@ -1102,6 +1168,7 @@ extern "C" int dnsb_imex_set_forcing(dnsb_imex *e, int nk, const double *bvecs,
   DNSB_REQUIRE(ctx, nk >= 0 && (nk == 0 || (bvecs && useries && ntimes >= 1)), "bad forcing");
   DNSB_CK(ctx, cudaSetDevice(ctx->device));
   e->nk = nk; e->ntimes = ntimes;
+  e->force_t0 = e->have_state ? e->step : 0;   // series starts at the current time level
   if (nk > 0) {
     DNSB_CK(ctx, e->Bk.upload(bvecs, (size_t)e->nv * nk, ctx->stream));
     DNSB_CK(ctx, e->useries.upload(useries, (size_t)ntimes * nk * e->nb, ctx->stream));
@@ -1122,6 +1189,7 @@ extern "C" int dnsb_imex_set_state(dnsb_imex *e, const double *v0, const double 
     DNSB_CK(ctx, e->p.zero(ctx->stream));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   e->step = 0; e->hist_cnt = 0; e->hist_pos = 0; e->nsnap = 0;
+  e->force_t0 = 0;
   e->have_state = true;
   e->p_stale = false;
   return 0;
@@ -1140,7 +1208,7 @@ static int imex_nonl(dnsb_imex *e, const double *v, double *nfc) {
 
 static const double *useries_at(dnsb_imex *e, long long n) {
   if (e->nk == 0) return nullptr;
-  long long k = std::min<long long>(std::max<long long>(n, 0), e->ntimes - 1);
+  long long k = std::min<long long>(std::max<long long>(n - e->force_t0, 0), e->ntimes - 1);
   return e->useries.p + (size_t)k * e->nk * e->nb;
 }
 
@@ -1307,6 +1375,7 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
     if (e->step == 0) { int rc = imex_snapshot(e); if (rc) return rc; }
   }
   const long long it0 = e->sl->stat_iters, ns0 = e->sl->stat_solves;
+  DNSB_CK(ctx, cudaEventRecord(e->ev0, ctx->stream));
   bool solved = false;
   int done = 0;
   // ======================= start-up (Heun) step =============================
@@ -1432,6 +1501,9 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
   }
   if (blown && ffflag) *ffflag = 1;
   imex_refresh_p(e);
+  DNSB_CK(ctx, cudaEventRecord(e->ev1, ctx->stream));
+  DNSB_CK(ctx, cudaEventSynchronize(e->ev1));
+  DNSB_CK(ctx, cudaEventElapsedTime(&e->last_run_ms, e->ev0, e->ev1));
   // relative residual of the last solve (max over members)
   {
     std::vector<double> res(nb), bn(nb);
@@ -1461,6 +1533,14 @@ extern "C" int dnsb_imex_get_state(dnsb_imex *e, double *v, double *p) {
 }
 
 extern "C" int dnsb_imex_num_snapshots(dnsb_imex *e) { return e ? e->nsnap : -2; }
+
+extern "C" int dnsb_imex_reset_snapshots(dnsb_imex *e) {
+  if (!e) return -2;
+  e->nsnap = 0;
+  return 0;
+}
+
+extern "C" double dnsb_imex_last_run_ms(dnsb_imex *e) { return e ? (double)e->last_run_ms : -1.0; }
 
 extern "C" int dnsb_imex_get_snapshots(dnsb_imex *e, double *out) {
   if (!e) return -2;

@@ -58,7 +58,16 @@ struct DBuf {
   }
 };
 
+struct ProfRec {
+  const char *name;
+  cudaEvent_t e0, e1;
+};
+
 struct dnsb_ctx {
+  // per-kernel CUDA-event timing (dnsb_profile_begin/end); off by default
+  bool prof = false;
+  size_t prof_cap = 0;
+  std::vector<ProfRec> recs;
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 0;

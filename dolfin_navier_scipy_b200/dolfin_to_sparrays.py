@@ -239,8 +239,9 @@ def get_convmats(u0_dolfun=None, u0_vec=None, V=None, invinds=None,
     n1d, n2d, fv = dev.convmats(u0)
     indptr, indices = dev.pattern
     NV = V.dim()
-    N1 = sps.csr_matrix((n1d, indices, indptr), shape=(NV, NV))
-    N2 = sps.csr_matrix((n2d, indices, indptr), shape=(NV, NV))
+    # copies: `eliminate_zeros` compacts the index arrays in place
+    N1 = sps.csr_matrix((n1d, indices.copy(), indptr.copy()), shape=(NV, NV))
+    N2 = sps.csr_matrix((n2d, indices.copy(), indptr.copy()), shape=(NV, NV))
     N1.eliminate_zeros()
     N2.eliminate_zeros()
     return N1, N2, fv.reshape(-1, 1)

@@ -1,0 +1,89 @@
+"""Batched ensembles of trajectories that share one mesh and sparsity pattern.
+
+BASELINE config 5: Reynolds-number / boundary-control sweeps of the cylinder
+wake with penalised Robin control (`tests/time_dep_nse_bcrob.py:26-34`):
+``A_m = nu_m*A0 + Arob/palpha``, ``f_m(t) = nu_m*fv_bc + u(t)*(B_1 - B_2)/palpha``.
+Members are independent: they are sharded over the GPUs with *no* collective
+on the step path; the only exchange is the all-reduce of the POD snapshot Gram
+matrix ``G = sum_m X_m^T M X_m`` (additive over members).
+"""
+import numpy as np
+
+from . import problem_setups as dnsps
+from . import time_int_utils as tiu
+
+__all__ = ['cylinder_ensemble', 'shard_members', 'gram_allreduce']
+
+
+def shard_members(nmembers, rank, world):
+    """contiguous slice of the members owned by ``rank``"""
+    per = nmembers // world
+    rem = nmembers % world
+    lo = rank*per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def cylinder_ensemble(N=4, Res=(60., 150.), nmembers=64, rank=0, world=1,
+                      dt=1./512, scheme='cnab', palpha=1e-5, bccontrol=True,
+                      control=np.sin, ntimes=513, t0=0., ctx=None, mesh=None,
+                      cheb_steps=3, restart=40):
+    """device integrator for this rank's shard of a Re-sweep ensemble
+
+    Returns ``(integ, info)``; ``integ`` is a `time_int_utils.DeviceImex` with
+    forcing and members set, ``info`` holds sizes and the host operators.
+    """
+    Re_all = np.linspace(Res[0], Res[1], nmembers)
+    lo, hi = shard_members(nmembers, rank, world)
+    Re = Re_all[lo:hi]
+    meshparams = dict(refinement_level=N)
+    if mesh is not None:
+        meshparams['mesh'] = mesh
+    # operators for nu = 1: A = nu*A0, boundary rhs = nu*fv_bc
+    femp, sm, rhs_vf, rhs_bc = dnsps.get_sysmats(
+        problem='cylinderwake', nu=1., bccontrol=bccontrol, scheme='TH',
+        meshparams=meshparams)
+    charlen = femp['charlen']
+    nus = charlen/Re                                   # `dnsps:138-141`
+    NP, NV = sm['J'].shape
+    Arob = sm['Arob']/palpha if bccontrol else None
+    integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'],
+                           femp['invinds'], femp['dbcinds'], femp['dbcvals'],
+                           dt, scheme=scheme, nus=nus, Arob=Arob,
+                           fp=rhs_bc['fp'] + rhs_vf['fp'], ctx=ctx,
+                           cheb_steps=cheb_steps, restart=restart)
+    trange = t0 + dt*np.arange(ntimes)
+    cols = [rhs_bc['fv'].reshape(NV, 1)]
+    if bccontrol:
+        Brob = sm['Brob']/palpha
+        cols.append(Brob[:, :1] - Brob[:, 1:])
+    B = np.hstack(cols)
+    U = np.zeros((ntimes, B.shape[1], nus.size))
+    U[:, 0, :] = nus[None, :]
+    if bccontrol:
+        U[:, 1, :] = control(trange)[:, None]
+    integ.set_forcing(B, U)
+    info = dict(femp=femp, sm=sm, nus=nus, Re=Re, NV=NV, NP=NP, B=B, U=U,
+                Arob=Arob, fp=rhs_bc['fp'] + rhs_vf['fp'], trange=trange,
+                members=(lo, hi))
+    return integ, info
+
+
+def gram_allreduce(integ, group=None):
+    """POD snapshot Gram matrix of the whole ensemble
+
+    Each rank computes ``sum_{m in shard} X_m^T M X_m`` on its device
+    (``dnsb_imex_gram_dev``); one ``all_reduce(SUM)`` over NCCL finishes it.
+    Returns a (ns, ns) torch tensor on the device (identical on all ranks).
+    """
+    import torch
+    ns = integ.engine.snapshots().shape[0] if False else \
+        integ.engine.ctx.lib.dnsb_imex_num_snapshots(integ.engine.h)
+    dev = torch.device('cuda', integ.ctx.device)
+    G = torch.zeros((ns, ns), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize(dev)
+    integ.engine.gram_dev(G.data_ptr())
+    if torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size(group) > 1:
+        torch.distributed.all_reduce(G, op=torch.distributed.ReduceOp.SUM,
+                                     group=group)
+    return G

@@ -16,36 +16,46 @@ __all__ = ['jacobi_spectrum', 'lumped_schur', 'sa_amg_hierarchy',
            'make_saddle_solver']
 
 
-def jacobi_spectrum(F, its=40, seed=0, ratio=None):
+def jacobi_spectrum(F, its=30, seed=0, ratio=None):
     """bounds ``(lmin, lmax)`` of the spectrum of ``D^-1 F`` (F ~ SPD)
 
-    ``lmax`` by power iteration (+5 %); ``lmin`` by a few Lanczos steps on the
-    symmetric part, or ``lmax/ratio`` when ``ratio`` is given (smoothers).
+    ``its`` Lanczos steps (full reorthogonalisation) on the symmetric part of
+    ``D^-1/2 F D^-1/2``: ``lmax`` = largest Ritz value (+5 %), ``lmin`` = 0.9 x
+    smallest Ritz value (an upper bound of the true one: fine for the
+    well-conditioned, mass dominated matrices; for ill-conditioned ones the
+    caller switches to multigrid and passes ``ratio``: ``lmin = lmax/ratio``).
     """
     F = sps.csr_matrix(F)
-    d = F.diagonal()
+    d = np.abs(F.diagonal())
+    ds = 1./np.sqrt(d)
+    Fs = .5*(F + F.T) if ratio is None else F
+
+    def op(x):
+        return ds*(Fs@(ds*x))
+    n = F.shape[0]
     rng = np.random.default_rng(seed)
-    x = rng.standard_normal(F.shape[0])
-    lam = 1.0
-    for _ in range(its):
-        x = (F@x)/d
-        lam = np.linalg.norm(x)
-        x /= lam
-    lmax = 1.05*lam
-    lmin = None
-    if ratio is None:
-        try:
-            dm = sps.diags(1./np.sqrt(np.abs(d)))
-            sym = dm@(.5*(F + F.T))@dm
-            ev = spsla.eigsh(sym, k=1, which='SA', tol=1e-2, maxiter=300,
-                             return_eigenvectors=False)
-            if ev[0] > 1e-8*lmax:
-                lmin = 0.9*float(ev[0])
-        except Exception:
-            lmin = None
-    if lmin is None:
-        lmin = lmax/(30. if ratio is None else ratio)
-    return float(lmin), float(lmax)
+    q = rng.standard_normal(n)
+    q /= np.linalg.norm(q)
+    its = min(its, n)
+    Q = np.zeros((its, n))
+    al, be = np.zeros(its), np.zeros(its)
+    k = 0
+    for k in range(its):
+        Q[k] = q
+        w = op(q)
+        al[k] = q@w
+        w -= Q[:k+1].T@(Q[:k+1]@w)
+        w -= Q[:k+1].T@(Q[:k+1]@w)
+        be[k] = np.linalg.norm(w)
+        if be[k] < 1e-12*abs(al[0]):
+            break
+        q = w/be[k]
+    T = np.diag(al[:k+1]) + np.diag(be[:k], 1) + np.diag(be[:k], -1)
+    ev = np.linalg.eigvalsh(T)
+    lmax = 1.05*float(ev[-1])
+    if ratio is not None:
+        return lmax/ratio, lmax
+    return 0.9*float(max(ev[0], 1e-12*lmax)), lmax
 
 
 def lumped_schur(fdiag, J):
@@ -159,7 +169,7 @@ def make_saddle_solver(ctx, F1, J, JT=None, F2=None, coef=None, nb=1,
                        restart=40, cheb_steps=3, schur='lumped',
                        schur_diag=None, coarse_max=4096, mp_diag=None,
                        mp_scale=None, spectrum=None, hierarchy=None,
-                       nsmooth=2, velocity_amg=False, vgroups=None,
+                       nsmooth=2, velocity_amg='auto', vgroups=None,
                        vhierarchy=None, Fsym=None, vcoarse_max=2048):
     """build a device ``SaddleSolver`` for ``[[F1 + coef_m*F2, JT], [J, 0]]``
 
@@ -168,7 +178,8 @@ def make_saddle_solver(ctx, F1, J, JT=None, F2=None, coef=None, nb=1,
     member matrix) plus, optionally, the Cahouet-Chabard mass term
     ``mp_scale_m * diag(mp_diag)^-1``; ``schur='mass'``: that mass term alone
     (Stokes/Oseen).  ``velocity_amg``: smoothed-aggregation V-cycle for the
-    velocity block (needed when F is not mass dominated).  Host-side
+    velocity block (needed when F is not mass dominated; ``'auto'`` decides by
+    the condition number of the Jacobi-scaled block).  Host-side
     hierarchies can be shared between solvers via ``hierarchy``/``vhierarchy``.
     Returns ``(solver, info)``.
     """
@@ -190,11 +201,16 @@ def make_saddle_solver(ctx, F1, J, JT=None, F2=None, coef=None, nb=1,
                               shape=F1.shape)
     else:
         Fmean = Fext = F1
-    if spectrum is None:
-        ratio = 10. if velocity_amg else None
-        lmin, lmax = jacobi_spectrum(Fext, ratio=ratio)
-        lmin2, lmax2 = jacobi_spectrum(Fmean, ratio=ratio)
-        spectrum = (min(lmin, lmin2), max(lmax, lmax2))
+    if spectrum is None or velocity_amg == 'auto':
+        lmin, lmax = jacobi_spectrum(Fext)
+        lmin2, lmax2 = jacobi_spectrum(Fmean)
+        spec = (min(lmin, lmin2), max(lmax, lmax2))
+        if velocity_amg == 'auto':
+            # mass dominated matrices have cond(D^-1 F) ~ 5; Stokes/Oseen
+            # blocks are Laplace-like and need the V-cycle
+            velocity_amg = spec[1]/spec[0] > 50.
+        if spectrum is None:
+            spectrum = (spec[1]/10., spec[1]) if velocity_amg else spec
     fmat = ctx.csr(F1, None if F2 is None else F2.data)
     jmat, jtmat = ctx.csr(J), ctx.csr(JT)
     solver = _lib.SaddleSolver(ctx, fmat, jmat, jtmat, coef=coef, nb=nb,
@@ -240,5 +256,5 @@ def make_saddle_solver(ctx, F1, J, JT=None, F2=None, coef=None, nb=1,
             solver.add_velocity_level(dense_inv=vdense)
     solver._keepalive = keep
     info = dict(spectrum=spectrum, hierarchy=hierarchy, vhierarchy=vhierarchy,
-                schur_levels=nlev)
+                schur_levels=nlev, velocity_amg=bool(velocity_amg))
     return solver, info

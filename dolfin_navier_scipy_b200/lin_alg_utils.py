@@ -20,14 +20,16 @@ class SadpntOperator(object):
 
     def __init__(self, amat, jmat, jmatT=None, ncols=1, ctx=None,
                  cheb_steps=3, restart=60, coarse_max=4096, schur_diag=None,
-                 spectrum=None, hierarchy=None):
+                 spectrum=None, hierarchy=None, velocity_amg='auto',
+                 vgroups=None, vhierarchy=None):
         self.ctx = _lib.default_context() if ctx is None else ctx
         self.NP, self.NV = jmat.shape
         self.ncols = ncols
         self.solver, self.info = hostsetup.make_saddle_solver(
             self.ctx, amat, jmat, jmatT, nb=ncols, restart=restart,
             cheb_steps=cheb_steps, coarse_max=coarse_max,
-            schur_diag=schur_diag, spectrum=spectrum, hierarchy=hierarchy)
+            schur_diag=schur_diag, spectrum=spectrum, hierarchy=hierarchy,
+            velocity_amg=velocity_amg, vgroups=vgroups, vhierarchy=vhierarchy)
 
     def solve(self, rhsv, rhsp=None, x0=None, tol=1e-12, maxit=800):
         rhsv = np.asarray(rhsv, dtype=float).reshape(self.NV, self.ncols)
@@ -46,7 +48,7 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
                      rhsp=None, umat=None, vmat=None, krylov=None,
                      krpslvprms={}, krplsprms={}, return_alu=False,
                      sadlu=None, decouplevp=False, solve_A=None,
-                     symmetric=False, cgtol=1e-8, **kw):
+                     symmetric=False, cgtol=1e-8, vgroups=None, **kw):
     """solve ``[[amat, jmatT], [jmat, 0]] [v; p] = [rhsv; rhsp]`` on the device
 
     Same arguments and return value as `lau.solve_sadpnt_smw` (stacked
@@ -65,7 +67,7 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
     k = rhsv.shape[1]
     op = sadlu if sadlu is not None else \
         SadpntOperator(sps.csr_matrix(amat), sps.csr_matrix(jmat), jmatT,
-                       ncols=k)
+                       ncols=k, vgroups=vgroups)
     tol = krpslvprms.get('tol', 1e-12) if krylov is not None else 1e-12
     maxit = krpslvprms.get('maxiter', 800) if krylov is not None else 800
     x0 = krpslvprms.get('x0', None) if krylov is not None else None

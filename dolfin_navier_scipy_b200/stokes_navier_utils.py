@@ -148,6 +148,8 @@ def solve_steadystate_nse(A=None, J=None, JT=None, M=None,
     def _solve(amat, rhsv):
         return lau.solve_sadpnt_smw(amat=amat, jmat=J, jmatT=JT, rhsv=rhsv,
                                     rhsp=fp, krylov='gmres',
+                                    vgroups=(np.asarray(invinds)//2,
+                                             np.asarray(invinds) % 2),
                                     krpslvprms=dict(tol=lin_tol, maxiter=2000))
 
     if vel_start_nwtn is None or only_stokes:
@@ -240,7 +242,7 @@ def solve_nse(A=None, M=None, J=None, JT=None,
               check_ff=False, check_ff_maxv=1e8,
               verbose=True,
               start_ssstokes=False,
-              lin_tol=1e-11, guess=8, cheb_steps=3,
+              lin_tol=1e-12, guess=8, cheb_steps=3,
               **kw):
     """time-dependent Navier-Stokes -- `snu:548-1599`
 
@@ -278,8 +280,9 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         return dts.append_bcs_vec(vvec, V=V, invinds=invinds,
                                   bcinds=dbcinds, bcvals=dbcvals)
 
-    krydict = dict(krylov='gmres', krpslvprms=dict(tol=lin_tol*1e-1,
-                                                   maxiter=2000))
+    vgroups = (invinds//2, invinds % 2)
+    krydict = dict(krylov='gmres', vgroups=vgroups,
+                   krpslvprms=dict(tol=lin_tol*1e-1, maxiter=2000))
     # ---- initial value (`snu:836-940`) --------------------------------------
     if iniv is None:
         if not start_ssstokes:

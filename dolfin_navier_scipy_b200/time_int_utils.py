@@ -176,7 +176,7 @@ class DeviceImex(object):
 def _run_imex(scheme, trange=None, inivel=None, inip=None, M=None, A=None,
               J=None, f_tdp=None, g_tdp=None, scalep=-1., V=None,
               invinds=None, dbcinds=None, dbcvals=None, savevp=None,
-              check_ff_maxv=1e8, ntimeslices=10, tol=1e-11, maxit=400,
+              check_ff_maxv=1e8, ntimeslices=10, tol=1e-12, maxit=400,
               guess=8, cheb_steps=3, f_vdp='convection', ctx=None,
               return_engine=False, **kw):
     if f_vdp != 'convection' and f_vdp is not None:

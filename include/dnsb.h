@@ -41,6 +41,12 @@ int dnsb_sync(dnsb_ctx *ctx);
 long long dnsb_launch_count(dnsb_ctx *ctx);
 void dnsb_launch_count_reset(dnsb_ctx *ctx);
 
+/* per-kernel device timing with CUDA events on the context's stream: begin
+ * records up to `max_records` launches, end writes "kernel count total_ms"
+ * lines (sorted by time) into buf and returns the bytes needed. */
+int dnsb_profile_begin(dnsb_ctx *ctx, int max_records);
+int dnsb_profile_end(dnsb_ctx *ctx, char *buf, int buflen);
+
 /* ---- mesh + convection assembly (K1a / K1b) ------------------------------
  * dnsb_set_mesh: P2 scalar cell dofmap (ncell*6, local order 3 vertices then
  * the edge opposite to vertex i), affine geometry per cell (ncell*5:
@@ -143,7 +149,9 @@ void dnsb_imex_destroy(dnsb_imex *e);
 int dnsb_imex_set_solvers(dnsb_imex *e, dnsb_solver *loop, dnsb_solver *pred,
                           dnsb_solver *corr);
 /* time-dependent forcing  f(t_n) = sum_k useries[(n*nk + k)*nb + m] * b[i*nk + k]
- * (nk input shapes b (nv x nk, row-major), ntimes = nsteps+1 samples) */
+ * (nk input shapes b (nv x nk, row-major), ntimes = nsteps+1 samples);
+ * useries[0] belongs to the time level at which this function is called, so a
+ * running integration can be fed chunk by chunk */
 int dnsb_imex_set_forcing(dnsb_imex *e, int nk, const double *bvecs,
                           int ntimes, const double *useries);
 /* initial state (inner velocity nv*nb, pressure np*nb) */
@@ -156,8 +164,13 @@ int dnsb_imex_set_state(dnsb_imex *e, const double *v0, const double *p0);
 int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double tol,
                   int maxit, int guess, double check_ff_maxv, int ntimeslices,
                   int *ffflag);
+/* device time of the last dnsb_imex_run, measured with CUDA events on the
+ * context's stream (milliseconds) */
+double dnsb_imex_last_run_ms(dnsb_imex *e);
 int dnsb_imex_get_state(dnsb_imex *e, double *v, double *p);
 int dnsb_imex_num_snapshots(dnsb_imex *e);
+/* forget the stored snapshots (the next run records from the current state) */
+int dnsb_imex_reset_snapshots(dnsb_imex *e);
 /* snapshots as (nsnap, nv+np, nb) */
 int dnsb_imex_get_snapshots(dnsb_imex *e, double *out);
 /* solver statistics of the last run: total FGMRES iterations (max over
