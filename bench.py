@@ -273,10 +273,13 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler.start()
     ctx.reset_launch_count()
+    # ncu --profile-from-start off captures exactly the timed region
+    torch.cuda.cudart().cudaProfilerStart()
     t0 = time.perf_counter()
     integ.run(args.steps, **runkw)
     dev_ms = integ.engine.last_run_ms()
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     wall = time.perf_counter() - t0
     launches = ctx.launch_count()
     clocks = sampler.stop()
@@ -349,6 +352,10 @@ def run_ours(args, rank, world, local_rank):
         tot = sum(v[1] for v in kern.values())
         line['kernel_share'] = {k: round(v[1]/tot, 4) for k, v in
                                 sorted(kern.items(), key=lambda kv: -kv[1][1])[:8]}
+        # name: [launches per step, mean us] (CUDA events around each launch)
+        line['kernels'] = {k: [round(v[0]/float(args.steps), 2),
+                               round(1e3*v[1]/v[0], 2)] for k, v in
+                           sorted(kern.items(), key=lambda kv: -kv[1][1])[:16]}
     return line
 
 

@@ -11,6 +11,8 @@
 
 #include "dnsb_common.cuh"
 #include "dnsb_kernels.cuh"
+#include "dnsb_batched.cuh"
+#include "dnsb_dense.cuh"
 
 #define DNSB_VERSION 100
 
@@ -41,19 +43,37 @@ static inline int pow2_floor(int x) {
   return p;
 }
 
-struct RedCfg {   // launch shape of the batched reductions
-  int nblocks, rpb, threads;
-  size_t smem;
+struct RedCfg {   // launch shape of the batched reductions / Gram-Schmidt
+  int nblocks, rpb, threads, rows_per_block;
+  size_t smem;   // of the single-vector reductions (k_dot1)
 };
 
+// Block = rpb x nb threads; a block owns `rows_per_block` contiguous rows, a
+// thread at most GS_RPT of them; about 4 blocks per SM when n allows.
 static RedCfg red_cfg(dnsb_ctx *ctx, int n, int nb) {
   RedCfg c;
-  c.rpb = pow2_floor(std::max(1, 256 / nb));
+  const int tmax = nb == 1 ? 64 : 256;
+  c.rpb = pow2_floor(std::max(1, tmax / nb));
   c.threads = c.rpb * nb;
-  int want = std::max(1, std::min(2 * ctx->sm_count, (n + c.rpb - 1) / c.rpb));
-  c.nblocks = want;
+  int rows = (n + 4 * ctx->sm_count - 1) / (4 * ctx->sm_count);
+  rows = ((rows + c.rpb - 1) / c.rpb) * c.rpb;
+  rows = std::max(c.rpb, std::min(rows, c.rpb * GS_RPT));
+  c.rows_per_block = rows;
+  c.nblocks = std::max(1, (n + rows - 1) / rows);
   c.smem = (size_t)c.threads * sizeof(double);
   return c;
+}
+
+// h[0..nvec) = <V_i, w>, h[nvec] = <w, w>  (per member), deterministic
+static void mdot_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vstride,
+                     int nvec, const double *w, int n, int nb, double *partial,
+                     double *h) {
+  const size_t smem = (size_t)(nvec + 1) * rc.threads * sizeof(double);
+  LAUNCH(ctx, k_mdot_b, rc.nblocks, rc.threads, smem, V, vstride, nvec, w, n, nb, rc.rpb,
+         rc.rows_per_block, partial);
+  const int count = (nvec + 1) * nb;
+  LAUNCH(ctx, k_reduce_partials2, cdiv(count, 32), 256, 0, (const double *)partial, rc.nblocks,
+         count, h);
 }
 
 // ===========================================================================
@@ -115,12 +135,25 @@ static void csr_free(dnsb_csr *m) {
   delete m;
 }
 
+// the batched row kernels pre-multiply column indices by nb in int32
+static inline bool batched_ok(const dnsb_csr *A, int nb) {
+  return nb > 1 && (size_t)A->ncols * nb < ((size_t)1 << 31);
+}
+
 // y = alpha*A*x + beta*z  on device pointers
 static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
                      const double *x, const double *z, double *y, int nb,
                      double alpha, double beta) {
   if (A->nrows == 0) return;
-  if (nb == 1) {
+  if (batched_ok(A, nb)) {
+    const size_t threads = (size_t)A->nrows * nb;
+    if (A->has2 && coef)
+      LAUNCH(ctx, k_spmm_b<true>, cdiv(threads, SPB_THREADS), SPB_THREADS, 0, A->view(), coef,
+             x, z, y, nb, alpha, beta);
+    else
+      LAUNCH(ctx, k_spmm_b<false>, cdiv(threads, SPB_THREADS), SPB_THREADS, 0, A->view(), coef,
+             x, z, y, nb, alpha, beta);
+  } else if (nb == 1) {
     const size_t threads = (size_t)A->nrows * 8;
     LAUNCH(ctx, k_spmm<8>, cdiv(threads, 256), 256, 0, A->view(), coef, x, z, y,
            nb, alpha, beta);
@@ -178,6 +211,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_phi, phi, sizeof phi));
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_dphi, dphi, sizeof dphi));
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
+  // k_mdot_b keeps (nvec+1) x 256 partial sums in dynamic shared memory
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_mdot_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return 0;
 }
 
@@ -472,6 +507,7 @@ struct MgLevel {
   int n = 0, nsmooth = 1, kind = MG_MULTI;
   double lmin = 0, lmax = 0;
   DBuf<double> dinv_dense;   // n*n (MG_DENSE)
+  DBuf<double> gpart;        // split-K partial sums of the dense solve
   DBuf<double> dinv_own;     // n*nb Jacobi (owned)
   const double *dinv = nullptr;
   DBuf<double> b, x, r, d0, d1, t;   // n*nb work vectors
@@ -489,7 +525,7 @@ struct dnsb_solver {
   DBuf<int> diagpos;
   DBuf<double> Vb, Zb, w;  // Krylov bases
   DBuf<double> cres, cd0, cd1;   // Chebyshev work (nv*nb)
-  DBuf<double> partial, partial2;
+  DBuf<double> partial, partial2, red;
   RedCfg rc;
   // GMRES scalars
   DBuf<double> gR, gcs, gsn, gg, gh, ginvh, gbnorm, gresid;
@@ -525,8 +561,8 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
                                   double lmax, dnsb_solver **out) {
   if (!ctx) return -2;
   DNSB_REQUIRE(ctx, fmat && jmat && jtmat && out, "null matrices");
-  DNSB_REQUIRE(ctx, nb >= 1 && nb <= 1024, "nb must be in 1..1024");
-  DNSB_REQUIRE(ctx, restart >= 2 && restart <= 200, "restart must be in 2..200");
+  DNSB_REQUIRE(ctx, nb >= 1 && nb <= 256, "nb must be in 1..256");
+  DNSB_REQUIRE(ctx, restart >= 2 && restart <= 96, "restart must be in 2..96");
   DNSB_REQUIRE(ctx, cheb_steps >= 1, "cheb_steps >= 1");
   DNSB_REQUIRE(ctx, lmax > lmin && lmin > 0, "need 0 < lmin < lmax");
   const int nv = fmat->nrows, np = jmat->nrows;
@@ -605,14 +641,15 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
   DNSB_CK(ctx, s->cd0.alloc(nvb));
   DNSB_CK(ctx, s->cd1.alloc(nvb));
   s->rc = red_cfg(ctx, s->ntot, nb);
-  DNSB_CK(ctx, s->partial.alloc((size_t)s->rc.nblocks * (s->mr + 1) * nb));
+  DNSB_CK(ctx, s->partial.alloc((size_t)s->rc.nblocks * (s->mr + 2) * nb));
   DNSB_CK(ctx, s->partial2.alloc((size_t)s->rc.nblocks * nb));
+  DNSB_CK(ctx, s->red.alloc(nb));
   const int mr = s->mr;
   DNSB_CK(ctx, s->gR.alloc((size_t)(mr + 1) * mr * nb));
   DNSB_CK(ctx, s->gcs.alloc((size_t)mr * nb));
   DNSB_CK(ctx, s->gsn.alloc((size_t)mr * nb));
   DNSB_CK(ctx, s->gg.alloc((size_t)(mr + 1) * nb));
-  DNSB_CK(ctx, s->gh.alloc((size_t)(mr + 1) * nb));
+  DNSB_CK(ctx, s->gh.alloc((size_t)(mr + 2) * nb));
   DNSB_CK(ctx, s->ginvh.alloc(nb));
   DNSB_CK(ctx, s->gbnorm.alloc(nb));
   DNSB_CK(ctx, s->gresid.alloc(nb));
@@ -631,9 +668,22 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
   return 0;
 }
 
+// split-K shape of the dense solve: row tiles x K splits x member tiles gives
+// about 2 CTAs per SM
+static void dense_split(dnsb_ctx *ctx, int n, int nb, int *tn, int *nsplit, int *kchunk) {
+  *tn = nb <= 16 ? 16 : (nb <= 32 ? 32 : 64);
+  const int rt = cdiv(n, DGK_TM), mt = cdiv(nb, *tn);
+  int ns = std::max(1, (2 * ctx->sm_count + rt * mt - 1) / (rt * mt));
+  ns = std::min(ns, std::max(1, n / (4 * DGK_TK)));
+  int kc = (n + ns - 1) / ns;
+  kc = ((kc + DGK_TK - 1) / DGK_TK) * DGK_TK;
+  *kchunk = kc;
+  *nsplit = (n + kc - 1) / kc;
+}
+
 static void level_free(MgLevel *L) {
   if (!L) return;
-  L->dinv_dense.release(); L->dinv_own.release(); L->b.release(); L->x.release();
+  L->dinv_dense.release(); L->gpart.release(); L->dinv_own.release(); L->b.release(); L->x.release();
   L->r.release(); L->d0.release(); L->d1.release(); L->t.release();
   delete L;
 }
@@ -646,7 +696,7 @@ extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   s->coef.release(); s->dinv.release(); s->diagpos.release();
   s->Vb.release(); s->Zb.release(); s->w.release();
   s->cres.release(); s->cd0.release(); s->cd1.release();
-  s->partial.release(); s->partial2.release();
+  s->partial.release(); s->partial2.release(); s->red.release();
   s->gR.release(); s->gcs.release(); s->gsn.release(); s->gg.release(); s->gh.release();
   s->ginvh.release(); s->gbnorm.release(); s->gresid.release();
   s->gdone.release(); s->gits.release(); s->gittot.release(); s->gflags.release();
@@ -681,6 +731,11 @@ static int solver_add_level(dnsb_solver *s, int block, dnsb_csr *amat, dnsb_csr 
   if (dense_inv) {
     L->kind = MG_DENSE;
     e = L->dinv_dense.upload(dense_inv, (size_t)nexpect * nexpect, ctx->stream);
+    if (e == cudaSuccess && s->nb > 8) {
+      int tn, nsplit, kchunk;
+      dense_split(ctx, nexpect, s->nb, &tn, &nsplit, &kchunk);
+      e = L->gpart.alloc((size_t)nsplit * nexpect * s->nb);
+    }
     if (e != cudaSuccess) { level_free(L); DNSB_CK(ctx, e); }
   } else {
     bool ok = amat && amat->nrows == nexpect && amat->ncols == nexpect && lmax > lmin &&
@@ -757,8 +812,8 @@ extern "C" int dnsb_solver_set_schur_mass(dnsb_solver *s, const double *mp_dinv,
 }
 
 // dense coarse solve  y = alpha*(Dinv x [+ scale_m*mp_dinv*x])
-static void dense_apply(dnsb_solver *s, const MgLevel *L, const double *x,
-                        double *y, double alpha, bool with_mass) {
+static int dense_apply(dnsb_solver *s, MgLevel *L, const double *x,
+                       double *y, double alpha, bool with_mass) {
   dnsb_ctx *ctx = s->ctx;
   const int n = L->n, nb = s->nb;
   const double *ad = with_mass ? s->mp_dinv.p : nullptr;
@@ -771,33 +826,74 @@ static void dense_apply(dnsb_solver *s, const MgLevel *L, const double *x,
     LAUNCH(ctx, k_dense_gemv<4>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
   else if (nb <= 8)
     LAUNCH(ctx, k_dense_gemv<8>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
-  else if (nb <= 16)
-    LAUNCH(ctx, k_dense_gemm<16>, dim3(cdiv(n, DG_TM), cdiv(nb, 16)), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
-  else if (nb <= 32)
-    LAUNCH(ctx, k_dense_gemm<32>, dim3(cdiv(n, DG_TM), cdiv(nb, 32)), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
-  else
-    LAUNCH(ctx, k_dense_gemm<64>, dim3(cdiv(n, DG_TM), cdiv(nb, 64)), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
+  else {
+    int tn, nsplit, kchunk;
+    dense_split(ctx, n, nb, &tn, &nsplit, &kchunk);
+    const dim3 grid(cdiv(n, DGK_TM), nsplit, cdiv(nb, tn));
+    if (tn == 16)
+      LAUNCH(ctx, k_dense_gemm_splitk<16>, grid, 128, 0, L->dinv_dense.p, x, L->gpart.p, n, nb, kchunk);
+    else if (tn == 32)
+      LAUNCH(ctx, k_dense_gemm_splitk<32>, grid, 128, 0, L->dinv_dense.p, x, L->gpart.p, n, nb, kchunk);
+    else
+      LAUNCH(ctx, k_dense_gemm_splitk<64>, grid, 128, 0, L->dinv_dense.p, x, L->gpart.p, n, nb, kchunk);
+    LAUNCH(ctx, k_dense_epilogue, cdiv((size_t)n * nb, 256), 256, 0, (const double *)L->gpart.p, nsplit, x,
+           y, n, nb, alpha, ad, as);
+  }
+  return 0;
 }
 
-// z = (k-step Jacobi-Chebyshev)(A) r  with zero initial guess; `res` may alias r
-static void cheb_plain(dnsb_solver *s, const dnsb_csr *A, const double *coef,
-                       const double *dinv, const double *r, double *z, double *res,
-                       double *d0, double *d1, int k, double lmin, double lmax) {
+// z = (k-step Jacobi-Chebyshev)(A) (r - C*zc)  with zero initial guess.
+// C/zc: optional coupling (the gradient block of the preconditioner); `res`
+// may alias r when there is no coupling.
+static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
+                     const double *dinv, const dnsb_csr *C, const double *zc,
+                     const double *r, double *z, double *res, double *d0, double *d1,
+                     int k, double lmin, double lmax) {
   dnsb_ctx *ctx = s->ctx;
-  const int nb = s->nb;
-  const size_t nn = (size_t)A->nrows * nb;
+  const int nb = s->nb, n = A->nrows;
+  const size_t nn = (size_t)n * nb;
   const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
   const double sigma = theta / delta;
   double rho = 1.0 / sigma;
-  LAUNCH(ctx, k_cheb_init_plain, cdiv(nn, 256), 256, 0, r, dinv, res, d0, z, nn, 1.0 / theta);
+  const bool batched = batched_ok(A, nb) && (!C || batched_ok(C, nb));
+  const bool has2 = A->has2 && coef;
+  double *dfirst = k == 1 ? z : d0;
+  if (C) {
+    if (batched)
+      LAUNCH(ctx, k_cheb_init_b, cdiv(nn, SPB_THREADS), SPB_THREADS, 0, C->view(), zc, r, dinv, res,
+             dfirst, nb, 1.0 / theta);
+    else if (nb == 1)
+      LAUNCH(ctx, k_cheb_init<8>, cdiv((size_t)n * 8, 256), 256, 0, C->view(), zc, r, dinv, res,
+             dfirst, nb, 1.0 / theta);
+    else
+      LAUNCH(ctx, k_cheb_init<1>, cdiv(nn, 256), 256, 0, C->view(), zc, r, dinv, res, dfirst, nb,
+             1.0 / theta);
+  } else {
+    LAUNCH(ctx, k_cheb_init_plain, cdiv(nn, 256), 256, 0, r, dinv, res, dfirst, nn, 1.0 / theta);
+  }
   double *dc = d0, *dn = d1;
   for (int i = 0; i + 1 < k; ++i) {
     const double rho_n = 1.0 / (2.0 * sigma - rho);
     const double c1 = rho_n * rho, c2 = 2.0 * rho_n / delta;
-    if (nb == 1)
-      LAUNCH(ctx, k_cheb_step<8>, cdiv((size_t)A->nrows * 8, 256), 256, 0, A->view(), coef, dc, dinv, res, dn, z, nb, c1, c2);
-    else
-      LAUNCH(ctx, k_cheb_step<1>, cdiv(nn, 256), 256, 0, A->view(), coef, dc, dinv, res, dn, z, nb, c1, c2);
+    const bool first = i == 0, last = i + 2 == k;
+#define CHEB_ARGS A->view(), coef, (const double *)dc, dinv, res, dn, z, nb, c1, c2
+#define CHEB_DISPATCH(KERN, GRID, BLK, ...)                                              \
+    do {                                                                                 \
+      if (first && last) LAUNCH(ctx, (KERN<__VA_ARGS__, true, true>), GRID, BLK, 0, CHEB_ARGS);       \
+      else if (first) LAUNCH(ctx, (KERN<__VA_ARGS__, true, false>), GRID, BLK, 0, CHEB_ARGS);         \
+      else if (last) LAUNCH(ctx, (KERN<__VA_ARGS__, false, true>), GRID, BLK, 0, CHEB_ARGS);          \
+      else LAUNCH(ctx, (KERN<__VA_ARGS__, false, false>), GRID, BLK, 0, CHEB_ARGS);                   \
+    } while (0)
+    if (batched) {
+      if (has2) CHEB_DISPATCH(k_cheb_step_b, cdiv(nn, SPB_THREADS), SPB_THREADS, true);
+      else CHEB_DISPATCH(k_cheb_step_b, cdiv(nn, SPB_THREADS), SPB_THREADS, false);
+    } else if (nb == 1) {
+      CHEB_DISPATCH(k_cheb_step, cdiv((size_t)n * 8, 256), 256, 8);
+    } else {
+      CHEB_DISPATCH(k_cheb_step, cdiv(nn, 256), 256, 1);
+    }
+#undef CHEB_DISPATCH
+#undef CHEB_ARGS
     std::swap(dc, dn);
     rho = rho_n;
   }
@@ -831,13 +927,13 @@ static void mg_vcycle(dnsb_solver *s, std::vector<MgLevel *> &lv, size_t l,
     return;
   }
   if (L->kind == MG_SMOOTH) {
-    cheb_plain(s, L->A, L->coef, L->dinv, b, x, L->r.p, L->d0.p, L->d1.p, L->nsmooth, L->lmin, L->lmax);
+    cheb_run(s, L->A, L->coef, L->dinv, nullptr, nullptr, b, x, L->r.p, L->d0.p, L->d1.p, L->nsmooth, L->lmin, L->lmax);
     return;
   }
   const size_t nn = (size_t)L->n * nb;
   MgLevel *C = lv[l + 1];
   // pre-smoothing from a zero guess
-  cheb_plain(s, L->A, L->coef, L->dinv, b, x, L->r.p, L->d0.p, L->d1.p, L->nsmooth, L->lmin, L->lmax);
+  cheb_run(s, L->A, L->coef, L->dinv, nullptr, nullptr, b, x, L->r.p, L->d0.p, L->d1.p, L->nsmooth, L->lmin, L->lmax);
   // residual and restriction
   spmm_dev(ctx, L->A, L->coef, x, b, L->r.p, nb, -1.0, 1.0);
   spmm_dev(ctx, L->R, nullptr, L->r.p, nullptr, C->b.p, nb, 1.0, 0.0);
@@ -846,8 +942,8 @@ static void mg_vcycle(dnsb_solver *s, std::vector<MgLevel *> &lv, size_t l,
   spmm_dev(ctx, L->P, nullptr, C->x.p, x, x, nb, 1.0, 1.0);
   // post-smoothing:  x += cheb(b - A x)
   spmm_dev(ctx, L->A, L->coef, x, b, L->r.p, nb, -1.0, 1.0);
-  cheb_plain(s, L->A, L->coef, L->dinv, L->r.p, L->t.p, L->r.p, L->d0.p, L->d1.p,
-             L->nsmooth, L->lmin, L->lmax);
+  cheb_run(s, L->A, L->coef, L->dinv, nullptr, nullptr, L->r.p, L->t.p, L->r.p, L->d0.p, L->d1.p,
+           L->nsmooth, L->lmin, L->lmax);
   LAUNCH(ctx, k_axpby, cdiv(nn, 256), 256, 0, 1.0, (const double *)x, 1.0, (const double *)L->t.p, x, nn);
 }
 
@@ -888,29 +984,8 @@ static int apply_prec(dnsb_solver *s, const double *r, double *z) {
     return 0;
   }
   // single level: Chebyshev only, fused with the gradient coupling
-  const double theta = 0.5 * (s->lmax + s->lmin), delta = 0.5 * (s->lmax - s->lmin);
-  const double sigma = theta / delta;
-  double rho = 1.0 / sigma;
-  if (nb == 1)
-    LAUNCH(ctx, k_cheb_init<8>, cdiv((size_t)nv * 8, 256), 256, 0, s->JT->view(), zp, rv,
-           s->dinv.p, s->cres.p, s->cd0.p, zv, nb, 1.0 / theta);
-  else
-    LAUNCH(ctx, k_cheb_init<1>, cdiv(nvb, 256), 256, 0, s->JT->view(), zp, rv, s->dinv.p,
-           s->cres.p, s->cd0.p, zv, nb, 1.0 / theta);
-  double *dc = s->cd0.p, *dn = s->cd1.p;
-  const double *coef = s->has_coef ? s->coef.p : nullptr;
-  for (int i = 0; i + 1 < s->kF; ++i) {
-    const double rho_n = 1.0 / (2.0 * sigma - rho);
-    const double c1 = rho_n * rho, c2 = 2.0 * rho_n / delta;
-    if (nb == 1)
-      LAUNCH(ctx, k_cheb_step<8>, cdiv((size_t)nv * 8, 256), 256, 0, s->F->view(), coef, dc,
-             s->dinv.p, s->cres.p, dn, zv, nb, c1, c2);
-    else
-      LAUNCH(ctx, k_cheb_step<1>, cdiv(nvb, 256), 256, 0, s->F->view(), coef, dc, s->dinv.p,
-             s->cres.p, dn, zv, nb, c1, c2);
-    std::swap(dc, dn);
-    rho = rho_n;
-  }
+  cheb_run(s, s->F, s->has_coef ? s->coef.p : nullptr, s->dinv.p, s->JT, zp, rv, zv, s->cres.p,
+           s->cd0.p, s->cd1.p, s->kF, s->lmin, s->lmax);
   return 0;
 }
 
@@ -931,7 +1006,8 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
   const double *coef = s->has_coef ? s->coef.p : nullptr;
   // |b|
   LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, b, b, ntot, nb, rc.rpb, s->partial2.p);
-  LAUNCH(ctx, k_set_bnorm, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, s->partial2.p, rc.nblocks, nb);
+  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
+  LAUNCH(ctx, k_set_bnorm, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p, 1, nb);
   if (zero_guess) DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
   int total = 0;
   bool first = true;
@@ -943,8 +1019,9 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
     else
       spmm_dev(ctx, s->K, coef, x, b, V0, nb, -1.0, 1.0);
     LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, V0, V0, ntot, nb, rc.rpb, s->partial2.p);
-    LAUNCH(ctx, k_gmres_begin, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, s->partial2.p,
-           rc.nblocks, nb, tol, first ? 1 : 0);
+    LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
+    LAUNCH(ctx, k_gmres_begin, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p,
+           1, nb, tol, first ? 1 : 0);
     LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, V0, s->gs.invh, V0, (size_t)ntot, nb);
     if (first && s->save_v0) {
       DNSB_CK(ctx, cudaMemcpyAsync(s->v0save.p, V0, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -960,16 +1037,16 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
       double *Zj = s->Zb.p + (size_t)j * ntb;
       if (apply_prec(s, Vj, Zj)) return -1;
       spmm_dev(ctx, s->K, coef, Zj, nullptr, s->w.p, nb, 1.0, 0.0);
-      LAUNCH(ctx, k_mdot, rc.nblocks, rc.threads, rc.smem, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb,
-             rc.rpb, s->partial.p);
-      LAUNCH(ctx, k_reduce_partials, cdiv((size_t)(j + 1) * nb, 128), 128, 0, s->partial.p,
-             rc.nblocks, (j + 1) * nb, s->gs.h);
-      LAUNCH(ctx, k_gs_update, rc.nblocks, rc.threads, rc.smem, s->Vb.p, ntb, j + 1, s->gs.h,
-             s->w.p, ntot, nb, rc.rpb, s->partial2.p);
-      LAUNCH(ctx, k_gmres_givens, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, s->partial2.p,
-             rc.nblocks, nb, j, tol);
-      LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, s->w.p, s->gs.invh,
-             s->Vb.p + (size_t)(j + 1) * ntb, (size_t)ntot, nb);
+      mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb, s->partial.p, s->gs.h);
+      double *Vn = s->Vb.p + (size_t)(j + 1) * ntb;
+      LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
+             (const double *)s->gs.h, (const double *)s->w.p, Vn, ntot, nb, rc.rpb,
+             rc.rows_per_block, s->partial2.p);
+      LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
+      LAUNCH(ctx, k_gmres_givens, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p,
+             1, nb, j, tol);
+      LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)Vn, (const double *)s->gs.invh, Vn,
+             (size_t)ntot, nb);
       // convergence poll: skipped while far from the expected iteration count
       if (total + 1 >= expect - 1 || j + 1 == mr || total + 1 == maxit) {
         if (read_flags(s)) return -1;
@@ -1261,10 +1338,7 @@ static int imex_guess(dnsb_imex *e, int guess, double *x) {
     return 0;
   }
   RedCfg rc = red_cfg(ctx, ntot, nb);
-  LAUNCH(ctx, k_mdot, rc.nblocks, rc.threads, rc.smem, e->bh.p, ntb, L, e->b.p, ntot, nb,
-         rc.rpb, e->partialh.p);
-  LAUNCH(ctx, k_reduce_partials, cdiv((size_t)L * nb, 128), 128, 0, e->partialh.p, rc.nblocks,
-         L * nb, e->gr.p);
+  mdot_dev(ctx, rc, e->bh.p, ntb, L, e->b.p, ntot, nb, e->partialh.p, e->gr.p);
   DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
   LAUNCH(ctx, k_gmres_update_x, cdiv(ntb, 256), 256, 0, e->xh.p, ntb, L, e->gr.p, x,
          (size_t)ntot, nb);
@@ -1308,7 +1382,7 @@ static int imex_blowup(dnsb_imex *e, const double *vc, double maxv, bool *bad) {
   const int nb = e->nb;
   RedCfg rcn = red_cfg(ctx, e->nv, nb);
   LAUNCH(ctx, k_dot1, rcn.nblocks, rcn.threads, rcn.smem, vc, vc, e->nv, nb, rcn.rpb, e->normpart.p);
-  LAUNCH(ctx, k_reduce_partials, cdiv(nb, 128), 128, 0, e->normpart.p, rcn.nblocks, nb, e->normout.p);
+  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)e->normpart.p, rcn.nblocks, nb, e->normout.p);
   std::vector<double> hn(nb);
   DNSB_CK(ctx, cudaMemcpyAsync(hn.data(), e->normout.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1342,8 +1416,8 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
       RedCfg rc = red_cfg(ctx, nv + np, nb);
       DNSB_CK(ctx, e->bh.alloc(ntb * L));
       DNSB_CK(ctx, e->bh.zero(ctx->stream));
-      DNSB_CK(ctx, e->gr.alloc((size_t)L * nb));
-      DNSB_CK(ctx, e->partialh.alloc((size_t)rc.nblocks * L * nb));
+      DNSB_CK(ctx, e->gr.alloc((size_t)(L + 1) * nb));
+      DNSB_CK(ctx, e->partialh.alloc((size_t)rc.nblocks * (L + 1) * nb));
       DNSB_CK(ctx, e->x0.alloc(ntb));
     }
   }
@@ -1600,7 +1674,7 @@ extern "C" int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev) {
   const int nchunks = 32;
   DNSB_CK(ctx, part.alloc((size_t)nchunks * ns * ns));
   LAUNCH(ctx, k_gram_partial, dim3(nchunks, ns * ns), 256, 256 * sizeof(double), e->snaps.p, ntb, MX.p, ns, nvb, part.p);
-  LAUNCH(ctx, k_reduce_partials, cdiv((size_t)ns * ns, 128), 128, 0, part.p, nchunks, ns * ns, g_dev);
+  LAUNCH(ctx, k_reduce_partials2, cdiv((size_t)ns * ns, 32), 256, 0, (const double *)part.p, nchunks, ns * ns, g_dev);
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   MX.release(); part.release();
   DNSB_CK(ctx, cudaGetLastError());

@@ -1,0 +1,265 @@
+// dnsb_batched.cuh -- the batched (ensemble, nb > 1) row kernels of libdnsb200
+//
+// Layout: x[i*nb + m] (member fastest).  One thread owns one (row, member)
+// pair; the 32 lanes of a warp therefore cover 32 consecutive members of one
+// row (nb >= 32) or a few consecutive rows (nb < 32).  The CSR entries of the
+// warp's rows are contiguous in memory: the warp loads them once, coalesced,
+// into its own shared-memory slice (column offset pre-multiplied by nb, value
+// pair (v1, v2) as one 16-byte word) and every lane then walks its row from
+// shared memory, so that the only global loads in the inner loop are the
+// (coalesced, independent, 4-way unrolled) gathers of x.  The sum over a row
+// runs in CSR order with one accumulator: results do not depend on the chunking
+// and are bit-reproducible.
+//
+// All kernels are HBM/L2-bandwidth bound (fp64, no tensor cores).
+#pragma once
+#include <cuda_runtime.h>
+
+#define SPB_THREADS 256
+#define SPB_WARPS (SPB_THREADS / 32)
+#define SPB_CAP 96   // CSR entries staged per warp and chunk
+
+struct SpbSmem2 {
+  double2 v[SPB_WARPS][SPB_CAP];
+  int off[SPB_WARPS][SPB_CAP];
+};
+struct SpbSmem1 {
+  double v[SPB_WARPS][SPB_CAP];
+  int off[SPB_WARPS][SPB_CAP];
+};
+
+// (row, member) of this thread and the row range of its warp
+#define SPB_ROWMAP()                                                            \
+  const long t_ = (long)blockIdx.x * SPB_THREADS + threadIdx.x;                 \
+  const long total_ = (long)A.nrows * nb;                                       \
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                    \
+  const long tw0_ = t_ - lane;                                                  \
+  if (tw0_ >= total_) return;                                                   \
+  const bool valid = t_ < total_;                                               \
+  const int row = valid ? (int)(t_ / nb) : A.nrows - 1;                         \
+  const int m = valid ? (int)(t_ - (long)row * nb) : 0;                         \
+  const int wrow0 = (int)(tw0_ / nb);                                           \
+  const long tw1_ = (tw0_ + 31 < total_ ? tw0_ + 31 : total_ - 1);              \
+  const int wrow1 = (int)(tw1_ / nb);
+
+// sum_k (v1[k] + cm*v2[k]) * x[indices[k]*nb + m] over the row of this lane
+template <bool HAS2>
+__device__ __forceinline__ double
+spb_rowdot(const CsrDev &A, double cm, const double *__restrict__ xm, int nb,
+           int row, bool valid, int wrow0, int wrow1, int lane, double2 *sv2,
+           double *sv1, int *soff) {
+  const int e_lo = A.indptr[wrow0], e_hi = A.indptr[wrow1 + 1];
+  const int k0 = valid ? A.indptr[row] : 0;
+  const int k1 = valid ? A.indptr[row + 1] : 0;
+  double acc = 0.0;
+  for (int base = e_lo; base < e_hi; base += SPB_CAP) {
+    const int cnt = min(SPB_CAP, e_hi - base);
+    __syncwarp();
+    for (int e = lane; e < cnt; e += 32) {
+      soff[e] = A.indices[base + e] * nb;
+      if (HAS2) sv2[e] = make_double2(A.v1[base + e], A.v2[base + e]);
+      else sv1[e] = A.v1[base + e];
+    }
+    __syncwarp();
+    int k = max(k0, base) - base;
+    const int kend = min(k1, base + cnt) - base;
+    for (; k + 4 <= kend; k += 4) {
+      const double x0 = xm[soff[k]], x1 = xm[soff[k + 1]];
+      const double x2 = xm[soff[k + 2]], x3 = xm[soff[k + 3]];
+      if (HAS2) {
+        const double2 a0 = sv2[k], a1 = sv2[k + 1], a2 = sv2[k + 2], a3 = sv2[k + 3];
+        acc += (a0.x + cm * a0.y) * x0;
+        acc += (a1.x + cm * a1.y) * x1;
+        acc += (a2.x + cm * a2.y) * x2;
+        acc += (a3.x + cm * a3.y) * x3;
+      } else {
+        acc += sv1[k] * x0;
+        acc += sv1[k + 1] * x1;
+        acc += sv1[k + 2] * x2;
+        acc += sv1[k + 3] * x3;
+      }
+    }
+    for (; k < kend; ++k) {
+      const double xv = xm[soff[k]];
+      if (HAS2) {
+        const double2 a = sv2[k];
+        acc += (a.x + cm * a.y) * xv;
+      } else {
+        acc += sv1[k] * xv;
+      }
+    }
+  }
+  return acc;
+}
+
+#define SPB_SMEM(HAS2)                                                          \
+  __shared__ typename SpbSel<HAS2>::type sm_;                                   \
+  double2 *sv2 = SpbSel<HAS2>::v2(sm_, wib);                                    \
+  double *sv1 = SpbSel<HAS2>::v1(sm_, wib);                                     \
+  int *soff = sm_.off[wib];
+
+template <bool HAS2> struct SpbSel;
+template <> struct SpbSel<true> {
+  typedef SpbSmem2 type;
+  static __device__ __forceinline__ double2 *v2(SpbSmem2 &s, int w) { return s.v[w]; }
+  static __device__ __forceinline__ double *v1(SpbSmem2 &, int) { return nullptr; }
+};
+template <> struct SpbSel<false> {
+  typedef SpbSmem1 type;
+  static __device__ __forceinline__ double2 *v2(SpbSmem1 &, int) { return nullptr; }
+  static __device__ __forceinline__ double *v1(SpbSmem1 &s, int w) { return s.v[w]; }
+};
+
+// y = alpha*A*x + beta*z   (z may alias y; ignored when beta == 0)
+// Algorithmic bytes: (12|20)*nnz + 4(nrows+1) + 8*nb*(ncols + nrows [+ nrows]).
+template <bool HAS2>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_spmm_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
+         const double *z, double *y, int nb, double alpha, double beta) {
+  SPB_ROWMAP()
+  SPB_SMEM(HAS2)
+  const double cm = HAS2 ? coef[m] : 0.0;
+  const double acc = spb_rowdot<HAS2>(A, cm, x + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+  if (valid) y[t_] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[t_];
+}
+
+// Chebyshev start, fused with the gradient coupling of the block-triangular
+// preconditioner (A = JT, may have nnz = 0 rows):
+//   res = rv - JT*zp ;  d = dinv*res/theta      (z is NOT written: the first
+//   step forms z = d0 + d1; with a single step the caller passes d = z)
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_init_b(CsrDev A, const double *__restrict__ zp, const double *__restrict__ rv,
+              const double *__restrict__ dinv, double *__restrict__ res,
+              double *__restrict__ d, int nb, double inv_theta) {
+  SPB_ROWMAP()
+  SPB_SMEM(false)
+  const double acc = spb_rowdot<false>(A, 0.0, zp + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+  if (valid) {
+    const double r = rv[t_] - acc;
+    res[t_] = r;
+    d[t_] = dinv[t_] * r * inv_theta;
+  }
+}
+
+// Chebyshev step:  r = res - F*d ;  dn = c1*d + c2*dinv*r ;  z (+)= dn
+//   FIRST: z = d + dn (z not read);  LAST: res and dn are not written.
+// Algorithmic bytes per (row, member): gather of d (8) + res (8) + dinv (8)
+// + z read (8, not FIRST) + z write (8) + res/dn write (16, not LAST);
+// matrix: 20 B/nnz (HAS2) shared by all members.
+template <bool HAS2, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_step_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ d,
+              const double *__restrict__ dinv, double *res, double *__restrict__ dn,
+              double *z, int nb, double c1, double c2) {
+  SPB_ROWMAP()
+  SPB_SMEM(HAS2)
+  const double cm = HAS2 ? coef[m] : 0.0;
+  const double acc = spb_rowdot<HAS2>(A, cm, d + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+  if (valid) {
+    const double r = res[t_] - acc;
+    const double dold = d[t_];
+    const double dd = c1 * dold + c2 * dinv[t_] * r;
+    if (!LAST) {
+      res[t_] = r;
+      dn[t_] = dd;
+    }
+    z[t_] = (FIRST ? dold : z[t_]) + dd;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Gram-Schmidt of FGMRES, batched and deterministic.
+// Block = RPB x nb threads (RPB a power of two), thread = (rr, m); the block
+// owns a contiguous chunk of rows and the thread the rows r0+rr, r0+rr+RPB, ...
+// of it (at most GS_RPT), which it keeps in registers.
+// ---------------------------------------------------------------------------
+#define GS_RPT 16   // rows per thread held in registers
+
+// partial[(b*(nvec+1) + i)*nb + m] = sum_chunk V_i*w  (i < nvec),  i = nvec: w*w
+// Algorithmic bytes: 8*n*nb*(nvec + 1).
+__global__ void __launch_bounds__(256)
+k_mdot_b(const double *__restrict__ V, size_t vstride, int nvec,
+         const double *__restrict__ w, int n, int nb, int rpb, int rows_per_block,
+         double *__restrict__ partial) {
+  extern __shared__ double sred[];   // (nvec+1) x blockDim
+  const int m = threadIdx.x % nb, rr = threadIdx.x / nb;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  const int nthr = rpb * nb;
+  double wr[GS_RPT];
+  double ww = 0.0;
+#pragma unroll
+  for (int q = 0; q < GS_RPT; ++q) {
+    const int r = r0 + rr + q * rpb;
+    wr[q] = (r < r1) ? w[(size_t)r * nb + m] : 0.0;
+    ww += wr[q] * wr[q];
+  }
+  for (int i = 0; i < nvec; ++i) {
+    const double *vi = V + (size_t)i * vstride;
+    double vv[GS_RPT];
+#pragma unroll
+    for (int q = 0; q < GS_RPT; ++q) {
+      const int r = r0 + rr + q * rpb;
+      vv[q] = (r < r1) ? vi[(size_t)r * nb + m] : 0.0;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < GS_RPT; ++q) acc += vv[q] * wr[q];
+    sred[(size_t)i * nthr + threadIdx.x] = acc;
+  }
+  sred[(size_t)nvec * nthr + threadIdx.x] = ww;
+  __syncthreads();
+  // fixed-order sum over rr
+  for (int o = threadIdx.x; o < (nvec + 1) * nb; o += nthr) {
+    const int i = o / nb, mm = o % nb;
+    double s = 0.0;
+    for (int q = 0; q < rpb; ++q) s += sred[(size_t)i * nthr + q * nb + mm];
+    partial[((size_t)blockIdx.x * (nvec + 1) + i) * nb + mm] = s;
+  }
+}
+
+// vnext = w - sum_i h[i,m]*V_i  (not normalised);
+// partial2[b*nb + m] = |vnext|^2 over the chunk of block b
+// Algorithmic bytes: 8*n*nb*(nvec + 2).
+__global__ void __launch_bounds__(256, 2)
+k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
+              const double *__restrict__ h, const double *__restrict__ w,
+              double *__restrict__ vnext, int n, int nb, int rpb, int rows_per_block,
+              double *__restrict__ partial2) {
+  extern __shared__ double sred[];   // blockDim
+  const int m = threadIdx.x % nb, rr = threadIdx.x / nb;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  double wr[GS_RPT];
+#pragma unroll
+  for (int q = 0; q < GS_RPT; ++q) {
+    const int r = r0 + rr + q * rpb;
+    wr[q] = (r < r1) ? w[(size_t)r * nb + m] : 0.0;
+  }
+  for (int i = 0; i < nvec; ++i) {
+    const double *vi = V + (size_t)i * vstride;
+    const double hi = h[(size_t)i * nb + m];
+    double vv[GS_RPT];
+#pragma unroll
+    for (int q = 0; q < GS_RPT; ++q) {
+      const int r = r0 + rr + q * rpb;
+      vv[q] = (r < r1) ? vi[(size_t)r * nb + m] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < GS_RPT; ++q) wr[q] -= hi * vv[q];
+  }
+  double nrm = 0.0;
+#pragma unroll
+  for (int q = 0; q < GS_RPT; ++q) {
+    const int r = r0 + rr + q * rpb;
+    if (r < r1) vnext[(size_t)r * nb + m] = wr[q];
+    nrm += wr[q] * wr[q];
+  }
+  sred[threadIdx.x] = nrm;
+  __syncthreads();
+  if (rr == 0) {
+    double s = 0.0;
+    for (int q = 0; q < rpb; ++q) s += sred[q * nb + m];
+    partial2[(size_t)blockIdx.x * nb + m] = s;
+  }
+}

@@ -232,57 +232,57 @@ k_spmm(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
 }
 
 // Chebyshev start, fused with the gradient coupling:
-//   res = rv - JT*zp ;  d = dinv*res/theta ;  z = d
+//   res = rv - JT*zp ;  d = dinv*res/theta
+// (z is not written: the first step forms z = d0 + d1; for a single step the
+// caller passes d = z)
 template <int LPR>
 __global__ void
 k_cheb_init(CsrDev A /*JT*/, const double *__restrict__ zp,
             const double *__restrict__ rv, const double *__restrict__ dinv,
-            double *__restrict__ res, double *__restrict__ d,
-            double *__restrict__ z, int nb, double inv_theta) {
+            double *__restrict__ res, double *__restrict__ d, int nb,
+            double inv_theta) {
   DNSB_ROWMAP(LPR)
   const double acc = csr_rowdot<LPR>(A, 0.0, zp, nb, row, m, lane, valid);
   if (valid && lane == 0) {
     const size_t i = (size_t)row * nb + m;
     const double r = rv[i] - acc;
-    const double dd = dinv[i] * r * inv_theta;
     res[i] = r;
-    d[i] = dd;
-    z[i] = dd;
+    d[i] = dinv[i] * r * inv_theta;
   }
 }
 
-// plain variant (no coupling): res = r ; d = dinv*r/theta ; z = d
-__global__ void k_cheb_init_plain(const double *__restrict__ r,
-                                  const double *__restrict__ dinv,
-                                  double *__restrict__ res,
-                                  double *__restrict__ d, double *__restrict__ z,
-                                  size_t n, double inv_theta) {
+// plain variant (no coupling): res = r ; d = dinv*r/theta   (res may alias r)
+__global__ void k_cheb_init_plain(const double *r, const double *__restrict__ dinv,
+                                  double *res, double *__restrict__ d, size_t n,
+                                  double inv_theta) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double rr = r[i];
-  const double dd = dinv[i] * rr * inv_theta;
   res[i] = rr;
-  d[i] = dd;
-  z[i] = dd;
+  d[i] = dinv[i] * rr * inv_theta;
 }
 
-// Chebyshev step:  res -= F*d ;  dn = c1*d + c2*dinv*res ;  z += dn
-template <int LPR>
+// Chebyshev step:  r = res - F*d ;  dn = c1*d + c2*dinv*r ;  z (+)= dn
+//   FIRST: z = d + dn (z not read);  LAST: res and dn are not written
+template <int LPR, bool FIRST, bool LAST>
 __global__ void
 k_cheb_step(CsrDev A /*F*/, const double *__restrict__ coef,
             const double *__restrict__ d, const double *__restrict__ dinv,
-            double *__restrict__ res, double *__restrict__ dn,
-            double *__restrict__ z, int nb, double c1, double c2) {
+            double *res, double *__restrict__ dn, double *z, int nb, double c1,
+            double c2) {
   DNSB_ROWMAP(LPR)
   const double cm = (valid && coef) ? coef[m] : 0.0;
   const double acc = csr_rowdot<LPR>(A, cm, d, nb, row, m, lane, valid);
   if (valid && lane == 0) {
     const size_t i = (size_t)row * nb + m;
     const double r = res[i] - acc;
-    const double dd = c1 * d[i] + c2 * dinv[i] * r;
-    res[i] = r;
-    dn[i] = dd;
-    z[i] += dd;
+    const double dold = d[i];
+    const double dd = c1 * dold + c2 * dinv[i] * r;
+    if (!LAST) {
+      res[i] = r;
+      dn[i] = dd;
+    }
+    z[i] = (FIRST ? dold : z[i]) + dd;
   }
 }
 
@@ -607,6 +607,27 @@ __global__ void k_gmres_givens(GmresState S, const double *__restrict__ partial2
   }
 }
 
+// out[c] = sum_b partial[b*count + c]; block = 32 outputs x 8 slices of b,
+// coalesced in c, fixed summation order
+__global__ void __launch_bounds__(256)
+k_reduce_partials2(const double *__restrict__ partial, int nblocks, int count,
+                   double *__restrict__ out) {
+  __shared__ double sp[8][33];
+  const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (c < count)
+    for (int b = by; b < nblocks; b += 8) s += partial[(size_t)b * count + c];
+  sp[by][cx] = s;
+  __syncthreads();
+  if (by == 0 && c < count) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sp[q][cx];
+    out[c] = t;
+  }
+}
+
 // y = R^-1 g (per member, using its[m] columns); stored in S.h[i*nb+m]
 __global__ void k_gmres_solve_y(GmresState S, int nb, int jmax) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -639,9 +660,8 @@ __global__ void k_gmres_update_x(const double *__restrict__ Z, size_t zstride,
 }
 
 // out = x * scale[m]
-__global__ void k_scale_member(const double *__restrict__ x,
-                               const double *__restrict__ scale,
-                               double *__restrict__ out, size_t n, int nb) {
+__global__ void k_scale_member(const double *x, const double *__restrict__ scale,
+                               double *out, size_t n, int nb) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * nb) return;
   out[idx] = x[idx] * scale[idx % nb];
