@@ -50,8 +50,10 @@ SIGNATURES = {
     'dnsb_solver_add_velocity_level': (_i, [_vp, _vp, _vp, _vp, _i, _d, _d,
                                             c_dbl_p]),
     'dnsb_solver_set_schur_mass': (_i, [_vp, c_dbl_p, c_dbl_p]),
+    'dnsb_solver_set_schur_lsc': (_i, [_vp, c_dbl_p]),
     'dnsb_solver_solve': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, _d, _i,
                                c_int_p, c_dbl_p]),
+    'dnsb_solver_apply_prec': (_i, [_vp, c_dbl_p, c_dbl_p]),
     'dnsb_imex_create': (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, c_dbl_p,
                               c_int_p, _i, _i, c_int_p, c_dbl_p, c_dbl_p,
                               c_dbl_p, c_void_pp]),
@@ -66,6 +68,10 @@ SIGNATURES = {
     'dnsb_imex_num_snapshots': (_i, [_vp]),
     'dnsb_imex_reset_snapshots': (_i, [_vp]),
     'dnsb_imex_get_snapshots': (_i, [_vp, c_dbl_p]),
+    'dnsb_imex_set_output_order': (_i, [_vp, c_int_p, c_int_p]),
+    'dnsb_imex_reserve_snapshots': (_i, [_vp, _i]),
+    'dnsb_imex_snapshots_host': (_i, [_vp, ctypes.POINTER(c_dbl_p),
+                                      ctypes.POINTER(_i)]),
     'dnsb_imex_stats': (_i, [_vp, ctypes.POINTER(_ll), ctypes.POINTER(_ll),
                              c_dbl_p]),
     'dnsb_imex_gram_dev': (_i, [_vp, _vp]),
@@ -345,6 +351,18 @@ class SaddleSolver(object):
         self.ctx.check(self.ctx.lib.dnsb_solver_set_schur_mass(
             self.h, _dp(mp_dinv), _dp(mp_scale)))
 
+    def apply_prec(self, r):
+        r = _f64(r).reshape(self.nv + self.np_, self.nb)
+        z = np.empty_like(r)
+        self.ctx.check(self.ctx.lib.dnsb_solver_apply_prec(self.h, _dp(r),
+                                                           _dp(z)))
+        return z
+
+    def set_schur_lsc(self, du_inv):
+        du_inv = _f64(du_inv)
+        self.ctx.check(self.ctx.lib.dnsb_solver_set_schur_lsc(self.h,
+                                                              _dp(du_inv)))
+
     def solve(self, rhsv, rhsp=None, x0=None, tol=1e-11, maxit=400):
         """returns ``(vp, iters, relres)``; arrays are (n, nb) or (n,)"""
         rhsv = _f64(rhsv)
@@ -416,7 +434,7 @@ class ImexEngine(object):
         self.ctx.check(self.ctx.lib.dnsb_imex_set_state(self.h, _dp(v0),
                                                         _dp(p0)))
 
-    def run(self, nsteps, snap_stride=0, tol=1e-12, maxit=400, guess=8,
+    def run(self, nsteps, snap_stride=0, tol=1e-12, maxit=400, guess=16,
             check_ff_maxv=1e8, ntimeslices=10):
         ff = ctypes.c_int(0)
         self.ctx.check(self.ctx.lib.dnsb_imex_run(
@@ -442,6 +460,26 @@ class ImexEngine(object):
             self.ctx.check(self.ctx.lib.dnsb_imex_get_snapshots(self.h,
                                                                 _dp(out)))
         return out
+
+    def set_output_order(self, vmap, pmap):
+        vmap, pmap = _i32(vmap), _i32(pmap)
+        self.ctx.check(self.ctx.lib.dnsb_imex_set_output_order(
+            self.h, _ip(vmap), _ip(pmap)))
+
+    def reserve_snapshots(self, nsnap):
+        self.ctx.check(self.ctx.lib.dnsb_imex_reserve_snapshots(self.h,
+                                                                int(nsnap)))
+
+    def snapshots_view(self):
+        """zero-copy (nsnap, nv+np, nb) view of the pinned host mirror; valid
+        until the next run / reserve / close"""
+        ptr, ns = c_dbl_p(), ctypes.c_int(0)
+        self.ctx.check(self.ctx.lib.dnsb_imex_snapshots_host(
+            self.h, ctypes.byref(ptr), ctypes.byref(ns)))
+        if ns.value == 0:
+            return np.empty((0, self.nv + self.np_, self.nb))
+        return np.ctypeslib.as_array(ptr, shape=(ns.value, self.nv + self.np_,
+                                                 self.nb))
 
     def reset_snapshots(self):
         self.ctx.check(self.ctx.lib.dnsb_imex_reset_snapshots(self.h))

@@ -28,19 +28,26 @@ struct SpbSmem1 {
   int off[SPB_WARPS][SPB_CAP];
 };
 
-// (row, member) of this thread and the row range of its warp
-#define SPB_ROWMAP()                                                            \
-  const long t_ = (long)blockIdx.x * SPB_THREADS + threadIdx.x;                 \
+// A CTA owns `gpc` consecutive groups of SPB_THREADS (row, member) pairs, i.e.
+// a chunk of gpc*SPB_THREADS/nb consecutive rows, and walks them group by
+// group: with the mesh-local (Hilbert) numbering of the unknowns the rows of a
+// chunk share most of their columns, so the gathered x rows are served by the
+// SM's L1 instead of L2 (measured reuse on cylinder_4: 9x for 64-row chunks).
+// Inside the loop: (row, member) of this thread, row range of its warp.
+#define SPB_FOR_GROUPS()                                                        \
   const long total_ = (long)A.nrows * nb;                                       \
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;                    \
+  const int lane = threadIdx.x & 31;                                           \
+  for (int g_ = 0; g_ < gpc; ++g_)
+
+#define SPB_ROWMAP()                                                            \
+  const long t_ = ((long)blockIdx.x * gpc + g_) * SPB_THREADS + threadIdx.x;    \
   const long tw0_ = t_ - lane;                                                  \
-  if (tw0_ >= total_) return;                                                   \
+  if (tw0_ >= total_) break;                                                    \
   const bool valid = t_ < total_;                                               \
-  const int row = valid ? (int)(t_ / nb) : A.nrows - 1;                         \
+  const int row = valid ? (int)((unsigned)t_ / (unsigned)nb) : A.nrows - 1;     \
   const int m = valid ? (int)(t_ - (long)row * nb) : 0;                         \
-  const int wrow0 = (int)(tw0_ / nb);                                           \
-  const long tw1_ = (tw0_ + 31 < total_ ? tw0_ + 31 : total_ - 1);              \
-  const int wrow1 = (int)(tw1_ / nb);
+  const int wrow0 = __shfl_sync(0xffffffffu, row, 0);                           \
+  const int wrow1 = __shfl_sync(0xffffffffu, row, 31);
 
 // sum_k (v1[k] + cm*v2[k]) * x[indices[k]*nb + m] over the row of this lane
 template <bool HAS2>
@@ -94,9 +101,9 @@ spb_rowdot(const CsrDev &A, double cm, const double *__restrict__ xm, int nb,
 
 #define SPB_SMEM(HAS2)                                                          \
   __shared__ typename SpbSel<HAS2>::type sm_;                                   \
-  double2 *sv2 = SpbSel<HAS2>::v2(sm_, wib);                                    \
-  double *sv1 = SpbSel<HAS2>::v1(sm_, wib);                                     \
-  int *soff = sm_.off[wib];
+  double2 *sv2 = SpbSel<HAS2>::v2(sm_, threadIdx.x >> 5);                       \
+  double *sv1 = SpbSel<HAS2>::v1(sm_, threadIdx.x >> 5);                        \
+  int *soff = sm_.off[threadIdx.x >> 5];
 
 template <bool HAS2> struct SpbSel;
 template <> struct SpbSel<true> {
@@ -115,12 +122,15 @@ template <> struct SpbSel<false> {
 template <bool HAS2>
 __global__ void __launch_bounds__(SPB_THREADS)
 k_spmm_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
-         const double *z, double *y, int nb, double alpha, double beta) {
-  SPB_ROWMAP()
+         const double *z, double *y, int nb, int gpc, double alpha, double beta) {
   SPB_SMEM(HAS2)
-  const double cm = HAS2 ? coef[m] : 0.0;
-  const double acc = spb_rowdot<HAS2>(A, cm, x + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
-  if (valid) y[t_] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[t_];
+  SPB_FOR_GROUPS() {
+    SPB_ROWMAP()
+    const double cm = HAS2 ? coef[m] : 0.0;
+    const double zin = (beta != 0.0 && valid) ? z[t_] : 0.0;
+    const double acc = spb_rowdot<HAS2>(A, cm, x + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+    if (valid) y[t_] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * zin;
+  }
 }
 
 // Chebyshev start, fused with the gradient coupling of the block-triangular
@@ -130,14 +140,18 @@ k_spmm_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x
 __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_init_b(CsrDev A, const double *__restrict__ zp, const double *__restrict__ rv,
               const double *__restrict__ dinv, double *__restrict__ res,
-              double *__restrict__ d, int nb, double inv_theta) {
-  SPB_ROWMAP()
+              double *__restrict__ d, int nb, int gpc, double inv_theta) {
   SPB_SMEM(false)
-  const double acc = spb_rowdot<false>(A, 0.0, zp + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
-  if (valid) {
-    const double r = rv[t_] - acc;
-    res[t_] = r;
-    d[t_] = dinv[t_] * r * inv_theta;
+  SPB_FOR_GROUPS() {
+    SPB_ROWMAP()
+    const long te_ = valid ? t_ : 0;
+    const double rv_ = rv[te_], di = dinv[te_];
+    const double acc = spb_rowdot<false>(A, 0.0, zp + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+    if (valid) {
+      const double r = rv_ - acc;
+      res[t_] = r;
+      d[t_] = di * r * inv_theta;
+    }
   }
 }
 
@@ -150,20 +164,25 @@ template <bool HAS2, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_step_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ d,
               const double *__restrict__ dinv, double *res, double *__restrict__ dn,
-              double *z, int nb, double c1, double c2) {
-  SPB_ROWMAP()
+              double *z, int nb, int gpc, double c1, double c2) {
   SPB_SMEM(HAS2)
-  const double cm = HAS2 ? coef[m] : 0.0;
-  const double acc = spb_rowdot<HAS2>(A, cm, d + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
-  if (valid) {
-    const double r = res[t_] - acc;
-    const double dold = d[t_];
-    const double dd = c1 * dold + c2 * dinv[t_] * r;
-    if (!LAST) {
-      res[t_] = r;
-      dn[t_] = dd;
+  SPB_FOR_GROUPS() {
+    SPB_ROWMAP()
+    const double cm = HAS2 ? coef[m] : 0.0;
+    // operands of the update first: their latency overlaps the row product
+    const long te_ = valid ? t_ : 0;
+    const double r_old = res[te_], dold = d[te_], di = dinv[te_];
+    const double z_old = FIRST ? 0.0 : z[te_];
+    const double acc = spb_rowdot<HAS2>(A, cm, d + m, nb, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+    if (valid) {
+      const double r = r_old - acc;
+      const double dd = c1 * dold + c2 * di * r;
+      if (!LAST) {
+        res[t_] = r;
+        dn[t_] = dd;
+      }
+      z[t_] = (FIRST ? dold : z_old) + dd;
     }
-    z[t_] = (FIRST ? dold : z[t_]) + dd;
   }
 }
 

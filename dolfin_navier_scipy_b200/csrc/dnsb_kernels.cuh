@@ -671,9 +671,8 @@ __global__ void k_scale_member(const double *x, const double *__restrict__ scale
 // elementwise helpers of the time stepper
 // ---------------------------------------------------------------------------
 // z = a*x + b*y  (y may be null)
-__global__ void k_axpby(double a, const double *__restrict__ x, double b,
-                        const double *__restrict__ y, double *__restrict__ z,
-                        size_t n) {
+__global__ void k_axpby(double a, const double *x, double b, const double *y,
+                        double *z, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   z[i] = y ? a * x[i] + b * y[i] : a * x[i];

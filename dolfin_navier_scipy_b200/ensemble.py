@@ -12,7 +12,8 @@ import numpy as np
 from . import problem_setups as dnsps
 from . import time_int_utils as tiu
 
-__all__ = ['cylinder_ensemble', 'shard_members', 'gram_allreduce']
+__all__ = ['cylinder_ensemble', 'shard_members', 'gram_allreduce',
+           'allreduce_gram']
 
 
 def shard_members(nmembers, rank, world):
@@ -26,7 +27,7 @@ def shard_members(nmembers, rank, world):
 def cylinder_ensemble(N=4, Res=(60., 150.), nmembers=64, rank=0, world=1,
                       dt=1./512, scheme='cnab', palpha=1e-5, bccontrol=True,
                       control=np.sin, ntimes=513, t0=0., ctx=None, mesh=None,
-                      cheb_steps=3, restart=40):
+                      cheb_steps=5, restart=40, schur_poly=2, coarse_max=4096):
     """device integrator for this rank's shard of a Re-sweep ensemble
 
     Returns ``(integ, info)``; ``integ`` is a `time_int_utils.DeviceImex` with
@@ -50,7 +51,8 @@ def cylinder_ensemble(N=4, Res=(60., 150.), nmembers=64, rank=0, world=1,
                            femp['invinds'], femp['dbcinds'], femp['dbcvals'],
                            dt, scheme=scheme, nus=nus, Arob=Arob,
                            fp=rhs_bc['fp'] + rhs_vf['fp'], ctx=ctx,
-                           cheb_steps=cheb_steps, restart=restart)
+                           cheb_steps=cheb_steps, restart=restart,
+                           schur_poly=schur_poly, coarse_max=coarse_max)
     trange = t0 + dt*np.arange(ntimes)
     cols = [rhs_bc['fv'].reshape(NV, 1)]
     if bccontrol:
@@ -68,6 +70,16 @@ def cylinder_ensemble(N=4, Res=(60., 150.), nmembers=64, rank=0, world=1,
     return integ, info
 
 
+def allreduce_gram(G, group=None):
+    """sum the per-rank partial Gram matrices in place (NCCL on the device,
+    gloo on the host); a no-op for a single process"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() \
+            and dist.get_world_size(group) > 1:
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+    return G
+
+
 def gram_allreduce(integ, group=None):
     """POD snapshot Gram matrix of the whole ensemble
 
@@ -76,14 +88,9 @@ def gram_allreduce(integ, group=None):
     Returns a (ns, ns) torch tensor on the device (identical on all ranks).
     """
     import torch
-    ns = integ.engine.snapshots().shape[0] if False else \
-        integ.engine.ctx.lib.dnsb_imex_num_snapshots(integ.engine.h)
+    ns = integ.engine.ctx.lib.dnsb_imex_num_snapshots(integ.engine.h)
     dev = torch.device('cuda', integ.ctx.device)
     G = torch.zeros((ns, ns), dtype=torch.float64, device=dev)
     torch.cuda.synchronize(dev)
     integ.engine.gram_dev(G.data_ptr())
-    if torch.distributed.is_available() and torch.distributed.is_initialized() \
-            and torch.distributed.get_world_size(group) > 1:
-        torch.distributed.all_reduce(G, op=torch.distributed.ReduceOp.SUM,
-                                     group=group)
-    return G
+    return allreduce_gram(G, group)

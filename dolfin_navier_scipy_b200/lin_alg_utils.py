@@ -19,17 +19,38 @@ class SadpntOperator(object):
     """reusable device solver for one saddle-point matrix (``return_alu``)"""
 
     def __init__(self, amat, jmat, jmatT=None, ncols=1, ctx=None,
-                 cheb_steps=3, restart=60, coarse_max=4096, schur_diag=None,
+                 cheb_steps=3, restart=None, coarse_max=4096, schur_diag=None,
                  spectrum=None, hierarchy=None, velocity_amg='auto',
-                 vgroups=None, vhierarchy=None):
+                 vgroups=None, vhierarchy=None, mass_diag=None, cache=None,
+                 schur='auto', nsmooth=2):
         self.ctx = _lib.default_context() if ctx is None else ctx
         self.NP, self.NV = jmat.shape
         self.ncols = ncols
+        if restart is None:
+            # long recurrences for single systems (the Oseen/Newton matrices
+            # need ~150 iterations), bounded basis memory for wide batches
+            restart = 250 if ncols == 1 else 60
+        amat = sps.csr_matrix(amat)
+        if cache is not None:
+            # Picard/Newton sequences: keep the (expensive, host-side)
+            # hierarchies of the first matrix for the later ones
+            hierarchy = cache.get('hierarchy', hierarchy)
+            vhierarchy = cache.get('vhierarchy', vhierarchy)
+        Fsym = None
+        if abs(amat - amat.T).max() > 1e-12*abs(amat).max():
+            Fsym = (.5*(amat + amat.T)).tocsr()
+            # convection: D^-1 F has complex eigenvalues, on which Chebyshev
+            # polynomials of degree > 2 amplify (the V-cycle diverges)
+            cheb_steps = min(cheb_steps, 2)
         self.solver, self.info = hostsetup.make_saddle_solver(
             self.ctx, amat, jmat, jmatT, nb=ncols, restart=restart,
             cheb_steps=cheb_steps, coarse_max=coarse_max,
             schur_diag=schur_diag, spectrum=spectrum, hierarchy=hierarchy,
-            velocity_amg=velocity_amg, vgroups=vgroups, vhierarchy=vhierarchy)
+            velocity_amg=velocity_amg, vgroups=vgroups, vhierarchy=vhierarchy,
+            mass_diag=mass_diag, Fsym=Fsym, schur=schur, nsmooth=nsmooth)
+        if cache is not None and self.info['velocity_amg']:
+            cache.setdefault('hierarchy', self.info['hierarchy'])
+            cache.setdefault('vhierarchy', self.info['vhierarchy'])
 
     def solve(self, rhsv, rhsp=None, x0=None, tol=1e-12, maxit=800):
         rhsv = np.asarray(rhsv, dtype=float).reshape(self.NV, self.ncols)
@@ -48,14 +69,20 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
                      rhsp=None, umat=None, vmat=None, krylov=None,
                      krpslvprms={}, krplsprms={}, return_alu=False,
                      sadlu=None, decouplevp=False, solve_A=None,
-                     symmetric=False, cgtol=1e-8, vgroups=None, **kw):
+                     symmetric=False, cgtol=1e-8, vgroups=None,
+                     mass_diag=None, cache=None, **kw):
     """solve ``[[amat, jmatT], [jmat, 0]] [v; p] = [rhsv; rhsp]`` on the device
 
     Same arguments and return value as `lau.solve_sadpnt_smw` (stacked
     ``(NV+NP, k)`` array [and the reusable operator with ``return_alu``]).
     ``krpslvprms['tol'|'maxiter'|'x0']`` are honoured; ``convstatsl`` receives
     the iteration counts like krypy's convergence statistics
-    (`tests/time_dep_nse_krylov.py:5,47`).  Low-rank updates (``umat``,
+    (`tests/time_dep_nse_krylov.py:5,47`).  Extensions (ignored by the
+    reference's signature): ``vgroups`` (node/component of the velocity
+    unknowns for the vector AMG), ``mass_diag`` (diagonal of the velocity mass
+    matrix for the LSC Schur approximation of stiffness dominated systems),
+    ``cache`` (dict that carries the host-side hierarchies through a
+    Picard/Newton sequence).  Low-rank updates (``umat``,
     ``vmat``) and ``decouplevp`` are outside the hot path and not supported.
     """
     if umat is not None or vmat is not None:
@@ -67,7 +94,8 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
     k = rhsv.shape[1]
     op = sadlu if sadlu is not None else \
         SadpntOperator(sps.csr_matrix(amat), sps.csr_matrix(jmat), jmatT,
-                       ncols=k, vgroups=vgroups)
+                       ncols=k, vgroups=vgroups, mass_diag=mass_diag,
+                       cache=cache)
     tol = krpslvprms.get('tol', 1e-12) if krylov is not None else 1e-12
     maxit = krpslvprms.get('maxiter', 800) if krylov is not None else 800
     x0 = krpslvprms.get('x0', None) if krylov is not None else None

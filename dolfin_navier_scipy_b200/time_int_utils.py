@@ -88,8 +88,8 @@ class DeviceImex(object):
 
     def __init__(self, M, A0, J, V, invinds, dbcinds, dbcvals, dt,
                  scheme='cnab', nus=(1.,), Arob=None, fv=None, fp=None,
-                 ctx=None, cheb_steps=3, restart=40, coarse_max=4096,
-                 mp_diag=None):
+                 ctx=None, cheb_steps=5, restart=40, coarse_max=4096,
+                 mp_diag=None, reorder=True, schur_poly=2):
         self.ctx = _lib.default_context() if ctx is None else ctx
         self.scheme = scheme
         self.dt = float(dt)
@@ -99,7 +99,28 @@ class DeviceImex(object):
         self.invinds = np.asarray(invinds, dtype=np.int32)
         M, A0, J = sps.csr_matrix(M), sps.csr_matrix(A0), sps.csr_matrix(J)
         self.NP, self.NV = J.shape
-        mats = [M, A0] + ([] if Arob is None else [sps.csr_matrix(Arob)])
+        # ---- device numbering: Hilbert order of the mesh nodes (locality of
+        # the SpMM gathers); all inputs/outputs are permuted at this boundary
+        reorder = reorder and hasattr(V, 'tabulate_dof_coordinates')
+        if reorder:
+            xy = np.asarray(V.tabulate_dof_coordinates())[self.invinds]
+            self.pv = hostsetup.locality_perm(xy, comp=self.invinds % 2)
+            pxy = np.asarray(V.mesh().coords)
+            if pxy.shape[0] == self.NP:
+                self.pp = hostsetup.locality_perm(pxy)
+            else:
+                self.pp = hostsetup.locality_perm(pattern=abs(J)@abs(J).T)
+        else:
+            self.pv, self.pp = np.arange(self.NV), np.arange(self.NP)
+        pv, pp = self.pv, self.pp
+        self.ipv, self.ipp = np.argsort(pv), np.argsort(pp)
+
+        def _pvv(X):
+            return sps.csr_matrix(X)[pv][:, pv].tocsr()
+        M, A0 = _pvv(M), _pvv(A0)
+        J = J[pp][:, pv].tocsr()
+        Arob = None if Arob is None else _pvv(Arob)
+        mats = [M, A0] + ([] if Arob is None else [Arob])
         pat = _union_pattern(mats)
         Mp, A0p = _on_pattern(M, pat), _on_pattern(A0, pat)
         Arp = _on_pattern(sps.csr_matrix(pat.shape) if Arob is None else Arob,
@@ -118,10 +139,15 @@ class DeviceImex(object):
         JT = J.T.tocsr()
         JT.sort_indices()
         self.jmat, self.jtmat = ctx.csr(J), ctx.csr(JT)
+        if fv is not None:
+            fv = np.asarray(fv, dtype=float).reshape(self.NV, -1)[pv]
+        if fp is not None:
+            fp = np.asarray(fp, dtype=float).reshape(self.NP, -1)[pp]
         self.engine = _lib.ImexEngine(ctx, scheme, self.nb, self.dt,
                                       self.mmat, self.amat, self.jmat,
-                                      self.jtmat, self.nus, self.invinds, bci,
-                                      bcv, fv=fv, fp=fp)
+                                      self.jtmat, self.nus,
+                                      self.invinds[pv], bci, bcv, fv=fv, fp=fp)
+        self.engine.set_output_order(pv, pp)
         # ---- solvers: loop (tau = theta*dt), Heun predictor (dt), corr (0) --
         theta = _THETA[scheme]
         taus = [theta*self.dt] if scheme == 'imexeuler' \
@@ -132,10 +158,13 @@ class DeviceImex(object):
         for tau in taus:
             F1 = sps.csr_matrix((Mp.data + tau*Arp.data, Mp.indices,
                                  Mp.indptr), shape=Mp.shape)
-            mpd = None if mp_diag is None or tau == 0. else mp_diag
+            mpd = None if mp_diag is None or tau == 0. else \
+                np.asarray(mp_diag)[pp]
             if hierarchy is None:
-                sd = F1.diagonal() + tau*numean*A0p.diagonal()
-                S = hostsetup.lumped_schur(sd, J)
+                # Schur approximation J Z J.T of the mean member's loop matrix
+                Fm = sps.csr_matrix((F1.data + tau*numean*A0p.data,
+                                     F1.indices, F1.indptr), shape=F1.shape)
+                S = hostsetup.poly_schur(Fm, J, k=schur_poly)
                 hierarchy = hostsetup.sa_amg_hierarchy(S,
                                                        coarse_max=coarse_max)
             s, info = hostsetup.make_saddle_solver(
@@ -148,21 +177,31 @@ class DeviceImex(object):
         self.engine.set_solvers(*self.solvers)
 
     def set_forcing(self, B, U):
-        self.engine.set_forcing(B, U)
+        B = np.asarray(B, dtype=float).reshape(self.NV, -1)
+        self.engine.set_forcing(B[self.pv], U)
 
     def set_state(self, v0, p0=None):
+        v0 = np.asarray(v0, dtype=float).reshape(self.NV, -1)[self.pv]
+        if p0 is not None:
+            p0 = np.asarray(p0, dtype=float).reshape(self.NP, -1)[self.pp]
         self.engine.set_state(v0, p0)
 
     def run(self, nsteps, **kw):
         return self.engine.run(nsteps, **kw)
 
     def state(self):
-        return self.engine.state()
+        v, p = self.engine.state()
+        return v[self.ipv], p[self.ipp]
 
-    def snapshots(self):
-        """(nsnap, NV, nb) velocities and (nsnap, NP, nb) pressures"""
-        s = self.engine.snapshots()
+    def snapshots(self, copy=True):
+        """(nsnap, NV, nb) velocities and (nsnap, NP, nb) pressures in the
+        caller's numbering; ``copy=False``: views of the pinned host mirror
+        (valid until the next run)"""
+        s = self.engine.snapshots() if copy else self.engine.snapshots_view()
         return s[:, :self.NV, :], s[:, self.NV:, :]
+
+    def reserve_snapshots(self, nsnap):
+        self.engine.reserve_snapshots(nsnap)
 
     def stats(self):
         return self.engine.stats()
@@ -177,7 +216,7 @@ def _run_imex(scheme, trange=None, inivel=None, inip=None, M=None, A=None,
               J=None, f_tdp=None, g_tdp=None, scalep=-1., V=None,
               invinds=None, dbcinds=None, dbcvals=None, savevp=None,
               check_ff_maxv=1e8, ntimeslices=10, tol=1e-12, maxit=400,
-              guess=8, cheb_steps=3, f_vdp='convection', ctx=None,
+              guess=16, cheb_steps=5, f_vdp='convection', ctx=None,
               return_engine=False, **kw):
     if f_vdp != 'convection' and f_vdp is not None:
         raise NotImplementedError(

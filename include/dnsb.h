@@ -123,11 +123,22 @@ int dnsb_solver_add_velocity_level(dnsb_solver *s, dnsb_csr *amat, dnsb_csr *pma
  * (scaled pressure mass matrix, the Stokes/Oseen choice) */
 int dnsb_solver_set_schur_mass(dnsb_solver *s, const double *mp_dinv,
                                const double *mp_scale);
+/* least-squares-commutator Schur approximation for stiffness dominated blocks
+ * (Stokes, Oseen/Picard, Newton; stokes_navier_utils.py:401,458,497):
+ *   Sh^-1 = L^-1 (J Du^-1 F Du^-1 JT) L^-1,   L = J Du^-1 JT,
+ * `du_inv` = 1/diag(velocity mass matrix) (nv); the Schur levels added before
+ * must be the hierarchy of L. */
+int dnsb_solver_set_schur_lsc(dnsb_solver *s, const double *du_inv);
 /* solve for nb members; x0 may be NULL (zero initial guess); vp has
  * (nv+np)*nb entries.  iters/relres: per-member outputs (may be NULL). */
 int dnsb_solver_solve(dnsb_solver *s, const double *rhsv, const double *rhsp,
                       const double *x0, double *vp, double tol, int maxit,
                       int *iters, double *relres);
+
+/* z = P^-1 r: one application of the block-triangular preconditioner to host
+ * vectors ((nv+np)*nb); used by the tests to check the multigrid / Schur
+ * pieces against a numpy restatement */
+int dnsb_solver_apply_prec(dnsb_solver *s, const double *r, double *z);
 
 /* ---- device-resident IMEX time stepping ----------------------------------
  * CNAB (time_int_utils.py:23-145), SBDF2 (:260-355) incl. the Heun start
@@ -171,8 +182,23 @@ int dnsb_imex_get_state(dnsb_imex *e, double *v, double *p);
 int dnsb_imex_num_snapshots(dnsb_imex *e);
 /* forget the stored snapshots (the next run records from the current state) */
 int dnsb_imex_reset_snapshots(dnsb_imex *e);
-/* snapshots as (nsnap, nv+np, nb) */
+/* snapshots as (nsnap, nv+np, nb), rows in output order */
 int dnsb_imex_get_snapshots(dnsb_imex *e, double *out);
+/* Output row order of the snapshots: output row of device row i is vmap[i]
+ * (velocity, nv entries) / pmap[i] (pressure, np entries); NULL = identity.
+ * The host-side mirror of the reference API numbers the unknowns along a
+ * space-filling curve on the device (locality of the SpMM gathers) and uses
+ * this map to hand trajectories back in the caller's numbering
+ * (the `savevp(appndbcs(v_n, bcs_n), p_n, time)` hook of
+ * time_int_utils.py:143). */
+int dnsb_imex_set_output_order(dnsb_imex *e, const int32_t *vmap, const int32_t *pmap);
+/* Snapshots are mirrored into pinned host memory by asynchronous D2H copies on
+ * a second stream while the integration runs.  `reserve` allocates the mirror
+ * ahead of time (nsnap snapshots); `snapshots_host` waits for the copies and
+ * returns the mirror itself (valid until the next reserve/run/destroy): a
+ * zero-copy view for the ctypes caller. */
+int dnsb_imex_reserve_snapshots(dnsb_imex *e, int nsnap);
+int dnsb_imex_snapshots_host(dnsb_imex *e, const double **ptr, int *nsnap);
 /* solver statistics of the last run: total FGMRES iterations (max over
  * members per solve, summed over the loop solves), number of loop solves,
  * relative residual of the last solve (max over members) */

@@ -204,3 +204,89 @@ def test_ensemble_members_equal_single_runs(cyl1, ctx):
                              inip=v0[0.0]['p'], return_final_vp=True, **sd)
         assert _rel(V[:, m:m+1], ref[0]) < 1e-8, m
         assert _rel(P[:, m:m+1], ref[1]) < 1e-7, m
+
+
+# ---------------------------------------------------------------------------
+# committed golden fixtures (tests/golden/, generated by make_golden.py)
+# ---------------------------------------------------------------------------
+import os                                                    # noqa: E402
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_golden_convection_device(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    g = np.load(os.path.join(GOLD, 'convection_cyl1.npz'))
+    V = cyl1[0]['V']
+    rng = np.random.default_rng(int(g['seed']))
+    u = rng.standard_normal(V.dim())
+    w = rng.standard_normal(V.dim())
+    assert _rel(dts.get_convvec(V=V, u0_vec=u).ravel(), g['c_uu']) < 1e-13
+    c2 = dts.get_convvec(V=V, u0_vec=u, uone_utwo_same=False, utwo_vec=w)
+    assert _rel(c2.ravel(), g['c_uw']) < 1e-13
+    N1, N2, f3 = dts.get_convmats(u0_vec=u, V=V)
+    assert _rel(N1@w, g['n1_times_w']) < 1e-13
+    assert _rel(N2@w, g['n2_times_w']) < 1e-13
+    assert _rel(np.ravel(f3), g['f3']) < 1e-13
+
+
+def test_golden_cnab_and_sbdf2_device(cyl1, ctx):
+    """BASELINE config 1 against the committed trajectory (tol 1e-8 per step)"""
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    femp, sm, rhsd = cyl1
+    g = np.load(os.path.join(GOLD, 'cnab_cyl1_re60.npz'))
+    got = snu.solve_nse(t0=0., tE=16./512, Nts=16, start_ssstokes=True,
+                        return_vp_dict=True, **soldict(femp, sm, rhsd))
+    for k, t in enumerate(g['t']):
+        assert _rel(got[float(t)]['v'], g['v'][:, k:k+1]) < 1e-8, t
+        if k > 0:
+            assert _rel(got[float(t)]['p'], g['p'][:, k:k+1]) < 1e-8, t
+    g = np.load(os.path.join(GOLD, 'sbdf2_cyl1_re60.npz'))
+    got = snu.solve_nse(t0=0., tE=16./512, Nts=16, start_ssstokes=True,
+                        return_vp_dict=True, time_int_scheme='sbdf2',
+                        **soldict(femp, sm, rhsd))
+    for k, t in enumerate((4./512, 16./512)):
+        assert _rel(got[float(t)]['v'], g['v'][:, k:k+1]) < 1e-8, t
+        assert _rel(got[float(t)]['p'], g['p'][:, k:k+1]) < 1e-8, t
+
+
+def test_golden_newton_cn_sweeps_device(cyl1, ctx):
+    """BASELINE config 3 (small): Picard + Newton sweeps with Crank-Nicolson"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    g = np.load(os.path.join(GOLD, 'newtoncn_cyl1_re100.npz'))
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=100,
+                                       scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=1))
+    sd = soldict(femp, sm, rhsd, t0=0., tE=6./512, Nts=6, start_ssstokes=True)
+    traj = snu.solve_nse(return_dictofvelstrs=True, **sd)
+    out = snu.solve_nse(lin_vel_point=traj, treat_nonl_explicit=False,
+                        vel_pcrd_stps=1, vel_nwtn_stps=2,
+                        return_dictofvelstrs=True, verbose=False, **sd)
+    for k, t in enumerate(g['t']):
+        assert _rel(out[float(t)], g['v'][:, k:k+1]) < 1e-8, t
+
+
+def test_golden_dfg_steady_state_device(ctx):
+    """BASELINE config 2: Stokes -> Picard -> Newton on karman2D-rotcyl_lvl1;
+    drag/lift within 1e-6 relative of the oracle, dP likewise"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from oracle import snu as osnu
+    g = np.load(os.path.join(GOLD, 'dfg2d1_lvl1.npz'))
+    femp, sm, rhsd = dnsps.get_sysmats(
+        problem='gen_bccont', nu=1e-3, charvel=.2, scheme='TH', mergerhs=True,
+        meshparams=dict(strtomeshfile='mesh/karman2D-rotcyl_lvl1.xml.gz',
+                        movingwallcntrl=False,
+                        strtophysicalregions='mesh/karman2D-rotcyl_lvl1_'
+                        'facet_region.xml.gz',
+                        strtobcsobs='mesh/karman2D-rotcyl-bm_geo_cntrlbc.json'))
+    v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False,
+                                     **soldict(femp, sm, rhsd))
+    assert _rel(v, g['v']) < 1e-8
+    assert _rel(p, g['p']) < 1e-7
+    cd, cl = osnu.drag_lift(sm['Afull'], sm['JTfull'], femp['V'], v, p,
+                            femp['ldsbcinds'])
+    dp = femp['Q'].eval_at(p, (.15, .2)) - femp['Q'].eval_at(p, (.25, .2))
+    assert abs(-cd - float(g['cd'])) < 1e-6*abs(float(g['cd']))
+    assert abs(-cl - float(g['cl'])) < 1e-6*abs(float(g['cl']))
+    assert abs(dp - float(g['dp'])) < 1e-6*abs(float(g['dp']))

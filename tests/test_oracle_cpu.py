@@ -1,5 +1,7 @@
 """CPU tests: the oracle against the reference's own identities / known answers
  and the host-side FEM shim."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sps
@@ -205,3 +207,45 @@ def test_schaefer_turek_dfg_2d1(lvl):
     assert abs(-cd - 5.57953523384) < 2e-3
     assert abs(-cl - 0.010618948146) < 2e-5
     assert abs(dp - 0.11752016697) < 5e-5
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures (tests/golden/make_golden.py): the oracle must reproduce them
+# ---------------------------------------------------------------------------
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b))/np.linalg.norm(b)
+
+
+def test_golden_convection_oracle(cyl1):
+    g = np.load(os.path.join(GOLD, 'convection_cyl1.npz'))
+    V = cyl1[0]['V']
+    rng = np.random.default_rng(int(g['seed']))
+    u = rng.standard_normal(V.dim())
+    w = rng.standard_normal(V.dim())
+    assert _rel(oconv.convvec(V, u), g['c_uu']) < 1e-13
+    assert _rel(oconv.convvec(V, u, w), g['c_uw']) < 1e-13
+    N1, N2, f3 = oconv.convmats(V, u)
+    assert _rel(N1@w, g['n1_times_w']) < 1e-13
+    assert _rel(N2@w, g['n2_times_w']) < 1e-13
+    assert _rel(np.ravel(f3), g['f3']) < 1e-13
+
+
+def test_golden_cnab_oracle(cyl1):
+    g = np.load(os.path.join(GOLD, 'cnab_cyl1_re60.npz'))
+    femp, sm, rhsd = cyl1
+    ref = osnu.solve_nse(t0=0., tE=16./512, Nts=16, start_ssstokes=True,
+                         return_vp_dict=True, **soldict(femp, sm, rhsd))
+    for k, t in enumerate(g['t']):
+        assert _rel(ref[float(t)]['v'], g['v'][:, k:k+1]) < 1e-11
+        assert _rel(ref[float(t)]['p'], g['p'][:, k:k+1]) < 1e-9
+
+
+def test_golden_dfg_numbers():
+    g = np.load(os.path.join(GOLD, 'dfg2d1_lvl1.npz'))
+    lit = g['literature']
+    assert abs(float(g['cd']) - lit[0]) < 2e-3
+    assert abs(float(g['cl']) - lit[1]) < 2e-5
+    assert abs(float(g['dp']) - lit[2]) < 5e-5
