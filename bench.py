@@ -116,7 +116,8 @@ class ClockSampler(object):
 def _cpu_member_worker(args):
     """CNAB steps of ONE member with the oracle (SuperLU + compiled cell loop);
     returns (steps done, seconds in the step loop)."""
-    (N, Re, nts, palpha, seconds, maxsteps) = args
+    (N, Re, nts, palpha, seconds, maxsteps, nwarm) = args
+    sys.stdout = sys.stderr        # worker process: keep the parent's stdout clean
     import scipy.sparse as sps
     import scipy.sparse.linalg as spsla
     from dolfin_navier_scipy_b200 import problem_setups as dnsps
@@ -146,9 +147,11 @@ def _cpu_member_worker(args):
                     sps.hstack([J, sps.csr_matrix((NP, NP))])], format='csc')
     lu = spsla.factorized(K)
     nfc_c = nfc(v)
-    t, n = 0., 0
+    t, n = 0., -nwarm
     tic = time.perf_counter()
     while n < maxsteps and time.perf_counter() - tic < seconds:
+        if n == 0:
+            tic = time.perf_counter()          # warm-up steps are not timed
         # loop body of `time_int_utils.py:104-143`
         nfc_o, nfc_c = nfc_c, nfc(v)
         rhs = M@v - .5*dt*(A@v) + .5*dt*(3*nfc_c - nfc_o) \
@@ -160,11 +163,11 @@ def _cpu_member_worker(args):
     return n, time.perf_counter() - tic
 
 
-def cpu_reference(args, nworkers, seconds, maxsteps=10**9):
+def cpu_reference(args, nworkers, seconds, maxsteps=10**9, nwarm=3):
     """all host cores: one member per worker process, Re spread over [60,150]"""
     import multiprocessing as mp
     Res = np.linspace(60., 150., max(nworkers, 2))[:nworkers]
-    jobs = [(args.mesh, float(Re), args.nts, 1e-5, seconds, maxsteps)
+    jobs = [(args.mesh, float(Re), args.nts, 1e-5, seconds, maxsteps, nwarm)
             for Re in Res]
     if nworkers == 1:
         res = [_cpu_member_worker(jobs[0])]
@@ -188,11 +191,12 @@ def run_reference(args, rank, world):
         return None
     ncores = os.cpu_count() or 1
     NV, NP = dofs_of(args.mesh)
-    # warm-up + K timed "steps": each step is a bounded sample (one CNAB step
-    # of one member per core); the LU factorisation is set-up, not timed
-    per_step_budget = 30.
-    res = cpu_reference(args, ncores, seconds=per_step_budget,
-                        maxsteps=args.warmup + args.steps)
+    # W untimed warm-up steps, then K timed "steps"; each step is a bounded
+    # sample of the workload: one CNAB step of `ncores` of the 64 members (one
+    # per core) -- throughput per member-step, so it extrapolates linearly;
+    # the LU factorisation is set-up (`tiu:89-91`), not timed
+    res = cpu_reference(args, ncores, seconds=120., maxsteps=args.steps,
+                        nwarm=max(args.warmup, 1))
     nsteps = min(r[0] for r in res)
     tmax = max(r[1] for r in res)
     members = len(res)
@@ -202,13 +206,15 @@ def run_reference(args, rank, world):
                 ms_per_step=1e3*tmax/max(nsteps, 1), higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f64',
                 data='synthetic',
-                config=workload_config(args, members, 1),
+                config=workload_config(args, args.members*world, world),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=ncores,
                                   kind='port',
-                                  sample='{0} members (one per core) x {1} CNAB '
-                                  'steps incl. warm-up, SuperLU solve + compiled '
-                                  'cell loop; factorisation excluded'.
-                                  format(members, nsteps)),
+                                  sample='{0} of the {1} members (one per core) '
+                                  'x {2} CNAB steps after {3} warm-up steps: '
+                                  'SuperLU solve of the prefactorised matrix + '
+                                  'compiled cell loop; factorisation excluded'.
+                                  format(members, args.members*world, nsteps,
+                                         max(args.warmup, 1))),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0,
                          d2h_bytes_per_step=0))
     return line
@@ -376,52 +382,92 @@ def measured_peak():
     return 6650., 'fallback'
 
 
-def roofline_of(kern, info, integ, args):
-    """algorithmic bytes of the dominant kernel / its mean CUDA-event duration
+def _kname(name):
+    return name.strip('()').replace('k_cheb_step_b2', 'k_cheb_step') \
+        .replace('k_cheb_step_b', 'k_cheb_step')
 
-    Byte counts: fused Chebyshev step on F (k_cheb_step):
-    20 B/nnz (fp64 value x2 arrays + int32 column) + 4(n+1) + 56 B per
-    (row, member); plain SpMM (k_spmm): (12|20) B/nnz + 4(n+1) + 8 B per
-    (column, member) + 8 B per (row, member).
-    """
-    peak, which = measured_peak()
-    name = max(kern.items(), key=lambda kv: kv[1][1])[0]
-    cnt, ms = kern[name]
+
+def kernel_bytes(name, info, integ):
+    """ALGORITHMIC bytes of one launch; None if the
+    kernel has no fixed byte count (depends on the Krylov column)"""
     nb = integ.nb
     host = integ._host
     nnzF, n = host['M'].nnz, host['M'].shape[0]
     J = host['J']
+    npp = J.shape[0]
+    name = name.strip('()')
     if name.startswith('k_cheb_step'):
-        bytes_ = 20.*nnzF + 4.*(n + 1) + 56.*n*nb
-    elif name.startswith('k_spmm'):
-        # dominated by the block matrix K = [F JT; J 0] (two value arrays)
+        flags = name.split('<')[1].rstrip('>').split(', ')
+        first, last = flags[1] == 'true', flags[2] == 'true'
+        passes = 7 - (1 if first else 0) - (2 if last else 0)
+        return 20.*nnzF + 4.*(n + 1) + 8.*passes*n*nb
+    if name.startswith('k_spmm'):
+        # the block matrix K = [F JT; J 0] (two value arrays): gather + store
         nnzK = nnzF + 2*J.nnz
-        nt = n + J.shape[0]
-        bytes_ = 20.*nnzK + 4.*(nt + 1) + 16.*nt*nb
-    elif name.startswith('k_cheb_init'):
-        bytes_ = 12.*J.nnz + 4.*(n + 1) + 8.*J.shape[0]*nb + 40.*n*nb
-    elif name.startswith('k_dense_gem'):
-        npp = J.shape[0]
-        bytes_ = 8.*npp*npp + 16.*npp*nb
-    else:
-        bytes_ = float('nan')
+        nt = n + npp
+        return 20.*nnzK + 4.*(nt + 1) + 16.*nt*nb
+    if name.startswith('k_cheb_init'):
+        return 12.*J.nnz + 4.*(n + 1) + 8.*npp*nb + 32.*n*nb
+    if name.startswith('k_dense_gemm'):
+        return 8.*npp*npp + 16.*npp*nb
+    if name.startswith('k_scale_member'):
+        return 16.*(n + npp)*nb
+    if name.startswith('k_convvec'):
+        return None
+    return None
+
+
+def roofline_of(kern, info, integ, args):
+    """roofline of the dominant HBM-bound kernel: algorithmic bytes (DESIGN.md
+    section 5) / mean CUDA-event duration of its launches in the timed step.
+    The dense Schur solve is a DFMA (fp64 CUDA core) kernel: its TFLOP/s are
+    reported beside it."""
+    peak, which = measured_peak()
+    J = integ._host['J']
+    npp, nb = J.shape[0], integ.nb
+    fam = {}
+    for name, (cnt, ms) in kern.items():
+        b = kernel_bytes(name, info, integ)
+        if b is None or name.strip('()').startswith('k_dense_gemm'):
+            continue
+        fam.setdefault(name, (cnt, ms, b))
+    name = max(fam.items(), key=lambda kv: kv[1][1])[0]
+    cnt, ms, bytes_ = fam[name]
     dur = ms*1e-3/cnt
     ach = bytes_/dur/1e9
-    return dict(bound='hbm', kernel=name, achieved=ach, peak=peak,
-                peak_source=which, unit='GB/s', frac=ach/peak, traffic=None,
-                launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
+    out = dict(bound='hbm', kernel=name.strip('()'), achieved=ach, peak=peak,
+               peak_source=which, unit='GB/s', frac=ach/peak, traffic=None,
+               launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
+    dn = [k for k in kern if k.strip('()').startswith('k_dense_gemm')]
+    if dn:
+        c, m = kern[dn[0]]
+        flops = 2.*npp*npp*nb
+        out['dense_schur'] = dict(kernel=dn[0], mean_us=1e3*m/c,
+                                  fp64_tflops=flops/(m*1e-3/c)/1e12,
+                                  fp64_peak_tflops=37.2,
+                                  note='DFMA bound (148 SM x 64 DFMA/clk x '
+                                  '1.965 GHz), no fp64 tensor path')
+    return out
 
 
 def main():
+    # the JSON line must be the only thing on stdout: library notes (e.g. the
+    # reference's own "Note: ..." prints, `dts:236-252`) go to stderr
+    import contextlib
+    out = sys.stdout
+    with contextlib.redirect_stdout(sys.stderr):
+        line = _main()
+    if line is not None:
+        print(json.dumps(line), file=out, flush=True)
+
+
+def _main():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
-        line = run_reference(args, rank, world)
-        if line is not None:
-            print(json.dumps(line))
-        return
+        return run_reference(args, rank, world)
     import torch
     import torch.distributed as dist
     if world > 1:
@@ -438,11 +484,10 @@ def main():
             kind='port',
             sample='1 member (Re=60), {0} CNAB steps in {1:.1f} s: SuperLU '
             'solve + compiled cell loop, factorisation excluded'.format(n, t))
-    if rank == 0:
-        print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == '__main__':

@@ -53,6 +53,7 @@ SIGNATURES = {
     'dnsb_solver_set_schur_lsc': (_i, [_vp, c_dbl_p]),
     'dnsb_solver_solve': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, _d, _i,
                                c_int_p, c_dbl_p]),
+    'dnsb_solver_update_fvalues': (_i, [_vp, c_dbl_p]),
     'dnsb_solver_apply_prec': (_i, [_vp, c_dbl_p, c_dbl_p]),
     'dnsb_imex_create': (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, c_dbl_p,
                               c_int_p, _i, _i, c_int_p, c_dbl_p, c_dbl_p,
@@ -357,6 +358,13 @@ class SaddleSolver(object):
         self.ctx.check(self.ctx.lib.dnsb_solver_apply_prec(self.h, _dp(r),
                                                            _dp(z)))
         return z
+
+    def update_fvalues(self, vals1):
+        vals1 = _f64(vals1)
+        if vals1.size != self.fmat.nnz:
+            raise ValueError('values do not match the pattern of F')
+        self.ctx.check(self.ctx.lib.dnsb_solver_update_fvalues(self.h,
+                                                               _dp(vals1)))
 
     def set_schur_lsc(self, du_inv):
         du_inv = _f64(du_inv)

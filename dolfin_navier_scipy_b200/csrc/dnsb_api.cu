@@ -73,7 +73,7 @@ static void mdot_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vs
   LAUNCH(ctx, k_mdot_b, rc.nblocks, rc.threads, smem, V, vstride, nvec, w, n, nb, rc.rpb,
          rc.rows_per_block, partial);
   const int count = (nvec + 1) * nb;
-  LAUNCH(ctx, k_reduce_partials2, cdiv(count, 32), 256, 0, (const double *)partial, rc.nblocks,
+  LAUNCH(ctx, k_reduce_partials2, cdiv(count, 32), 1024, 0, (const double *)partial, rc.nblocks,
          count, h);
 }
 
@@ -146,6 +146,7 @@ static inline bool batched_ok(const dnsb_csr *A, int nb) {
 // but not fewer than ~2 CTAs per SM
 static int g_rows_per_cta = 4;
 static int g_dense_ctas_per_sm = 2;
+static int g_graphs = 1;
 static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
   const long total = (long)nrows * nb;
   long gpc = std::max<long>(1, ((long)g_rows_per_cta * nb) / SPB_THREADS);
@@ -153,6 +154,16 @@ static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
   while (gpc > 1 && (groups + gpc - 1) / gpc < 2L * ctx->sm_count) gpc /= 2;
   return (int)gpc;
 }
+// member-pair kernels (double2 elements): nb even
+static int g_pair = 1;
+static inline bool pair_ok(const dnsb_csr *A, int nb) {
+  return g_pair && batched_ok(A, nb) && nb % 2 == 0;
+}
+static inline unsigned spb2_grid(int nrows, int nb) {
+  return cdiv((size_t)nrows * (nb / 2), SPB_THREADS);
+}
+#define D2C(p) reinterpret_cast<const double2 *>(p)
+#define D2(p) reinterpret_cast<double2 *>(p)
 static inline unsigned spb_grid(int nrows, int nb, int gpc) {
   return cdiv((size_t)nrows * nb, (size_t)SPB_THREADS * gpc);
 }
@@ -162,7 +173,14 @@ static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
                      const double *x, const double *z, double *y, int nb,
                      double alpha, double beta) {
   if (A->nrows == 0) return;
-  if (batched_ok(A, nb)) {
+  if (pair_ok(A, nb)) {
+    if (A->has2 && coef)
+      LAUNCH(ctx, k_spmm_b2<true>, spb2_grid(A->nrows, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
+             D2C(z), D2(y), nb, alpha, beta);
+    else
+      LAUNCH(ctx, k_spmm_b2<false>, spb2_grid(A->nrows, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
+             D2C(z), D2(y), nb, alpha, beta);
+  } else if (batched_ok(A, nb)) {
     const int gpc = spb_gpc(ctx, A->nrows, nb);
     if (A->has2 && coef)
       LAUNCH(ctx, k_spmm_b<true>, spb_grid(A->nrows, nb, gpc), SPB_THREADS, 0, A->view(), coef,
@@ -216,6 +234,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (!ctx) return -3;
   ctx->device = device;
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
+  if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
+  if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
   if (const char *ev = getenv("DNSB_DENSE_CTAS_PER_SM")) g_dense_ctas_per_sm = std::max(1, atoi(ev));
   *out = ctx;   // returned even on failure so that the message can be read
   DNSB_CK(ctx, cudaSetDevice(device));
@@ -561,9 +581,15 @@ struct dnsb_solver {
   int expect_its = 0;
   // user-facing staging
   DBuf<double> sb, sx;
+  // CUDA graphs of the Arnoldi steps (one per column j), valid for one tol
+  std::vector<cudaGraphExec_t> igraph;
+  std::vector<int> igraph_launches;
+  double igraph_tol = -1.0;
   long long stat_iters = 0, stat_solves = 0, stat_launched = 0;
   double stat_max_relres = 0;
 };
+
+static void solver_drop_graphs(dnsb_solver *s);
 
 static int find_diagpos(dnsb_ctx *ctx, const dnsb_csr *A, std::vector<int> &dp) {
   dp.assign(A->nrows, -1);
@@ -714,6 +740,8 @@ extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
+  for (cudaGraphExec_t g : s->igraph) if (g) cudaGraphExecDestroy(g);
+  s->igraph.clear();
   csr_free(s->K);
   s->coef.release(); s->dinv.release(); s->diagpos.release();
   s->Vb.release(); s->Zb.release(); s->w.release();
@@ -737,6 +765,7 @@ static int solver_add_level(dnsb_solver *s, int block, dnsb_csr *amat, dnsb_csr 
   dnsb_ctx *ctx = s->ctx;
   DNSB_CK(ctx, cudaSetDevice(ctx->device));
   std::vector<MgLevel *> &lv = block == 0 ? s->levels : s->vlevels;
+  solver_drop_graphs(s);   // the preconditioner changes: captured launch sequences are stale
   int nexpect;
   if (lv.empty()) {
     DNSB_REQUIRE(ctx, block == 0, "velocity level 0 is the matrix F itself");
@@ -809,6 +838,7 @@ extern "C" int dnsb_solver_set_velocity_transfer(dnsb_solver *s, dnsb_csr *pmat,
   DNSB_REQUIRE(ctx, pmat && rmat && pmat->nrows == s->nv && rmat->ncols == s->nv &&
                rmat->nrows == pmat->ncols, "inconsistent velocity transfer operators");
   DNSB_REQUIRE(ctx, s->vlevels.size() == 1, "velocity hierarchy already built");
+  solver_drop_graphs(s);
   s->vlevels[0]->P = pmat; s->vlevels[0]->R = rmat;
   s->vlevels[0]->kind = MG_MULTI;
   return 0;
@@ -831,6 +861,7 @@ extern "C" int dnsb_solver_set_schur_mass(dnsb_solver *s, const double *mp_dinv,
   DNSB_CK(ctx, s->mp_dinv.upload(mp_dinv, s->np, ctx->stream));
   DNSB_CK(ctx, s->mp_scale.upload(mp_scale, s->nb, ctx->stream));
   s->has_mass = true;
+  solver_drop_graphs(s);
   return 0;
 }
 
@@ -845,6 +876,7 @@ extern "C" int dnsb_solver_set_schur_lsc(dnsb_solver *s, const double *du_inv) {
   DNSB_CK(ctx, s->lsc_t1.alloc(nvb)); DNSB_CK(ctx, s->lsc_t2.alloc(nvb));
   DNSB_CK(ctx, s->lsc_p1.alloc(npb)); DNSB_CK(ctx, s->lsc_p2.alloc(npb));
   s->has_lsc = true;
+  solver_drop_graphs(s);
   return 0;
 }
 
@@ -897,8 +929,12 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
   const bool has2 = A->has2 && coef;
   double *dfirst = k == 1 ? z : d0;
   const int gpc = batched ? spb_gpc(ctx, n, nb) : 1;
+  const bool pair = pair_ok(A, nb) && (!C || pair_ok(C, nb));
   if (C) {
-    if (batched)
+    if (pair)
+      LAUNCH(ctx, k_cheb_init_b2, spb2_grid(n, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
+             D2C(dinv), D2(res), D2(dfirst), nb, 1.0 / theta);
+    else if (batched)
       LAUNCH(ctx, k_cheb_init_b, spb_grid(n, nb, gpc), SPB_THREADS, 0, C->view(), zc, r, dinv, res,
              dfirst, nb, gpc, 1.0 / theta);
     else if (nb == 1)
@@ -932,7 +968,21 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
       else if (last) LAUNCH(ctx, (KERN<__VA_ARGS__, false, true>), GRID, BLK, 0, CHEB_ARGS);          \
       else LAUNCH(ctx, (KERN<__VA_ARGS__, false, false>), GRID, BLK, 0, CHEB_ARGS);                   \
     } while (0)
-    if (batched) {
+    if (pair) {
+#define CHEB_ARGS_P A->view(), coef, D2C(dc), D2C(dinv), D2(res), D2(dn), D2(z), nb, c1, c2
+#define CHEB_DISPATCH_P(HAS2)                                                                       \
+    do {                                                                                            \
+      const unsigned grid_ = spb2_grid(n, nb);                                                      \
+      if (first && last) LAUNCH(ctx, (k_cheb_step_b2<HAS2, true, true>), grid_, SPB_THREADS, 0, CHEB_ARGS_P);   \
+      else if (first) LAUNCH(ctx, (k_cheb_step_b2<HAS2, true, false>), grid_, SPB_THREADS, 0, CHEB_ARGS_P);     \
+      else if (last) LAUNCH(ctx, (k_cheb_step_b2<HAS2, false, true>), grid_, SPB_THREADS, 0, CHEB_ARGS_P);      \
+      else LAUNCH(ctx, (k_cheb_step_b2<HAS2, false, false>), grid_, SPB_THREADS, 0, CHEB_ARGS_P);               \
+    } while (0)
+      if (has2) CHEB_DISPATCH_P(true);
+      else CHEB_DISPATCH_P(false);
+#undef CHEB_DISPATCH_P
+#undef CHEB_ARGS_P
+    } else if (batched) {
       if (has2) CHEB_DISPATCH_B(true);
       else CHEB_DISPATCH_B(false);
     } else if (nb == 1) {
@@ -1064,6 +1114,86 @@ static int apply_prec(dnsb_solver *s, const double *r, double *z) {
   return 0;
 }
 
+// One Arnoldi step of FGMRES (column j): z_j = P^-1 v_j, w = K z_j, Gram-Schmidt
+// against v_0..v_j, Givens update, v_{j+1}.  All arguments are fixed device
+// buffers, so the launch sequence of a column is captured once as a CUDA graph
+// and replayed (one graph launch instead of ~20 kernel launches: the single
+// trajectory is launch-latency bound).
+static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
+  dnsb_ctx *ctx = s->ctx;
+  const int nb = s->nb, ntot = s->ntot;
+  const size_t ntb = (size_t)ntot * nb;
+  const RedCfg &rc = s->rc;
+  const double *coef = s->has_coef ? s->coef.p : nullptr;
+  double *Vj = s->Vb.p + (size_t)j * ntb;
+  double *Zj = s->Zb.p + (size_t)j * ntb;
+  if (apply_prec(s, Vj, Zj)) return -1;
+  spmm_dev(ctx, s->K, coef, Zj, nullptr, s->w.p, nb, 1.0, 0.0);
+  // classical Gram-Schmidt; a second pass (CGS2) for long recurrences,
+  // where one pass loses the orthogonality of the basis and FGMRES stalls
+  // (the Oseen/Newton systems of the steady solver need 150-300 iterations)
+  const bool reorth = (nb == 1) || j >= 16;
+  double *Vn = s->Vb.p + (size_t)(j + 1) * ntb;
+  mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb, s->partial.p, s->gs.h);
+  LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
+         (const double *)s->gs.h, (const double *)s->w.p, Vn, ntot, nb, rc.rpb,
+         rc.rows_per_block, s->partial2.p);
+  const double *unscaled = Vn;
+  if (reorth) {
+    mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, Vn, ntot, nb, s->partial.p, s->gh2.p);
+    LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
+           (const double *)s->gh2.p, (const double *)Vn, s->w.p, ntot, nb, rc.rpb,
+           rc.rows_per_block, s->partial2.p);
+    LAUNCH(ctx, k_axpby, cdiv((size_t)(j + 1) * nb, 256), 256, 0, 1.0, (const double *)s->gs.h, 1.0,
+           (const double *)s->gh2.p, s->gs.h, (size_t)(j + 1) * nb);
+    unscaled = s->w.p;
+  }
+  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 1024, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
+  LAUNCH(ctx, k_gmres_givens, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p,
+         1, nb, j, tol);
+  LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, unscaled, (const double *)s->gs.invh, Vn,
+         (size_t)ntot, nb);
+  return 0;
+}
+
+static void solver_drop_graphs(dnsb_solver *s) {
+  if (s->igraph.empty() && s->mr <= 0) return;
+  for (cudaGraphExec_t g : s->igraph) if (g) cudaGraphExecDestroy(g);
+  s->igraph.assign(s->mr, nullptr);
+  s->igraph_launches.assign(s->mr, 0);
+}
+
+static int gmres_iteration(dnsb_solver *s, int j, double tol) {
+  dnsb_ctx *ctx = s->ctx;
+  if (!g_graphs || ctx->prof) return gmres_iteration_launch(s, j, tol);
+  if (s->igraph.empty() || s->igraph_tol != tol) {
+    solver_drop_graphs(s);
+    s->igraph_tol = tol;
+  }
+  if (!s->igraph[j]) {
+    const long long l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    DNSB_CK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = gmres_iteration_launch(s, j, tol);
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc || e != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      if (!rc) DNSB_CK(ctx, e);
+      return -1;
+    }
+    s->igraph_launches[j] = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t e2 = cudaGraphInstantiate(&ex, graph, 0);
+    cudaGraphDestroy(graph);
+    DNSB_CK(ctx, e2);
+    s->igraph[j] = ex;
+  }
+  DNSB_CK(ctx, cudaGraphLaunch(s->igraph[j], ctx->stream));
+  ctx->launches += s->igraph_launches[j];
+  return 0;
+}
+
 static int read_flags(dnsb_solver *s) {
   dnsb_ctx *ctx = s->ctx;
   DNSB_CK(ctx, cudaMemcpyAsync(s->h_flags, s->gs.flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1081,7 +1211,7 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
   const double *coef = s->has_coef ? s->coef.p : nullptr;
   // |b|
   LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, b, b, ntot, nb, rc.rpb, s->partial2.p);
-  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
+  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 1024, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
   LAUNCH(ctx, k_set_bnorm, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p, 1, nb);
   if (zero_guess) DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
   int total = 0;
@@ -1094,7 +1224,7 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
     else
       spmm_dev(ctx, s->K, coef, x, b, V0, nb, -1.0, 1.0);
     LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, V0, V0, ntot, nb, rc.rpb, s->partial2.p);
-    LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
+    LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 1024, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
     LAUNCH(ctx, k_gmres_begin, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p,
            1, nb, tol, first ? 1 : 0);
     LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, V0, s->gs.invh, V0, (size_t)ntot, nb);
@@ -1104,34 +1234,7 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
     int j = 0;
     bool alldone = false;
     for (; j < mr && total < maxit; ++j, ++total) {
-      double *Vj = s->Vb.p + (size_t)j * ntb;
-      double *Zj = s->Zb.p + (size_t)j * ntb;
-      if (apply_prec(s, Vj, Zj)) return -1;
-      spmm_dev(ctx, s->K, coef, Zj, nullptr, s->w.p, nb, 1.0, 0.0);
-      // classical Gram-Schmidt; a second pass (CGS2) for long recurrences,
-      // where one pass loses the orthogonality of the basis and FGMRES stalls
-      // (the Oseen/Newton systems of the steady solver need 150-300 iterations)
-      const bool reorth = (nb == 1) || j >= 16;
-      double *Vn = s->Vb.p + (size_t)(j + 1) * ntb;
-      mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb, s->partial.p, s->gs.h);
-      LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
-             (const double *)s->gs.h, (const double *)s->w.p, Vn, ntot, nb, rc.rpb,
-             rc.rows_per_block, s->partial2.p);
-      const double *unscaled = Vn;
-      if (reorth) {
-        mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, Vn, ntot, nb, s->partial.p, s->gh2.p);
-        LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
-               (const double *)s->gh2.p, (const double *)Vn, s->w.p, ntot, nb, rc.rpb,
-               rc.rows_per_block, s->partial2.p);
-        LAUNCH(ctx, k_axpby, cdiv((size_t)(j + 1) * nb, 256), 256, 0, 1.0, (const double *)s->gs.h, 1.0,
-               (const double *)s->gh2.p, s->gs.h, (size_t)(j + 1) * nb);
-        unscaled = s->w.p;
-      }
-      LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
-      LAUNCH(ctx, k_gmres_givens, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p,
-             1, nb, j, tol);
-      LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, unscaled, (const double *)s->gs.invh, Vn,
-             (size_t)ntot, nb);
+      if (gmres_iteration(s, j, tol)) return -1;
       // convergence poll: skipped while far from the expected iteration count
       if (total + 1 >= expect - 1 || j + 1 == mr || total + 1 == maxit) {
         if (read_flags(s)) return -1;
@@ -1190,6 +1293,42 @@ extern "C" int dnsb_solver_solve(dnsb_solver *s, const double *rhsv, const doubl
     if (iters) iters[m] = it[m];
     if (relres) relres[m] = bn[m] > 0 ? res[m] / bn[m] : 0.0;
   }
+  return 0;
+}
+
+// K.v1[kpos(i, k)] = F.v1[k] for the entries k of row i of F (K row i holds the
+// F entries first, then the JT entries)
+__global__ void k_copy_f_into_k(CsrDev F, const int *__restrict__ kindptr,
+                                double *__restrict__ kv1) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= F.nrows) return;
+  const int f0 = F.indptr[row], f1 = F.indptr[row + 1], k0 = kindptr[row];
+  for (int k = f0 + lane; k < f1; k += 32) kv1[k0 + (k - f0)] = F.v1[k];
+}
+
+// New values of the velocity block on the unchanged pattern (Picard/Newton
+// and Crank-Nicolson sweeps: stokes_navier_utils.py:1484-1512 builds and
+// factorises a new matrix every step; here only the values move, the
+// preconditioner set-up -- Schur approximation, Chebyshev bounds -- is kept).
+extern "C" int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1) {
+  if (!s) return -2;
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_REQUIRE(ctx, vals1 != nullptr, "null values");
+  DNSB_REQUIRE(ctx, !s->F->has2, "matrices with two value arrays are updated through their coefficients");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  dnsb_csr *F = s->F;
+  DNSB_CK(ctx, cudaMemcpyAsync(F->v1.p, vals1, (size_t)F->nnz * sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));   // host buffer is borrowed
+  std::copy(vals1, vals1 + F->nnz, F->h_v1.begin());
+  LAUNCH(ctx, k_copy_f_into_k, cdiv((size_t)F->nrows * 32, 256), 256, 0, F->view(),
+         (const int *)s->K->indptr.p, s->K->v1.p);
+  const size_t nvb = (size_t)s->nv * s->nb;
+  LAUNCH(ctx, k_diag_inv, cdiv(nvb, 256), 256, 0, F->view(), s->diagpos.p,
+         (const double *)nullptr, s->dinv.p, s->nb);
+  s->expect_its = 0;
+  DNSB_CK(ctx, cudaGetLastError());
   return 0;
 }
 
@@ -1533,8 +1672,11 @@ __global__ void k_inv_norm(const double *__restrict__ n2, const double *__restri
   inv[m] = (v > eps * ref[m] && v > 0.0) ? 1.0 / sqrt(v) : 0.0;
 }
 
-// append the direction d (ntb, destroyed) to the projection space
-static int proj_add(dnsb_imex *e, double *d) {
+// append the direction d (ntb, destroyed) to the projection space; `npass`
+// Gram-Schmidt passes: the image of a correction x - x0 is orthogonal to the
+// space already (up to the solver tolerance), one pass cleans it; a raw
+// solution (rebuild) lies almost inside the space and needs two
+static int proj_add(dnsb_imex *e, double *d, int npass) {
   dnsb_ctx *ctx = e->ctx;
   const int nb = e->nb, ntot = e->nv + e->np;
   const size_t ntb = (size_t)ntot * nb;
@@ -1545,7 +1687,7 @@ static int proj_add(dnsb_imex *e, double *d) {
   spmm_dev(ctx, sl->K, coef, d, nullptr, w, nb, 1.0, 0.0);
   const int k = e->pcnt;
   // |K d|^2 before the orthogonalisation (reference for the breakdown test)
-  for (int pass = 0; pass < 2 && k > 0; ++pass) {
+  for (int pass = 0; pass < npass && k > 0; ++pass) {
     mdot_dev(ctx, rc, e->bq.p, ntb, k, w, ntot, nb, e->partialh.p, e->gr.p);
     if (pass == 0)
       DNSB_CK(ctx, cudaMemcpyAsync(e->normout.p, e->gr.p + (size_t)k * nb, nb * sizeof(double),
@@ -1564,7 +1706,7 @@ static int proj_add(dnsb_imex *e, double *d) {
            rc.rpb, e->normpart.p);
   }
   // |w|^2 of the orthogonalised image
-  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)e->normpart.p, rc.nblocks, nb,
+  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 1024, 0, (const double *)e->normpart.p, rc.nblocks, nb,
          e->pinv.p + nb);
   if (k == 0)
     DNSB_CK(ctx, cudaMemcpyAsync(e->normout.p, e->pinv.p + nb, nb * sizeof(double),
@@ -1606,7 +1748,7 @@ static int imex_push_history(dnsb_imex *e, int guess) {
     else
       LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
              (const double *)e->x0.p, e->pd0.p, ntb);
-    return proj_add(e, e->pd0.p);
+    return proj_add(e, e->pd0.p, e->pcnt == 0 ? 2 : 1);
   }
   // space full: rebuild it from the last K raw solutions, oldest first
   e->pcnt = 0;
@@ -1615,7 +1757,7 @@ static int imex_push_history(dnsb_imex *e, int guess) {
     const int slot = (e->hist_pos - q) % K;
     DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->xh.p + (size_t)slot * ntb, ntb * sizeof(double),
                                  cudaMemcpyDeviceToDevice, ctx->stream));
-    int rc = proj_add(e, e->pd0.p);
+    int rc = proj_add(e, e->pd0.p, 2);
     if (rc) return rc;
   }
   return 0;
@@ -1627,7 +1769,7 @@ static int imex_blowup(dnsb_imex *e, const double *vc, double maxv, bool *bad) {
   const int nb = e->nb;
   RedCfg rcn = red_cfg(ctx, e->nv, nb);
   LAUNCH(ctx, k_dot1, rcn.nblocks, rcn.threads, rcn.smem, vc, vc, e->nv, nb, rcn.rpb, e->normpart.p);
-  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 256, 0, (const double *)e->normpart.p, rcn.nblocks, nb, e->normout.p);
+  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 1024, 0, (const double *)e->normpart.p, rcn.nblocks, nb, e->normout.p);
   std::vector<double> hn(nb);
   DNSB_CK(ctx, cudaMemcpyAsync(hn.data(), e->normout.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1976,7 +2118,7 @@ extern "C" int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev) {
   const int nchunks = 32;
   DNSB_CK(ctx, part.alloc((size_t)nchunks * ns * ns));
   LAUNCH(ctx, k_gram_partial, dim3(nchunks, ns * ns), 256, 256 * sizeof(double), e->snaps.p, ntb, MX.p, ns, nvb, part.p);
-  LAUNCH(ctx, k_reduce_partials2, cdiv((size_t)ns * ns, 32), 256, 0, (const double *)part.p, nchunks, ns * ns, g_dev);
+  LAUNCH(ctx, k_reduce_partials2, cdiv((size_t)ns * ns, 32), 1024, 0, (const double *)part.p, nchunks, ns * ns, g_dev);
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   MX.release(); part.release();
   DNSB_CK(ctx, cudaGetLastError());

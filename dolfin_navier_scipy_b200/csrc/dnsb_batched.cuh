@@ -282,3 +282,134 @@ k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
     partial2[(size_t)blockIdx.x * nb + m] = s;
   }
 }
+
+// ---------------------------------------------------------------------------
+// Two members per thread (nb even): the same kernels on double2 elements,
+// x2[i*(nb/2) + mp] = (x[i*nb + 2mp], x[i*nb + 2mp + 1]).  The ncu source page
+// of the one-member kernels (profiles/r1c) shows ~25 issued instructions per
+// (entry, warp), two thirds of them address arithmetic, shared-memory reads of
+// the staged entry and loop control -- all of it independent of the member.
+// With a member pair per thread a warp covers 64 members per pass: that
+// overhead, and the shared-memory wavefronts of the entries, are halved per
+// member; the gather becomes one LDG.128.  Sums run in the same CSR order:
+// results are bit-identical to the one-member kernels.
+// ---------------------------------------------------------------------------
+#define SPB2_ROWMAP()                                                           \
+  const int nb2 = nb >> 1;                                                      \
+  const long total_ = (long)A.nrows * nb2;                                      \
+  const int lane = threadIdx.x & 31;                                            \
+  const long t_ = (long)blockIdx.x * SPB_THREADS + threadIdx.x;                 \
+  const long tw0_ = t_ - lane;                                                  \
+  if (tw0_ >= total_) return;                                                   \
+  const bool valid = t_ < total_;                                               \
+  const int row = valid ? (int)((unsigned)t_ / (unsigned)nb2) : A.nrows - 1;    \
+  const int mp = valid ? (int)(t_ - (long)row * nb2) : 0;                       \
+  const int wrow0 = __shfl_sync(0xffffffffu, row, 0);                           \
+  const int wrow1 = __shfl_sync(0xffffffffu, row, 31);
+
+template <bool HAS2>
+__device__ __forceinline__ double2
+spb2_rowdot(const CsrDev &A, double2 cm, const double2 *__restrict__ xm, int nb2,
+            int row, bool valid, int wrow0, int wrow1, int lane, double2 *sv2,
+            double *sv1, int *soff) {
+  const int e_lo = A.indptr[wrow0], e_hi = A.indptr[wrow1 + 1];
+  const int k0 = valid ? A.indptr[row] : 0;
+  const int k1 = valid ? A.indptr[row + 1] : 0;
+  double ax = 0.0, ay = 0.0;
+  for (int base = e_lo; base < e_hi; base += SPB_CAP) {
+    const int cnt = min(SPB_CAP, e_hi - base);
+    __syncwarp();
+    for (int e = lane; e < cnt; e += 32) {
+      soff[e] = A.indices[base + e] * nb2;
+      if (HAS2) sv2[e] = make_double2(A.v1[base + e], A.v2[base + e]);
+      else sv1[e] = A.v1[base + e];
+    }
+    __syncwarp();
+    int k = max(k0, base) - base;
+    const int kend = min(k1, base + cnt) - base;
+    for (; k + 4 <= kend; k += 4) {
+      const double2 x0 = xm[soff[k]], x1 = xm[soff[k + 1]];
+      const double2 x2 = xm[soff[k + 2]], x3 = xm[soff[k + 3]];
+      if (HAS2) {
+        const double2 a0 = sv2[k], a1 = sv2[k + 1], a2 = sv2[k + 2], a3 = sv2[k + 3];
+        ax += (a0.x + cm.x * a0.y) * x0.x;  ay += (a0.x + cm.y * a0.y) * x0.y;
+        ax += (a1.x + cm.x * a1.y) * x1.x;  ay += (a1.x + cm.y * a1.y) * x1.y;
+        ax += (a2.x + cm.x * a2.y) * x2.x;  ay += (a2.x + cm.y * a2.y) * x2.y;
+        ax += (a3.x + cm.x * a3.y) * x3.x;  ay += (a3.x + cm.y * a3.y) * x3.y;
+      } else {
+        const double b0 = sv1[k], b1 = sv1[k + 1], b2 = sv1[k + 2], b3 = sv1[k + 3];
+        ax += b0 * x0.x;  ay += b0 * x0.y;
+        ax += b1 * x1.x;  ay += b1 * x1.y;
+        ax += b2 * x2.x;  ay += b2 * x2.y;
+        ax += b3 * x3.x;  ay += b3 * x3.y;
+      }
+    }
+    for (; k < kend; ++k) {
+      const double2 xv = xm[soff[k]];
+      if (HAS2) {
+        const double2 a = sv2[k];
+        ax += (a.x + cm.x * a.y) * xv.x;
+        ay += (a.x + cm.y * a.y) * xv.y;
+      } else {
+        const double b = sv1[k];
+        ax += b * xv.x;
+        ay += b * xv.y;
+      }
+    }
+  }
+  return make_double2(ax, ay);
+}
+
+template <bool HAS2>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_spmm_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
+          const double2 *z, double2 *y, int nb, double alpha, double beta) {
+  SPB2_ROWMAP()
+  SPB_SMEM(HAS2)
+  const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
+  const double2 zin = (beta != 0.0 && valid) ? z[t_] : make_double2(0.0, 0.0);
+  const double2 acc = spb2_rowdot<HAS2>(A, cm, x + mp, nb2, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+  if (valid)
+    y[t_] = (beta == 0.0) ? make_double2(alpha * acc.x, alpha * acc.y)
+                          : make_double2(alpha * acc.x + beta * zin.x, alpha * acc.y + beta * zin.y);
+}
+
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_init_b2(CsrDev A, const double2 *__restrict__ zp, const double2 *__restrict__ rv,
+               const double2 *__restrict__ dinv, double2 *__restrict__ res,
+               double2 *__restrict__ d, int nb, double inv_theta) {
+  SPB2_ROWMAP()
+  SPB_SMEM(false)
+  const long te_ = valid ? t_ : 0;
+  const double2 rv_ = rv[te_], di = dinv[te_];
+  const double2 acc = spb2_rowdot<false>(A, make_double2(0.0, 0.0), zp + mp, nb2, row, valid, wrow0,
+                                         wrow1, lane, sv2, sv1, soff);
+  if (valid) {
+    const double rx = rv_.x - acc.x, ry = rv_.y - acc.y;
+    res[t_] = make_double2(rx, ry);
+    d[t_] = make_double2(di.x * rx * inv_theta, di.y * ry * inv_theta);
+  }
+}
+
+template <bool HAS2, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_step_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ d,
+               const double2 *__restrict__ dinv, double2 *res, double2 *__restrict__ dn,
+               double2 *z, int nb, double c1, double c2) {
+  SPB2_ROWMAP()
+  SPB_SMEM(HAS2)
+  const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
+  const long te_ = valid ? t_ : 0;
+  const double2 r_old = res[te_], dold = d[te_], di = dinv[te_];
+  const double2 z_old = FIRST ? make_double2(0.0, 0.0) : z[te_];
+  const double2 acc = spb2_rowdot<HAS2>(A, cm, d + mp, nb2, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+  if (valid) {
+    const double rx = r_old.x - acc.x, ry = r_old.y - acc.y;
+    const double ddx = c1 * dold.x + c2 * di.x * rx, ddy = c1 * dold.y + c2 * di.y * ry;
+    if (!LAST) {
+      res[t_] = make_double2(rx, ry);
+      dn[t_] = make_double2(ddx, ddy);
+    }
+    z[t_] = make_double2((FIRST ? dold.x : z_old.x) + ddx, (FIRST ? dold.y : z_old.y) + ddy);
+  }
+}

@@ -569,13 +569,19 @@ __global__ void k_gmres_givens(GmresState S, const double *__restrict__ partial2
       for (int b = 0; b < nblocks; ++b) s += partial2[(size_t)b * nb + m];
       const double hn = sqrt(s);
       const int mr = S.mr;
-      double hprev = S.h[m];   // h[0]
+      // the loads of (c, s, h) do not alias the stores to R: let them pipeline
+      const double *__restrict__ pcs = S.cs;
+      const double *__restrict__ psn = S.sn;
+      const double *__restrict__ ph = S.h;
+      double *__restrict__ pR = S.R;
+      double hprev = ph[m];   // h[0]
+#pragma unroll 4
       for (int i = 0; i < j; ++i) {
-        const double c = S.cs[(size_t)i * nb + m], sn = S.sn[(size_t)i * nb + m];
-        const double hnext = S.h[(size_t)(i + 1) * nb + m];
+        const double c = pcs[(size_t)i * nb + m], sn = psn[(size_t)i * nb + m];
+        const double hnext = ph[(size_t)(i + 1) * nb + m];
         const double t = c * hprev + sn * hnext;
         hprev = -sn * hprev + c * hnext;
-        S.R[((size_t)i * mr + j) * nb + m] = t;
+        pR[((size_t)i * mr + j) * nb + m] = t;
       }
       const double dd = hypot(hprev, hn);
       double c = 1.0, sn = 0.0;
@@ -607,23 +613,32 @@ __global__ void k_gmres_givens(GmresState S, const double *__restrict__ partial2
   }
 }
 
-// out[c] = sum_b partial[b*count + c]; block = 32 outputs x 8 slices of b,
-// coalesced in c, fixed summation order
-__global__ void __launch_bounds__(256)
+// out[c] = sum_b partial[b*count + c]; block = 32 outputs x 32 slices of b,
+// coalesced in c, 4 independent loads in flight per thread, fixed summation
+// order (deterministic)
+__global__ void __launch_bounds__(1024)
 k_reduce_partials2(const double *__restrict__ partial, int nblocks, int count,
                    double *__restrict__ out) {
-  __shared__ double sp[8][33];
+  __shared__ double sp[32][33];
   const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  double s = 0.0;
-  if (c < count)
-    for (int b = by; b < nblocks; b += 8) s += partial[(size_t)b * count + c];
-  sp[by][cx] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (c < count) {
+    int b = by;
+    for (; b + 96 < nblocks; b += 128) {
+      s0 += partial[(size_t)b * count + c];
+      s1 += partial[(size_t)(b + 32) * count + c];
+      s2 += partial[(size_t)(b + 64) * count + c];
+      s3 += partial[(size_t)(b + 96) * count + c];
+    }
+    for (; b < nblocks; b += 32) s0 += partial[(size_t)b * count + c];
+  }
+  sp[by][cx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (by == 0 && c < count) {
     double t = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += sp[q][cx];
+    for (int q = 0; q < 32; ++q) t += sp[q][cx];
     out[c] = t;
   }
 }

@@ -61,6 +61,10 @@ class SadpntOperator(object):
         self.last_iters, self.last_relres = iters, relres
         return vp
 
+    def update_values(self, vals):
+        """new values of ``amat`` on the pattern given at construction"""
+        self.solver.update_fvalues(vals)
+
     def close(self):
         self.solver.close()
 

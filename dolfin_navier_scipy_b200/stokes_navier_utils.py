@@ -372,18 +372,56 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         return
 
     # ---- Picard / Newton sweeps with the trapezoidal rule (`snu:1304-1587`) --
+    # The reference builds `M + dt/2 (A + N_n)` and factorises it anew every
+    # step (`snu:1484-1512`).  Here all step matrices live on ONE pattern (the
+    # union of M, A and the condensed P2 convection pattern): per step the
+    # convection values come from the device kernel K1b, are gathered into that
+    # pattern, and only the VALUES of the device matrix are replaced
+    # (`dnsb_solver_update_fvalues`); the preconditioner (Schur approximation,
+    # Chebyshev bounds) is set up once per sweep matrix family.
+    from . import _lib
+    from .time_int_utils import _on_pattern, _union_pattern
     cur_linvel_point = lin_vel_point
     newtk, norm_nwtnupd = 0, 1
     nwtnupd_norms = []
+    M, A = sps.csr_matrix(M), sps.csr_matrix(A)
+    dev = _lib.device_for(V)
+    cip, cix = dev.pattern
+    nvf = V.dim()
+    # condensed convection pattern; its data are the (1-based) slots of the
+    # full device pattern
+    Pc = sps.csr_matrix((np.arange(1, cix.size + 1, dtype=float), cix, cip),
+                        shape=(nvf, nvf))[invinds, :][:, invinds].tocsr()
+    Pc.sort_indices()
+    src = Pc.data.astype(np.int64) - 1
+    pat = _union_pattern([M, A, Pc])
+    pos = _on_pattern(sps.csr_matrix((np.arange(1, Pc.nnz + 1, dtype=float),
+                                      Pc.indices, Pc.indptr), shape=Pc.shape),
+                      pat)
+    convpos = np.nonzero(pos.data)[0]
+    assert np.array_equal(pos.data[convpos], np.arange(1, Pc.nnz + 1))
+    Mv, Av = _on_pattern(M, pat).data, _on_pattern(A, pat).data
+    ubc = np.zeros((nvf, 1))
+    if len(dbcinds) > 0:
+        ubc[np.asarray(dbcinds), 0] = dbcvals
+    zerov = np.zeros((cnv, 1))
+
+    def _csr(vals):
+        return sps.csr_matrix((vals, pat.indices, pat.indptr), shape=pat.shape)
 
     def _convconts(vfull, picard):
+        """values of the condensed convection matrix on `pat`, N(v)v[inv] (0
+        for Picard), -(N u_bc)[inv]  -- `snu:40-133`"""
         if stokes_flow:
-            return (sps.csr_matrix((cnv, cnv)), np.zeros((cnv, 1)),
-                    np.zeros((cnv, 1)))
-        cm, rc, rbc = get_v_conv_conts(vvec=vfull, V=V, invinds=invinds,
-                                       dbcinds=dbcinds, dbcvals=dbcvals,
-                                       Picard=picard)
-        return cm, (0. if picard else rc), rbc
+            return np.zeros(pat.nnz), zerov, zerov
+        n1, n2, f3 = dev.convmats(np.asarray(vfull, dtype=float).reshape(-1))
+        nfull = n1 if picard else n1 + n2
+        vals = np.zeros(pat.nnz)
+        vals[convpos] = nfull[src]
+        Nfull = sps.csr_matrix((nfull, cix, cip), shape=(nvf, nvf))
+        rbc = -(Nfull@ubc)[invinds, :]
+        rc = zerov if picard else f3.reshape(-1, 1)[invinds, :]
+        return vals, rc, rbc
 
     def _lookup(pnt, t):
         try:
@@ -391,6 +429,7 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         except KeyError:
             return pnt[None]
 
+    op = None
     while newtk < vel_nwtn_stps and norm_nwtnupd > vel_nwtn_tol:
         v_old, p_old = iniv, inip
         if vel_pcrd_stps > 0:
@@ -401,8 +440,8 @@ def solve_nse(A=None, M=None, J=None, JT=None,
             newtk += 1
         dictofvelstrs = {float(trange[0]): _appbcs(iniv)}
         dictofpstrs = {float(trange[0]): inip}
-        convc_mat_c, rhs_con_c, rhsv_conbc_c = _convconts(_appbcs(v_old),
-                                                          pcrd_anyone)
+        nv_c, rhs_con_c, rhsv_conbc_c = _convconts(_appbcs(v_old),
+                                                   pcrd_anyone)
         fvn_c = fv + rhsv_conbc_c + rhs_con_c
         norm_nwtnupd = 0
         x0 = None
@@ -410,20 +449,27 @@ def solve_nse(A=None, M=None, J=None, JT=None,
             cts = t - trange[tk]
             prev_v = v_old if stokes_flow else \
                 np.asarray(_lookup(cur_linvel_point, float(t)))
-            convc_mat_n, rhs_con_n, rhsv_conbc_n = _convconts(prev_v,
-                                                              pcrd_anyone)
+            prev_full = prev_v if len(prev_v) == nvf else _appbcs(prev_v)
+            nv_n, rhs_con_n, rhsv_conbc_n = _convconts(prev_full, pcrd_anyone)
             fvn_n = fv + rhsv_conbc_n + rhs_con_n
-            solvmat = M + 0.5*cts*(A + convc_mat_n)              # snu:1034
-            rhsv = M*v_old + 0.5*cts*(fvn_n + fvn_c -
-                                      (A + convc_mat_c)*v_old)   # snu:1035
-            kd = dict(krylov='gmres',
-                      krpslvprms=dict(tol=lin_tol, maxiter=2000, x0=x0))
-            vp_new = lau.solve_sadpnt_smw(amat=solvmat, jmat=J, jmatT=JT,
-                                          rhsv=rhsv, rhsp=fp, **kd)
+            solvvals = Mv + 0.5*cts*(Av + nv_n)                   # snu:1034
+            rhsv = M@v_old + 0.5*cts*(fvn_n + fvn_c -
+                                      _csr(Av + nv_c)@v_old)      # snu:1035
+            if op is None:
+                op = lau.SadpntOperator(_csr(solvvals), J, JT, ncols=1,
+                                        velocity_amg=False, schur='lumped',
+                                        cheb_steps=min(cheb_steps, 3))
+            else:
+                op.update_values(solvvals)
+            if x0 is None:
+                x0 = np.vstack([v_old, -cts*p_old])
+            vp_new = op.solve(rhsv, fp, x0=x0, tol=lin_tol, maxit=2000)
+            if 'convstatsl' in krpslvprms:
+                krpslvprms['convstatsl'].append(int(op.last_iters.max()))
             x0 = vp_new
             v_old = vp_new[:cnv, ]
-            convc_mat_c, rhs_con_c, rhsv_conbc_c = _convconts(_appbcs(v_old),
-                                                              pcrd_anyone)
+            nv_c, rhs_con_c, rhsv_conbc_c = _convconts(_appbcs(v_old),
+                                                       pcrd_anyone)
             fvn_c = fvn_n - rhs_con_n - rhsv_conbc_n + rhsv_conbc_c \
                 + rhs_con_c                                      # snu:1537
             p_old = -1/cts*vp_new[cnv:, ]                        # snu:1542
@@ -441,6 +487,8 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         cur_linvel_point = dictofvelstrs
         if stokes_flow:
             break
+    if op is not None:
+        op.close()
 
     if return_final_vp:
         return (_appbcs(v_old), p_old)

@@ -135,6 +135,12 @@ int dnsb_solver_solve(dnsb_solver *s, const double *rhsv, const double *rhsp,
                       const double *x0, double *vp, double tol, int maxit,
                       int *iters, double *relres);
 
+/* new values of the velocity block `fmat` (single value array, nnz entries in
+ * the order of the pattern given at creation): the per-step matrices
+ * M + dt/2 (A + N(v)) of the Picard/Newton + Crank-Nicolson sweeps
+ * (stokes_navier_utils.py:1484-1512) and of the steady Picard/Newton iteration
+ * (:438-525) change values, not pattern; the preconditioner set-up is kept. */
+int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1);
 /* z = P^-1 r: one application of the block-triangular preconditioner to host
  * vectors ((nv+np)*nb); used by the tests to check the multigrid / Schur
  * pieces against a numpy restatement */
