@@ -246,7 +246,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     ctx = _lib.default_context(local_rank)
     nmembers = args.members*world
-    ntimes = args.warmup + 3*args.steps + 8
+    ntimes = max(args.warmup, 3) + 4*args.steps + 8
     integ, info = ens.cylinder_ensemble(
         N=args.mesh, nmembers=nmembers, rank=rank, world=world,
         dt=1./args.nts, ntimes=ntimes, ctx=ctx, cheb_steps=args.cheb,
@@ -308,18 +308,22 @@ def run_ours(args, rank, world, local_rank):
     # running integration is fed the next chunk of the control series and the
     # full trajectory is read back
     B = info['B']
-    U = np.ascontiguousarray(info['U'][nwarm + args.steps:
-                                       nwarm + 2*args.steps + 1])
-    integ.engine.reset_snapshots()
     integ.reserve_snapshots(args.steps + 2)     # pinned mirror, allocated once
-    barrier()
-    t0 = time.perf_counter()
-    integ.set_forcing(B, U)
-    integ.run(args.steps, snap_stride=1, **runkw)
-    vs, ps = integ.snapshots(copy=False)        # views of the pinned mirror
-    chk = float(np.abs(vs[-1]).sum() + np.abs(ps[-1]).sum())   # host reads it
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = None
+    for rep in range(2):     # first pass warms the e2e path up (untimed)
+        Urep = np.ascontiguousarray(
+            info['U'][nwarm + (1 + rep)*args.steps:
+                      nwarm + (2 + rep)*args.steps + 1])
+        integ.engine.reset_snapshots()
+        barrier()
+        t0 = time.perf_counter()
+        integ.set_forcing(B, Urep)
+        integ.run(args.steps, snap_stride=1, **runkw)
+        vs, ps = integ.snapshots(copy=False)    # views of the pinned mirror
+        chk = float(np.abs(vs[-1]).sum() + np.abs(ps[-1]).sum())  # host reads
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    U = Urep
     te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

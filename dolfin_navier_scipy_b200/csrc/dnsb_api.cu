@@ -86,6 +86,7 @@ struct dnsb_csr {
   DBuf<int> indptr, indices;
   DBuf<double> v1, v2;
   bool has2 = false;
+  int npair_rows = 0;   // leading rows that pair up (2k, 2k+1) with identical column lists
   // host copies (setup only: assembling the block matrix K, diagonal positions)
   std::vector<int> h_indptr, h_indices;
   std::vector<double> h_v1, h_v2;
@@ -112,6 +113,11 @@ static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
   DNSB_REQUIRE(ctx, m != nullptr, "out of host memory");
   m->ctx = ctx; m->nrows = nrows; m->ncols = ncols; m->nnz = nnz;
   m->has2 = vals2 != nullptr;
+  for (int r = 0; r + 1 < nrows; r += 2) {
+    const int a0 = indptr[r], a1 = indptr[r + 1], a2 = indptr[r + 2];
+    if (a1 - a0 != a2 - a1 || a1 == a0 || !std::equal(indices + a0, indices + a1, indices + a1)) break;
+    m->npair_rows = r + 2;
+  }
   m->h_indptr.assign(indptr, indptr + nrows + 1);
   m->h_indices.assign(indices, indices + nnz);
   m->h_v1.assign(vals1, vals1 + nnz);
@@ -162,6 +168,14 @@ static inline bool pair_ok(const dnsb_csr *A, int nb) {
 static inline unsigned spb2_grid(int nrows, int nb) {
   return cdiv((size_t)nrows * (nb / 2), SPB_THREADS);
 }
+// row-pair kernels: member pairs AND the leading rows pair up
+static int g_rowpair = 1;
+static inline int rowpairs_of(const dnsb_csr *A, int nb) {
+  return (g_rowpair && pair_ok(A, nb)) ? A->npair_rows / 2 : 0;
+}
+static inline unsigned spp_grid(int npairs, int nb) {
+  return cdiv((size_t)npairs * (nb / 2), SPB_THREADS);
+}
 #define D2C(p) reinterpret_cast<const double2 *>(p)
 #define D2(p) reinterpret_cast<double2 *>(p)
 static inline unsigned spb_grid(int nrows, int nb, int gpc) {
@@ -174,12 +188,34 @@ static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
                      double alpha, double beta) {
   if (A->nrows == 0) return;
   if (pair_ok(A, nb)) {
-    if (A->has2 && coef)
-      LAUNCH(ctx, k_spmm_b2<true>, spb2_grid(A->nrows, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
-             D2C(z), D2(y), nb, alpha, beta);
-    else
-      LAUNCH(ctx, k_spmm_b2<false>, spb2_grid(A->nrows, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
-             D2C(z), D2(y), nb, alpha, beta);
+    const bool h2 = A->has2 && coef;
+    const int npairs = rowpairs_of(A, nb);
+    const int row_begin = 2 * npairs;
+    if (npairs > 0 && row_begin < A->nrows) {
+      // paired rows and a tail of single rows (K = [F JT; J 0]) in one launch
+      const unsigned tb = spb2_grid(A->nrows - row_begin, nb);
+      const unsigned grid = tb + spp_grid(npairs, nb);
+      if (h2)
+        LAUNCH(ctx, k_spmm_k2<true>, grid, SPB_THREADS, 0, A->view(), coef, D2C(x), D2C(z), D2(y), nb,
+               npairs, (int)tb, alpha, beta);
+      else
+        LAUNCH(ctx, k_spmm_k2<false>, grid, SPB_THREADS, 0, A->view(), coef, D2C(x), D2C(z), D2(y), nb,
+               npairs, (int)tb, alpha, beta);
+    } else if (npairs > 0) {
+      if (h2)
+        LAUNCH(ctx, k_spmm_p2<true>, spp_grid(npairs, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
+               D2C(z), D2(y), nb, npairs, alpha, beta);
+      else
+        LAUNCH(ctx, k_spmm_p2<false>, spp_grid(npairs, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
+               D2C(z), D2(y), nb, npairs, alpha, beta);
+    } else {
+      if (h2)
+        LAUNCH(ctx, k_spmm_b2<true>, spb2_grid(A->nrows, nb), SPB_THREADS, 0, A->view(),
+               coef, D2C(x), D2C(z), D2(y), nb, 0, alpha, beta);
+      else
+        LAUNCH(ctx, k_spmm_b2<false>, spb2_grid(A->nrows, nb), SPB_THREADS, 0, A->view(),
+               coef, D2C(x), D2C(z), D2(y), nb, 0, alpha, beta);
+    }
   } else if (batched_ok(A, nb)) {
     const int gpc = spb_gpc(ctx, A->nrows, nb);
     if (A->has2 && coef)
@@ -235,6 +271,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   ctx->device = device;
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
   if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
+  if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
   if (const char *ev = getenv("DNSB_DENSE_CTAS_PER_SM")) g_dense_ctas_per_sm = std::max(1, atoi(ev));
   *out = ctx;   // returned even on failure so that the message can be read
@@ -930,8 +967,13 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
   double *dfirst = k == 1 ? z : d0;
   const int gpc = batched ? spb_gpc(ctx, n, nb) : 1;
   const bool pair = pair_ok(A, nb) && (!C || pair_ok(C, nb));
+  // all rows pair up (both components of every node are unknowns)?
+  const bool rowpair = pair && rowpairs_of(A, nb) * 2 == n;
   if (C) {
-    if (pair)
+    if (pair && rowpairs_of(C, nb) * 2 == n)
+      LAUNCH(ctx, k_cheb_init_p2, spp_grid(n / 2, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
+             D2C(dinv), D2(res), D2(dfirst), nb, n / 2, 1.0 / theta);
+    else if (pair)
       LAUNCH(ctx, k_cheb_init_b2, spb2_grid(n, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
              D2C(dinv), D2(res), D2(dfirst), nb, 1.0 / theta);
     else if (batched)
@@ -968,7 +1010,21 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
       else if (last) LAUNCH(ctx, (KERN<__VA_ARGS__, false, true>), GRID, BLK, 0, CHEB_ARGS);          \
       else LAUNCH(ctx, (KERN<__VA_ARGS__, false, false>), GRID, BLK, 0, CHEB_ARGS);                   \
     } while (0)
-    if (pair) {
+    if (rowpair) {
+#define CHEB_ARGS_R A->view(), coef, D2C(dc), D2C(dinv), D2(res), D2(dn), D2(z), nb, n / 2, c1, c2
+#define CHEB_DISPATCH_R(HAS2)                                                                       \
+    do {                                                                                            \
+      const unsigned grid_ = spp_grid(n / 2, nb);                                                   \
+      if (first && last) LAUNCH(ctx, (k_cheb_step_p2<HAS2, true, true>), grid_, SPB_THREADS, 0, CHEB_ARGS_R);   \
+      else if (first) LAUNCH(ctx, (k_cheb_step_p2<HAS2, true, false>), grid_, SPB_THREADS, 0, CHEB_ARGS_R);     \
+      else if (last) LAUNCH(ctx, (k_cheb_step_p2<HAS2, false, true>), grid_, SPB_THREADS, 0, CHEB_ARGS_R);      \
+      else LAUNCH(ctx, (k_cheb_step_p2<HAS2, false, false>), grid_, SPB_THREADS, 0, CHEB_ARGS_R);               \
+    } while (0)
+      if (has2) CHEB_DISPATCH_R(true);
+      else CHEB_DISPATCH_R(false);
+#undef CHEB_DISPATCH_R
+#undef CHEB_ARGS_R
+    } else if (pair) {
 #define CHEB_ARGS_P A->view(), coef, D2C(dc), D2C(dinv), D2(res), D2(dn), D2(z), nb, c1, c2
 #define CHEB_DISPATCH_P(HAS2)                                                                       \
     do {                                                                                            \

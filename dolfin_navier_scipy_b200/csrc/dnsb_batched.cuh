@@ -363,8 +363,19 @@ spb2_rowdot(const CsrDev &A, double2 cm, const double2 *__restrict__ xm, int nb2
 template <bool HAS2>
 __global__ void __launch_bounds__(SPB_THREADS)
 k_spmm_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
-          const double2 *z, double2 *y, int nb, double alpha, double beta) {
-  SPB2_ROWMAP()
+          const double2 *z, double2 *y, int nb, int row_begin, double alpha, double beta) {
+  // rows [row_begin, nrows): the tail after the paired rows, or everything
+  const int nb2 = nb >> 1;
+  const long total_ = (long)(A.nrows - row_begin) * nb2;
+  const int lane = threadIdx.x & 31;
+  const long tl_ = (long)blockIdx.x * SPB_THREADS + threadIdx.x;
+  if (tl_ - lane >= total_) return;
+  const bool valid = tl_ < total_;
+  const int row = valid ? row_begin + (int)((unsigned)tl_ / (unsigned)nb2) : A.nrows - 1;
+  const int mp = valid ? (int)(tl_ - (long)(row - row_begin) * nb2) : 0;
+  const int wrow0 = __shfl_sync(0xffffffffu, row, 0);
+  const int wrow1 = __shfl_sync(0xffffffffu, row, 31);
+  const long t_ = (long)row * nb2 + mp;
   SPB_SMEM(HAS2)
   const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
   const double2 zin = (beta != 0.0 && valid) ? z[t_] : make_double2(0.0, 0.0);
@@ -411,5 +422,248 @@ k_cheb_step_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restr
       dn[t_] = make_double2(ddx, ddy);
     }
     z[t_] = make_double2((FIRST ? dold.x : z_old.x) + ddx, (FIRST ? dold.y : z_old.y) + ddy);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Row-pair kernels.  The ncu capture of the member-pair kernels
+// (profiles/r1f_ncu_full.md) shows them bound by the L1 data path, not by
+// DRAM (DRAM 21-25 %, L1 60 %, 50-65 % long-scoreboard stalls): every gathered
+// x value travels L1 -> register for ONE multiply-add.  The two velocity
+// components of a P2 node (rows 2k, 2k+1 of F, K and JT in the device
+// numbering) have identical column lists, so one gather can feed both rows:
+// a thread owns (row pair, member pair), i.e. a 2x2 register tile, and the L1
+// traffic of the gather is halved.  `npairs` leading row pairs of the matrix
+// are handled (csr->npair_rows / 2, verified on the host when the matrix is
+// created); the sums run in CSR order per row: bit-identical results.
+// ---------------------------------------------------------------------------
+#define SPP_CAP 192   // CSR entries (both rows of the warp's pairs) staged per warp
+
+struct SppSmem2 {
+  double2 v[SPB_WARPS][SPP_CAP];
+  int off[SPB_WARPS][SPP_CAP];
+};
+struct SppSmem1 {
+  double v[SPB_WARPS][SPP_CAP];
+  int off[SPB_WARPS][SPP_CAP];
+};
+template <bool HAS2> struct SppSel;
+template <> struct SppSel<true> {
+  typedef SppSmem2 type;
+  static __device__ __forceinline__ double2 *v2(SppSmem2 &s, int w) { return s.v[w]; }
+  static __device__ __forceinline__ double *v1(SppSmem2 &, int) { return nullptr; }
+};
+template <> struct SppSel<false> {
+  typedef SppSmem1 type;
+  static __device__ __forceinline__ double2 *v2(SppSmem1 &, int) { return nullptr; }
+  static __device__ __forceinline__ double *v1(SppSmem1 &s, int w) { return s.v[w]; }
+};
+
+#define SPP_MAP(HAS2)                                                           \
+  const int nb2 = nb >> 1;                                                      \
+  const long total_ = (long)npairs * nb2;                                       \
+  const int lane = threadIdx.x & 31;                                            \
+  const long t_ = (long)blockIdx.x * SPB_THREADS + threadIdx.x;                 \
+  const long tw0_ = t_ - lane;                                                  \
+  if (tw0_ >= total_) return;                                                   \
+  const bool valid = t_ < total_;                                               \
+  const int rp = valid ? (int)((unsigned)t_ / (unsigned)nb2) : npairs - 1;      \
+  const int mp = valid ? (int)(t_ - (long)rp * nb2) : 0;                        \
+  const int wp0 = __shfl_sync(0xffffffffu, rp, 0);                              \
+  const int wp1 = __shfl_sync(0xffffffffu, rp, 31);                             \
+  __shared__ typename SppSel<HAS2>::type sm_;                                   \
+  double2 *sv2 = SppSel<HAS2>::v2(sm_, threadIdx.x >> 5);                       \
+  double *sv1 = SppSel<HAS2>::v1(sm_, threadIdx.x >> 5);                        \
+  int *soff = sm_.off[threadIdx.x >> 5];                                        \
+  const size_t ta_ = (size_t)(2 * rp) * nb2 + mp, tb_ = ta_ + nb2;
+
+// (accA, accB) of rows (2rp, 2rp+1) for the member pair of this lane
+template <bool HAS2>
+__device__ __forceinline__ void
+spp_rowdots(const CsrDev &A, double2 cm, const double2 *__restrict__ xm, int nb2, int rp,
+            bool valid, int wp0, int wp1, int lane, double2 *sv2, double *sv1, int *soff,
+            double2 &accA, double2 &accB) {
+  const int e_lo = A.indptr[2 * wp0], e_hi = A.indptr[2 * wp1 + 2];
+  const int k0 = valid ? A.indptr[2 * rp] : 0;
+  const int k1 = valid ? A.indptr[2 * rp + 1] : 0;
+  const int L = k1 - k0;
+  double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+  if (e_hi - e_lo <= SPP_CAP) {
+    for (int e = lane; e < e_hi - e_lo; e += 32) {
+      soff[e] = A.indices[e_lo + e] * nb2;
+      if (HAS2) sv2[e] = make_double2(A.v1[e_lo + e], A.v2[e_lo + e]);
+      else sv1[e] = A.v1[e_lo + e];
+    }
+    __syncwarp();
+    int k = k0 - e_lo;
+    const int kend = k1 - e_lo;
+    for (; k + 2 <= kend; k += 2) {
+      const double2 x0 = xm[soff[k]], x1 = xm[soff[k + 1]];
+      if (HAS2) {
+        const double2 a0 = sv2[k], a1 = sv2[k + 1], b0 = sv2[k + L], b1 = sv2[k + 1 + L];
+        ax += (a0.x + cm.x * a0.y) * x0.x;  ay += (a0.x + cm.y * a0.y) * x0.y;
+        bx += (b0.x + cm.x * b0.y) * x0.x;  by += (b0.x + cm.y * b0.y) * x0.y;
+        ax += (a1.x + cm.x * a1.y) * x1.x;  ay += (a1.x + cm.y * a1.y) * x1.y;
+        bx += (b1.x + cm.x * b1.y) * x1.x;  by += (b1.x + cm.y * b1.y) * x1.y;
+      } else {
+        const double a0 = sv1[k], a1 = sv1[k + 1], b0 = sv1[k + L], b1 = sv1[k + 1 + L];
+        ax += a0 * x0.x;  ay += a0 * x0.y;  bx += b0 * x0.x;  by += b0 * x0.y;
+        ax += a1 * x1.x;  ay += a1 * x1.y;  bx += b1 * x1.x;  by += b1 * x1.y;
+      }
+    }
+    for (; k < kend; ++k) {
+      const double2 xv = xm[soff[k]];
+      if (HAS2) {
+        const double2 a = sv2[k], b = sv2[k + L];
+        ax += (a.x + cm.x * a.y) * xv.x;  ay += (a.x + cm.y * a.y) * xv.y;
+        bx += (b.x + cm.x * b.y) * xv.x;  by += (b.x + cm.y * b.y) * xv.y;
+      } else {
+        const double a = sv1[k], b = sv1[k + L];
+        ax += a * xv.x;  ay += a * xv.y;  bx += b * xv.x;  by += b * xv.y;
+      }
+    }
+  } else {
+    // rows too long for the staging area: straight from global memory
+    for (int k = k0; k < k1; ++k) {
+      const double2 xv = xm[(size_t)A.indices[k] * nb2];
+      const double a1 = A.v1[k], b1 = A.v1[k + L];
+      const double a2 = HAS2 ? A.v2[k] : 0.0, b2 = HAS2 ? A.v2[k + L] : 0.0;
+      ax += (a1 + cm.x * a2) * xv.x;  ay += (a1 + cm.y * a2) * xv.y;
+      bx += (b1 + cm.x * b2) * xv.x;  by += (b1 + cm.y * b2) * xv.y;
+    }
+  }
+  accA = make_double2(ax, ay);
+  accB = make_double2(bx, by);
+}
+
+template <bool HAS2>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_spmm_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
+          const double2 *z, double2 *y, int nb, int npairs, double alpha, double beta) {
+  SPP_MAP(HAS2)
+  const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
+  const double2 zero = make_double2(0.0, 0.0);
+  const double2 za = (beta != 0.0 && valid) ? z[ta_] : zero;
+  const double2 zb = (beta != 0.0 && valid) ? z[tb_] : zero;
+  double2 a, b;
+  spp_rowdots<HAS2>(A, cm, x + mp, nb2, rp, valid, wp0, wp1, lane, sv2, sv1, soff, a, b);
+  if (valid) {
+    if (beta == 0.0) {
+      y[ta_] = make_double2(alpha * a.x, alpha * a.y);
+      y[tb_] = make_double2(alpha * b.x, alpha * b.y);
+    } else {
+      y[ta_] = make_double2(alpha * a.x + beta * za.x, alpha * a.y + beta * za.y);
+      y[tb_] = make_double2(alpha * b.x + beta * zb.x, alpha * b.y + beta * zb.y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_init_p2(CsrDev A, const double2 *__restrict__ zp, const double2 *__restrict__ rv,
+               const double2 *__restrict__ dinv, double2 *__restrict__ res,
+               double2 *__restrict__ d, int nb, int npairs, double inv_theta) {
+  SPP_MAP(false)
+  const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
+  const double2 ra = rv[sa_], rb = rv[sb_], da = dinv[sa_], db = dinv[sb_];
+  double2 a, b;
+  spp_rowdots<false>(A, make_double2(0.0, 0.0), zp + mp, nb2, rp, valid, wp0, wp1, lane, sv2, sv1,
+                     soff, a, b);
+  if (valid) {
+    const double rax = ra.x - a.x, ray = ra.y - a.y, rbx = rb.x - b.x, rby = rb.y - b.y;
+    res[ta_] = make_double2(rax, ray);
+    res[tb_] = make_double2(rbx, rby);
+    d[ta_] = make_double2(da.x * rax * inv_theta, da.y * ray * inv_theta);
+    d[tb_] = make_double2(db.x * rbx * inv_theta, db.y * rby * inv_theta);
+  }
+}
+
+template <bool HAS2, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_step_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ d,
+               const double2 *__restrict__ dinv, double2 *res, double2 *__restrict__ dn,
+               double2 *z, int nb, int npairs, double c1, double c2) {
+  SPP_MAP(HAS2)
+  const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
+  const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
+  const double2 zero = make_double2(0.0, 0.0);
+  const double2 ra = res[sa_], rb = res[sb_], oa = d[sa_], ob = d[sb_];
+  const double2 da = dinv[sa_], db = dinv[sb_];
+  const double2 za = FIRST ? zero : z[sa_], zb = FIRST ? zero : z[sb_];
+  double2 a, b;
+  spp_rowdots<HAS2>(A, cm, d + mp, nb2, rp, valid, wp0, wp1, lane, sv2, sv1, soff, a, b);
+  if (valid) {
+    const double rax = ra.x - a.x, ray = ra.y - a.y, rbx = rb.x - b.x, rby = rb.y - b.y;
+    const double dax = c1 * oa.x + c2 * da.x * rax, day = c1 * oa.y + c2 * da.y * ray;
+    const double dbx = c1 * ob.x + c2 * db.x * rbx, dby = c1 * ob.y + c2 * db.y * rby;
+    if (!LAST) {
+      res[ta_] = make_double2(rax, ray);
+      res[tb_] = make_double2(rbx, rby);
+      dn[ta_] = make_double2(dax, day);
+      dn[tb_] = make_double2(dbx, dby);
+    }
+    z[ta_] = make_double2((FIRST ? oa.x : za.x) + dax, (FIRST ? oa.y : za.y) + day);
+    z[tb_] = make_double2((FIRST ? ob.x : zb.x) + dbx, (FIRST ? ob.y : zb.y) + dby);
+  }
+}
+
+// y = alpha*A*x + beta*z for a matrix whose first 2*npairs rows pair up and
+// whose remaining rows do not (the saddle-point matrix K = [F JT; J 0]: the
+// velocity rows pair, the divergence rows J are long single rows).  One
+// launch: the first `tail_blocks` CTAs take the (long, latency-bound) tail rows
+// so that they overlap with the bulk of the paired rows.
+template <bool HAS2>
+__global__ void __launch_bounds__(SPB_THREADS)
+k_spmm_k2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
+          const double2 *z, double2 *y, int nb, int npairs, int tail_blocks,
+          double alpha, double beta) {
+  const int nb2 = nb >> 1;
+  const int lane = threadIdx.x & 31;
+  const double2 zero = make_double2(0.0, 0.0);
+  if ((int)blockIdx.x < tail_blocks) {
+    const int row_begin = 2 * npairs;
+    const long total_ = (long)(A.nrows - row_begin) * nb2;
+    const long tl_ = (long)blockIdx.x * SPB_THREADS + threadIdx.x;
+    if (tl_ - lane >= total_) return;
+    const bool valid = tl_ < total_;
+    const int row = valid ? row_begin + (int)((unsigned)tl_ / (unsigned)nb2) : A.nrows - 1;
+    const int mp = valid ? (int)(tl_ - (long)(row - row_begin) * nb2) : 0;
+    const int wrow0 = __shfl_sync(0xffffffffu, row, 0);
+    const int wrow1 = __shfl_sync(0xffffffffu, row, 31);
+    const long t_ = (long)row * nb2 + mp;
+    SPB_SMEM(HAS2)
+    const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : zero;
+    const double2 zin = (beta != 0.0 && valid) ? z[t_] : zero;
+    const double2 acc = spb2_rowdot<HAS2>(A, cm, x + mp, nb2, row, valid, wrow0, wrow1, lane, sv2, sv1, soff);
+    if (valid)
+      y[t_] = (beta == 0.0) ? make_double2(alpha * acc.x, alpha * acc.y)
+                            : make_double2(alpha * acc.x + beta * zin.x, alpha * acc.y + beta * zin.y);
+    return;
+  }
+  const long total_ = (long)npairs * nb2;
+  const long t_ = (long)(blockIdx.x - tail_blocks) * SPB_THREADS + threadIdx.x;
+  if (t_ - lane >= total_) return;
+  const bool valid = t_ < total_;
+  const int rp = valid ? (int)((unsigned)t_ / (unsigned)nb2) : npairs - 1;
+  const int mp = valid ? (int)(t_ - (long)rp * nb2) : 0;
+  const int wp0 = __shfl_sync(0xffffffffu, rp, 0);
+  const int wp1 = __shfl_sync(0xffffffffu, rp, 31);
+  __shared__ typename SppSel<HAS2>::type smp_;
+  double2 *pv2 = SppSel<HAS2>::v2(smp_, threadIdx.x >> 5);
+  double *pv1 = SppSel<HAS2>::v1(smp_, threadIdx.x >> 5);
+  int *poff = smp_.off[threadIdx.x >> 5];
+  const size_t ta_ = (size_t)(2 * rp) * nb2 + mp, tb_ = ta_ + nb2;
+  const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : zero;
+  const double2 za = (beta != 0.0 && valid) ? z[ta_] : zero;
+  const double2 zb = (beta != 0.0 && valid) ? z[tb_] : zero;
+  double2 a, b;
+  spp_rowdots<HAS2>(A, cm, x + mp, nb2, rp, valid, wp0, wp1, lane, pv2, pv1, poff, a, b);
+  if (valid) {
+    if (beta == 0.0) {
+      y[ta_] = make_double2(alpha * a.x, alpha * a.y);
+      y[tb_] = make_double2(alpha * b.x, alpha * b.y);
+    } else {
+      y[ta_] = make_double2(alpha * a.x + beta * za.x, alpha * a.y + beta * za.y);
+      y[tb_] = make_double2(alpha * b.x + beta * zb.x, alpha * b.y + beta * zb.y);
+    }
   }
 }

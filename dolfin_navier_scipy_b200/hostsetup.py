@@ -13,7 +13,8 @@ import scipy.sparse.linalg as spsla
 from . import _lib
 
 __all__ = ['jacobi_spectrum', 'lumped_schur', 'poly_schur', 'sa_amg_hierarchy',
-           'make_saddle_solver', 'hilbert_key', 'locality_perm']
+           'make_saddle_solver', 'hilbert_key', 'locality_perm',
+           'pad_row_pairs']
 
 
 def hilbert_key(xy, order=16):
@@ -53,11 +54,37 @@ def locality_perm(coords=None, comp=None, pattern=None):
     if coords is not None:
         key = hilbert_key(coords)
         comp = np.zeros(len(key), dtype=np.int64) if comp is None else comp
-        return np.lexsort((np.asarray(comp), key)).astype(np.int64)
+        # by curve index, then by node (two nodes may share a curve cell), then
+        # by component: the components of a node stay adjacent, which the
+        # row-pair SpMM kernels rely on
+        _, node = np.unique(np.round(np.asarray(coords), 14), axis=0,
+                            return_inverse=True)
+        return np.lexsort((np.asarray(comp), node.ravel(), key)).astype(np.int64)
     from scipy.sparse.csgraph import reverse_cuthill_mckee
     pat = sps.csr_matrix(pattern)
     return np.asarray(reverse_cuthill_mckee(pat, symmetric_mode=True),
                       dtype=np.int64)
+
+
+def pad_row_pairs(P):
+    """pattern of ``P`` with the rows (2k, 2k+1) given the union of their
+    column lists (explicit zeros)
+
+    In the device numbering the two velocity components of a node are
+    adjacent rows; structurally they couple to the same columns, but assembly
+    drops entries that happen to be exactly zero.  With identical lists the
+    row-pair SpMM kernels load every gathered ``x`` once for both rows.
+    """
+    P = sps.csr_matrix(P)
+    n = P.shape[0]
+    ones = sps.csr_matrix((np.ones(P.nnz), P.indices, P.indptr), shape=P.shape)
+    if n % 2:
+        return ones
+    swap = np.arange(n).reshape(-1, 2)[:, ::-1].ravel()
+    out = (ones + ones[swap, :]).tocsr()
+    out.data[:] = 1.
+    out.sort_indices()
+    return out
 
 
 def jacobi_spectrum(F, its=30, seed=0, ratio=None):

@@ -122,6 +122,8 @@ class DeviceImex(object):
         Arob = None if Arob is None else _pvv(Arob)
         mats = [M, A0] + ([] if Arob is None else [Arob])
         pat = _union_pattern(mats)
+        if reorder:
+            pat = hostsetup.pad_row_pairs(pat)
         Mp, A0p = _on_pattern(M, pat), _on_pattern(A0, pat)
         Arp = _on_pattern(sps.csr_matrix(pat.shape) if Arob is None else Arob,
                           pat)
@@ -138,6 +140,8 @@ class DeviceImex(object):
         self.amat = ctx.csr(Arp, A0p.data)
         JT = J.T.tocsr()
         JT.sort_indices()
+        if reorder:
+            JT = _on_pattern(JT, hostsetup.pad_row_pairs(JT))
         self.jmat, self.jtmat = ctx.csr(J), ctx.csr(JT)
         if fv is not None:
             fv = np.asarray(fv, dtype=float).reshape(self.NV, -1)[pv]
