@@ -194,6 +194,17 @@ k_cheb_step_b(CsrDev A, const double *__restrict__ coef, const double *__restric
 // ---------------------------------------------------------------------------
 #define GS_RPT 16   // rows per thread held in registers
 
+// The rows of w stay in registers; the basis vectors are streamed in two
+// halves of GS_RPT/2 rows with the loads of the next half issued before the
+// current one is consumed (software pipeline): 8-16 independent loads are in
+// flight per thread at any time, without a bubble between two vectors.
+#define GS_H (GS_RPT / 2)
+#define GS_LOAD(dst, vec, half)                                                 \
+  _Pragma("unroll") for (int q = 0; q < GS_H; ++q) {                            \
+    const int r = r0 + rr + ((half) * GS_H + q) * rpb;                          \
+    dst[q] = (r < r1) ? (vec)[(size_t)r * nb + m] : 0.0;                        \
+  }
+
 // partial[(b*(nvec+1) + i)*nb + m] = sum_chunk V_i*w  (i < nvec),  i = nvec: w*w
 // Algorithmic bytes: 8*n*nb*(nvec + 1).
 __global__ void __launch_bounds__(256)
@@ -205,25 +216,24 @@ k_mdot_b(const double *__restrict__ V, size_t vstride, int nvec,
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(n, r0 + rows_per_block);
   const int nthr = rpb * nb;
-  double wr[GS_RPT];
+  double wa[GS_H], wb[GS_H], va[GS_H], vb[GS_H];
+  GS_LOAD(wa, w, 0)
+  GS_LOAD(wb, w, 1)
+  if (nvec > 0) { GS_LOAD(va, V, 0) }
   double ww = 0.0;
 #pragma unroll
-  for (int q = 0; q < GS_RPT; ++q) {
-    const int r = r0 + rr + q * rpb;
-    wr[q] = (r < r1) ? w[(size_t)r * nb + m] : 0.0;
-    ww += wr[q] * wr[q];
-  }
+  for (int q = 0; q < GS_H; ++q) ww += wa[q] * wa[q];
+#pragma unroll
+  for (int q = 0; q < GS_H; ++q) ww += wb[q] * wb[q];
   for (int i = 0; i < nvec; ++i) {
     const double *vi = V + (size_t)i * vstride;
-    double vv[GS_RPT];
-#pragma unroll
-    for (int q = 0; q < GS_RPT; ++q) {
-      const int r = r0 + rr + q * rpb;
-      vv[q] = (r < r1) ? vi[(size_t)r * nb + m] : 0.0;
-    }
+    GS_LOAD(vb, vi, 1)
     double acc = 0.0;
 #pragma unroll
-    for (int q = 0; q < GS_RPT; ++q) acc += vv[q] * wr[q];
+    for (int q = 0; q < GS_H; ++q) acc += va[q] * wa[q];
+    if (i + 1 < nvec) { GS_LOAD(va, vi + vstride, 0) }
+#pragma unroll
+    for (int q = 0; q < GS_H; ++q) acc += vb[q] * wb[q];
     sred[(size_t)i * nthr + threadIdx.x] = acc;
   }
   sred[(size_t)nvec * nthr + threadIdx.x] = ww;
@@ -249,31 +259,33 @@ k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
   const int m = threadIdx.x % nb, rr = threadIdx.x / nb;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(n, r0 + rows_per_block);
-  double wr[GS_RPT];
-#pragma unroll
-  for (int q = 0; q < GS_RPT; ++q) {
-    const int r = r0 + rr + q * rpb;
-    wr[q] = (r < r1) ? w[(size_t)r * nb + m] : 0.0;
-  }
+  double wa[GS_H], wb[GS_H], va[GS_H], vb[GS_H];
+  GS_LOAD(wa, w, 0)
+  GS_LOAD(wb, w, 1)
+  if (nvec > 0) { GS_LOAD(va, V, 0) }
+  double hi = nvec > 0 ? h[m] : 0.0;
   for (int i = 0; i < nvec; ++i) {
     const double *vi = V + (size_t)i * vstride;
-    const double hi = h[(size_t)i * nb + m];
-    double vv[GS_RPT];
+    GS_LOAD(vb, vi, 1)
+    const double hn = (i + 1 < nvec) ? h[(size_t)(i + 1) * nb + m] : 0.0;
 #pragma unroll
-    for (int q = 0; q < GS_RPT; ++q) {
-      const int r = r0 + rr + q * rpb;
-      vv[q] = (r < r1) ? vi[(size_t)r * nb + m] : 0.0;
-    }
+    for (int q = 0; q < GS_H; ++q) wa[q] -= hi * va[q];
+    if (i + 1 < nvec) { GS_LOAD(va, vi + vstride, 0) }
 #pragma unroll
-    for (int q = 0; q < GS_RPT; ++q) wr[q] -= hi * vv[q];
+    for (int q = 0; q < GS_H; ++q) wb[q] -= hi * vb[q];
+    hi = hn;
   }
   double nrm = 0.0;
 #pragma unroll
-  for (int q = 0; q < GS_RPT; ++q) {
-    const int r = r0 + rr + q * rpb;
-    if (r < r1) vnext[(size_t)r * nb + m] = wr[q];
-    nrm += wr[q] * wr[q];
+  for (int q = 0; q < GS_H; ++q) {
+    const int ra = r0 + rr + q * rpb, rb = r0 + rr + (GS_H + q) * rpb;
+    if (ra < r1) vnext[(size_t)ra * nb + m] = wa[q];
+    if (rb < r1) vnext[(size_t)rb * nb + m] = wb[q];
   }
+#pragma unroll
+  for (int q = 0; q < GS_H; ++q) nrm += wa[q] * wa[q];
+#pragma unroll
+  for (int q = 0; q < GS_H; ++q) nrm += wb[q] * wb[q];
   sred[threadIdx.x] = nrm;
   __syncthreads();
   if (rr == 0) {

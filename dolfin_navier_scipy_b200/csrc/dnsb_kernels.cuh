@@ -625,11 +625,25 @@ k_reduce_partials2(const double *__restrict__ partial, int nblocks, int count,
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (c < count) {
     int b = by;
+    // 8 independent loads per round: one memory round trip covers 256 blocks
+    for (; b + 224 < nblocks; b += 256) {
+      const double p0 = partial[(size_t)b * count + c];
+      const double p1 = partial[(size_t)(b + 32) * count + c];
+      const double p2 = partial[(size_t)(b + 64) * count + c];
+      const double p3 = partial[(size_t)(b + 96) * count + c];
+      const double p4 = partial[(size_t)(b + 128) * count + c];
+      const double p5 = partial[(size_t)(b + 160) * count + c];
+      const double p6 = partial[(size_t)(b + 192) * count + c];
+      const double p7 = partial[(size_t)(b + 224) * count + c];
+      s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+      s0 += p4; s1 += p5; s2 += p6; s3 += p7;
+    }
     for (; b + 96 < nblocks; b += 128) {
-      s0 += partial[(size_t)b * count + c];
-      s1 += partial[(size_t)(b + 32) * count + c];
-      s2 += partial[(size_t)(b + 64) * count + c];
-      s3 += partial[(size_t)(b + 96) * count + c];
+      const double p0 = partial[(size_t)b * count + c];
+      const double p1 = partial[(size_t)(b + 32) * count + c];
+      const double p2 = partial[(size_t)(b + 64) * count + c];
+      const double p3 = partial[(size_t)(b + 96) * count + c];
+      s0 += p0; s1 += p1; s2 += p2; s3 += p3;
     }
     for (; b < nblocks; b += 32) s0 += partial[(size_t)b * count + c];
   }
