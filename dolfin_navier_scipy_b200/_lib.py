@@ -233,7 +233,12 @@ class Csr(object):
 
 
 class ConvDevice(object):
-    """mesh + convection kernels (K1a/K1b) bound to a P2 vector space"""
+    """mesh + convection kernels (K1a/K1b) bound to a P2 vector space
+
+    A context holds ONE mesh at a time (``dnsb_set_mesh``); several function
+    spaces may share a context, so every entry point re-binds its own mesh
+    first if another space used the context in between.
+    """
 
     def __init__(self, V, ctx=None):
         self.ctx = default_context() if ctx is None else ctx
@@ -243,15 +248,28 @@ class ConvDevice(object):
         geom = np.stack([gl[:, 1, 0], gl[:, 1, 1], gl[:, 2, 0], gl[:, 2, 1],
                          detj], axis=1)
         ncol, colour = V.colouring()
-        cn = _i32(V.cell_nodes)
-        geom = _f64(geom)
-        colour = _i32(colour)
+        self._cn = _i32(V.cell_nodes)
+        self._geom = _f64(geom)
+        self._colour = _i32(colour)
+        self._ncell, self._nnodes = mesh.num_cells, V.num_nodes
         self.ncolours = ncol
         self.nvf = V.dim()
-        self.ctx.check(self.ctx.lib.dnsb_set_mesh(
-            self.ctx.h, mesh.num_cells, V.num_nodes, _ip(cn), _dp(geom), ncol,
-            _ip(colour)))
         self._pattern = None
+        self._slots = None
+        self.bind()
+
+    def bind(self):
+        """make this space's mesh (and pattern) the context's current one"""
+        if getattr(self.ctx, '_mesh_owner', None) is self:
+            return
+        self.ctx.check(self.ctx.lib.dnsb_set_mesh(
+            self.ctx.h, self._ncell, self._nnodes, _ip(self._cn),
+            _dp(self._geom), self.ncolours, _ip(self._colour)))
+        if self._pattern is not None:
+            indptr, indices = self._pattern
+            self.ctx.check(self.ctx.lib.dnsb_set_conv_pattern(
+                self.ctx.h, _ip(indptr), _ip(indices), _ip(self._slots)))
+        self.ctx._mesh_owner = self
 
     @property
     def pattern(self):
@@ -268,13 +286,14 @@ class ConvDevice(object):
             indptr = np.zeros(NV + 1, dtype=np.int64)
             np.add.at(indptr, rows + 1, 1)
             indptr = np.cumsum(indptr).astype(np.int32)
-            slots = np.searchsorted(ukeys, keys).astype(np.int32)
-            self.ctx.check(self.ctx.lib.dnsb_set_conv_pattern(
-                self.ctx.h, _ip(indptr), _ip(indices), _ip(slots)))
+            self._slots = np.searchsorted(ukeys, keys).astype(np.int32)
             self._pattern = (indptr, indices)
+            self.ctx._mesh_owner = None      # force the upload of the pattern
+        self.bind()
         return self._pattern
 
     def convvec(self, u1, u2=None):
+        self.bind()
         u1 = _f64(u1)
         nb = 1 if u1.ndim == 1 else u1.shape[1]
         if u1.shape[0] != self.nvf:
@@ -297,11 +316,12 @@ class ConvDevice(object):
 
 
 def device_for(V, ctx=None):
-    """the (cached) device object of a function space"""
+    """the (cached) device object of a function space, bound to its context"""
     dev = getattr(V, '_dnsb_dev', None)
     if dev is None or (ctx is not None and dev.ctx is not ctx):
         dev = ConvDevice(V, ctx)
         V._dnsb_dev = dev
+    dev.bind()
     return dev
 
 

@@ -417,6 +417,14 @@ extern "C" int dnsb_set_mesh(dnsb_ctx *ctx, int ncell, int nnodes,
   DNSB_CK(ctx, ctx->cn.upload(cn.data(), cn.size(), ctx->stream));
   DNSB_CK(ctx, ctx->geom.upload(gm.data(), gm.size(), ctx->stream));
   ctx->ncell = ncell; ctx->nnodes = nnodes; ctx->ncolours = ncolours;
+  {
+    unsigned long long hsh = 1469598103934665603ull;   // FNV-1a
+    const unsigned char *pb = reinterpret_cast<const unsigned char *>(cell_nodes);
+    for (size_t k = 0; k < (size_t)6 * ncell * sizeof(int32_t); ++k) { hsh ^= pb[k]; hsh *= 1099511628211ull; }
+    pb = reinterpret_cast<const unsigned char *>(geom);
+    for (size_t k = 0; k < (size_t)5 * ncell * sizeof(double); ++k) { hsh ^= pb[k]; hsh *= 1099511628211ull; }
+    ctx->mesh_hash = hsh;
+  }
   ctx->cnnz = 0;
   return 0;
 }
@@ -1412,6 +1420,7 @@ extern "C" int dnsb_solver_apply_prec(dnsb_solver *s, const double *r, double *z
 // ===========================================================================
 struct dnsb_imex {
   dnsb_ctx *ctx = nullptr;
+  unsigned long long mesh_hash = 0;
   int scheme = 0, nb = 1, nv = 0, np = 0, nvf = 0, nbc = 0;
   double dt = 0;
   dnsb_csr *M = nullptr, *A = nullptr, *J = nullptr, *JT = nullptr;
@@ -1485,6 +1494,7 @@ extern "C" int dnsb_imex_create(dnsb_ctx *ctx, int scheme, int nb, double dt,
   DNSB_REQUIRE(ctx, e != nullptr, "out of host memory");
   *out = e;
   e->ctx = ctx; e->scheme = scheme; e->nb = nb; e->dt = dt;
+  e->mesh_hash = ctx->mesh_hash;
   e->nv = nv; e->np = jmat->nrows; e->nvf = nvf; e->nbc = nbc;
   e->M = mmat; e->A = amat; e->J = jmat; e->JT = jtmat;
   DNSB_CK(ctx, e->nu.upload(nu, nb, ctx->stream));
@@ -1841,6 +1851,8 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, e->have_state, "set the initial state first");
+  DNSB_REQUIRE(ctx, e->mesh_hash == ctx->mesh_hash,
+               "the mesh of the context is not the one this integrator was created on (dnsb_set_mesh)");
   DNSB_REQUIRE(ctx, e->sl != nullptr, "set the solvers first");
   DNSB_REQUIRE(ctx, nsteps >= 1 && tol > 0 && maxit >= 1 && guess >= 0 && guess <= 64, "bad run arguments");
   DNSB_CK(ctx, cudaSetDevice(ctx->device));

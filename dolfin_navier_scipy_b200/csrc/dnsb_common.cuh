@@ -78,6 +78,7 @@ struct dnsb_ctx {
 
   // ---- mesh / convection data (cells permuted into colour order) ----------
   int ncell = 0, nnodes = 0, ncolours = 0;
+  unsigned long long mesh_hash = 0;   // of the cell table + geometry: integrators check they run on their mesh
   DBuf<int> cn;          // 6*ncell, SoA: cn[k*ncell + c]
   DBuf<double> geom;     // 5*ncell, SoA
   std::vector<int> colour_ptr;   // ncolours+1 offsets into the permuted cells

@@ -191,6 +191,7 @@ class DeviceImex(object):
         self.engine.set_state(v0, p0)
 
     def run(self, nsteps, **kw):
+        self.dev.bind()       # the loop assembles the convection on this mesh
         return self.engine.run(nsteps, **kw)
 
     def state(self):

@@ -290,3 +290,105 @@ def test_golden_dfg_steady_state_device(ctx):
     assert abs(-cd - float(g['cd'])) < 1e-6*abs(float(g['cd']))
     assert abs(-cl - float(g['cl'])) < 1e-6*abs(float(g['cl']))
     assert abs(dp - float(g['dp'])) < 1e-6*abs(float(g['dp']))
+
+
+# ---------------------------------------------------------------------------
+# remaining rows of the scope table and edge cases
+# ---------------------------------------------------------------------------
+def test_semi_implicit_euler_matches_oracle(cyl1, ctx):
+    """a8: `tiu.semi_implicit_euler` (`tiu:566-635`) with rhs fv - N(v)v"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import tiu as otiu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    sd = soldict(femp, sm, rhsd)
+    v0 = osnu.solve_nse(t0=0, tE=1./512, Nts=1, start_ssstokes=True,
+                        return_vp_dict=True, **sd)[0.0]['v'][inv]
+    trange = np.linspace(0., 12./512, 13)
+
+    def rhsv(t, v):
+        _, nfc, _ = osnu.get_v_conv_conts(vvec=v, V=femp['V'], invinds=inv,
+                                          dbcinds=femp['dbcinds'],
+                                          dbcvals=femp['dbcvals'],
+                                          semi_explicit=True)
+        return rhsd['fv'] + nfc
+    ref = otiu.semi_implicit_euler(iniv=v0, jmat=sm['J'], mmat=sm['M'],
+                                   amat=sm['A'], rhsv=rhsv, trange=trange,
+                                   fp=rhsd['fp'])
+    got = tiu.semi_implicit_euler(iniv=v0, jmat=sm['J'], mmat=sm['M'],
+                                  amat=sm['A'], trange=trange, fp=rhsd['fp'],
+                                  V=femp['V'], invinds=inv,
+                                  dbcinds=femp['dbcinds'],
+                                  dbcvals=femp['dbcvals'], fv=rhsd['fv'])
+    assert len(got) == len(ref)
+    for a, b in zip(got[1:], ref[1:]):
+        assert _rel(a, b) < 1e-8
+
+
+def test_get_pfromv_matches_oracle(cyl1, ctx):
+    """a12: `snu.get_pfromv` (`snu:1602-1633`)"""
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    rng = np.random.default_rng(5)
+    v = 0.1*rng.standard_normal((inv.size, 1))
+    kw = dict(v=v, V=femp['V'], M=sm['M'], A=sm['A'], J=sm['J'],
+              fv=rhsd['fv'], dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'],
+              invinds=inv)
+    assert _rel(snu.get_pfromv(**kw), osnu.get_pfromv(**kw)) < 1e-8
+
+
+def test_blowup_guard_sets_ffflag(cyl1, ctx):
+    """`check_ff` (`tiu:94-103`, `snu:1281-1285`): an unstable step size must
+    trip the guard, a stable one must not"""
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    femp, sm, rhsd = cyl1
+    sd = soldict(femp, sm, rhsd, start_ssstokes=True, return_final_vp=True,
+                 check_ff=True, check_ff_maxv=1e3)
+    (v, p), ff = snu.solve_nse(t0=0., tE=40./512, Nts=40, **sd)
+    assert ff == 0 and np.all(np.isfinite(v))
+    # explicit convection with a huge step: CFL violated by orders of magnitude
+    _, ff = snu.solve_nse(t0=0., tE=400., Nts=40, **sd)
+    assert ff == 1
+
+
+def test_krylov_statistics_and_tolerance(cyl1, ctx):
+    """config 4 (`tests/time_dep_nse_krylov.py:4-7,47`): `krpslvprms` tol /
+    maxiter are honoured, `convstatsl` collects the iteration counts"""
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from oracle.lau import solve_sadpnt_smw as olu
+    femp, sm, rhsd = cyl1
+    F = (sm['M'] + .5/512*sm['A']).tocsr()
+    b = sm['M']@np.random.default_rng(6).standard_normal((F.shape[0], 1))
+    ref = olu(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b)
+    its = []
+    for tol in (1e-3, 1e-8, 1e-12):
+        vp = lau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b,
+                                  krylov='Gmres',
+                                  krpslvprms=dict(tol=tol, maxiter=800,
+                                                  convstatsl=its))
+        assert _rel(vp[:F.shape[0]], ref[:F.shape[0]]) < 50*tol
+    assert its[0] < its[1] < its[2]
+
+
+@pytest.mark.parametrize('nb', [1, 3, 4, 33])
+def test_spmm_all_batch_widths(cyl1, ctx, nb):
+    """every kernel family: nb = 1 (lanes per row), odd (one member per
+    thread), even (member pairs / row pairs), > 32"""
+    femp, sm, rhsd = cyl1
+    from dolfin_navier_scipy_b200.time_int_utils import _on_pattern, _union_pattern
+    M, A = sps.csr_matrix(sm['M']), sps.csr_matrix(sm['A'])
+    pat = _union_pattern([M, A])
+    Mp, Ap = _on_pattern(M, pat), _on_pattern(A, pat)
+    m2 = ctx.csr(Mp, Ap.data)
+    rng = np.random.default_rng(nb)
+    X = rng.standard_normal((A.shape[1], nb))
+    coef = rng.standard_normal(nb)
+    Y = m2.spmm(X, coef=coef)
+    for k in range(nb):
+        assert _rel(Y[:, k], M@X[:, k] + coef[k]*(A@X[:, k])) < 1e-13
+    JT = sps.csr_matrix(sm['JT'])
+    P = rng.standard_normal((JT.shape[1], nb))
+    assert _rel(ctx.csr(JT).spmm(P), JT@P) < 1e-13
