@@ -153,6 +153,7 @@ static inline bool batched_ok(const dnsb_csr *A, int nb) {
 static int g_rows_per_cta = 4;
 static int g_dense_ctas_per_sm = 2;
 static int g_graphs = 1;
+static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
 static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
   const long total = (long)nrows * nb;
   long gpc = std::max<long>(1, ((long)g_rows_per_cta * nb) / SPB_THREADS);
@@ -271,6 +272,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   ctx->device = device;
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
   if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
+  if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
   if (const char *ev = getenv("DNSB_DENSE_CTAS_PER_SM")) g_dense_ctas_per_sm = std::max(1, atoi(ev));
@@ -297,6 +299,7 @@ extern "C" void dnsb_ctx_destroy(dnsb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->cn.release(); ctx->geom.release();
+  ctx->n2c_ptr.release(); ctx->n2c_idx.release(); ctx->elem.release();
   ctx->cindptr.release(); ctx->cindices.release(); ctx->cslots.release();
   ctx->stage_a.release(); ctx->stage_b.release();
   ctx->stage_c.release(); ctx->stage_d.release();
@@ -414,6 +417,18 @@ extern "C" int dnsb_set_mesh(dnsb_ctx *ctx, int ncell, int nnodes,
     for (int a = 0; a < 6; ++a) cn[(size_t)a * ncell + q] = cell_nodes[c * 6 + a];
     for (int a = 0; a < 5; ++a) gm[(size_t)a * ncell + q] = geom[c * 5 + a];
   }
+  {
+    // node -> incident (cell, local node) pairs, in ascending (permuted) cell order
+    std::vector<int> ptr(nnodes + 1, 0), idx((size_t)6 * ncell);
+    for (int q = 0; q < ncell; ++q)
+      for (int a = 0; a < 6; ++a) ptr[cn[(size_t)a * ncell + q] + 1]++;
+    for (int k = 0; k < nnodes; ++k) ptr[k + 1] += ptr[k];
+    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+    for (int q = 0; q < ncell; ++q)
+      for (int a = 0; a < 6; ++a) idx[fill[cn[(size_t)a * ncell + q]]++] = q * 6 + a;
+    DNSB_CK(ctx, ctx->n2c_ptr.upload(ptr.data(), ptr.size(), ctx->stream));
+    DNSB_CK(ctx, ctx->n2c_idx.upload(idx.data(), idx.size(), ctx->stream));
+  }
   DNSB_CK(ctx, ctx->cn.upload(cn.data(), cn.size(), ctx->stream));
   DNSB_CK(ctx, ctx->geom.upload(gm.data(), gm.size(), ctx->stream));
   ctx->ncell = ncell; ctx->nnodes = nnodes; ctx->ncolours = ncolours;
@@ -454,22 +469,42 @@ extern "C" int dnsb_set_conv_pattern(dnsb_ctx *ctx, const int32_t *indptr,
   return 0;
 }
 
-// out = c(u1,u2) on device vectors (2*nnodes*nb), out is overwritten
+// out = sign * c(u1,u2) on device vectors: all 2*nnodes dofs (dofs == null,
+// nout = 2*nnodes) or the listed dofs only; out is overwritten.
+// Gather formulation by default (2 launches); DNSB_CONV_COLOURS=1 selects the
+// coloured scatter (one launch per colour), which only writes full vectors.
 static int convvec_dev(dnsb_ctx *ctx, const double *u1, const double *u2,
-                       double *out, int nb) {
-  const size_t nfull = (size_t)2 * ctx->nnodes * nb;
-  DNSB_CK(ctx, cudaMemsetAsync(out, 0, nfull * sizeof(double), ctx->stream));
-  for (int k = 0; k < ctx->ncolours; ++k) {
-    const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
-    if (c1 <= c0) continue;
-    const size_t threads = (size_t)(c1 - c0) * nb;
-    if (u2 == nullptr || u2 == u1)
-      LAUNCH(ctx, k_convvec<true>, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell,
-             ctx->cn.p, ctx->geom.p, u1, u1, out, nb);
-    else
-      LAUNCH(ctx, k_convvec<false>, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell,
-             ctx->cn.p, ctx->geom.p, u1, u2, out, nb);
+                       double *out, int nb, const int *dofs = nullptr, int nout = -1,
+                       double sign = 1.0) {
+  const bool same = (u2 == nullptr || u2 == u1);
+  if (g_conv_colours && dofs == nullptr && sign == 1.0) {
+    const size_t nfull = (size_t)2 * ctx->nnodes * nb;
+    DNSB_CK(ctx, cudaMemsetAsync(out, 0, nfull * sizeof(double), ctx->stream));
+    for (int k = 0; k < ctx->ncolours; ++k) {
+      const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
+      if (c1 <= c0) continue;
+      const size_t threads = (size_t)(c1 - c0) * nb;
+      if (same)
+        LAUNCH(ctx, k_convvec<true>, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell,
+               ctx->cn.p, ctx->geom.p, u1, u1, out, nb);
+      else
+        LAUNCH(ctx, k_convvec<false>, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell,
+               ctx->cn.p, ctx->geom.p, u1, u2, out, nb);
+    }
+    return 0;
   }
+  DNSB_CK(ctx, ctx->elem.alloc((size_t)12 * ctx->ncell * nb));
+  const size_t threads = (size_t)ctx->ncell * nb;
+  if (same)
+    LAUNCH(ctx, k_conv_elem<true>, cdiv(threads, 128), 128, 0, ctx->ncell, ctx->cn.p, ctx->geom.p,
+           u1, u1, ctx->elem.p, nb);
+  else
+    LAUNCH(ctx, k_conv_elem<false>, cdiv(threads, 128), 128, 0, ctx->ncell, ctx->cn.p, ctx->geom.p,
+           u1, u2, ctx->elem.p, nb);
+  if (nout < 0) nout = 2 * ctx->nnodes;
+  LAUNCH(ctx, k_conv_gather, cdiv((size_t)nout * nb, 256), 256, 0, nout, dofs,
+         (const int *)ctx->n2c_ptr.p, (const int *)ctx->n2c_idx.p, (const double *)ctx->elem.p, out,
+         nb, sign);
   return 0;
 }
 
@@ -1613,10 +1648,13 @@ static int imex_nonl(dnsb_imex *e, const double *v, double *nfc) {
   dnsb_ctx *ctx = e->ctx;
   const size_t nvb = (size_t)e->nv * e->nb;
   LAUNCH(ctx, k_scatter_inner, cdiv(nvb, 256), 256, 0, v, e->inv.p, e->vfull.p, e->nv, e->nb);
-  int rc = convvec_dev(ctx, e->vfull.p, nullptr, e->cfull.p, e->nb);
-  if (rc) return rc;
-  LAUNCH(ctx, k_gather_neg, cdiv(nvb, 256), 256, 0, e->cfull.p, e->inv.p, nfc, e->nv, e->nb);
-  return 0;
+  if (g_conv_colours) {
+    int rc = convvec_dev(ctx, e->vfull.p, nullptr, e->cfull.p, e->nb);
+    if (rc) return rc;
+    LAUNCH(ctx, k_gather_neg, cdiv(nvb, 256), 256, 0, e->cfull.p, e->inv.p, nfc, e->nv, e->nb);
+    return 0;
+  }
+  return convvec_dev(ctx, e->vfull.p, nullptr, nfc, e->nb, e->inv.p, e->nv, -1.0);
 }
 
 static const double *useries_at(dnsb_imex *e, long long n) {

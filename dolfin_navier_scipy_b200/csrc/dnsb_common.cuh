@@ -81,6 +81,8 @@ struct dnsb_ctx {
   unsigned long long mesh_hash = 0;   // of the cell table + geometry: integrators check they run on their mesh
   DBuf<int> cn;          // 6*ncell, SoA: cn[k*ncell + c]
   DBuf<double> geom;     // 5*ncell, SoA
+  DBuf<int> n2c_ptr, n2c_idx;   // node -> (permuted cell*6 + local node), ascending
+  DBuf<double> elem;            // element vectors ncell*12*nb (K1a gather formulation)
   std::vector<int> colour_ptr;   // ncolours+1 offsets into the permuted cells
   std::vector<int> perm;         // permuted position -> original cell
   // fixed pattern of the P2 vector space + per-cell slots (144*ncell SoA)

@@ -93,6 +93,101 @@ k_convvec(int c0, int c1, int ncell, const int *__restrict__ cn,
 }
 
 // ---------------------------------------------------------------------------
+// K1a, gather formulation (two launches, no colours, no atomics):
+//   k_conv_elem:   thread <-> (cell, member): element vector (6 nodes x 2
+//                  components) -> E[((cell*6 + a)*2 + c)*nb + m]
+//   k_conv_gather: thread <-> (output dof, member): sum of the element
+//                  contributions of the incident cells in the fixed order of
+//                  the node->(cell, local node) table  => deterministic.
+// Same algorithmic bytes as the coloured scatter (the read-modify-write of the
+// 12 dofs becomes a write + a read of E), but every cell is in flight at once
+// instead of one colour (a tenth of the mesh) per launch.  The gather can
+// restrict itself to the inner dofs and apply the sign of the explicit
+// convection term: nfc[i] = -c[inv[i]] (stokes_navier_utils.py:1136-1140).
+// ---------------------------------------------------------------------------
+template <bool SAME>
+__global__ void __launch_bounds__(128)
+k_conv_elem(int ncell, const int *__restrict__ cn, const double *__restrict__ geom,
+            const double *__restrict__ u1, const double *__restrict__ u2,
+            double *__restrict__ E, int nb) {
+  long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = (int)(tid / nb);
+  int m = (int)(tid % nb);
+  if (cell >= ncell) return;
+  int n[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) n[k] = cn[k * ncell + cell];
+  const double g1x = geom[0 * ncell + cell], g1y = geom[1 * ncell + cell];
+  const double g2x = geom[2 * ncell + cell], g2y = geom[3 * ncell + cell];
+  const double detj = geom[4 * ncell + cell];
+  const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+  double U1[6][2], U2[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    U1[k][0] = u1[(size_t)(2 * n[k]) * nb + m];
+    U1[k][1] = u1[(size_t)(2 * n[k] + 1) * nb + m];
+    if (SAME) {
+      U2[k][0] = U1[k][0];
+      U2[k][1] = U1[k][1];
+    } else {
+      U2[k][0] = u2[(size_t)(2 * n[k]) * nb + m];
+      U2[k][1] = u2[(size_t)(2 * n[k] + 1) * nb + m];
+    }
+  }
+  double acc[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc[k][0] = acc[k][1] = 0.0;
+  const double wdet = 0.5 * fabs(detj);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    double ux = 0, uy = 0, dxx = 0, dxy = 0, dyx = 0, dyy = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double gx = c_dphi[q][a][0] * g0x + c_dphi[q][a][1] * g1x +
+                        c_dphi[q][a][2] * g2x;
+      const double gy = c_dphi[q][a][0] * g0y + c_dphi[q][a][1] * g1y +
+                        c_dphi[q][a][2] * g2y;
+      ux += U2[a][0] * c_phi[q][a];
+      uy += U2[a][1] * c_phi[q][a];
+      dxx += U1[a][0] * gx;
+      dxy += U1[a][0] * gy;
+      dyx += U1[a][1] * gx;
+      dyy += U1[a][1] * gy;
+    }
+    const double w = c_qw[q] * wdet;
+    const double ax = w * (dxx * ux + dxy * uy);
+    const double ay = w * (dyx * ux + dyy * uy);
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      acc[a][0] += ax * c_phi[q][a];
+      acc[a][1] += ay * c_phi[q][a];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    E[((size_t)(cell * 6 + k) * 2 + 0) * nb + m] = acc[k][0];
+    E[((size_t)(cell * 6 + k) * 2 + 1) * nb + m] = acc[k][1];
+  }
+}
+
+// out[o, m] = sign * sum_{(cell,a) incident to node(dof)} E[((cell*6+a)*2 + comp)*nb + m]
+//   dofs == null: o = dof = all 2*nnodes dofs;  else dof = dofs[o] (inner dofs)
+__global__ void k_conv_gather(int nout, const int *__restrict__ dofs,
+                              const int *__restrict__ n2c_ptr, const int *__restrict__ n2c_idx,
+                              const double *__restrict__ E, double *__restrict__ out, int nb,
+                              double sign) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nout * nb) return;
+  const int o = (int)(t / nb), m = (int)(t % nb);
+  const int dof = dofs ? dofs[o] : o;
+  const int node = dof >> 1, comp = dof & 1;
+  double s = 0.0;
+  for (int k = n2c_ptr[node]; k < n2c_ptr[node + 1]; ++k)
+    s += E[((size_t)n2c_idx[k] * 2 + comp) * nb + m];
+  out[t] = sign * s;
+}
+
+// ---------------------------------------------------------------------------
 // K1b: convection matrices into the fixed CSR pattern.  thread <-> (cell,
 // local row n): 6 N1 entries (block diagonal, written for both components),
 // 24 N2 entries, 2 f3 entries.  Cells of one colour own disjoint slots.
