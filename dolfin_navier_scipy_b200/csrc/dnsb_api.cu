@@ -153,6 +153,7 @@ static inline bool batched_ok(const dnsb_csr *A, int nb) {
 static int g_rows_per_cta = 4;
 static int g_dense_ctas_per_sm = 2;
 static int g_graphs = 1;
+static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur solve
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
 static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
   const long total = (long)nrows * nb;
@@ -272,6 +273,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   ctx->device = device;
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
   if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
+  if (const char *ev = getenv("DNSB_DMMA")) g_dmma = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
@@ -291,6 +293,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
   // k_mdot_b keeps (nvec+1) x 256 partial sums in dynamic shared memory
   DNSB_CK(ctx, cudaFuncSetAttribute(k_mdot_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_dmma_streamk, cudaFuncAttributeMaxDynamicSharedMemorySize, DMM_SMEM_BYTES));
   return 0;
 }
 
@@ -980,7 +983,9 @@ static int dense_apply(dnsb_solver *s, MgLevel *L, const double *x,
     DenseSplit sp;
     dense_split(ctx, n, nb, &tn, &sp);
     const dim3 grid(sp.nctas, cdiv(nb, tn));
-    if (tn == 16)
+    if (g_dmma && nb > 32 && n % 2 == 0 && nb % 2 == 0)
+      LAUNCH(ctx, k_dense_dmma_streamk, grid, 128, DMM_SMEM_BYTES, L->dinv_dense.p, x, L->gpart.p, n, nb, sp);
+    else if (tn == 16)
       LAUNCH(ctx, k_dense_gemm_streamk<16>, grid, 128, 0, L->dinv_dense.p, x, L->gpart.p, n, nb, sp);
     else if (tn == 32)
       LAUNCH(ctx, k_dense_gemm_streamk<32>, grid, 128, 0, L->dinv_dense.p, x, L->gpart.p, n, nb, sp);

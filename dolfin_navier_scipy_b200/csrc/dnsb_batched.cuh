@@ -589,8 +589,11 @@ k_cheb_init_p2(CsrDev A, const double2 *__restrict__ zp, const double2 *__restri
   }
 }
 
+#ifndef SPP_MINB
+#define SPP_MINB 3
+#endif
 template <bool HAS2, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SPB_THREADS)
+__global__ void __launch_bounds__(SPB_THREADS, SPP_MINB)
 k_cheb_step_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ d,
                const double2 *__restrict__ dinv, double2 *res, double2 *__restrict__ dn,
                double2 *z, int nb, int npairs, double c1, double c2) {

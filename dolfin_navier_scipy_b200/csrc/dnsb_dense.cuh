@@ -157,3 +157,132 @@ __global__ void k_dense_epilogue(const double *__restrict__ part, DenseSplit sp,
   if (add_dinv) v += add_scale[m] * add_dinv[i] * X[t];
   Y[t] = alpha * v;
 }
+
+// ---------------------------------------------------------------------------
+// Tensor-core variant of the stream-K dense solve: fp64 DMMA
+// (mma.sync.m8n8k4.f64 -- the only fp64 matrix instruction; tcgen05 has no
+// fp64 kind) fed by a 3-stage cp.async pipeline.  Same decomposition and
+// partial-tile layout as k_dense_gemm_streamk (same epilogue); requires n and
+// nb even (16-byte cp.async chunks).
+//   CTA = 4 warps, tile 64 rows x 64 members; warp w owns rows 16w..16w+15:
+//   2 m-tiles x 8 n-tiles of 8x8 accumulators (32 doubles per lane).
+//   Shared tiles: D row-major [64][16] (row stride 20 doubles), X [16][64]
+//   (row stride 68 doubles): the fragment loads are bank-conflict free.
+// ---------------------------------------------------------------------------
+#define DMM_STAGES 3
+#define DMM_DS 20   // row stride of the D tile (doubles)
+#define DMM_XS 68   // row stride of the X tile (doubles)
+#define DMM_STAGE_DOUBLES (DGK_TM * DMM_DS + DGK_TK * DMM_XS)
+#define DMM_SMEM_BYTES (DMM_STAGES * DMM_STAGE_DOUBLES * 8)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+k_dense_dmma_streamk(const double *__restrict__ D, const double *__restrict__ X,
+                     double *__restrict__ part, int n, int nb, DenseSplit sp) {
+  extern __shared__ __align__(16) double dsm[];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int m0 = blockIdx.y * 64;
+  const long utotal = (long)((n + DGK_TM - 1) / DGK_TM) * sp.ksteps;
+  long u = (long)blockIdx.x * sp.upc;
+  const long uend = min(utotal, u + sp.upc);
+  int seg = 0;
+  while (u < uend) {
+    const int rt = (int)(u / sp.ksteps);
+    const int ks0 = (int)(u - (long)rt * sp.ksteps);
+    const int ks1 = (int)min((long)sp.ksteps, ks0 + (uend - u));
+    const int row0 = rt * DGK_TM;
+    const int nk = ks1 - ks0;
+    double acc[2][8][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    auto issue = [&](int kstep, int stage) {
+      double *sD = dsm + (size_t)stage * DMM_STAGE_DOUBLES;
+      double *sX = sD + DGK_TM * DMM_DS;
+      const int k0 = (ks0 + kstep) * DGK_TK;
+      // D tile: 64 rows x 8 chunks of 2 doubles
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = tid + 128 * q;
+        const int r = c >> 3, ch = c & 7;
+        const int gi = row0 + r, gk = k0 + 2 * ch;
+        const bool ok = gi < n && gk < n;
+        cp_async16(sD + r * DMM_DS + 2 * ch, ok ? (const void *)(D + (size_t)gi * n + gk) : (const void *)D,
+                   ok ? 16 : 0);
+      }
+      // X tile: 16 rows x 32 chunks of 2 members
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = tid + 128 * q;
+        const int r = c >> 5, ch = c & 31;
+        const int gk = k0 + r, gm = m0 + 2 * ch;
+        const bool ok = gk < n && gm < nb;
+        cp_async16(sX + r * DMM_XS + 2 * ch, ok ? (const void *)(X + (size_t)gk * nb + gm) : (const void *)X,
+                   ok ? 16 : 0);
+      }
+    };
+
+    __syncthreads();   // the previous segment is done with the buffers
+#pragma unroll
+    for (int s = 0; s < DMM_STAGES - 1; ++s) {
+      if (s < nk) issue(s, s);
+      cp_async_commit();
+    }
+    for (int ks = 0; ks < nk; ++ks) {
+      cp_async_wait<DMM_STAGES - 2>();
+      __syncthreads();
+      // prefetch the tile DMM_STAGES-1 steps ahead into the stage freed last
+      const int nxt = ks + DMM_STAGES - 1;
+      if (nxt < nk) issue(nxt, nxt % DMM_STAGES);
+      cp_async_commit();
+      const double *sD = dsm + (size_t)(ks % DMM_STAGES) * DMM_STAGE_DOUBLES;
+      const double *sX = sD + DGK_TM * DMM_DS;
+#pragma unroll
+      for (int kk = 0; kk < DGK_TK; kk += 4) {
+        const double a0 = sD[(16 * w + (lane >> 2)) * DMM_DS + kk + (lane & 3)];
+        const double a1 = sD[(16 * w + 8 + (lane >> 2)) * DMM_DS + kk + (lane & 3)];
+        double b[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) b[t] = sX[(kk + (lane & 3)) * DMM_XS + 8 * t + (lane >> 2)];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          dmma884(acc[0][t][0], acc[0][t][1], a0, b[t]);
+          dmma884(acc[1][t][0], acc[1][t][1], a1, b[t]);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    double *out = part + ((size_t)blockIdx.x * sp.maxseg + seg) * DGK_TM * nb;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int rl = 16 * w + 8 * a + (lane >> 2);
+      if (row0 + rl >= n) continue;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int gm = m0 + 8 * t + 2 * (lane & 3);
+        if (gm + 1 < nb) {
+          *reinterpret_cast<double2 *>(out + (size_t)rl * nb + gm) = make_double2(acc[a][t][0], acc[a][t][1]);
+        } else if (gm < nb) {
+          out[(size_t)rl * nb + gm] = acc[a][t][0];
+        }
+      }
+    }
+    u += nk;
+    ++seg;
+  }
+}

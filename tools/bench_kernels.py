@@ -44,7 +44,7 @@ for r in range(rmax + 1):
         U = rng.standard_normal((nvf, nb)) if nb > 1 else rng.standard_normal(nvf)
         t = sum(timed(lambda: dev.convvec(U)).values())
         by = 352.*ncell*nb
-        out.append(dict(kernel='k_convvec (K1a, %d colour launches)' % dev.ncolours, refine=r, ncell=ncell,
+        out.append(dict(kernel='k_conv_elem+k_conv_gather (K1a)', refine=r, ncell=ncell,
                         dofs=nvf, nb=nb, us=t*1e6, algorithmic_MB=by/1e6, GBs=by/t/1e9, frac=by/t/1e9/PEAK))
     u = rng.standard_normal(nvf)
     indptr, indices = dev.pattern
