@@ -439,8 +439,18 @@ def roofline_of(kern, info, integ, args):
     cnt, ms, bytes_ = fam[name]
     dur = ms*1e-3/cnt
     ach = bytes_/dur/1e9
+    # DRAM traffic per launch of the same kernel from the committed ncu
+    # `--set full` capture (profiles/ncu_traffic.json, written by
+    # tools/ncu_summary.py); None if that kernel was not captured
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            tr = json.load(f)
+        key = name.strip('()').replace('true', '1').replace('false', '0')
+        traffic = tr.get(key, {}).get('traffic_bytes')
     out = dict(bound='hbm', kernel=name.strip('()'), achieved=ach, peak=peak,
-               peak_source=which, unit='GB/s', frac=ach/peak, traffic=None,
+               peak_source=which, unit='GB/s', frac=ach/peak, traffic=traffic,
                launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
     dn = [k for k in kern if k.strip('()').startswith('k_dense_gemm')]
     if dn:

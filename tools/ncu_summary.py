@@ -26,7 +26,7 @@ STALLS = ['long_scoreboard', 'short_scoreboard', 'wait', 'math_pipe_throttle',
           'tex_throttle', 'drain', 'imc_miss', 'sleeping']
 
 
-def main(rep, title=''):
+def main(rep, title='', traffic_json=None):
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -41,6 +41,7 @@ def main(rep, title=''):
           'traffic MB | DRAM % | L2 % | L1 % | SM % | L1 hit % | L2 hit % | '
           'occupancy % | fp64 pipe % | top stalls (share of samples) |')
     print('|' + '---|'*17)
+    traffic = {}
     for r in rows[2:]:
         g = lambda k: r[col[k]] if k in col else ''
         f = lambda k: float(g(k).replace(',', '')) if g(k) not in ('', 'n/a') else float('nan')
@@ -63,6 +64,10 @@ def main(rep, title=''):
                         sorted(st.items(), key=lambda kv: -kv[1])[:3])
         name = g('Kernel Name').split('(')[0].replace('void ', '')
         rd, wr = mb('dram__bytes_read.sum'), mb('dram__bytes_write.sum')
+        t = traffic.setdefault(name, dict(launches=0, traffic_bytes=0., us=0.))
+        t['traffic_bytes'] = (t['traffic_bytes']*t['launches'] + 1e6*(rd + wr))/(t['launches'] + 1)
+        t['us'] = (t['us']*t['launches'] + dur)/(t['launches'] + 1)
+        t['launches'] += 1
         print('| %s | `%s` | %s x %s | %s | %.1f | %.1f | %.1f | %.1f | %.0f | %.0f | %.0f | %.0f | %.0f | %.0f | %.0f | %.0f | %s |' % (
             g('ID'), name, g('launch__grid_size'), g('launch__block_size'),
             g('launch__registers_per_thread'), dur, rd, wr, rd + wr,
@@ -75,5 +80,13 @@ def main(rep, title=''):
             f('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'), top))
 
 
+    if traffic_json:
+        import json
+        with open(traffic_json, 'w') as f:
+            json.dump(dict(source=rep, note='mean dram__bytes_read.sum + '
+                           'dram__bytes_write.sum per launch (ncu --set full)',
+                           **traffic), f, indent=1, sort_keys=True)
+
+
 if __name__ == '__main__':
-    main(*sys.argv[1:3])
+    main(*sys.argv[1:4])
