@@ -55,6 +55,13 @@ SIGNATURES = {
                                c_int_p, c_dbl_p]),
     'dnsb_solver_update_fvalues': (_i, [_vp, c_dbl_p]),
     'dnsb_solver_apply_prec': (_i, [_vp, c_dbl_p, c_dbl_p]),
+    'dnsb_cnsweep_create': (_i, [_vp, _vp, c_dbl_p, c_dbl_p, _i, c_int_p, c_int_p,
+                                 c_int_p, _i, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p,
+                                 c_void_pp]),
+    'dnsb_cnsweep_destroy': (None, [_vp]),
+    'dnsb_cnsweep_run': (_i, [_vp, _i, c_dbl_p, _i, c_dbl_p, c_dbl_p, c_dbl_p, _d,
+                              _i, c_dbl_p, c_dbl_p, c_dbl_p,
+                              ctypes.POINTER(_ll)]),
     'dnsb_imex_create': (_i, [_vp, _i, _i, _d, _vp, _vp, _vp, _vp, c_dbl_p,
                               c_int_p, _i, _i, c_int_p, c_dbl_p, c_dbl_p,
                               c_dbl_p, c_void_pp]),
@@ -525,4 +532,46 @@ class ImexEngine(object):
     def close(self):
         if self.h:
             self.ctx.lib.dnsb_imex_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+
+class CnSweep(object):
+    """``dnsb_cnsweep``: device-resident Picard/Newton + Crank-Nicolson sweep"""
+
+    def __init__(self, solver, mmat, mvals, avals, src, pos, invinds, bcinds,
+                 bcvals, fv, fp, nvf):
+        self.ctx = solver.ctx
+        self.solver, self.mmat = solver, mmat
+        self.nv, self.np_, self.nvf = solver.nv, solver.np_, int(nvf)
+        mvals, avals = _f64(mvals), _f64(avals)
+        src, pos = _i32(src), _i32(pos)
+        invinds, bcinds = _i32(invinds), _i32(bcinds)
+        bcvals = _f64(bcvals)
+        fv, fp = _f64(fv, (-1,)), _f64(fp, (-1,))
+        h = ctypes.c_void_p()
+        self.ctx.check(self.ctx.lib.dnsb_cnsweep_create(
+            solver.h, mmat.h, _dp(mvals), _dp(avals), src.size, _ip(src),
+            _ip(pos), _ip(invinds), bcinds.size, _ip(bcinds), _dp(bcvals),
+            _dp(fv), _dp(fp), ctypes.byref(h)))
+        self.h = h
+
+    def run(self, dts, linpoint, v0, p0, picard, tol=1e-12, maxit=2000):
+        """returns ``(vtraj (n+1, V.dim()), ptraj (n+1, NP), upd_norm, iters)``"""
+        dts = _f64(dts)
+        n = dts.size
+        linpoint = _f64(linpoint, (n + 1, self.nvf))
+        v0 = _f64(v0, (-1,))
+        p0 = _f64(p0, (-1,)) if p0 is not None else None
+        vtraj = np.empty((n + 1, self.nvf))
+        ptraj = np.empty((n + 1, self.np_))
+        nrm, its = ctypes.c_double(0.), _ll(0)
+        self.ctx.check(self.ctx.lib.dnsb_cnsweep_run(
+            self.h, n, _dp(dts), int(bool(picard)), _dp(linpoint), _dp(v0),
+            _dp(p0), float(tol), int(maxit), _dp(vtraj), _dp(ptraj),
+            ctypes.byref(nrm), ctypes.byref(its)))
+        return vtraj, ptraj, nrm.value, its.value
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dnsb_cnsweep_destroy(self.h)
             self.h = ctypes.c_void_p()

@@ -1436,6 +1436,274 @@ extern "C" int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1) {
   return 0;
 }
 
+// ===========================================================================
+// device-resident Picard/Newton + Crank-Nicolson sweep
+// ===========================================================================
+// vals[pos[k]] = n1[src[k]] (+ n2[src[k]]);  vals is zeroed by the caller
+__global__ void k_conv_to_pattern(const double *__restrict__ n1, const double *__restrict__ n2,
+                                  const int *__restrict__ src, const int *__restrict__ pos,
+                                  double *__restrict__ vals, int nconv) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nconv) return;
+  const int sk = src[k];
+  vals[pos[k]] = n2 ? n1[sk] + n2[sk] : n1[sk];
+}
+
+// out[i] = fv[i] - sum_k (n1[k] (+ n2[k])) * ubc[col_k]  over row inv[i] of the
+// full convection pattern  (+ f3[inv[i]] for Newton);  8 lanes per row
+__global__ void k_conv_rhs(const int *__restrict__ cindptr, const int *__restrict__ cindices,
+                           const double *__restrict__ n1, const double *__restrict__ n2,
+                           const double *__restrict__ ubc, const double *__restrict__ f3,
+                           const double *__restrict__ fv, const int *__restrict__ inv,
+                           double *__restrict__ out, int nv) {
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid >> 3), lane = (int)(tid & 7);
+  double acc = 0.0;
+  if (i < nv) {
+    const int r = inv[i];
+    for (int k = cindptr[r] + lane; k < cindptr[r + 1]; k += 8)
+      acc += (n2 ? n1[k] + n2[k] : n1[k]) * ubc[cindices[k]];
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, 8);
+  if (i < nv && lane == 0) out[i] = fv[i] - acc + (f3 ? f3[inv[i]] : 0.0);
+}
+
+// out = a + c*(b + n)   (value arrays on one pattern)
+__global__ void k_vals_combine(const double *__restrict__ a, const double *__restrict__ b,
+                               const double *__restrict__ n, double c, double *__restrict__ out,
+                               size_t nnz) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  out[k] = a[k] + c * (b[k] + n[k]);
+}
+
+// rhs = rhs + c*(fa + fb - y)
+__global__ void k_cn_rhs(double *__restrict__ rhs, const double *__restrict__ fa,
+                         const double *__restrict__ fb, const double *__restrict__ y, double c,
+                         int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rhs[i] += c * (fa[i] + fb[i] - y[i]);
+}
+
+// d = v - lin[inv]   (difference to the linearisation point, inner dofs)
+__global__ void k_diff_inner(const double *__restrict__ v, const double *__restrict__ linfull,
+                             const int *__restrict__ inv, double *__restrict__ d, int nv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  d[i] = v[i] - linfull[inv[i]];
+}
+
+struct dnsb_cnsweep {
+  dnsb_ctx *ctx = nullptr;
+  unsigned long long mesh_hash = 0;
+  dnsb_solver *s = nullptr;
+  dnsb_csr *M = nullptr;      // mass matrix (own pattern)
+  dnsb_csr *C = nullptr;      // owned: (A + N_c) on the pattern of F
+  int nv = 0, np = 0, nvf = 0, nconv = 0, nbc = 0;
+  DBuf<double> mv, av, nvn, nvc;          // value arrays on the pattern of F
+  DBuf<int> src, pos, inv, bcinds;
+  DBuf<double> bcvals, ubc, fv, fp;
+  DBuf<double> n1, n2, f3;                // K1b outputs on the full convection pattern
+  DBuf<double> vfull, fn, fc, b, x, y, dvec, mdv, lin, vtraj, ptraj, v, p;
+  DBuf<double> npart, nout;
+};
+
+// K1b on device vectors: n1, n2 (full pattern values), f3 (full vector)
+static int convmats_dev(dnsb_ctx *ctx, const double *u0, double *n1, double *n2, double *f3) {
+  const size_t nfull = (size_t)2 * ctx->nnodes, nnz = ctx->cnnz;
+  DNSB_CK(ctx, cudaMemsetAsync(n1, 0, nnz * sizeof(double), ctx->stream));
+  if (n2) DNSB_CK(ctx, cudaMemsetAsync(n2, 0, nnz * sizeof(double), ctx->stream));
+  if (f3) DNSB_CK(ctx, cudaMemsetAsync(f3, 0, nfull * sizeof(double), ctx->stream));
+  for (int k = 0; k < ctx->ncolours; ++k) {
+    const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
+    if (c1 <= c0) continue;
+    const size_t threads = (size_t)(c1 - c0) * 6;
+    LAUNCH(ctx, k_convmats, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell, ctx->cn.p, ctx->geom.p,
+           ctx->cslots.p, u0, n1, n2, f3);
+  }
+  return 0;
+}
+
+extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double *mvals,
+                                   const double *avals, int nconv, const int32_t *src,
+                                   const int32_t *pos, const int32_t *invinds, int nbc,
+                                   const int32_t *bcinds, const double *bcvals, const double *fv,
+                                   const double *fp, dnsb_cnsweep **out) {
+  if (!s) return -2;
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_REQUIRE(ctx, out && mmat && mvals && avals && src && pos && invinds && fv, "null arguments");
+  DNSB_REQUIRE(ctx, s->nb == 1 && !s->F->has2, "the sweep needs a single-system solver with one value array");
+  DNSB_REQUIRE(ctx, ctx->ncell > 0 && ctx->cnnz > 0, "set the mesh and the convection pattern first");
+  DNSB_REQUIRE(ctx, mmat->nrows == s->nv && mmat->ncols == s->nv, "mass matrix shape");
+  const int nv = s->nv, np = s->np, nvf = 2 * ctx->nnodes;
+  const int nnz = s->F->nnz;
+  for (int k = 0; k < nconv; ++k)
+    DNSB_REQUIRE(ctx, src[k] >= 0 && src[k] < ctx->cnnz && pos[k] >= 0 && pos[k] < nnz, "convection map out of range");
+  for (int i = 0; i < nv; ++i) DNSB_REQUIRE(ctx, invinds[i] >= 0 && invinds[i] < nvf, "invinds out of range");
+  for (int i = 0; i < nbc; ++i) DNSB_REQUIRE(ctx, bcinds[i] >= 0 && bcinds[i] < nvf, "bcinds out of range");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  dnsb_cnsweep *w = new (std::nothrow) dnsb_cnsweep();
+  DNSB_REQUIRE(ctx, w != nullptr, "out of host memory");
+  *out = w;
+  w->ctx = ctx; w->mesh_hash = ctx->mesh_hash; w->s = s; w->M = mmat;
+  w->nv = nv; w->np = np; w->nvf = nvf; w->nconv = nconv; w->nbc = nbc;
+  {
+    int rc = csr_build(ctx, nv, nv, s->F->h_indptr.data(), s->F->h_indices.data(), avals, nullptr, &w->C);
+    if (rc) return rc;
+  }
+  DNSB_CK(ctx, w->mv.upload(mvals, nnz, ctx->stream));
+  DNSB_CK(ctx, w->av.upload(avals, nnz, ctx->stream));
+  DNSB_CK(ctx, w->nvn.alloc(nnz)); DNSB_CK(ctx, w->nvc.alloc(nnz));
+  DNSB_CK(ctx, w->src.upload(src, nconv, ctx->stream));
+  DNSB_CK(ctx, w->pos.upload(pos, nconv, ctx->stream));
+  DNSB_CK(ctx, w->inv.upload(invinds, nv, ctx->stream));
+  std::vector<double> ub(nvf, 0.0);
+  for (int i = 0; i < nbc; ++i) ub[bcinds[i]] = bcvals[i];
+  DNSB_CK(ctx, w->ubc.upload(ub.data(), nvf, ctx->stream));
+  if (nbc > 0) {
+    DNSB_CK(ctx, w->bcinds.upload(bcinds, nbc, ctx->stream));
+    DNSB_CK(ctx, w->bcvals.upload(bcvals, nbc, ctx->stream));
+  }
+  std::vector<double> zero(np, 0.0);
+  DNSB_CK(ctx, w->fv.upload(fv, nv, ctx->stream));
+  DNSB_CK(ctx, w->fp.upload(fp ? fp : zero.data(), np, ctx->stream));
+  DNSB_CK(ctx, w->n1.alloc(ctx->cnnz)); DNSB_CK(ctx, w->n2.alloc(ctx->cnnz));
+  DNSB_CK(ctx, w->f3.alloc(nvf));
+  DNSB_CK(ctx, w->vfull.alloc(nvf)); DNSB_CK(ctx, w->fn.alloc(nv)); DNSB_CK(ctx, w->fc.alloc(nv));
+  DNSB_CK(ctx, w->b.alloc(nv + np)); DNSB_CK(ctx, w->x.alloc(nv + np)); DNSB_CK(ctx, w->y.alloc(nv));
+  DNSB_CK(ctx, w->dvec.alloc(nv)); DNSB_CK(ctx, w->mdv.alloc(nv));
+  DNSB_CK(ctx, w->v.alloc(nv)); DNSB_CK(ctx, w->p.alloc(np));
+  RedCfg rc = red_cfg(ctx, nv, 1);
+  DNSB_CK(ctx, w->npart.alloc(rc.nblocks)); DNSB_CK(ctx, w->nout.alloc(1));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+extern "C" void dnsb_cnsweep_destroy(dnsb_cnsweep *w) {
+  if (!w) return;
+  cudaSetDevice(w->ctx->device);
+  cudaStreamSynchronize(w->ctx->stream);
+  csr_free(w->C);
+  w->mv.release(); w->av.release(); w->nvn.release(); w->nvc.release();
+  w->src.release(); w->pos.release(); w->inv.release(); w->bcinds.release();
+  w->bcvals.release(); w->ubc.release(); w->fv.release(); w->fp.release();
+  w->n1.release(); w->n2.release(); w->f3.release();
+  w->vfull.release(); w->fn.release(); w->fc.release(); w->b.release(); w->x.release();
+  w->y.release(); w->dvec.release(); w->mdv.release(); w->lin.release(); w->vtraj.release();
+  w->ptraj.release(); w->v.release(); w->p.release(); w->npart.release(); w->nout.release();
+  delete w;
+}
+
+// values of the condensed convection matrix of `vfull` on the pattern of F
+// (into `vals`) and f = fv - (N u_bc)[inv] (+ N(v)v[inv] for Newton)
+static int cnsweep_conv(dnsb_cnsweep *w, const double *vfull, bool picard, double *vals, double *f) {
+  dnsb_ctx *ctx = w->ctx;
+  int rc = convmats_dev(ctx, vfull, w->n1.p, picard ? nullptr : w->n2.p, picard ? nullptr : w->f3.p);
+  if (rc) return rc;
+  const double *n2 = picard ? nullptr : w->n2.p;
+  DNSB_CK(ctx, cudaMemsetAsync(vals, 0, (size_t)w->s->F->nnz * sizeof(double), ctx->stream));
+  LAUNCH(ctx, k_conv_to_pattern, cdiv(w->nconv, 256), 256, 0, (const double *)w->n1.p, n2,
+         (const int *)w->src.p, (const int *)w->pos.p, vals, w->nconv);
+  LAUNCH(ctx, k_conv_rhs, cdiv((size_t)w->nv * 8, 256), 256, 0, (const int *)ctx->cindptr.p,
+         (const int *)ctx->cindices.p, (const double *)w->n1.p, n2, (const double *)w->ubc.p,
+         picard ? (const double *)nullptr : (const double *)w->f3.p, (const double *)w->fv.p,
+         (const int *)w->inv.p, f, w->nv);
+  return 0;
+}
+
+// One sweep over the time grid (stokes_navier_utils.py:1402-1566): step n
+// linearises the "next" side about linpoint[n] (the previous sweep's state,
+// full vectors incl. boundary values) and the "current" side about the
+// sweep's own state.  dts: nsteps step sizes.  vtraj ((nsteps+1)*nvf) and
+// ptraj ((nsteps+1)*np) receive the trajectory (index 0 = initial state);
+// upd_norm = sum_n dt_n (v_n - lin_n)^T M (v_n - lin_n)  (:1557-1560).
+extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, int picard,
+                                const double *linpoint, const double *v0, const double *p0,
+                                double tol, int maxit, double *vtraj, double *ptraj,
+                                double *upd_norm, long long *iters_total) {
+  if (!w) return -2;
+  dnsb_ctx *ctx = w->ctx;
+  DNSB_REQUIRE(ctx, nsteps >= 1 && dts && linpoint && v0 && vtraj && ptraj, "bad arguments");
+  DNSB_REQUIRE(ctx, w->mesh_hash == ctx->mesh_hash, "the mesh of the context is not the one this sweep was created on");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  dnsb_solver *s = w->s;
+  const int nv = w->nv, np = w->np, nvf = w->nvf, nnz = s->F->nnz;
+  DNSB_CK(ctx, w->lin.upload(linpoint, (size_t)(nsteps + 1) * nvf, ctx->stream));
+  DNSB_CK(ctx, w->vtraj.alloc((size_t)(nsteps + 1) * nvf));
+  DNSB_CK(ctx, w->ptraj.alloc((size_t)(nsteps + 1) * np));
+  DNSB_CK(ctx, cudaMemcpyAsync(w->v.p, v0, nv * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (p0) DNSB_CK(ctx, cudaMemcpyAsync(w->p.p, p0, np * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  else DNSB_CK(ctx, w->p.zero(ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  RedCfg rcn = red_cfg(ctx, nv, 1);
+  // full velocity of the initial state (boundary values included)
+  DNSB_CK(ctx, w->vfull.zero(ctx->stream));
+  if (w->nbc > 0)
+    LAUNCH(ctx, k_set_bcs, cdiv((size_t)w->nbc, 256), 256, 0, w->bcinds.p, w->bcvals.p, w->vfull.p, w->nbc, 1);
+  LAUNCH(ctx, k_scatter_inner, cdiv((size_t)nv, 256), 256, 0, (const double *)w->v.p, w->inv.p, w->vfull.p, nv, 1);
+  DNSB_CK(ctx, cudaMemcpyAsync(w->vtraj.p, w->vfull.p, nvf * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DNSB_CK(ctx, cudaMemcpyAsync(w->ptraj.p, w->p.p, np * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  int rc = cnsweep_conv(w, w->vfull.p, picard != 0, w->nvc.p, w->fc.p);
+  if (rc) return rc;
+  // x0 of the first solve: [v; -dt p]
+  DNSB_CK(ctx, cudaMemcpyAsync(w->x.p, w->v.p, nv * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  LAUNCH(ctx, k_axpby, cdiv((size_t)np, 256), 256, 0, -dts[0], (const double *)w->p.p, 0.0,
+         (const double *)nullptr, w->x.p + nv, (size_t)np);
+  double norm_acc = 0.0;
+  long long its0 = s->stat_iters;
+  for (int n = 1; n <= nsteps; ++n) {
+    const double dt = dts[n - 1];
+    const double *lin_n = w->lin.p + (size_t)n * nvf;
+    // "next" side: linearised about the previous sweep's state at t_n
+    rc = cnsweep_conv(w, lin_n, picard != 0, w->nvn.p, w->fn.p);
+    if (rc) return rc;
+    // F = M + dt/2 (A + N_n)  -> solver (values of F, its copy inside K, Jacobi diagonal)
+    LAUNCH(ctx, k_vals_combine, cdiv((size_t)nnz, 256), 256, 0, (const double *)w->mv.p,
+           (const double *)w->av.p, (const double *)w->nvn.p, 0.5 * dt, s->F->v1.p, (size_t)nnz);
+    LAUNCH(ctx, k_copy_f_into_k, cdiv((size_t)nv * 32, 256), 256, 0, s->F->view(),
+           (const int *)s->K->indptr.p, s->K->v1.p);
+    LAUNCH(ctx, k_diag_inv, cdiv((size_t)nv, 256), 256, 0, s->F->view(), s->diagpos.p,
+           (const double *)nullptr, s->dinv.p, 1);
+    // rhs = M v + dt/2 (f_n + f_c - (A + N_c) v)
+    LAUNCH(ctx, k_axpby, cdiv((size_t)nnz, 256), 256, 0, 1.0, (const double *)w->av.p, 1.0,
+           (const double *)w->nvc.p, w->C->v1.p, (size_t)nnz);
+    spmm_dev(ctx, w->C, nullptr, w->v.p, nullptr, w->y.p, 1, 1.0, 0.0);
+    spmm_dev(ctx, w->M, nullptr, w->v.p, nullptr, w->b.p, 1, 1.0, 0.0);
+    LAUNCH(ctx, k_cn_rhs, cdiv(nv, 256), 256, 0, w->b.p, (const double *)w->fn.p, (const double *)w->fc.p,
+           (const double *)w->y.p, 0.5 * dt, nv);
+    DNSB_CK(ctx, cudaMemcpyAsync(w->b.p + nv, w->fp.p, np * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    s->expect_its = 0;
+    rc = solver_solve_dev(s, w->b.p, w->x.p, tol, maxit, false);
+    if (rc) return rc;
+    DNSB_CK(ctx, cudaMemcpyAsync(w->v.p, w->x.p, nv * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(ctx, k_extract_p, cdiv((size_t)np, 256), 256, 0, (const double *)w->x.p, w->p.p, nv, np, 1, -1.0 / dt);
+    // "current" side about the new state
+    LAUNCH(ctx, k_scatter_inner, cdiv((size_t)nv, 256), 256, 0, (const double *)w->v.p, w->inv.p, w->vfull.p, nv, 1);
+    rc = cnsweep_conv(w, w->vfull.p, picard != 0, w->nvc.p, w->fc.p);
+    if (rc) return rc;
+    DNSB_CK(ctx, cudaMemcpyAsync(w->vtraj.p + (size_t)n * nvf, w->vfull.p, nvf * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    DNSB_CK(ctx, cudaMemcpyAsync(w->ptraj.p + (size_t)n * np, w->p.p, np * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    // update norm  dt (v - lin)^T M (v - lin)
+    LAUNCH(ctx, k_diff_inner, cdiv(nv, 256), 256, 0, (const double *)w->v.p, lin_n, (const int *)w->inv.p, w->dvec.p, nv);
+    spmm_dev(ctx, w->M, nullptr, w->dvec.p, nullptr, w->mdv.p, 1, 1.0, 0.0);
+    LAUNCH(ctx, k_dot1, rcn.nblocks, rcn.threads, rcn.smem, (const double *)w->dvec.p, (const double *)w->mdv.p, nv, 1, rcn.rpb, w->npart.p);
+    LAUNCH(ctx, k_reduce_partials2, 1, 1024, 0, (const double *)w->npart.p, rcn.nblocks, 1, w->nout.p);
+    double hn = 0.0;
+    DNSB_CK(ctx, cudaMemcpyAsync(&hn, w->nout.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    norm_acc += dt * hn;
+  }
+  DNSB_CK(ctx, cudaMemcpyAsync(vtraj, w->vtraj.p, (size_t)(nsteps + 1) * nvf * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaMemcpyAsync(ptraj, w->ptraj.p, (size_t)(nsteps + 1) * np * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (upd_norm) *upd_norm = norm_acc;
+  if (iters_total) *iters_total = s->stat_iters - its0;
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
 // z = P^-1 r on host vectors: the preconditioner alone (tests compare it with
 // a numpy restatement of the same hierarchy)
 extern "C" int dnsb_solver_apply_prec(dnsb_solver *s, const double *r, double *z) {

@@ -278,8 +278,23 @@ def sa_amg_hierarchy(A, coarse_max=4096, theta=0.08, max_levels=10,
             groups = (newcols // ncomp, newcols % ncomp)
     Ad = A.toarray()
     sym = np.allclose(Ad, Ad.T, rtol=1e-10, atol=1e-14*np.abs(Ad).max())
-    dense_inv = np.linalg.pinv(Ad, hermitian=True) if sym \
-        else np.linalg.pinv(Ad)
+    dense_inv = None
+    if sym:
+        # SPD (the usual case: Schur approximations with an outflow boundary,
+        # Galerkin coarse operators): Cholesky inverse, 4x faster than the
+        # eigenvalue-based pseudo-inverse
+        import scipy.linalg as sla
+        try:
+            cf = sla.cho_factor(.5*(Ad + Ad.T), check_finite=True)
+            dg = np.abs(np.diag(cf[0]))
+            if dg.min() > 1e-7*dg.max():
+                dense_inv = sla.cho_solve(cf, np.eye(Ad.shape[0]))
+        except (sla.LinAlgError, ValueError):
+            dense_inv = None
+    if dense_inv is None:
+        # singular (enclosed flow: constant pressure mode) or nonsymmetric
+        dense_inv = np.linalg.pinv(Ad, hermitian=True) if sym \
+            else np.linalg.pinv(Ad)
     return levels, dense_inv
 
 

@@ -429,64 +429,83 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         except KeyError:
             return pnt[None]
 
-    op = None
+    # ---- the sweeps: device resident (`dnsb_cnsweep_run`) ---------------------
+    # per sweep the host uploads the linearisation trajectory and receives the
+    # new one; assembly (K1b), matrix update, right-hand side, FGMRES and the
+    # update norm of every step stay on the device.
+    dts_all = np.diff(trange)
+    nsteps = dts_all.size
+    uniq = {}
+    for i, v in zip(dbcinds, dbcvals):
+        uniq[int(i)] = float(v)
+    bci = np.array(sorted(uniq.keys()), dtype=np.int32)
+    bcv = np.array([uniq[i] for i in bci], dtype=float)
+    op = sweep = None
+    if not stokes_flow:
+        dt0 = float(dts_all[0])
+        nv0, _, _ = _convconts(_appbcs(iniv), vel_pcrd_stps > 0)
+        op = lau.SadpntOperator(_csr(Mv + 0.5*dt0*(Av + nv0)), J, JT, ncols=1,
+                                velocity_amg=False, schur='lumped',
+                                cheb_steps=min(cheb_steps, 3))
+        mmat = op.ctx.csr(M)
+        dev.bind()
+        sweep = _lib.CnSweep(op.solver, mmat, Mv, Av, src, convpos, invinds,
+                             bci, bcv, fv, fp, nvf)
     while newtk < vel_nwtn_stps and norm_nwtnupd > vel_nwtn_tol:
-        v_old, p_old = iniv, inip
         if vel_pcrd_stps > 0:
             vel_pcrd_stps -= 1
             pcrd_anyone = True
         else:
             pcrd_anyone = False
             newtk += 1
-        dictofvelstrs = {float(trange[0]): _appbcs(iniv)}
-        dictofpstrs = {float(trange[0]): inip}
-        nv_c, rhs_con_c, rhsv_conbc_c = _convconts(_appbcs(v_old),
-                                                   pcrd_anyone)
-        fvn_c = fv + rhsv_conbc_c + rhs_con_c
-        norm_nwtnupd = 0
-        x0 = None
-        for tk, t in enumerate(trange[1:]):
-            cts = t - trange[tk]
-            prev_v = v_old if stokes_flow else \
-                np.asarray(_lookup(cur_linvel_point, float(t)))
-            prev_full = prev_v if len(prev_v) == nvf else _appbcs(prev_v)
-            nv_n, rhs_con_n, rhsv_conbc_n = _convconts(prev_full, pcrd_anyone)
-            fvn_n = fv + rhsv_conbc_n + rhs_con_n
-            solvvals = Mv + 0.5*cts*(Av + nv_n)                   # snu:1034
-            rhsv = M@v_old + 0.5*cts*(fvn_n + fvn_c -
-                                      _csr(Av + nv_c)@v_old)      # snu:1035
-            if op is None:
-                op = lau.SadpntOperator(_csr(solvvals), J, JT, ncols=1,
-                                        velocity_amg=False, schur='lumped',
-                                        cheb_steps=min(cheb_steps, 3))
-            else:
-                op.update_values(solvvals)
-            if x0 is None:
-                x0 = np.vstack([v_old, -cts*p_old])
-            vp_new = op.solve(rhsv, fp, x0=x0, tol=lin_tol, maxit=2000)
-            if 'convstatsl' in krpslvprms:
-                krpslvprms['convstatsl'].append(int(op.last_iters.max()))
-            x0 = vp_new
-            v_old = vp_new[:cnv, ]
-            nv_c, rhs_con_c, rhsv_conbc_c = _convconts(_appbcs(v_old),
-                                                       pcrd_anyone)
-            fvn_c = fvn_n - rhs_con_n - rhsv_conbc_n + rhsv_conbc_c \
-                + rhs_con_c                                      # snu:1537
-            p_old = -1/cts*vp_new[cnv:, ]                        # snu:1542
-            dictofvelstrs[float(t)] = _appbcs(v_old)
-            dictofpstrs[float(t)] = p_old
-            if stokes_flow:
-                norm_nwtnupd = None
-            else:
-                prev_in = prev_v[invinds, :] if len(prev_v) > cnv else prev_v
-                norm_nwtnupd += float((cts*m_innerproduct(
-                    M, v_old - prev_in)).flatten()[0])           # snu:1559
+        if stokes_flow:
+            # linear problem: one "sweep" without convection, host-driven
+            v_old, p_old = iniv, inip
+            dictofvelstrs = {float(trange[0]): _appbcs(iniv)}
+            dictofpstrs = {float(trange[0]): inip}
+            x0 = None
+            for tk, t in enumerate(trange[1:]):
+                cts = t - trange[tk]
+                solvvals = Mv + 0.5*cts*Av
+                rhsv = M@v_old + 0.5*cts*(2*fv - A@v_old)
+                if op is None:
+                    op = lau.SadpntOperator(_csr(solvvals), J, JT, ncols=1,
+                                            velocity_amg=False, schur='lumped',
+                                            cheb_steps=min(cheb_steps, 3))
+                else:
+                    op.update_values(solvvals)
+                x0 = np.vstack([v_old, -cts*p_old]) if x0 is None else x0
+                x0 = op.solve(rhsv, fp, x0=x0, tol=lin_tol, maxit=2000)
+                v_old, p_old = x0[:cnv, ], -1/cts*x0[cnv:, ]
+                dictofvelstrs[float(t)] = _appbcs(v_old)
+                dictofpstrs[float(t)] = p_old
+            norm_nwtnupd = None
+            nwtnupd_norms.append(norm_nwtnupd)
+            break
+        lin = np.vstack([np.asarray(_lookup(cur_linvel_point, float(t))).
+                         reshape(1, -1) if
+                         np.asarray(_lookup(cur_linvel_point, float(t))).size
+                         == nvf else
+                         _appbcs(_lookup(cur_linvel_point, float(t))).
+                         reshape(1, -1) for t in trange])
+        dev.bind()
+        vtraj, ptraj, norm_nwtnupd, its = sweep.run(
+            dts_all, lin, iniv, inip, pcrd_anyone, tol=lin_tol, maxit=2000)
+        if 'convstatsl' in krpslvprms:
+            krpslvprms['convstatsl'].append(its/float(nsteps))
+        dictofvelstrs = {float(t): vtraj[k].reshape(-1, 1)
+                         for k, t in enumerate(trange)}
+        dictofpstrs = {float(t): ptraj[k].reshape(-1, 1)
+                       for k, t in enumerate(trange)}
+        dictofpstrs[float(trange[0])] = inip
+        v_old = vtraj[-1].reshape(-1, 1)[invinds, :]
+        p_old = ptraj[-1].reshape(-1, 1)
         nwtnupd_norms.append(norm_nwtnupd)
         if verbose:
             print('norm of current Newton update: {}'.format(norm_nwtnupd))
         cur_linvel_point = dictofvelstrs
-        if stokes_flow:
-            break
+    if sweep is not None:
+        sweep.close()
     if op is not None:
         op.close()
 

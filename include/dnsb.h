@@ -28,6 +28,7 @@ typedef struct dnsb_ctx dnsb_ctx;
 typedef struct dnsb_csr dnsb_csr;       /* CSR pattern + 1..2 value arrays on the device */
 typedef struct dnsb_solver dnsb_solver; /* saddle-point FGMRES solver */
 typedef struct dnsb_imex dnsb_imex;     /* device-resident IMEX time stepper */
+typedef struct dnsb_cnsweep dnsb_cnsweep; /* device-resident Picard/Newton + Crank-Nicolson sweep */
 
 /* ---- context ------------------------------------------------------------ */
 int dnsb_ctx_create(int device, dnsb_ctx **out);
@@ -215,6 +216,36 @@ int dnsb_imex_stats(dnsb_imex *e, long long *total_iters, long long *nsolves,
  * all-reduce it in place) -- stokes_navier_utils.py:136-143 is the only
  * Gram-like op of the reference. */
 int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev);
+
+/* ---- device-resident Picard/Newton + Crank-Nicolson sweep -------------------
+ * One sweep of stokes_navier_utils.py:1402-1566 over the whole time grid:
+ *   (M + dt/2 (A + N_n)) v+ + JT q = M v + dt/2 (f_n + f_c - (A + N_c) v),
+ *   J v+ = fp,  p = -q/dt,
+ * N_n = condensed Picard (N1) or Newton (N1+N2) matrix about the PREVIOUS
+ * sweep's state at t_n (`linpoint`), N_c about the sweep's own state
+ * (:1529-1538); f = fv - (N u_bc)[inv] (+ N(v)v[inv] for Newton, :1365,1459).
+ * `solver`: single-system solver whose velocity block lives on the union
+ * pattern of M, A and the condensed convection pattern; `mvals`/`avals`: M and
+ * A on that pattern; (src, pos): slot k of the condensed convection matrix is
+ * entry src[k] of the full pattern (dnsb_set_conv_pattern) and entry pos[k] of
+ * the solver's pattern.  The reference re-assembles with dolfin and
+ * re-factorises with SuperLU every step and passes the trajectory through
+ * .npy files (:1424-1431, :1505-1512, :1540-1541); here the step never leaves
+ * the device. */
+int dnsb_cnsweep_create(dnsb_solver *solver, dnsb_csr *mmat, const double *mvals,
+                        const double *avals, int nconv, const int32_t *src,
+                        const int32_t *pos, const int32_t *invinds, int nbc,
+                        const int32_t *bcinds, const double *bcvals, const double *fv,
+                        const double *fp, dnsb_cnsweep **out);
+void dnsb_cnsweep_destroy(dnsb_cnsweep *w);
+/* dts: nsteps step sizes; linpoint: (nsteps+1) full velocities (V.dim() each);
+ * v0 (nv), p0 (np): initial state; vtraj ((nsteps+1)*V.dim()), ptraj
+ * ((nsteps+1)*np): the sweep's trajectory; upd_norm = sum_n dt_n |v_n -
+ * lin_n|_M^2 (:1557-1560); iters_total: FGMRES iterations of the sweep. */
+int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, int picard,
+                     const double *linpoint, const double *v0, const double *p0,
+                     double tol, int maxit, double *vtraj, double *ptraj,
+                     double *upd_norm, long long *iters_total);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,28 @@
+"""Newton/CN sweep rate (BASELINE config 3): cylinder_<N>, Re=100, two-call
+recipe (IMEX trajectory -> lin_vel_point), 1 Picard + 1 Newton sweep.
+usage: python tools/bench_sweep.py <mesh> <Nts> [oracle]"""
+import sys
+import time
+import numpy as np
+sys.path.insert(0, '.')
+from dolfin_navier_scipy_b200 import problem_setups as dnsps, stokes_navier_utils as snu
+N, Nts = int(sys.argv[1]), int(sys.argv[2])
+femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=100, scheme='TH', mergerhs=True,
+                                   meshparams=dict(refinement_level=N))
+sd = dict(A=sm['A'], M=sm['M'], J=sm['J'], JT=sm['JT'], fv=rhsd['fv'], fp=rhsd['fp'], V=femp['V'],
+          invinds=femp['invinds'], dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'],
+          t0=0., tE=Nts/2048., Nts=Nts, start_ssstokes=True)
+mod = snu
+if len(sys.argv) > 3:
+    from oracle import snu as mod
+t0 = time.perf_counter()
+traj = mod.solve_nse(return_dictofvelstrs=True, **sd)
+t1 = time.perf_counter()
+its = []
+kw = dict(krpslvprms=dict(convstatsl=its)) if mod is snu else {}
+out = mod.solve_nse(lin_vel_point=traj, treat_nonl_explicit=False, vel_pcrd_stps=1, vel_nwtn_stps=1,
+                    return_dictofvelstrs=True, verbose=False, **kw, **sd)
+t2 = time.perf_counter()
+print('%s mesh %d: IMEX call %.2f s (%d steps), 2 sweeps %.2f s = %.1f ms per sweep step, mean FGMRES its %s'
+      % ('oracle' if mod is not snu else 'device', N, t1 - t0, Nts, t2 - t1, 1e3*(t2 - t1)/(2*Nts),
+         np.mean(its) if its else '-'))
