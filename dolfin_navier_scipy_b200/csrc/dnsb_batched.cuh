@@ -589,8 +589,12 @@ k_cheb_init_p2(CsrDev A, const double2 *__restrict__ zp, const double2 *__restri
   }
 }
 
+// 64 registers -> 4 CTAs per SM: measured 34.6 us per full step (3 CTAs at 80
+// registers: 37.9 us, 5 CTAs at 48 registers with spills: 41.0 us); the
+// operands of the update other than `res` are loaded after the row product
+// to stay within 64 registers
 #ifndef SPP_MINB
-#define SPP_MINB 3
+#define SPP_MINB 4
 #endif
 template <bool HAS2, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(SPB_THREADS, SPP_MINB)
@@ -601,11 +605,12 @@ k_cheb_step_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restr
   const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
   const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
   const double2 zero = make_double2(0.0, 0.0);
-  const double2 ra = res[sa_], rb = res[sb_], oa = d[sa_], ob = d[sb_];
-  const double2 da = dinv[sa_], db = dinv[sb_];
-  const double2 za = FIRST ? zero : z[sa_], zb = FIRST ? zero : z[sb_];
+  const double2 ra = res[sa_], rb = res[sb_];
   double2 a, b;
   spp_rowdots<HAS2>(A, cm, d + mp, nb2, rp, valid, wp0, wp1, lane, sv2, sv1, soff, a, b);
+  const double2 oa = d[sa_], ob = d[sb_];
+  const double2 da = dinv[sa_], db = dinv[sb_];
+  const double2 za = FIRST ? zero : z[sa_], zb = FIRST ? zero : z[sb_];
   if (valid) {
     const double rax = ra.x - a.x, ray = ra.y - a.y, rbx = rb.x - b.x, rby = rb.y - b.y;
     const double dax = c1 * oa.x + c2 * da.x * rax, day = c1 * oa.y + c2 * da.y * ray;
