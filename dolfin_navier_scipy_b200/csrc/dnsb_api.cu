@@ -1252,9 +1252,7 @@ static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
            (const double *)s->gh2.p, s->gs.h, (size_t)(j + 1) * nb);
     unscaled = s->w.p;
   }
-  LAUNCH(ctx, k_reduce_partials2, cdiv(nb, 32), 1024, 0, (const double *)s->partial2.p, rc.nblocks, nb, s->red.p);
-  LAUNCH(ctx, k_gmres_givens, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, (const double *)s->red.p,
-         1, nb, j, tol);
+  LAUNCH(ctx, k_gmres_givens, 1, 1024, 0, s->gs, (const double *)s->partial2.p, rc.nblocks, nb, j, tol);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, unscaled, (const double *)s->gs.invh, Vn,
          (size_t)ntot, nb);
   return 0;

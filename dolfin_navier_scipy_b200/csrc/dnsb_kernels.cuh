@@ -653,15 +653,45 @@ __global__ void k_set_bnorm(GmresState S, const double *__restrict__ partial,
 
 // after CGS of column j: h[0..j] known, |w|^2 in partial2.  Apply the old
 // rotations, build the new one, update g, test convergence.
-__global__ void k_gmres_givens(GmresState S, const double *__restrict__ partial2,
-                               int nblocks, int nb, int j, double tol) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
+// Launched as ONE block of 1024 threads: the block first sums the per-CTA
+// partial norms (32 members x 32 slices at a time, fixed order), then thread m
+// does the scalar work of member m.
+__global__ void __launch_bounds__(1024)
+k_gmres_givens(GmresState S, const double *__restrict__ partial2,
+               int nblocks, int nb, int j, double tol) {
+  __shared__ double sp[32][33];
+  __shared__ double snorm[1024];
+  {
+    const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
+    for (int m0 = 0; m0 < nb; m0 += 32) {
+      const int c = m0 + cx;
+      double s0 = 0.0, s1 = 0.0;
+      if (c < nb) {
+        int b = by;
+        for (; b + 32 < nblocks; b += 64) {
+          const double p0 = partial2[(size_t)b * nb + c];
+          const double p1 = partial2[(size_t)(b + 32) * nb + c];
+          s0 += p0; s1 += p1;
+        }
+        for (; b < nblocks; b += 32) s0 += partial2[(size_t)b * nb + c];
+      }
+      sp[by][cx] = s0 + s1;
+      __syncthreads();
+      if (by == 0 && c < nb) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) t += sp[q][cx];
+        snorm[c] = t;
+      }
+      __syncthreads();
+    }
+  }
+  int m = threadIdx.x;
   if (m < nb) {
     if (S.done[m]) {
       S.invh[m] = 0.0;
     } else {
-      double s = 0.0;
-      for (int b = 0; b < nblocks; ++b) s += partial2[(size_t)b * nb + m];
+      const double s = snorm[m];
       const double hn = sqrt(s);
       const int mr = S.mr;
       // the loads of (c, s, h) do not alias the stores to R: let them pipeline

@@ -392,3 +392,69 @@ def test_spmm_all_batch_widths(cyl1, ctx, nb):
     JT = sps.csr_matrix(sm['JT'])
     P = rng.standard_normal((JT.shape[1], nb))
     assert _rel(ctx.csr(JT).spmm(P), JT@P) < 1e-13
+
+
+def _cheb_np(Fm, dinv, r, k, lmin, lmax):
+    """numpy restatement of the device Jacobi-Chebyshev smoother (zero guess)"""
+    th, de = .5*(lmax + lmin), .5*(lmax - lmin)
+    sigma = th/de
+    rho = 1./sigma
+    z = np.zeros_like(r)
+    res = r.copy()
+    d = dinv*res/th
+    for i in range(k):
+        z = z + d
+        if i == k - 1:
+            break
+        res = res - Fm@d
+        rho_n = 1./(2*sigma - rho)
+        d = rho_n*rho*d + 2*rho_n/de*(dinv*res)
+        rho = rho_n
+    return z
+
+
+@pytest.mark.parametrize('kind', ['stokes', 'picard'])
+def test_preconditioner_matches_numpy_restatement(cyl1, ctx, kind):
+    """one application of the block-triangular preconditioner with the LSC
+    Schur approximation and the 2-level SA-AMG V-cycle (`dnsb_solver_apply_prec`)
+    against a numpy restatement built from the SAME host-side hierarchy"""
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from oracle import convection as oconv
+    from oracle import snu as osnu
+    from oracle.lau import solve_sadpnt_smw as olu
+    femp, sm, rhsd = cyl1
+    A, M, J = sm['A'].tocsr(), sm['M'].tocsr(), sm['J'].tocsr()
+    NP, NV = J.shape
+    inv = np.asarray(femp['invinds'])
+    F = A
+    if kind == 'picard':
+        ref = olu(amat=A, jmat=J, jmatT=J.T, rhsv=rhsd['fv'], rhsp=rhsd['fp'])
+        vfull = osnu.append_bcs_vec(ref[:NV], femp['V'].dim(), inv,
+                                    femp['dbcinds'], femp['dbcvals'])
+        N1, _, _ = oconv.convmats(femp['V'], vfull.ravel())
+        F = (A + N1[inv][:, inv]).tocsr()
+    op = lau.SadpntOperator(F, J, J.T.tocsr(), vgroups=(inv//2, inv % 2),
+                            mass_diag=M.diagonal())
+    info = op.info
+    assert info['velocity_amg']
+    kF = 2 if kind == 'picard' else 3
+    vlevels, vdense = info['vhierarchy']
+    slevels, sdense = info['hierarchy']
+    assert len(vlevels) == 1 and len(slevels) == 0
+    lmin0, lmax0 = info['spectrum']
+    du_inv = 1./M.diagonal()
+    r = np.random.default_rng(11).standard_normal(NV + NP)
+    z = op.solver.apply_prec(r).ravel()
+    rv, rp = r[:NV], r[NV:]
+    t = sdense@rp                                    # LSC: L^-1 (J D F D JT) L^-1
+    t = du_inv*(J.T@t)
+    t = du_inv*(F@t)
+    zp = -(sdense@(J@t))
+    b = rv - J.T@zp
+    dinv = 1./F.diagonal()
+    x = _cheb_np(F, dinv, b, kF, lmin0, lmax0)       # V-cycle, 2 levels
+    x = x + vlevels[0]['P']@(vdense@(vlevels[0]['R']@(b - F@x)))
+    zv = x + _cheb_np(F, dinv, b - F@x, kF, lmin0, lmax0)
+    op.close()
+    assert _rel(z[NV:], zp) < 1e-11
+    assert _rel(z[:NV], zv) < 1e-11
