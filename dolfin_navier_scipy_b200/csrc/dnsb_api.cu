@@ -1504,7 +1504,7 @@ struct dnsb_cnsweep {
   DBuf<int> src, pos, inv, bcinds;
   DBuf<double> bcvals, ubc, fv, fp;
   DBuf<double> n1, n2, f3;                // K1b outputs on the full convection pattern
-  DBuf<double> vfull, fn, fc, b, x, y, dvec, mdv, lin, vtraj, ptraj, v, p;
+  DBuf<double> vfull, fn, fc, b, x, xprev, xguess, y, dvec, mdv, lin, vtraj, ptraj, v, p;
   DBuf<double> npart, nout;
 };
 
@@ -1571,6 +1571,7 @@ extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double 
   DNSB_CK(ctx, w->f3.alloc(nvf));
   DNSB_CK(ctx, w->vfull.alloc(nvf)); DNSB_CK(ctx, w->fn.alloc(nv)); DNSB_CK(ctx, w->fc.alloc(nv));
   DNSB_CK(ctx, w->b.alloc(nv + np)); DNSB_CK(ctx, w->x.alloc(nv + np)); DNSB_CK(ctx, w->y.alloc(nv));
+  DNSB_CK(ctx, w->xprev.alloc(nv + np)); DNSB_CK(ctx, w->xguess.alloc(nv + np));
   DNSB_CK(ctx, w->dvec.alloc(nv)); DNSB_CK(ctx, w->mdv.alloc(nv));
   DNSB_CK(ctx, w->v.alloc(nv)); DNSB_CK(ctx, w->p.alloc(np));
   RedCfg rc = red_cfg(ctx, nv, 1);
@@ -1589,6 +1590,7 @@ extern "C" void dnsb_cnsweep_destroy(dnsb_cnsweep *w) {
   w->bcvals.release(); w->ubc.release(); w->fv.release(); w->fp.release();
   w->n1.release(); w->n2.release(); w->f3.release();
   w->vfull.release(); w->fn.release(); w->fc.release(); w->b.release(); w->x.release();
+  w->xprev.release(); w->xguess.release();
   w->y.release(); w->dvec.release(); w->mdv.release(); w->lin.release(); w->vtraj.release();
   w->ptraj.release(); w->v.release(); w->p.release(); w->npart.release(); w->nout.release();
   delete w;
@@ -1672,6 +1674,16 @@ extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, 
     LAUNCH(ctx, k_cn_rhs, cdiv(nv, 256), 256, 0, w->b.p, (const double *)w->fn.p, (const double *)w->fc.p,
            (const double *)w->y.p, 0.5 * dt, nv);
     DNSB_CK(ctx, cudaMemcpyAsync(w->b.p + nv, w->fp.p, np * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    // initial guess: linear extrapolation 2 x_{n-1} - x_{n-2} of the saddle
+    // solutions (the reference's `krylovini='upd'`, snu:1496-1501)
+    if (n >= 3 && dts[n - 1] == dts[n - 2]) {
+      LAUNCH(ctx, k_axpby, cdiv((size_t)(nv + np), 256), 256, 0, 2.0, (const double *)w->x.p, -1.0,
+             (const double *)w->xprev.p, w->xguess.p, (size_t)(nv + np));
+      DNSB_CK(ctx, cudaMemcpyAsync(w->xprev.p, w->x.p, (nv + np) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      DNSB_CK(ctx, cudaMemcpyAsync(w->x.p, w->xguess.p, (nv + np) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      DNSB_CK(ctx, cudaMemcpyAsync(w->xprev.p, w->x.p, (nv + np) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     s->expect_its = 0;
     rc = solver_solve_dev(s, w->b.p, w->x.p, tol, maxit, false);
     if (rc) return rc;
