@@ -304,6 +304,7 @@ extern "C" void dnsb_ctx_destroy(dnsb_ctx *ctx) {
   ctx->cn.release(); ctx->geom.release();
   ctx->n2c_ptr.release(); ctx->n2c_idx.release(); ctx->elem.release();
   ctx->cindptr.release(); ctx->cindices.release(); ctx->cslots.release();
+  ctx->cslot_ptr.release(); ctx->cslot_src.release(); ctx->en1.release(); ctx->en2.release();
   ctx->stage_a.release(); ctx->stage_b.release();
   ctx->stage_c.release(); ctx->stage_d.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -468,6 +469,17 @@ extern "C" int dnsb_set_conv_pattern(dnsb_ctx *ctx, const int32_t *indptr,
   DNSB_CK(ctx, ctx->cindptr.upload(indptr, nrows + 1, ctx->stream));
   DNSB_CK(ctx, ctx->cindices.upload(indices, nnz, ctx->stream));
   DNSB_CK(ctx, ctx->cslots.upload(sl.data(), sl.size(), ctx->stream));
+  {
+    // slot -> contributions (e*ncell + permuted cell), ascending cell order
+    std::vector<int> sp(nnz + 1, 0), ss((size_t)144 * ncell);
+    for (size_t k = 0; k < sl.size(); ++k) sp[sl[k] + 1]++;
+    for (int k = 0; k < nnz; ++k) sp[k + 1] += sp[k];
+    std::vector<int> fill(sp.begin(), sp.end() - 1);
+    for (int q = 0; q < ncell; ++q)
+      for (int e = 0; e < 144; ++e) ss[fill[sl[(size_t)e * ncell + q]]++] = e * ncell + q;
+    DNSB_CK(ctx, ctx->cslot_ptr.upload(sp.data(), sp.size(), ctx->stream));
+    DNSB_CK(ctx, ctx->cslot_src.upload(ss.data(), ss.size(), ctx->stream));
+  }
   ctx->cnnz = nnz;
   return 0;
 }
@@ -531,6 +543,34 @@ extern "C" int dnsb_convvec(dnsb_ctx *ctx, const double *u1, const double *u2,
   return 0;
 }
 
+// K1b on device vectors: n1, n2 (full pattern values), f3 (full vector); any of
+// n1 / n2 / f3 may be null.  Gather formulation (2 launches + K1a for f3);
+// DNSB_CONV_COLOURS=1 selects the coloured scatter (one launch per colour).
+static int convmats_dev(dnsb_ctx *ctx, const double *u0, double *n1, double *n2, double *f3) {
+  const size_t nfull = (size_t)2 * ctx->nnodes, nnz = ctx->cnnz;
+  if (g_conv_colours) {
+    if (n1) DNSB_CK(ctx, cudaMemsetAsync(n1, 0, nnz * sizeof(double), ctx->stream));
+    if (n2) DNSB_CK(ctx, cudaMemsetAsync(n2, 0, nnz * sizeof(double), ctx->stream));
+    if (f3) DNSB_CK(ctx, cudaMemsetAsync(f3, 0, nfull * sizeof(double), ctx->stream));
+    for (int k = 0; k < ctx->ncolours; ++k) {
+      const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
+      if (c1 <= c0) continue;
+      const size_t threads = (size_t)(c1 - c0) * 6;
+      LAUNCH(ctx, k_convmats, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell, ctx->cn.p, ctx->geom.p,
+             ctx->cslots.p, u0, n1, n2, f3);
+    }
+    return 0;
+  }
+  DNSB_CK(ctx, ctx->en1.alloc((size_t)36 * ctx->ncell));
+  DNSB_CK(ctx, ctx->en2.alloc((size_t)144 * ctx->ncell));
+  LAUNCH(ctx, k_convmats_elem, cdiv((size_t)6 * ctx->ncell, 128), 128, 0, ctx->ncell, ctx->cn.p,
+         ctx->geom.p, u0, ctx->en1.p, ctx->en2.p);
+  LAUNCH(ctx, k_convmats_gather, cdiv(nnz, 256), 256, 0, (int)nnz, ctx->ncell, (const int *)ctx->cslot_ptr.p,
+         (const int *)ctx->cslot_src.p, (const double *)ctx->en1.p, (const double *)ctx->en2.p, n1, n2);
+  if (f3) return convvec_dev(ctx, u0, nullptr, f3, 1);
+  return 0;
+}
+
 extern "C" int dnsb_convmats(dnsb_ctx *ctx, const double *u0, double *n1_data,
                              double *n2_data, double *f3) {
   if (!ctx) return -2;
@@ -543,17 +583,10 @@ extern "C" int dnsb_convmats(dnsb_ctx *ctx, const double *u0, double *n1_data,
   DNSB_CK(ctx, ctx->stage_b.alloc(nnz));
   DNSB_CK(ctx, ctx->stage_c.alloc(nnz));
   DNSB_CK(ctx, ctx->stage_d.alloc(nfull));
-  DNSB_CK(ctx, ctx->stage_b.zero(ctx->stream));
-  DNSB_CK(ctx, ctx->stage_c.zero(ctx->stream));
-  DNSB_CK(ctx, ctx->stage_d.zero(ctx->stream));
-  for (int k = 0; k < ctx->ncolours; ++k) {
-    const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
-    if (c1 <= c0) continue;
-    const size_t threads = (size_t)(c1 - c0) * 6;
-    LAUNCH(ctx, k_convmats, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell, ctx->cn.p,
-           ctx->geom.p, ctx->cslots.p, ctx->stage_a.p,
-           n1_data ? ctx->stage_b.p : nullptr, n2_data ? ctx->stage_c.p : nullptr,
-           f3 ? ctx->stage_d.p : nullptr);
+  {
+    int rc = convmats_dev(ctx, ctx->stage_a.p, n1_data ? ctx->stage_b.p : nullptr, n2_data ? ctx->stage_c.p : nullptr,
+                          f3 ? ctx->stage_d.p : nullptr);
+    if (rc) return rc;
   }
   if (n1_data) DNSB_CK(ctx, cudaMemcpyAsync(n1_data, ctx->stage_b.p, nnz * sizeof(double),
                                             cudaMemcpyDeviceToHost, ctx->stream));
@@ -1507,22 +1540,6 @@ struct dnsb_cnsweep {
   DBuf<double> vfull, fn, fc, b, x, xprev, xguess, y, dvec, mdv, lin, vtraj, ptraj, v, p;
   DBuf<double> npart, nout;
 };
-
-// K1b on device vectors: n1, n2 (full pattern values), f3 (full vector)
-static int convmats_dev(dnsb_ctx *ctx, const double *u0, double *n1, double *n2, double *f3) {
-  const size_t nfull = (size_t)2 * ctx->nnodes, nnz = ctx->cnnz;
-  DNSB_CK(ctx, cudaMemsetAsync(n1, 0, nnz * sizeof(double), ctx->stream));
-  if (n2) DNSB_CK(ctx, cudaMemsetAsync(n2, 0, nnz * sizeof(double), ctx->stream));
-  if (f3) DNSB_CK(ctx, cudaMemsetAsync(f3, 0, nfull * sizeof(double), ctx->stream));
-  for (int k = 0; k < ctx->ncolours; ++k) {
-    const int c0 = ctx->colour_ptr[k], c1 = ctx->colour_ptr[k + 1];
-    if (c1 <= c0) continue;
-    const size_t threads = (size_t)(c1 - c0) * 6;
-    LAUNCH(ctx, k_convmats, cdiv(threads, 128), 128, 0, c0, c1, ctx->ncell, ctx->cn.p, ctx->geom.p,
-           ctx->cslots.p, u0, n1, n2, f3);
-  }
-  return 0;
-}
 
 extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double *mvals,
                                    const double *avals, int nconv, const int32_t *src,

@@ -88,6 +88,8 @@ struct dnsb_ctx {
   // fixed pattern of the P2 vector space + per-cell slots (144*ncell SoA)
   int cnnz = 0;
   DBuf<int> cindptr, cindices, cslots;
+  DBuf<int> cslot_ptr, cslot_src;   // slot -> element contributions (K1b gather formulation)
+  DBuf<double> en1, en2;            // element matrices 36*ncell / 144*ncell
   // staging buffers for the host-pointer entry points
   DBuf<double> stage_a, stage_b, stage_c, stage_d;
 

@@ -275,6 +275,100 @@ k_convmats(int c0, int c1, int ncell, const int *__restrict__ cn,
 }
 
 // ---------------------------------------------------------------------------
+// K1b, gather formulation (two launches, no colours, no atomics):
+//   k_convmats_elem:   thread <-> (local row n, cell), cells fastest (coalesced):
+//                      6 N1 entries -> EN1[(n*6 + m)*ncell + cell],
+//                      24 N2 entries -> EN2[((2n+a)*12 + 2m+b)*ncell + cell]
+//   k_convmats_gather: thread <-> CSR slot of the fixed pattern: sums the
+//                      element contributions listed for the slot (ascending
+//                      cell order => deterministic); N1 gets the (a == b) ones.
+// f3 = N(u0)u0 is the convection vector: the K1a kernels compute it.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_convmats_elem(int ncell, const int *__restrict__ cn, const double *__restrict__ geom,
+                const double *__restrict__ u0, double *__restrict__ EN1,
+                double *__restrict__ EN2) {
+  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = (int)(tid / ncell);
+  const int cell = (int)(tid - (long)n * ncell);
+  if (n >= 6) return;
+  int nd[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) nd[k] = cn[k * ncell + cell];
+  const double g1x = geom[0 * ncell + cell], g1y = geom[1 * ncell + cell];
+  const double g2x = geom[2 * ncell + cell], g2y = geom[3 * ncell + cell];
+  const double detj = geom[4 * ncell + cell];
+  const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+  double U[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    U[k][0] = u0[2 * nd[k]];
+    U[k][1] = u0[2 * nd[k] + 1];
+  }
+  double a1[6], a2[2][6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    a1[k] = 0;
+    a2[0][k][0] = a2[0][k][1] = a2[1][k][0] = a2[1][k][1] = 0;
+  }
+  const double wdet = 0.5 * fabs(detj);
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    double gx[6], gy[6];
+    double ux = 0, uy = 0, dxx = 0, dxy = 0, dyx = 0, dyy = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      gx[a] = c_dphi[q][a][0] * g0x + c_dphi[q][a][1] * g1x + c_dphi[q][a][2] * g2x;
+      gy[a] = c_dphi[q][a][0] * g0y + c_dphi[q][a][1] * g1y + c_dphi[q][a][2] * g2y;
+      ux += U[a][0] * c_phi[q][a];
+      uy += U[a][1] * c_phi[q][a];
+      dxx += U[a][0] * gx[a];
+      dxy += U[a][0] * gy[a];
+      dyx += U[a][1] * gx[a];
+      dyy += U[a][1] * gy[a];
+    }
+    const double w = c_qw[q] * wdet * c_phi[q][n];
+#pragma unroll
+    for (int mm = 0; mm < 6; ++mm) {
+      a1[mm] += w * (ux * gx[mm] + uy * gy[mm]);
+      const double wp = w * c_phi[q][mm];
+      a2[0][mm][0] += wp * dxx;
+      a2[0][mm][1] += wp * dxy;
+      a2[1][mm][0] += wp * dyx;
+      a2[1][mm][1] += wp * dyy;
+    }
+  }
+#pragma unroll
+  for (int mm = 0; mm < 6; ++mm) {
+    EN1[(size_t)(n * 6 + mm) * ncell + cell] = a1[mm];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+        EN2[(size_t)((2 * n + a) * 12 + 2 * mm + b) * ncell + cell] = a2[a][mm][b];
+  }
+}
+
+// contributions of slot s: src = e*ncell + cell, e = r*12 + c (r = 2n+a, c = 2m+b)
+__global__ void k_convmats_gather(int nnz, int ncell, const int *__restrict__ sptr,
+                                  const int *__restrict__ ssrc, const double *__restrict__ EN1,
+                                  const double *__restrict__ EN2, double *__restrict__ n1,
+                                  double *__restrict__ n2) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnz) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = sptr[s]; k < sptr[s + 1]; ++k) {
+    const int src = ssrc[k];
+    const int e = src / ncell, cell = src - e * ncell;
+    const int r = e / 12, c = e - r * 12;
+    if (n2) s2 += EN2[src];
+    if (n1 && ((r ^ c) & 1) == 0) s1 += EN1[(size_t)((r >> 1) * 6 + (c >> 1)) * ncell + cell];
+  }
+  if (n1) n1[s] = s1;
+  if (n2) n2[s] = s2;
+}
+
+// ---------------------------------------------------------------------------
 // K2: CSR SpMV / SpMM.  LPR lanes cooperate on one (row, member) pair; LPR=1
 // is thread per (row, member) -- the batched case, where the nb lanes of a row
 // read one matrix entry (broadcast) and nb contiguous x values (coalesced).

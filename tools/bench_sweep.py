@@ -13,8 +13,19 @@ sd = dict(A=sm['A'], M=sm['M'], J=sm['J'], JT=sm['JT'], fv=rhsd['fv'], fp=rhsd['
           invinds=femp['invinds'], dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'],
           t0=0., tE=Nts/2048., Nts=Nts, start_ssstokes=True)
 mod = snu
+sweep_times = []
 if len(sys.argv) > 3:
     from oracle import snu as mod
+else:
+    from dolfin_navier_scipy_b200 import _lib
+    _run = _lib.CnSweep.run
+
+    def timed_run(self, *a, **k):
+        t = time.perf_counter()
+        out = _run(self, *a, **k)
+        sweep_times.append(time.perf_counter() - t)
+        return out
+    _lib.CnSweep.run = timed_run
 t0 = time.perf_counter()
 traj = mod.solve_nse(return_dictofvelstrs=True, **sd)
 t1 = time.perf_counter()
@@ -26,3 +37,6 @@ t2 = time.perf_counter()
 print('%s mesh %d: IMEX call %.2f s (%d steps), 2 sweeps %.2f s = %.1f ms per sweep step, mean FGMRES its %s'
       % ('oracle' if mod is not snu else 'device', N, t1 - t0, Nts, t2 - t1, 1e3*(t2 - t1)/(2*Nts),
          np.mean(its) if its else '-'))
+if sweep_times:
+    print('   dnsb_cnsweep_run alone (incl. upload of the linearisation trajectory and download of the new one): '
+          + ', '.join('%.2f ms/step' % (1e3*t/Nts) for t in sweep_times))
