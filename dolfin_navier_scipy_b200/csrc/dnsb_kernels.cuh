@@ -530,141 +530,10 @@ k_dense_gemv(const double *__restrict__ D, const double *__restrict__ X,
   }
 }
 
-// larger nb: shared-memory tiled GEMM; block = 256 threads computes a
-// TM x nb tile of Y; thread (tr, tc) accumulates rows tr+{0,16} x members
-// tc + 16*k.
-#define DG_TM 32
-#define DG_TK 32
-template <int NBT>   // members per block tile: 16, 32 or 64
-__global__ void
-k_dense_gemm(const double *__restrict__ D, const double *__restrict__ X,
-             double *__restrict__ Y, int n, int nb, double alpha,
-             const double *__restrict__ add_dinv,
-             const double *__restrict__ add_scale) {
-  __shared__ double sD[DG_TM][DG_TK + 1];
-  __shared__ double sX[DG_TK][NBT];
-  const int tr = threadIdx.x / 16;       // 0..15
-  const int tc = threadIdx.x % 16;       // 0..15
-  const int row0 = blockIdx.x * DG_TM;
-  const int m0 = blockIdx.y * NBT;
-  constexpr int MC = NBT / 16;           // member columns per thread
-  double acc[2][MC];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int c = 0; c < MC; ++c) acc[r][c] = 0.0;
-  for (int j0 = 0; j0 < n; j0 += DG_TK) {
-    // stage D tile (TM x TK): 1024 elements / 256 threads
-    for (int e = threadIdx.x; e < DG_TM * DG_TK; e += 256) {
-      const int r = e / DG_TK, c = e % DG_TK;
-      const int gi = row0 + r, gj = j0 + c;
-      sD[r][c] = (gi < n && gj < n) ? D[(size_t)gi * n + gj] : 0.0;
-    }
-    for (int e = threadIdx.x; e < DG_TK * NBT; e += 256) {
-      const int r = e / NBT, c = e % NBT;
-      const int gj = j0 + r, gm = m0 + c;
-      sX[r][c] = (gj < n && gm < nb) ? X[(size_t)gj * nb + gm] : 0.0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < DG_TK; ++k) {
-      const double d0 = sD[tr][k], d1 = sD[tr + 16][k];
-#pragma unroll
-      for (int c = 0; c < MC; ++c) {
-        const double xv = sX[k][tc + 16 * c];
-        acc[0][c] += d0 * xv;
-        acc[1][c] += d1 * xv;
-      }
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int gi = row0 + tr + 16 * r;
-    if (gi >= n) continue;
-#pragma unroll
-    for (int c = 0; c < MC; ++c) {
-      const int gm = m0 + tc + 16 * c;
-      if (gm >= nb) continue;
-      double v = acc[r][c];
-      if (add_dinv) v += add_scale[gm] * add_dinv[gi] * X[(size_t)gi * nb + gm];
-      Y[(size_t)gi * nb + gm] = alpha * v;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
 // batched reductions (deterministic two-stage: block partials, then a serial
 // sum over blocks in fixed order).  Block = RPB x nb threads (RPB power of 2).
 // ---------------------------------------------------------------------------
-// partial[(b*nvec + i)*nb + m] = sum_{rows in chunk b} V_i[row,m]*w[row,m]
-__global__ void k_mdot(const double *__restrict__ V, size_t vstride, int nvec,
-                       const double *__restrict__ w, int n, int nb, int rpb,
-                       double *__restrict__ partial) {
-  extern __shared__ double sred[];
-  const int m = threadIdx.x % nb;
-  const int rr = threadIdx.x / nb;
-  const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(n, r0 + rows_per_block);
-  for (int i = 0; i < nvec; ++i) {
-    const double *vi = V + (size_t)i * vstride;
-    double acc = 0.0;
-    for (int r = r0 + rr; r < r1; r += rpb) {
-      const size_t idx = (size_t)r * nb + m;
-      acc += vi[idx] * w[idx];
-    }
-    sred[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = rpb >> 1; s > 0; s >>= 1) {
-      if (rr < s) sred[threadIdx.x] += sred[threadIdx.x + s * nb];
-      __syncthreads();
-    }
-    if (rr == 0) partial[((size_t)blockIdx.x * nvec + i) * nb + m] = sred[m];
-    __syncthreads();
-  }
-}
-
-// out[c] = sum_b partial[b*count + c]
-__global__ void k_reduce_partials(const double *__restrict__ partial,
-                                  int nblocks, int count,
-                                  double *__restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= count) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * count + c];
-  out[c] = s;
-}
-
-// w -= sum_i h[i*nb+m]*V_i ;  partial2[b*nb+m] = sum |w|^2 over the chunk
-__global__ void k_gs_update(const double *__restrict__ V, size_t vstride,
-                            int nvec, const double *__restrict__ h,
-                            double *__restrict__ w, int n, int nb, int rpb,
-                            double *__restrict__ partial2) {
-  extern __shared__ double sred[];
-  const int m = threadIdx.x % nb;
-  const int rr = threadIdx.x / nb;
-  const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(n, r0 + rows_per_block);
-  double nrm = 0.0;
-  for (int r = r0 + rr; r < r1; r += rpb) {
-    const size_t idx = (size_t)r * nb + m;
-    double wv = w[idx];
-    for (int i = 0; i < nvec; ++i)
-      wv -= h[(size_t)i * nb + m] * V[(size_t)i * vstride + idx];
-    w[idx] = wv;
-    nrm += wv * wv;
-  }
-  sred[threadIdx.x] = nrm;
-  __syncthreads();
-  for (int s = rpb >> 1; s > 0; s >>= 1) {
-    if (rr < s) sred[threadIdx.x] += sred[threadIdx.x + s * nb];
-    __syncthreads();
-  }
-  if (rr == 0) partial2[(size_t)blockIdx.x * nb + m] = sred[m];
-}
-
 // partial[b*nb+m] = sum over chunk of x*y  (norms / single dots)
 __global__ void k_dot1(const double *__restrict__ x, const double *__restrict__ y,
                        int n, int nb, int rpb, double *__restrict__ partial) {
@@ -1001,47 +870,3 @@ __global__ void k_extract_p(const double *__restrict__ x, double *__restrict__ p
   p[t] = scale * x[(size_t)nv * nb + t];
 }
 
-// small dense per-member least squares for the projection guess:
-// solves (G + eps I) c = r for each member, G: L x L (row-major, nb batched)
-__global__ void k_small_spd_solve(double *__restrict__ G, double *__restrict__ r,
-                                  int L, int nb, int last) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= nb) return;
-  // Cholesky in place (lower), tiny L (<= 16)
-  double tr = 0.0;
-  for (int i = 0; i < L; ++i) tr += G[((size_t)i * L + i) * nb + m];
-  const double eps = 1e-14 * tr / L;
-  bool ok = true;
-  for (int j = 0; j < L && ok; ++j) {
-    double s = G[((size_t)j * L + j) * nb + m] + eps;
-    for (int k = 0; k < j; ++k) {
-      const double l = G[((size_t)j * L + k) * nb + m];
-      s -= l * l;
-    }
-    if (!(s > 0.0)) { ok = false; break; }
-    const double ljj = sqrt(s);
-    G[((size_t)j * L + j) * nb + m] = ljj;
-    for (int i = j + 1; i < L; ++i) {
-      double t = G[((size_t)i * L + j) * nb + m];
-      for (int k = 0; k < j; ++k)
-        t -= G[((size_t)i * L + k) * nb + m] * G[((size_t)j * L + k) * nb + m];
-      G[((size_t)i * L + j) * nb + m] = t / ljj;
-    }
-  }
-  if (!ok) {   // fall back to "previous solution" as the guess
-    for (int i = 0; i < L; ++i) r[(size_t)i * nb + m] = (i == last) ? 1.0 : 0.0;
-    return;
-  }
-  for (int i = 0; i < L; ++i) {
-    double t = r[(size_t)i * nb + m];
-    for (int k = 0; k < i; ++k)
-      t -= G[((size_t)i * L + k) * nb + m] * r[(size_t)k * nb + m];
-    r[(size_t)i * nb + m] = t / G[((size_t)i * L + i) * nb + m];
-  }
-  for (int i = L - 1; i >= 0; --i) {
-    double t = r[(size_t)i * nb + m];
-    for (int k = i + 1; k < L; ++k)
-      t -= G[((size_t)k * L + i) * nb + m] * r[(size_t)k * nb + m];
-    r[(size_t)i * nb + m] = t / G[((size_t)i * L + i) * nb + m];
-  }
-}

@@ -458,3 +458,33 @@ def test_preconditioner_matches_numpy_restatement(cyl1, ctx, kind):
     op.close()
     assert _rel(z[NV:], zp) < 1e-11
     assert _rel(z[:NV], zv) < 1e-11
+
+
+def test_cnab_with_multilevel_schur_hierarchy(cyl1, ctx):
+    """pressure meshes beyond the dense-inverse limit use a smoothed-aggregation
+    V-cycle for the Schur approximation: force that path (coarse_max=200) on
+    the small mesh, single trajectory and a 64-member batch (row-pair kernels,
+    DMMA coarse solve), and check CNAB against the LU oracle"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    sd = soldict(femp, sm, rhsd)
+    nsteps, dt = 8, 1./512
+    v0d = osnu.solve_nse(t0=0, tE=dt, Nts=1, start_ssstokes=True,
+                         return_vp_dict=True, **sd)[0.0]
+    ref = osnu.solve_nse(t0=0, tE=nsteps*dt, Nts=nsteps, iniv=v0d['v'],
+                         inip=v0d['p'], return_final_vp=True, **sd)
+    for nb in (1, 64):
+        integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv,
+                               femp['dbcinds'], femp['dbcvals'], dt,
+                               nus=np.ones(nb), fv=rhsd['fv'], fp=rhsd['fp'],
+                               coarse_max=200)
+        assert integ.infos[0]['schur_levels'] >= 2
+        integ.set_state(v0d['v'][inv], v0d['p'])
+        integ.run(nsteps, tol=1e-12)
+        V, P = integ.state()
+        integ.close()
+        for m in (0, nb - 1):
+            assert _rel(V[:, m:m+1], ref[0]) < 1e-8, (nb, m)
+            assert _rel(P[:, m:m+1], ref[1]) < 1e-7, (nb, m)
