@@ -27,7 +27,7 @@ def shard_members(nmembers, rank, world):
 def cylinder_ensemble(N=4, Res=(60., 150.), nmembers=64, rank=0, world=1,
                       dt=1./512, scheme='cnab', palpha=1e-5, bccontrol=True,
                       control=np.sin, ntimes=513, t0=0., ctx=None, mesh=None,
-                      cheb_steps=5, restart=40, schur_poly=2, coarse_max=4096):
+                      cheb_steps=4, restart=40, schur_poly=2, coarse_max=4096):
     """device integrator for this rank's shard of a Re-sweep ensemble
 
     Returns ``(integ, info)``; ``integ`` is a `time_int_utils.DeviceImex` with

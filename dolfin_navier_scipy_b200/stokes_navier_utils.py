@@ -250,7 +250,7 @@ def solve_nse(A=None, M=None, J=None, JT=None,
               check_ff=False, check_ff_maxv=1e8,
               verbose=True,
               start_ssstokes=False,
-              lin_tol=1e-12, guess=16, cheb_steps=5,
+              lin_tol=1e-12, guess=16, cheb_steps=4,
               **kw):
     """time-dependent Navier-Stokes -- `snu:548-1599`
 

@@ -88,7 +88,7 @@ class DeviceImex(object):
 
     def __init__(self, M, A0, J, V, invinds, dbcinds, dbcvals, dt,
                  scheme='cnab', nus=(1.,), Arob=None, fv=None, fp=None,
-                 ctx=None, cheb_steps=5, restart=40, coarse_max=4096,
+                 ctx=None, cheb_steps=4, restart=40, coarse_max=4096,
                  mp_diag=None, reorder=True, schur_poly=2):
         self.ctx = _lib.default_context() if ctx is None else ctx
         self.scheme = scheme
@@ -221,7 +221,7 @@ def _run_imex(scheme, trange=None, inivel=None, inip=None, M=None, A=None,
               J=None, f_tdp=None, g_tdp=None, scalep=-1., V=None,
               invinds=None, dbcinds=None, dbcvals=None, savevp=None,
               check_ff_maxv=1e8, ntimeslices=10, tol=1e-12, maxit=400,
-              guess=16, cheb_steps=5, f_vdp='convection', ctx=None,
+              guess=16, cheb_steps=4, f_vdp='convection', ctx=None,
               return_engine=False, **kw):
     if f_vdp != 'convection' and f_vdp is not None:
         raise NotImplementedError(
