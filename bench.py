@@ -412,7 +412,7 @@ def kernel_bytes(name, info, integ):
         return 20.*nnzK + 4.*(nt + 1) + 16.*nt*nb
     if name.startswith('k_cheb_init'):
         return 12.*J.nnz + 4.*(n + 1) + 8.*npp*nb + 32.*n*nb
-    if name.startswith('k_dense_gemm'):
+    if name.startswith(('k_dense_gemm', 'k_dense_dmma')):
         return 8.*npp*npp + 16.*npp*nb
     if name.startswith('k_scale_member'):
         return 16.*(n + npp)*nb
@@ -429,38 +429,55 @@ def roofline_of(kern, info, integ, args):
     peak, which = measured_peak()
     J = integ._host['J']
     npp, nb = J.shape[0], integ.nb
+    # template instantiations of one kernel (FIRST/LAST variants of the
+    # Chebyshev step) are one kernel family: launches, time and bytes add up
     fam = {}
     for name, (cnt, ms) in kern.items():
         b = kernel_bytes(name, info, integ)
-        if b is None or name.strip('()').startswith('k_dense_gemm'):
+        base = name.strip('()')
+        if b is None or base.startswith('k_dense_'):
             continue
-        fam.setdefault(name, (cnt, ms, b))
-    name = max(fam.items(), key=lambda kv: kv[1][1])[0]
-    cnt, ms, bytes_ = fam[name]
+        f = fam.setdefault(base.split('<')[0], dict(cnt=0, ms=0., bytes=0., names=[]))
+        f['cnt'] += cnt
+        f['ms'] += ms
+        f['bytes'] += cnt*b
+        f['names'].append((base, cnt))
+    key = max(fam.items(), key=lambda kv: kv[1]['ms'])[0]
+    f = fam[key]
+    cnt, ms = f['cnt'], f['ms']
+    bytes_ = f['bytes']/cnt
     dur = ms*1e-3/cnt
     ach = bytes_/dur/1e9
-    # DRAM traffic per launch of the same kernel from the committed ncu
+    # DRAM traffic per launch of the same kernels from the committed ncu
     # `--set full` capture (profiles/ncu_traffic.json, written by
-    # tools/ncu_summary.py); None if that kernel was not captured
+    # tools/ncu_summary.py), weighted like the launches; None if not captured
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if os.path.isfile(tpath):
-        with open(tpath) as f:
-            tr = json.load(f)
-        key = name.strip('()').replace('true', '1').replace('false', '0')
-        traffic = tr.get(key, {}).get('traffic_bytes')
-    out = dict(bound='hbm', kernel=name.strip('()'), achieved=ach, peak=peak,
+        with open(tpath) as fh:
+            tr = json.load(fh)
+        tot, n = 0., 0
+        for nm, c in f['names']:
+            t = tr.get(nm.replace('true', '1').replace('false', '0'), {})
+            if 'traffic_bytes' in t:
+                tot += c*t['traffic_bytes']
+                n += c
+        traffic = tot/n if n else None
+    out = dict(bound='hbm', kernel=key + ('<...>' if len(f['names']) > 1 else ''),
+               variants=[nm for nm, _ in f['names']],
+               achieved=ach, peak=peak,
                peak_source=which, unit='GB/s', frac=ach/peak, traffic=traffic,
                launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
-    dn = [k for k in kern if k.strip('()').startswith('k_dense_gemm')]
+    dn = [k for k in kern if k.strip('()').startswith(('k_dense_gemm', 'k_dense_dmma'))]
     if dn:
         c, m = kern[dn[0]]
         flops = 2.*npp*npp*nb
         out['dense_schur'] = dict(kernel=dn[0], mean_us=1e3*m/c,
                                   fp64_tflops=flops/(m*1e-3/c)/1e12,
                                   fp64_peak_tflops=37.2,
-                                  note='DFMA bound (148 SM x 64 DFMA/clk x '
-                                  '1.965 GHz), no fp64 tensor path')
+                                  note='fp64 pipe bound (148 SM x 64 FMA/clk x '
+                                  '1.965 GHz; DMMA m8n8k4 kernel, no '
+                                  'tcgen05 kind for fp64)')
     return out
 
 
