@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 import scipy.sparse as sps
 
 import __graft_entry__ as ge
@@ -118,3 +119,25 @@ def test_condense_and_append_roundtrip(cyl1):
                                          dbcinds=femp['dbcinds'],
                                          dbcvals=femp['dbcvals'])
     assert abs(Ac - sm['A']).max() < 1e-15
+
+
+def test_device_path_fails_loudly_without_a_gpu():
+    """no CPU fallback: without a CUDA device the context cannot be created and
+    every device entry point of the Python mirror raises"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a CUDA device is present')
+    from dolfin_navier_scipy_b200 import _lib
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    from dolfin_navier_scipy_b200 import fem
+    with pytest.raises(_lib.DnsbError):
+        _lib.Context(0)
+    V = fem.VectorP2Space(fem.unit_square_mesh(2))
+    with pytest.raises(RuntimeError):
+        dts.get_convvec(V=V, u0_vec=np.zeros(V.dim()))
+
+
+def test_missing_library_is_an_error(tmp_path):
+    from dolfin_navier_scipy_b200 import _lib
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        _lib.load(str(tmp_path / 'libdnsb200.so'))
