@@ -14,6 +14,7 @@
 #include "dnsb_kernels.cuh"
 #include "dnsb_batched.cuh"
 #include "dnsb_dense.cuh"
+#include "dnsb_stream.cuh"
 
 #define DNSB_VERSION 100
 
@@ -87,6 +88,7 @@ struct dnsb_csr {
   DBuf<double> v1, v2;
   bool has2 = false;
   int npair_rows = 0;   // leading rows that pair up (2k, 2k+1) with identical column lists
+  SptPlan spt;          // TMA-staged row tiles (dnsb_stream.cuh)
   // host copies (setup only: assembling the block matrix K, diagonal positions)
   std::vector<int> h_indptr, h_indices;
   std::vector<double> h_v1, h_v2;
@@ -98,6 +100,48 @@ struct dnsb_csr {
     return a;
   }
 };
+
+template <typename T>
+static cudaError_t upload_padded(DBuf<T> &b, const T *h, size_t count, size_t pad, cudaStream_t s) {
+  cudaError_t e = b.alloc(count + pad);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(b.p + count, 0, pad * sizeof(T), s)) != cudaSuccess) return e;
+  if (count && (e = cudaMemcpyAsync(b.p, h, count * sizeof(T), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+    return e;
+  return cudaStreamSynchronize(s);   // host buffer is borrowed: finish now
+}
+
+static int g_tma_stages = 2;
+static int g_tma_rows = 64;
+static size_t spt_stage_bytes(int cap, bool h2) {
+  const size_t off_ip = (size_t)cap * (h2 ? 20 : 12);
+  return (off_ip + (SPT_ROWS + 4) * 4 + 127) & ~(size_t)127;
+}
+// row tiles of the TMA-staged SpMM: the largest 4-entry aligned span of a tile fixes the stage size
+static SptPlan spt_plan(int nrows, const int32_t *indptr, bool h2) {
+  SptPlan p;
+  if (nrows == 0 || indptr[nrows] == 0) return p;
+  p.rt = g_tma_rows;
+  p.ntiles = (nrows + p.rt - 1) / p.rt;
+  int span = 0;
+  for (int t = 0; t < p.ntiles; ++t) {
+    const int r0 = t * p.rt, r1 = std::min(nrows, r0 + p.rt);
+    span = std::max(span, ((indptr[r1] + 3) & ~3) - (indptr[r0] & ~3));
+  }
+  p.cap = (span + 15) & ~15;
+  p.stage_bytes = spt_stage_bytes(p.cap, h2);
+  // a short ring per CTA and as many CTAs per SM as fit (the CTAs overlap each other's
+  // gather and row-sum phases); 228 KB per SM, 1 KB reserved + 1152 B static per CTA
+  p.stages = g_tma_stages;
+  p.ctas_per_sm = (int)std::min<size_t>(7, (size_t)233472 / (p.stages * p.stage_bytes + 2304));
+  if (p.ctas_per_sm < 1) {
+    p.ctas_per_sm = 1;
+    p.stages = (int)std::min<size_t>(SPT_MAX_STAGES, (size_t)220 * 1024 / p.stage_bytes);
+    if (p.stages < 2) p.stages = 0;
+  }
+  p.smem = p.stages * p.stage_bytes;
+  return p;
+}
 
 static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
                      const int32_t *indices, const double *vals1,
@@ -118,15 +162,17 @@ static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
     if (a1 - a0 != a2 - a1 || a1 == a0 || !std::equal(indices + a0, indices + a1, indices + a1)) break;
     m->npair_rows = r + 2;
   }
+  m->spt = spt_plan(nrows, indptr, m->has2);
   m->h_indptr.assign(indptr, indptr + nrows + 1);
   m->h_indices.assign(indices, indices + nnz);
   m->h_v1.assign(vals1, vals1 + nnz);
   if (vals2) m->h_v2.assign(vals2, vals2 + nnz);
   cudaError_t e;
-  if ((e = m->indptr.upload(indptr, nrows + 1, ctx->stream)) != cudaSuccess ||
-      (e = m->indices.upload(indices, nnz, ctx->stream)) != cudaSuccess ||
-      (e = m->v1.upload(vals1, nnz, ctx->stream)) != cudaSuccess ||
-      (vals2 && (e = m->v2.upload(vals2, nnz, ctx->stream)) != cudaSuccess)) {
+  // the bulk copies of the staged kernels read whole 16-byte groups: pad the arrays
+  if ((e = upload_padded(m->indptr, indptr, nrows + 1, 8, ctx->stream)) != cudaSuccess ||
+      (e = upload_padded(m->indices, indices, nnz, 4, ctx->stream)) != cudaSuccess ||
+      (e = upload_padded(m->v1, vals1, nnz, 4, ctx->stream)) != cudaSuccess ||
+      (vals2 && (e = upload_padded(m->v2, vals2, nnz, 4, ctx->stream)) != cudaSuccess)) {
     ctx->fail(std::string("csr upload: ") + cudaGetErrorString(e), __FILE__, __LINE__);
     m->indptr.release(); m->indices.release(); m->v1.release(); m->v2.release();
     delete m;
@@ -184,11 +230,32 @@ static inline unsigned spb_grid(int nrows, int nb, int gpc) {
   return cdiv((size_t)nrows * nb, (size_t)SPB_THREADS * gpc);
 }
 
+// TMA-staged SpMM (dnsb_stream.cuh): operators too large for L2 residency
+static int g_tma_min_rows = 65536;
+static inline bool spt_ok(const dnsb_csr *A, int nb) {
+  return nb == 1 && A->spt.stages >= 2 && A->nrows >= g_tma_min_rows;
+}
+static void spt_launch(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef, const double *x,
+                       const double *z, double *y, double alpha, double beta) {
+  const SptPlan &p = A->spt;
+  const unsigned grid = (unsigned)std::min(p.ntiles, ctx->sm_count * p.ctas_per_sm);
+  if (A->has2 && coef)
+    LAUNCH(ctx, k_spmv_tma<true>, grid, SPT_THREADS, p.smem, A->view(), coef, x, z, y, alpha, beta,
+           p.ntiles, p.cap, p.stages, p.rt);
+  else
+    LAUNCH(ctx, k_spmv_tma<false>, grid, SPT_THREADS, p.smem, A->view(), coef, x, z, y, alpha, beta,
+           p.ntiles, p.cap, p.stages, p.rt);
+}
+
 // y = alpha*A*x + beta*z  on device pointers
 static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
                      const double *x, const double *z, double *y, int nb,
                      double alpha, double beta) {
   if (A->nrows == 0) return;
+  if (spt_ok(A, nb)) {
+    spt_launch(ctx, A, coef, x, z, y, alpha, beta);
+    return;
+  }
   if (pair_ok(A, nb)) {
     const bool h2 = A->has2 && coef;
     const int npairs = rowpairs_of(A, nb);
@@ -273,6 +340,9 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   ctx->device = device;
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
   if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
+  if (const char *ev = getenv("DNSB_TMA_MIN_ROWS")) g_tma_min_rows = atoi(ev);
+  if (const char *ev = getenv("DNSB_TMA_ROWS")) g_tma_rows = std::min(SPT_ROWS, std::max(4, atoi(ev) & ~3));
+  if (const char *ev = getenv("DNSB_TMA_STAGES")) g_tma_stages = std::min(SPT_MAX_STAGES, std::max(2, atoi(ev)));
   if (const char *ev = getenv("DNSB_DMMA")) g_dmma = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
@@ -293,6 +363,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
   // k_mdot_b keeps (nvec+1) x 256 partial sums in dynamic shared memory
   DNSB_CK(ctx, cudaFuncSetAttribute(k_mdot_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_dmma_streamk, cudaFuncAttributeMaxDynamicSharedMemorySize, DMM_SMEM_BYTES));
   return 0;
 }

@@ -1,0 +1,171 @@
+// dnsb_stream.cuh -- CSR SpMV/SpMM with the matrix stream staged through shared
+// memory by the TMA engine (1-D bulk copies, cp.async.bulk + mbarrier), for
+// operators that do not fit L2 (refined meshes).
+//
+// The row kernels of dnsb_kernels.cuh / dnsb_batched.cuh walk
+// indptr -> (column, value) -> x with three dependent global loads per row; on
+// short P2 rows (about 23 entries) that leaves too few bytes in flight for
+// HBM3e (25-29 % of the copy peak at 0.5 M rows).  Here one producer thread per
+// CTA streams the (indptr, column, value) slices of row tiles into a ring of
+// shared-memory stages.  The consumer threads take the staged entries one per
+// thread, whatever row they belong to (all gathers of a tile are independent
+// and in flight together), leave the products in the stage and then sum them
+// row by row (a few lanes per row).  Only the gather of x goes to L1/L2.
+// Persistent CTAs, row tiles dealt round-robin, summation order fixed =>
+// deterministic.
+//
+// replaces: scipy.sparse CSR matvec at reference time_int_utils.py:123-127,
+// stokes_navier_utils.py:139-143 (same arithmetic as k_spmm).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SPT_ROWS 128          // most rows per tile (runtime `rt`, multiple of 4: 16-byte aligned indptr slices)
+#define SPT_CONSUMERS 256     // consumer threads per CTA (2-8 lanes per tile row) + 1 producer warp
+#define SPT_THREADS (SPT_CONSUMERS + 32)
+#define SPT_MAX_STAGES 4
+
+struct SptPlan {
+  int ntiles = 0;
+  int rt = SPT_ROWS; // rows per tile
+  int cap = 0;       // entries per stage (max tile span, multiple of 16)
+  int stages = 0;    // 0: operator not eligible
+  int ctas_per_sm = 1;
+  size_t stage_bytes = 0, smem = 0;
+};
+
+__device__ __forceinline__ uint32_t spt_smem(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void spt_mbar_init(uint64_t *b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spt_smem(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void spt_mbar_expect(uint64_t *b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(spt_smem(b)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void spt_mbar_arrive(uint64_t *b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(spt_smem(b)) : "memory");
+}
+__device__ __forceinline__ void spt_mbar_wait(uint64_t *b, uint32_t parity) {
+  const uint32_t a = spt_smem(b);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void spt_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   spt_smem(dst)),
+               "l"(src), "r"(bytes), "r"(spt_smem(bar))
+               : "memory");
+}
+
+// y = alpha*A*x + beta*z for one right-hand side (nb == 1)
+template <bool H2>
+__global__ void __launch_bounds__(SPT_THREADS)
+k_spmv_tma(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
+           const double *z, double *y, double alpha, double beta, int ntiles, int cap,
+           int stages, int rt) {
+  constexpr int NWARP = SPT_CONSUMERS / 32;
+  constexpr int UN = 6;
+  extern __shared__ __align__(128) unsigned char spt_raw[];
+  __shared__ __align__(8) uint64_t full[SPT_MAX_STAGES], empty[SPT_MAX_STAGES];
+
+  const size_t off_v2 = (size_t)cap * 8;
+  const size_t off_ci = off_v2 + (H2 ? (size_t)cap * 8 : 0);
+  const size_t off_ip = off_ci + (size_t)cap * 4;
+  const size_t stage_bytes = (off_ip + (SPT_ROWS + 4) * 4 + 127) & ~(size_t)127;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      spt_mbar_init(&full[s], 1);
+      spt_mbar_init(&empty[s], NWARP);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == NWARP) {
+    // ---- producer: one thread streams the tiles of this CTA ----
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % stages;
+        const int r0 = t * rt, r1 = min(A.nrows, r0 + rt);
+        const int k0 = A.indptr[r0] & ~3, k1 = (A.indptr[r1] + 3) & ~3;
+        const uint32_t ne = (uint32_t)(k1 - k0);
+        const uint32_t nip = (uint32_t)((r1 - r0 + 1 + 3) & ~3);
+        unsigned char *st = spt_raw + (size_t)s * stage_bytes;
+        if (it >= stages) spt_mbar_wait(&empty[s], ((it / stages) - 1) & 1);
+        spt_mbar_expect(&full[s], ne * (H2 ? 20u : 12u) + nip * 4u);
+        spt_bulk_g2s(st + off_ip, A.indptr + r0, nip * 4u, &full[s]);
+        if (ne) {
+          spt_bulk_g2s(st + off_ci, A.indices + k0, ne * 4u, &full[s]);
+          spt_bulk_g2s(st, A.v1 + k0, ne * 8u, &full[s]);
+          if (H2) spt_bulk_g2s(st + off_v2, A.v2 + k0, ne * 8u, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int tid = threadIdx.x;
+  const int lsh = rt <= 32 ? 3 : (rt <= 64 ? 2 : 1);   // lanes per row = 1 << lsh
+  const double cm = (H2 && coef) ? coef[0] : 0.0;
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+    const int s = it % stages;
+    spt_mbar_wait(&full[s], (it / stages) & 1);
+    unsigned char *st = spt_raw + (size_t)s * stage_bytes;
+    double *sv1 = reinterpret_cast<double *>(st);
+    const double *sv2 = reinterpret_cast<const double *>(st + off_v2);
+    const int *sci = reinterpret_cast<const int *>(st + off_ci);
+    const int *sip = reinterpret_cast<const int *>(st + off_ip);
+    const int r0 = t * rt, nr = min(A.nrows - r0, rt);
+    const int k0 = sip[0] & ~3;
+    const int ne = ((sip[nr] + 3) & ~3) - k0;
+    // phase 1: one entry per thread, products left in place of the values
+    for (int k = tid; k < ne; k += UN * SPT_CONSUMERS) {
+      double v[UN], xv[UN];
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int kk = min(k + j * SPT_CONSUMERS, ne - 1);
+        v[j] = sv1[kk];
+        if (H2) v[j] += cm * sv2[kk];
+        xv[j] = x[sci[kk]];
+      }
+#pragma unroll
+      for (int j = 0; j < UN; ++j)
+        if (k + j * SPT_CONSUMERS < ne) sv1[k + j * SPT_CONSUMERS] = v[j] * xv[j];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(SPT_CONSUMERS) : "memory");
+    // phase 2: SPT_CONSUMERS / rt lanes per row (a power of two, 2..8)
+    {
+      const int lr = tid >> lsh, h = tid & ((1 << lsh) - 1);
+      double acc = 0.0;
+      if (lr < nr) {
+        const int b = sip[lr] - k0, e = sip[lr + 1] - k0;
+        for (int k = b + h; k < e; k += 1 << lsh) acc += sv1[k];
+      }
+      for (int o = 1; o < (1 << lsh); o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lr < nr && h == 0) {
+        const size_t i = (size_t)(r0 + lr);
+        y[i] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[i];
+      }
+    }
+    // the stage is handed back to the async proxy (next bulk copy overwrites the products)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) spt_mbar_arrive(&empty[s]);
+  }
+}

@@ -488,3 +488,67 @@ def test_cnab_with_multilevel_schur_hierarchy(cyl1, ctx):
         for m in (0, nb - 1):
             assert _rel(V[:, m:m+1], ref[0]) < 1e-8, (nb, m)
             assert _rel(P[:, m:m+1], ref[1]) < 1e-7, (nb, m)
+
+
+@pytest.fixture
+def staged_ctx():
+    """a context with the TMA-staged SpMM forced on for every matrix size
+    (DNSB_TMA_MIN_ROWS is read when a context is created)"""
+    import os
+    from dolfin_navier_scipy_b200 import _lib
+    old = os.environ.get('DNSB_TMA_MIN_ROWS')
+    os.environ['DNSB_TMA_MIN_ROWS'] = '0'
+    yield _lib.Context(0)
+    os.environ['DNSB_TMA_MIN_ROWS'] = old if old is not None else '65536'
+    _lib.Context(0)
+    if old is None:
+        del os.environ['DNSB_TMA_MIN_ROWS']
+
+
+@pytest.mark.parametrize('nb', [1, 2])
+def test_staged_spmv_matches_scipy(cyl1, staged_ctx, nb):
+    """k_spmv_tma (bulk-copy staged row tiles, nb = 1; nb = 2 checks that the
+    dispatch leaves the other widths alone): operators of the mesh, two value
+    arrays, alpha/beta, a row count that is not a tile multiple"""
+    femp, sm, rhsd = cyl1
+    from dolfin_navier_scipy_b200.time_int_utils import _on_pattern, _union_pattern
+    ctx = staged_ctx
+    M, A = sps.csr_matrix(sm['M']), sps.csr_matrix(sm['A'])
+    assert A.shape[0] % 128 != 0
+    rng = np.random.default_rng(100 + nb)
+    X = rng.standard_normal((A.shape[1], nb))
+    Y0 = rng.standard_normal((A.shape[0], nb))
+    Y = ctx.csr(A).spmm(X, alpha=-.5, beta=2., y=Y0)
+    assert _rel(Y, -.5*(A@X) + 2*Y0) < 1e-14
+    pat = _union_pattern([M, A])
+    Mp, Ap = _on_pattern(M, pat), _on_pattern(A, pat)
+    coef = rng.standard_normal(nb)
+    Y = ctx.csr(Mp, Ap.data).spmm(X, coef=coef)
+    for k in range(nb):
+        assert _rel(Y[:, k], M@X[:, k] + coef[k]*(A@X[:, k])) < 1e-13
+    J = sps.csr_matrix(sm['J'])
+    assert _rel(ctx.csr(J).spmm(X), J@X) < 1e-14
+    # more tiles than CTAs: every stage of the ring is reused
+    big = sps.block_diag([A]*4, format='csr')
+    assert big.shape[0] > 148*128
+    Xb = rng.standard_normal((big.shape[1], nb))
+    assert _rel(ctx.csr(big).spmm(Xb), big@Xb) < 1e-14
+
+
+def test_staged_spmv_ragged_rows(staged_ctx):
+    """empty rows, an empty leading tile, one long row, a single row"""
+    ctx = staged_ctx
+    rng = np.random.default_rng(7)
+    n = 1000
+    R = sps.random(n, 300, density=.03, random_state=3, format='lil')
+    R[0:200, :] = 0
+    R[555, :] = rng.standard_normal(300)
+    R[700:720, :] = 0
+    R = sps.csr_matrix(R)
+    R.eliminate_zeros()
+    for nb in (1, 1, 4):
+        X = rng.standard_normal((300, nb))
+        assert _rel(ctx.csr(R).spmm(X), R@X) < 1e-14
+    one = sps.csr_matrix(rng.standard_normal((1, 300)))
+    x = rng.standard_normal(300)
+    assert _rel(ctx.csr(one).spmm(x), one@x) < 1e-14
