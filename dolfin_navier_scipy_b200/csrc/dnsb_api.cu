@@ -542,13 +542,13 @@ extern "C" int dnsb_set_conv_pattern(dnsb_ctx *ctx, const int32_t *indptr,
   DNSB_CK(ctx, ctx->cindices.upload(indices, nnz, ctx->stream));
   DNSB_CK(ctx, ctx->cslots.upload(sl.data(), sl.size(), ctx->stream));
   {
-    // slot -> contributions (e*ncell + permuted cell), ascending cell order
+    // slot -> contributions (permuted cell*144 + e), ascending cell order
     std::vector<int> sp(nnz + 1, 0), ss((size_t)144 * ncell);
     for (size_t k = 0; k < sl.size(); ++k) sp[sl[k] + 1]++;
     for (int k = 0; k < nnz; ++k) sp[k + 1] += sp[k];
     std::vector<int> fill(sp.begin(), sp.end() - 1);
     for (int q = 0; q < ncell; ++q)
-      for (int e = 0; e < 144; ++e) ss[fill[sl[(size_t)e * ncell + q]]++] = e * ncell + q;
+      for (int e = 0; e < 144; ++e) ss[fill[sl[(size_t)e * ncell + q]]++] = q * 144 + e;
     DNSB_CK(ctx, ctx->cslot_ptr.upload(sp.data(), sp.size(), ctx->stream));
     DNSB_CK(ctx, ctx->cslot_src.upload(ss.data(), ss.size(), ctx->stream));
   }
@@ -635,7 +635,7 @@ static int convmats_dev(dnsb_ctx *ctx, const double *u0, double *n1, double *n2,
   }
   DNSB_CK(ctx, ctx->en1.alloc((size_t)36 * ctx->ncell));
   DNSB_CK(ctx, ctx->en2.alloc((size_t)144 * ctx->ncell));
-  LAUNCH(ctx, k_convmats_elem, cdiv((size_t)6 * ctx->ncell, 128), 128, 0, ctx->ncell, ctx->cn.p,
+  LAUNCH(ctx, k_convmats_elem, cdiv((size_t)ctx->ncell, CME_CELLS), 6 * CME_CELLS, 0, ctx->ncell, ctx->cn.p,
          ctx->geom.p, u0, ctx->en1.p, ctx->en2.p);
   LAUNCH(ctx, k_convmats_gather, cdiv(nnz, 256), 256, 0, (int)nnz, ctx->ncell, (const int *)ctx->cslot_ptr.p,
          (const int *)ctx->cslot_src.p, (const double *)ctx->en1.p, (const double *)ctx->en2.p, n1, n2);

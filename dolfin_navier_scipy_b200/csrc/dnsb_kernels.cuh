@@ -276,22 +276,30 @@ k_convmats(int c0, int c1, int ncell, const int *__restrict__ cn,
 
 // ---------------------------------------------------------------------------
 // K1b, gather formulation (two launches, no colours, no atomics):
-//   k_convmats_elem:   thread <-> (local row n, cell), cells fastest (coalesced):
-//                      6 N1 entries -> EN1[(n*6 + m)*ncell + cell],
-//                      24 N2 entries -> EN2[((2n+a)*12 + 2m+b)*ncell + cell]
+//   k_convmats_elem:   thread <-> (local row n, cell), cells fastest (coalesced
+//                      input): element matrices stored cell by cell,
+//                      6 N1 entries -> EN1[cell*36 + n*6 + m],
+//                      24 N2 entries -> EN2[cell*144 + (2n+a)*12 + 2m+b]
+//                      (the slots of one CSR row read whole 96-byte rows of it)
 //   k_convmats_gather: thread <-> CSR slot of the fixed pattern: sums the
 //                      element contributions listed for the slot (ascending
 //                      cell order => deterministic); N1 gets the (a == b) ones.
 // f3 = N(u0)u0 is the convection vector: the K1a kernels compute it.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// CTA = CME_CELLS consecutive cells x 6 local rows; the element matrices are
+// staged in shared memory (row stride padded to CME_LD doubles: conflict-free
+// 16-byte stores) and written out as one contiguous block per CTA.
+#define CME_CELLS 32
+#define CME_LD 182   // 144 + 36 entries per cell, + 2: stride = 4 words mod 32 banks
+__global__ void __launch_bounds__(6 * CME_CELLS, 2)
 k_convmats_elem(int ncell, const int *__restrict__ cn, const double *__restrict__ geom,
                 const double *__restrict__ u0, double *__restrict__ EN1,
                 double *__restrict__ EN2) {
-  const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = (int)(tid / ncell);
-  const int cell = (int)(tid - (long)n * ncell);
-  if (n >= 6) return;
+  __shared__ __align__(16) double sm[CME_CELLS * CME_LD];
+  const int cl = threadIdx.x % CME_CELLS, n = threadIdx.x / CME_CELLS;
+  const int cell0 = blockIdx.x * CME_CELLS;
+  const int nc = min(CME_CELLS, ncell - cell0);
+  const int cell = cell0 + min(cl, nc - 1);   // surplus threads repeat the last cell (no divergence)
   int nd[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) nd[k] = cn[k * ncell + cell];
@@ -338,18 +346,22 @@ k_convmats_elem(int ncell, const int *__restrict__ cn, const double *__restrict_
       a2[1][mm][1] += wp * dyy;
     }
   }
+  double *row = sm + cl * CME_LD;
 #pragma unroll
-  for (int mm = 0; mm < 6; ++mm) {
-    EN1[(size_t)(n * 6 + mm) * ncell + cell] = a1[mm];
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int mm = 0; mm < 6; ++mm)
+      *reinterpret_cast<double2 *>(row + (2 * n + a) * 12 + 2 * mm) = make_double2(a2[a][mm][0], a2[a][mm][1]);
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
-        EN2[(size_t)((2 * n + a) * 12 + 2 * mm + b) * ncell + cell] = a2[a][mm][b];
-  }
+  for (int mm = 0; mm < 6; mm += 2)
+    *reinterpret_cast<double2 *>(row + 144 + n * 6 + mm) = make_double2(a1[mm], a1[mm + 1]);
+  __syncthreads();
+  double *o2 = EN2 + (size_t)cell0 * 144, *o1 = EN1 + (size_t)cell0 * 36;
+  for (int i = threadIdx.x; i < nc * 144; i += 6 * CME_CELLS) o2[i] = sm[(i / 144) * CME_LD + i % 144];
+  for (int i = threadIdx.x; i < nc * 36; i += 6 * CME_CELLS) o1[i] = sm[(i / 36) * CME_LD + 144 + i % 36];
 }
 
-// contributions of slot s: src = e*ncell + cell, e = r*12 + c (r = 2n+a, c = 2m+b)
+// contributions of slot s: src = cell*144 + e, e = r*12 + c (r = 2n+a, c = 2m+b)
 __global__ void k_convmats_gather(int nnz, int ncell, const int *__restrict__ sptr,
                                   const int *__restrict__ ssrc, const double *__restrict__ EN1,
                                   const double *__restrict__ EN2, double *__restrict__ n1,
@@ -359,10 +371,10 @@ __global__ void k_convmats_gather(int nnz, int ncell, const int *__restrict__ sp
   double s1 = 0.0, s2 = 0.0;
   for (int k = sptr[s]; k < sptr[s + 1]; ++k) {
     const int src = ssrc[k];
-    const int e = src / ncell, cell = src - e * ncell;
+    const int cell = src / 144, e = src - cell * 144;
     const int r = e / 12, c = e - r * 12;
     if (n2) s2 += EN2[src];
-    if (n1 && ((r ^ c) & 1) == 0) s1 += EN1[(size_t)((r >> 1) * 6 + (c >> 1)) * ncell + cell];
+    if (n1 && ((r ^ c) & 1) == 0) s1 += EN1[(size_t)cell * 36 + (r >> 1) * 6 + (c >> 1)];
   }
   if (n1) n1[s] = s1;
   if (n2) n2[s] = s2;
