@@ -70,7 +70,47 @@ class ClockSampler(object):
         self.rows = []
         self.proc = None
 
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                       # CUDA ordinal -> NVML handle through the UUID
+            import torch
+            uuid = 'GPU-' + str(torch.cuda.get_device_properties(self.device).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.device)
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        masks = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40),
+                 ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
+        while not self.halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(self.device), str(sm), str(self.smax), '',
+                                  ] + ['Active' if bits & m else 'Not Active'
+                                       for _, m in masks])
+            except Exception:
+                break
+            time.sleep(0.002)
+
     def start(self):
+        # NVML polled from a thread (the library calls release the GIL): a few
+        # hundred samples over a 0.1 s timed region; nvidia-smi as the fallback
+        try:
+            self.nvml = self._nvml_handle()
+            nv, h = self.nvml
+            self.smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.halt = threading.Event()
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            self.source = 'nvml'
+            return
+        except Exception:
+            self.nvml = None
+        self.source = 'nvidia-smi'
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.Q,
@@ -86,13 +126,17 @@ class ClockSampler(object):
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
-        if self.proc is None:
+        if getattr(self, 'nvml', None) is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+        elif self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['unavailable'])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
                  'sw_power_cap']
@@ -107,7 +151,7 @@ class ClockSampler(object):
                 pass
         return dict(sm_mhz=float(np.median(sm)) if sm else None,
                     sm_max_mhz=max(smax) if smax else None,
-                    samples=len(sm), reasons=sorted(reasons))
+                    samples=len(sm), source=self.source, reasons=sorted(reasons))
 
 
 # --------------------------------------------------------------------------

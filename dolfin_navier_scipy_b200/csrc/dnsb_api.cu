@@ -235,16 +235,22 @@ static int g_tma_min_rows = 65536;
 static inline bool spt_ok(const dnsb_csr *A, int nb) {
   return nb == 1 && A->spt.stages >= 2 && A->nrows >= g_tma_min_rows;
 }
-static void spt_launch(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef, const double *x,
-                       const double *z, double *y, double alpha, double beta) {
+template <int EPI>
+static void spt_launch_epi(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef, const double *x,
+                           const SptEpi &ep) {
   const SptPlan &p = A->spt;
   const unsigned grid = (unsigned)std::min(p.ntiles, ctx->sm_count * p.ctas_per_sm);
   if (A->has2 && coef)
-    LAUNCH(ctx, k_spmv_tma<true>, grid, SPT_THREADS, p.smem, A->view(), coef, x, z, y, alpha, beta,
-           p.ntiles, p.cap, p.stages, p.rt);
+    LAUNCH(ctx, (k_spmv_tma<true, EPI>), grid, SPT_THREADS, p.smem, A->view(), coef, x, ep, p.ntiles,
+           p.cap, p.stages, p.rt);
   else
-    LAUNCH(ctx, k_spmv_tma<false>, grid, SPT_THREADS, p.smem, A->view(), coef, x, z, y, alpha, beta,
-           p.ntiles, p.cap, p.stages, p.rt);
+    LAUNCH(ctx, (k_spmv_tma<false, EPI>), grid, SPT_THREADS, p.smem, A->view(), coef, x, ep, p.ntiles,
+           p.cap, p.stages, p.rt);
+}
+static void spt_launch(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef, const double *x,
+                       const double *z, double *y, double alpha, double beta) {
+  SptEpi ep{z, nullptr, y, nullptr, nullptr, alpha, beta};
+  spt_launch_epi<SPT_AXPBY>(ctx, A, coef, x, ep);
 }
 
 // y = alpha*A*x + beta*z  on device pointers
@@ -363,8 +369,14 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
   // k_mdot_b keeps (nvec+1) x 256 partial sums in dynamic shared memory
   DNSB_CK(ctx, cudaFuncSetAttribute(k_mdot_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
-  DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+#define SPT_ATTR(E)                                                                                  \
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<true, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                    216 * 1024));                                                    \
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<false, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    216 * 1024));
+  SPT_ATTR(SPT_AXPBY) SPT_ATTR(SPT_CHEB_INIT) SPT_ATTR(SPT_CHEB_STEP) SPT_ATTR(SPT_CHEB_STEP_FIRST)
+  SPT_ATTR(SPT_CHEB_STEP_LAST) SPT_ATTR(SPT_CHEB_STEP_ONLY)
+#undef SPT_ATTR
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_dmma_streamk, cudaFuncAttributeMaxDynamicSharedMemorySize, DMM_SMEM_BYTES));
   return 0;
 }
@@ -1132,7 +1144,10 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
     else if (batched)
       LAUNCH(ctx, k_cheb_init_b, spb_grid(n, nb, gpc), SPB_THREADS, 0, C->view(), zc, r, dinv, res,
              dfirst, nb, gpc, 1.0 / theta);
-    else if (nb == 1)
+    else if (spt_ok(C, nb)) {
+      SptEpi ep{r, dinv, res, dfirst, nullptr, 1.0 / theta, 0.0};
+      spt_launch_epi<SPT_CHEB_INIT>(ctx, C, nullptr, zc, ep);
+    } else if (nb == 1)
       LAUNCH(ctx, k_cheb_init<8>, cdiv((size_t)n * 8, 256), 256, 0, C->view(), zc, r, dinv, res,
              dfirst, nb, 1.0 / theta);
     else
@@ -1194,6 +1209,12 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
     } else if (batched) {
       if (has2) CHEB_DISPATCH_B(true);
       else CHEB_DISPATCH_B(false);
+    } else if (spt_ok(A, nb)) {
+      SptEpi ep{nullptr, dinv, res, dn, z, c1, c2};
+      if (first && last) spt_launch_epi<SPT_CHEB_STEP_ONLY>(ctx, A, coef, dc, ep);
+      else if (first) spt_launch_epi<SPT_CHEB_STEP_FIRST>(ctx, A, coef, dc, ep);
+      else if (last) spt_launch_epi<SPT_CHEB_STEP_LAST>(ctx, A, coef, dc, ep);
+      else spt_launch_epi<SPT_CHEB_STEP>(ctx, A, coef, dc, ep);
     } else if (nb == 1) {
       CHEB_DISPATCH(k_cheb_step, cdiv((size_t)n * 8, 256), 256, 8);
     } else {

@@ -67,12 +67,24 @@ __device__ __forceinline__ void spt_bulk_g2s(void *dst, const void *src, uint32_
                : "memory");
 }
 
-// y = alpha*A*x + beta*z for one right-hand side (nb == 1)
-template <bool H2>
+// what is done with the row product acc_i = (A x)_i  (one right-hand side):
+//   SPT_AXPBY      y = alpha*acc + beta*z                       (k_spmm)
+//   SPT_CHEB_INIT  r = a - acc ; o1 = r ; o2 = b*r*alpha        (k_cheb_init: a = rv, b = dinv,
+//                                                                 o1 = res, o2 = d, alpha = 1/theta)
+//   SPT_CHEB_STEP  r = o1 - acc ; dd = alpha*x_i + beta*b*r ;   (k_cheb_step: x = d, b = dinv, o1 = res,
+//                  [o1 = r ; o2 = dd] ; o3 = (FIRST ? x_i : o3) + dd        o2 = dn, o3 = z, alpha = c1, beta = c2)
+enum { SPT_AXPBY = 0, SPT_CHEB_INIT = 1, SPT_CHEB_STEP = 2, SPT_CHEB_STEP_FIRST = 3,
+       SPT_CHEB_STEP_LAST = 4, SPT_CHEB_STEP_ONLY = 5 };
+struct SptEpi {
+  const double *a, *b;
+  double *o1, *o2, *o3;
+  double alpha, beta;
+};
+
+template <bool H2, int EPI>
 __global__ void __launch_bounds__(SPT_THREADS)
-k_spmv_tma(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
-           const double *z, double *y, double alpha, double beta, int ntiles, int cap,
-           int stages, int rt) {
+k_spmv_tma(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x, SptEpi ep,
+           int ntiles, int cap, int stages, int rt) {
   constexpr int NWARP = SPT_CONSUMERS / 32;
   constexpr int UN = 6;
   extern __shared__ __align__(128) unsigned char spt_raw[];
@@ -160,7 +172,24 @@ k_spmv_tma(CsrDev A, const double *__restrict__ coef, const double *__restrict__
       for (int o = 1; o < (1 << lsh); o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (lr < nr && h == 0) {
         const size_t i = (size_t)(r0 + lr);
-        y[i] = (beta == 0.0) ? alpha * acc : alpha * acc + beta * z[i];
+        if (EPI == SPT_AXPBY) {
+          ep.o1[i] = (ep.beta == 0.0) ? ep.alpha * acc : ep.alpha * acc + ep.beta * ep.a[i];
+        } else if (EPI == SPT_CHEB_INIT) {
+          const double r = ep.a[i] - acc;
+          ep.o1[i] = r;
+          ep.o2[i] = ep.b[i] * r * ep.alpha;
+        } else {
+          constexpr bool FIRST = EPI == SPT_CHEB_STEP_FIRST || EPI == SPT_CHEB_STEP_ONLY;
+          constexpr bool LAST = EPI == SPT_CHEB_STEP_LAST || EPI == SPT_CHEB_STEP_ONLY;
+          const double r = ep.o1[i] - acc;
+          const double dold = x[i];
+          const double dd = ep.alpha * dold + ep.beta * ep.b[i] * r;
+          if (!LAST) {
+            ep.o1[i] = r;
+            ep.o2[i] = dd;
+          }
+          ep.o3[i] = (FIRST ? dold : ep.o3[i]) + dd;
+        }
       }
     }
     // the stage is handed back to the async proxy (next bulk copy overwrites the products)

@@ -1,6 +1,7 @@
 """single-trajectory step rate (BASELINE configs 1 and 3, IMEX part): CNAB on
 cylinder_<N>, one member, device-resident loop vs. the oracle's SuperLU loop
-usage: python tools/bench_single.py <mesh> <Re> <nts> <nsteps> [guess] [tol]"""
+usage: python tools/bench_single.py <mesh> <Re> <nts> <nsteps> [guess] [tol] [refine]
+(refine = r: r-fold uniform refinement of the mesh)"""
 import sys
 import time
 import numpy as np
@@ -9,8 +10,13 @@ from dolfin_navier_scipy_b200 import problem_setups as dnsps, time_int_utils as 
 N, Re, nts, nsteps = int(sys.argv[1]), float(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 guess = int(sys.argv[5]) if len(sys.argv) > 5 else 16
 tol = float(sys.argv[6]) if len(sys.argv) > 6 else 1e-12
+refine = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+meshparams = dict(refinement_level=N)
+if refine:
+    from dolfin_navier_scipy_b200 import fem
+    meshparams['mesh'] = fem.refine_uniform(fem.load_mesh('cylinder_%d' % N), refine)
 femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=Re, scheme='TH', mergerhs=True,
-                                   meshparams=dict(refinement_level=N))
+                                   meshparams=meshparams)
 inv = np.asarray(femp['invinds'])
 NP, NV = sm['J'].shape
 vp = lau.solve_sadpnt_smw(amat=sm['A'], jmat=sm['J'], jmatT=sm['JT'], rhsv=rhsd['fv'], rhsp=rhsd['fp'],
