@@ -15,7 +15,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef SPB_THREADS
 #define SPB_THREADS 256
+#endif
 #define SPB_WARPS (SPB_THREADS / 32)
 #define SPB_CAP 96   // CSR entries staged per warp and chunk
 
@@ -449,7 +451,10 @@ k_cheb_step_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restr
 // are handled (csr->npair_rows / 2, verified on the host when the matrix is
 // created); the sums run in CSR order per row: bit-identical results.
 // ---------------------------------------------------------------------------
-#define SPP_CAP 192   // CSR entries (both rows of the warp's pairs) staged per warp
+#ifndef SPP_CAP
+#define SPP_CAP 192
+#endif
+// SPP_CAP: CSR entries (both rows of the warp's pairs) staged per warp
 
 struct SppSmem2 {
   double2 v[SPB_WARPS][SPP_CAP];
