@@ -201,6 +201,17 @@ k_cheb_step_b(CsrDev A, const double *__restrict__ coef, const double *__restric
 // current one is consumed (software pipeline): 8-16 independent loads are in
 // flight per thread at any time, without a bubble between two vectors.
 #define GS_H (GS_RPT / 2)
+// basis vectors: streamed once per kernel (evict-first in L2 with DNSB_L2_HINTS >= 2)
+#if DNSB_L2_HINTS >= 2
+#define GS_LDV(p) __ldcs(p)
+#else
+#define GS_LDV(p) (*(p))
+#endif
+#define GS_LOADV(dst, vec, half)                                                \
+  _Pragma("unroll") for (int q = 0; q < GS_H; ++q) {                            \
+    const int r = r0 + rr + ((half) * GS_H + q) * rpb;                          \
+    dst[q] = (r < r1) ? GS_LDV((vec) + (size_t)r * nb + m) : 0.0;               \
+  }
 #define GS_LOAD(dst, vec, half)                                                 \
   _Pragma("unroll") for (int q = 0; q < GS_H; ++q) {                            \
     const int r = r0 + rr + ((half) * GS_H + q) * rpb;                          \
@@ -221,7 +232,7 @@ k_mdot_b(const double *__restrict__ V, size_t vstride, int nvec,
   double wa[GS_H], wb[GS_H], va[GS_H], vb[GS_H];
   GS_LOAD(wa, w, 0)
   GS_LOAD(wb, w, 1)
-  if (nvec > 0) { GS_LOAD(va, V, 0) }
+  if (nvec > 0) { GS_LOADV(va, V, 0) }
   double ww = 0.0;
 #pragma unroll
   for (int q = 0; q < GS_H; ++q) ww += wa[q] * wa[q];
@@ -229,11 +240,11 @@ k_mdot_b(const double *__restrict__ V, size_t vstride, int nvec,
   for (int q = 0; q < GS_H; ++q) ww += wb[q] * wb[q];
   for (int i = 0; i < nvec; ++i) {
     const double *vi = V + (size_t)i * vstride;
-    GS_LOAD(vb, vi, 1)
+    GS_LOADV(vb, vi, 1)
     double acc = 0.0;
 #pragma unroll
     for (int q = 0; q < GS_H; ++q) acc += va[q] * wa[q];
-    if (i + 1 < nvec) { GS_LOAD(va, vi + vstride, 0) }
+    if (i + 1 < nvec) { GS_LOADV(va, vi + vstride, 0) }
 #pragma unroll
     for (int q = 0; q < GS_H; ++q) acc += vb[q] * wb[q];
     sred[(size_t)i * nthr + threadIdx.x] = acc;
@@ -264,15 +275,15 @@ k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
   double wa[GS_H], wb[GS_H], va[GS_H], vb[GS_H];
   GS_LOAD(wa, w, 0)
   GS_LOAD(wb, w, 1)
-  if (nvec > 0) { GS_LOAD(va, V, 0) }
+  if (nvec > 0) { GS_LOADV(va, V, 0) }
   double hi = nvec > 0 ? h[m] : 0.0;
   for (int i = 0; i < nvec; ++i) {
     const double *vi = V + (size_t)i * vstride;
-    GS_LOAD(vb, vi, 1)
+    GS_LOADV(vb, vi, 1)
     const double hn = (i + 1 < nvec) ? h[(size_t)(i + 1) * nb + m] : 0.0;
 #pragma unroll
     for (int q = 0; q < GS_H; ++q) wa[q] -= hi * va[q];
-    if (i + 1 < nvec) { GS_LOAD(va, vi + vstride, 0) }
+    if (i + 1 < nvec) { GS_LOADV(va, vi + vstride, 0) }
 #pragma unroll
     for (int q = 0; q < GS_H; ++q) wb[q] -= hi * vb[q];
     hi = hn;

@@ -1,5 +1,10 @@
 // dnsb_common.cuh -- context, device buffers, error handling (host side)
 #pragma once
+// L2 residency hints: 1 = the dense Schur inverse is read evict-first,
+// 2 = also the Krylov basis in the Gram-Schmidt kernels
+#ifndef DNSB_L2_HINTS
+#define DNSB_L2_HINTS 2
+#endif
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>

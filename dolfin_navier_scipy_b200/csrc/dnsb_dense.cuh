@@ -179,6 +179,19 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
+// the same with an L2 evict-first policy: the dense inverse (118 MB at np = 3836) is read once per
+// application and must not sweep the vectors and sparse operators of the other step kernels out of L2
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_stream(void *smem, const void *gmem, int src_bytes,
+                                                  unsigned long long pol) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(s), "l"(gmem),
+               "r"(src_bytes), "l"(pol));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
@@ -211,6 +224,9 @@ k_dense_dmma_streamk(const double *__restrict__ D, const double *__restrict__ X,
 #pragma unroll
       for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
+#if DNSB_L2_HINTS
+    const unsigned long long l2pol = l2_evict_first_policy();
+#endif
     auto issue = [&](int kstep, int stage) {
       double *sD = dsm + (size_t)stage * DMM_STAGE_DOUBLES;
       double *sX = sD + DGK_TM * DMM_DS;
@@ -222,8 +238,13 @@ k_dense_dmma_streamk(const double *__restrict__ D, const double *__restrict__ X,
         const int r = c >> 3, ch = c & 7;
         const int gi = row0 + r, gk = k0 + 2 * ch;
         const bool ok = gi < n && gk < n;
+#if DNSB_L2_HINTS
+        cp_async16_stream(sD + r * DMM_DS + 2 * ch, ok ? (const void *)(D + (size_t)gi * n + gk) : (const void *)D,
+                          ok ? 16 : 0, l2pol);
+#else
         cp_async16(sD + r * DMM_DS + 2 * ch, ok ? (const void *)(D + (size_t)gi * n + gk) : (const void *)D,
                    ok ? 16 : 0);
+#endif
       }
       // X tile: 16 rows x 32 chunks of 2 members
 #pragma unroll
