@@ -48,6 +48,9 @@ def parse():
     ap.add_argument('--cheb', type=int, default=4)
     ap.add_argument('--schur-poly', type=int, default=2)
     ap.add_argument('--coarse-max', type=int, default=4096)
+    ap.add_argument('--schur-precision', default='f64', choices=['f64', 'tf32x3', 'tf32x2', 'tf32'],
+                    help='dense Schur block of the preconditioner: fp64 (default) or 3xTF32 '
+                         '(fp32 copy of the inverse; FGMRES residuals stay fp64)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-seconds', type=float, default=12.)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -274,6 +277,7 @@ def workload_config(args, members_total, world):
                 % world,
                 tol=args.tol, guess=args.guess, cheb_steps=args.cheb,
                 schur_poly=args.schur_poly,
+                schur_precision=args.schur_precision,
                 l2_note='ensemble working set (vectors %d members) exceeds L2'
                 % args.members)
 
@@ -288,6 +292,8 @@ def run_ours(args, rank, world, local_rank):
     from dolfin_navier_scipy_b200 import ensemble as ens
 
     torch.cuda.set_device(local_rank)
+    if args.schur_precision != 'f64':      # read when the context is created
+        os.environ['DNSB_SCHUR_TF32'] = dict(tf32x3='1', tf32x2='2', tf32='3')[args.schur_precision]
     ctx = _lib.default_context(local_rank)
     nmembers = args.members*world
     ntimes = max(args.warmup, 3) + 4*args.steps + 8
@@ -512,6 +518,17 @@ def roofline_of(kern, info, integ, args):
                achieved=ach, peak=peak,
                peak_source=which, unit='GB/s', frac=ach/peak, traffic=traffic,
                launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
+    # where the step goes: the six largest kernels of the timed region by summed event time
+    tot_ms = sum(ms for _, ms in kern.values()) or 1.
+    out['kernel_shares'] = [dict(kernel=k.strip('()'), launches=c, mean_us=1e3*m/c, share=m/tot_ms)
+                            for k, (c, m) in sorted(kern.items(), key=lambda kv: -kv[1][1])[:6]]
+    tf = [k for k in kern if k.strip('()').startswith('k_dense_tf32')]
+    if tf:
+        c, m = kern[tf[0]]
+        out['dense_schur'] = dict(kernel=tf[0], mean_us=1e3*m/c,
+                                  tf32_tflops=3*2.*npp*npp*nb/(m*1e-3/c)/1e12,
+                                  note='3xTF32 mma.sync (fp32 copy of the inverse), '
+                                  'preconditioner block only; FGMRES residuals fp64')
     dn = [k for k in kern if k.strip('()').startswith(('k_dense_gemm', 'k_dense_dmma'))]
     if dn:
         c, m = kern[dn[0]]

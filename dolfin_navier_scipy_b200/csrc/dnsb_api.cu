@@ -199,6 +199,7 @@ static inline bool batched_ok(const dnsb_csr *A, int nb) {
 static int g_rows_per_cta = 4;
 static int g_dense_ctas_per_sm = 2;
 static int g_graphs = 1;
+static int g_schur_tf32 = 0;   // 1: dense Schur inverse applied in 3xTF32 (fp32 copy), see dnsb_dense.cuh
 static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur solve
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
 static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
@@ -350,6 +351,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_TMA_ROWS")) g_tma_rows = std::min(SPT_ROWS, std::max(4, atoi(ev) & ~3));
   if (const char *ev = getenv("DNSB_TMA_STAGES")) g_tma_stages = std::min(SPT_MAX_STAGES, std::max(2, atoi(ev)));
   if (const char *ev = getenv("DNSB_DMMA")) g_dmma = atoi(ev);
+  if (const char *ev = getenv("DNSB_SCHUR_TF32")) g_schur_tf32 = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
@@ -378,6 +380,9 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   SPT_ATTR(SPT_CHEB_STEP_LAST) SPT_ATTR(SPT_CHEB_STEP_ONLY)
 #undef SPT_ATTR
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_dmma_streamk, cudaFuncAttributeMaxDynamicSharedMemorySize, DMM_SMEM_BYTES));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   return 0;
 }
 
@@ -747,6 +752,8 @@ struct MgLevel {
   double lmin = 0, lmax = 0;
   DBuf<double> dinv_dense;   // n*n (MG_DENSE)
   DBuf<double> gpart;        // split-K partial sums of the dense solve
+  DBuf<float> dinv_f32, x_f32;   // fp32 copies for the optional TF32 variant (DNSB_SCHUR_TF32)
+  int ldf = 0;
   DBuf<double> dinv_own;     // n*nb Jacobi (owned)
   const double *dinv = nullptr;
   DBuf<double> b, x, r, d0, d1, t;   // n*nb work vectors
@@ -931,7 +938,7 @@ static void dense_split(dnsb_ctx *ctx, int n, int nb, int *tn, DenseSplit *sp) {
 
 static void level_free(MgLevel *L) {
   if (!L) return;
-  L->dinv_dense.release(); L->gpart.release(); L->dinv_own.release(); L->b.release(); L->x.release();
+  L->dinv_dense.release(); L->gpart.release(); L->dinv_f32.release(); L->x_f32.release(); L->dinv_own.release(); L->b.release(); L->x.release();
   L->r.release(); L->d0.release(); L->d1.release(); L->t.release();
   delete L;
 }
@@ -987,6 +994,13 @@ static int solver_add_level(dnsb_solver *s, int block, dnsb_csr *amat, dnsb_csr 
       DenseSplit sp;
       dense_split(ctx, nexpect, s->nb, &tn, &sp);
       e = L->gpart.alloc((size_t)sp.nctas * sp.maxseg * DGK_TM * s->nb);
+      if (e == cudaSuccess && g_schur_tf32 && s->nb % 4 == 0) {
+        L->ldf = (nexpect + 3) & ~3;
+        if ((e = L->dinv_f32.alloc((size_t)nexpect * L->ldf)) == cudaSuccess &&
+            (e = L->x_f32.alloc((size_t)nexpect * s->nb)) == cudaSuccess)
+          LAUNCH(ctx, k_f64_to_f32, cdiv((size_t)nexpect * L->ldf, 256), 256, 0, (const double *)L->dinv_dense.p,
+                 L->dinv_f32.p, (size_t)nexpect, (size_t)nexpect, (size_t)L->ldf);
+      }
     }
     if (e != cudaSuccess) { level_free(L); DNSB_CK(ctx, e); }
   } else {
@@ -1100,7 +1114,16 @@ static int dense_apply(dnsb_solver *s, MgLevel *L, const double *x,
     DenseSplit sp;
     dense_split(ctx, n, nb, &tn, &sp);
     const dim3 grid(sp.nctas, cdiv(nb, tn));
-    if (g_dmma && nb > 32 && n % 2 == 0 && nb % 2 == 0)
+    if (L->dinv_f32.p && tn == 64) {
+      LAUNCH(ctx, k_f64_to_f32, cdiv((size_t)n * nb, 256), 256, 0, x, L->x_f32.p, (size_t)n, (size_t)nb, (size_t)nb);
+const float *df_ = L->dinv_f32.p, *xf_ = L->x_f32.p;
+      if (g_schur_tf32 == 1)
+        LAUNCH(ctx, k_dense_tf32_streamk<3>, grid, 128, TFM_SMEM_BYTES, df_, L->ldf, xf_, L->gpart.p, n, nb, sp);
+      else if (g_schur_tf32 == 2)
+        LAUNCH(ctx, k_dense_tf32_streamk<2>, grid, 128, TFM_SMEM_BYTES, df_, L->ldf, xf_, L->gpart.p, n, nb, sp);
+      else
+        LAUNCH(ctx, k_dense_tf32_streamk<1>, grid, 128, TFM_SMEM_BYTES, df_, L->ldf, xf_, L->gpart.p, n, nb, sp);
+    } else if (g_dmma && nb > 32 && n % 2 == 0 && nb % 2 == 0)
       LAUNCH(ctx, k_dense_dmma_streamk, grid, 128, DMM_SMEM_BYTES, L->dinv_dense.p, x, L->gpart.p, n, nb, sp);
     else if (tn == 16)
       LAUNCH(ctx, k_dense_gemm_streamk<16>, grid, 128, 0, L->dinv_dense.p, x, L->gpart.p, n, nb, sp);

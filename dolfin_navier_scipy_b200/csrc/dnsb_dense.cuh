@@ -307,3 +307,156 @@ k_dense_dmma_streamk(const double *__restrict__ D, const double *__restrict__ X,
     ++seg;
   }
 }
+
+// ---------------------------------------------------------------------------
+// Optional reduced-precision variant of the dense Schur solve (DNSB_SCHUR_TF32=1,
+// off by default): the dense inverse is kept as an fp32 copy and applied with
+// the TF32 tensor-core instruction mma.sync.m16n8k8 in the 3xTF32 split
+// (a = a_hi + a_lo, b = b_hi + b_lo; a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32
+// accumulation): fp32-accurate products.  It is a PRECONDITIONER block inside a
+// flexible GMRES whose residuals, bases and stopping test stay fp64, so the
+// computed solution meets the same fp64 residual tolerance; only the iteration
+// count can change.  Half the bytes of D (4 n^2) and no fp64-pipe bound.
+// Same stream-K decomposition, partial-tile layout (fp64) and epilogue as the
+// fp64 kernels.  Requires nb % 4 == 0; D32 has leading dimension ld (ld % 4 == 0).
+//   CTA = 4 warps, tile 64 rows x 64 members, warp w owns rows 16w..16w+15:
+//   8 n-tiles of m16n8 accumulators (32 floats per lane).
+//   Shared tiles: D [64][16] floats (row stride 20), X [16][64] floats (row
+//   stride 72): conflict-free fragment loads.
+// ---------------------------------------------------------------------------
+#define TFM_STAGES 6
+#define TFM_DS 20
+#define TFM_XS 72
+#define TFM_STAGE_FLOATS (DGK_TM * TFM_DS + DGK_TK * TFM_XS)
+#define TFM_SMEM_BYTES (TFM_STAGES * TFM_STAGE_FLOATS * 4)
+
+__device__ __forceinline__ void tf32_split(float v, unsigned &hi, unsigned &lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(hi) : "f"(v));
+  const float r = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void k_f64_to_f32(const double *__restrict__ src, float *__restrict__ dst, size_t rows,
+                             size_t cols, size_t ld) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * ld) return;
+  const size_t r = t / ld, c = t - r * ld;
+  dst[t] = c < cols ? (float)src[r * cols + c] : 0.0f;
+}
+
+//   PASSES = 3: 3xTF32 as above; 2: a_hi (b_hi + b_lo) -- D rounded to TF32 once, X fp32-accurate;
+//   1: a_hi b_hi (plain TF32)
+template <int PASSES>
+__global__ void __launch_bounds__(128)
+k_dense_tf32_streamk(const float *__restrict__ D, int ld, const float *__restrict__ X,
+                     double *__restrict__ part, int n, int nb, DenseSplit sp) {
+  extern __shared__ __align__(16) float fsm[];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int m0 = blockIdx.y * 64;
+  const long utotal = (long)((n + DGK_TM - 1) / DGK_TM) * sp.ksteps;
+  long u = (long)blockIdx.x * sp.upc;
+  const long uend = min(utotal, u + sp.upc);
+  int seg = 0;
+#if DNSB_L2_HINTS
+  const unsigned long long l2pol = l2_evict_first_policy();
+#endif
+  while (u < uend) {
+    const int rt = (int)(u / sp.ksteps);
+    const int ks0 = (int)(u - (long)rt * sp.ksteps);
+    const int ks1 = (int)min((long)sp.ksteps, ks0 + (uend - u));
+    const int row0 = rt * DGK_TM;
+    const int nk = ks1 - ks0;
+    float acc[8][4];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.0f;
+
+    auto issue = [&](int kstep, int stage) {
+      float *sD = fsm + (size_t)stage * TFM_STAGE_FLOATS;
+      float *sX = sD + DGK_TM * TFM_DS;
+      const int k0 = (ks0 + kstep) * DGK_TK;
+      // D tile: 64 rows x 4 chunks of 4 floats
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = tid + 128 * q;
+        const int r = c >> 2, ch = c & 3;
+        const int gi = row0 + r, gk = k0 + 4 * ch;
+        const bool ok = gi < n && gk < ld;
+        const void *src = ok ? (const void *)(D + (size_t)gi * ld + gk) : (const void *)D;
+#if DNSB_L2_HINTS
+        cp_async16_stream(sD + r * TFM_DS + 4 * ch, src, ok ? 16 : 0, l2pol);
+#else
+        cp_async16(sD + r * TFM_DS + 4 * ch, src, ok ? 16 : 0);
+#endif
+      }
+      // X tile: 16 rows x 16 chunks of 4 members
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = tid + 128 * q;
+        const int r = c >> 4, ch = c & 15;
+        const int gk = k0 + r, gm = m0 + 4 * ch;
+        const bool ok = gk < n && gm < nb;
+        cp_async16(sX + r * TFM_XS + 4 * ch, ok ? (const void *)(X + (size_t)gk * nb + gm) : (const void *)X,
+                   ok ? 16 : 0);
+      }
+    };
+
+    __syncthreads();   // the previous segment is done with the buffers
+#pragma unroll
+    for (int s = 0; s < TFM_STAGES - 1; ++s) {
+      if (s < nk) issue(s, s);
+      cp_async_commit();
+    }
+    for (int ks = 0; ks < nk; ++ks) {
+      cp_async_wait<TFM_STAGES - 2>();
+      __syncthreads();
+      const int nxt = ks + TFM_STAGES - 1;
+      if (nxt < nk) issue(nxt, nxt % TFM_STAGES);
+      cp_async_commit();
+      const float *sD = fsm + (size_t)(ks % TFM_STAGES) * TFM_STAGE_FLOATS;
+      const float *sX = sD + DGK_TM * TFM_DS;
+#pragma unroll
+      for (int kk = 0; kk < DGK_TK; kk += 8) {
+        unsigned ah[4], al[4];
+        tf32_split(sD[(16 * w + g) * TFM_DS + kk + t4], ah[0], al[0]);
+        tf32_split(sD[(16 * w + 8 + g) * TFM_DS + kk + t4], ah[1], al[1]);
+        tf32_split(sD[(16 * w + g) * TFM_DS + kk + 4 + t4], ah[2], al[2]);
+        tf32_split(sD[(16 * w + 8 + g) * TFM_DS + kk + 4 + t4], ah[3], al[3]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          unsigned bh0, bl0, bh1, bl1;
+          tf32_split(sX[(kk + t4) * TFM_XS + 8 * t + g], bh0, bl0);
+          tf32_split(sX[(kk + 4 + t4) * TFM_XS + 8 * t + g], bh1, bl1);
+          if (PASSES >= 3) mma_tf32_1688(acc[t], al, bh0, bh1);
+          if (PASSES >= 2) mma_tf32_1688(acc[t], ah, bl0, bl1);
+          mma_tf32_1688(acc[t], ah, bh0, bh1);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    double *out = part + ((size_t)blockIdx.x * sp.maxseg + seg) * DGK_TM * nb;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int rl = 16 * w + 8 * a + g;
+      if (row0 + rl >= n) continue;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int gm = m0 + 8 * t + 2 * t4;
+        if (gm + 1 < nb) {
+          *reinterpret_cast<double2 *>(out + (size_t)rl * nb + gm) =
+              make_double2((double)acc[t][2 * a], (double)acc[t][2 * a + 1]);
+        } else if (gm < nb) {
+          out[(size_t)rl * nb + gm] = (double)acc[t][2 * a];
+        }
+      }
+    }
+    u += nk;
+    ++seg;
+  }
+}

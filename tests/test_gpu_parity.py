@@ -552,3 +552,39 @@ def test_staged_spmv_ragged_rows(staged_ctx):
     one = sps.csr_matrix(rng.standard_normal((1, 300)))
     x = rng.standard_normal(300)
     assert _rel(ctx.csr(one).spmm(x), one@x) < 1e-14
+
+
+def test_schur_tf32_variant_meets_the_fp64_tolerance(cyl1):
+    """DNSB_SCHUR_TF32=1: the dense Schur block of the preconditioner applied
+    in 3xTF32 (fp32 copy of the inverse).  FGMRES is flexible and keeps its
+    residuals in fp64: same solution to the same tolerance, iteration count
+    within one of the fp64 preconditioner."""
+    import os
+    from dolfin_navier_scipy_b200 import _lib, lin_alg_utils as lau
+    from oracle.lau import solve_sadpnt_smw as olu
+    femp, sm, rhsd = cyl1
+    dt = 1./512
+    F = (sm['M'] + .5*dt*sm['A']).tocsr()
+    ncols = 64
+    rng = np.random.default_rng(11)
+    b = sm['M']@rng.standard_normal((F.shape[0], ncols))
+    g = sm['J']@rng.standard_normal((F.shape[0], ncols))*1e-3
+    ref = olu(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b, rhsp=g)
+    NV = F.shape[0]
+    its = {}
+    try:
+        for flag in ('0', '1'):
+            os.environ['DNSB_SCHUR_TF32'] = flag
+            ctx = _lib.Context(0)
+            op = lau.SadpntOperator(F, sm['J'], sm['JT'], ncols=ncols, ctx=ctx)
+            vp = op.solve(b, g, tol=1e-12, maxit=200)
+            its[flag] = op.last_iters.copy()
+            for k in range(ncols):
+                assert _rel(vp[:NV, k], ref[:NV, k]) < 1e-9, (flag, k)
+                assert _rel(vp[NV:, k], ref[NV:, k]) < 1e-8, (flag, k)
+            op.close()
+    finally:
+        os.environ['DNSB_SCHUR_TF32'] = '0'
+        _lib.Context(0)
+        del os.environ['DNSB_SCHUR_TF32']
+    assert abs(int(np.max(its['1'])) - int(np.max(its['0']))) <= 1, its
