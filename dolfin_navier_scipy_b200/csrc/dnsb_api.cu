@@ -66,13 +66,48 @@ static RedCfg red_cfg(dnsb_ctx *ctx, int n, int nb) {
   return c;
 }
 
+// TMA-streamed Gram-Schmidt kernels (dnsb_stream.cuh): stages of the basis ring that fit beside the
+// reduction scratch in 111 KB (two CTAs per SM); 0 = use the register-pipelined kernels
+static int g_gs_tma = 1;
+static int gst_stages(const RedCfg &rc, int nb, size_t scratch_doubles) {
+  if (!g_gs_tma || nb % 2 || nb < 16 || rc.threads % 32 || rc.threads > 256 ||
+      rc.rows_per_block > rc.rpb * GST_RPT)
+    return 0;
+  const size_t tile = (size_t)rc.rows_per_block * nb * sizeof(double);
+  const size_t budget = 111 * 1024, scratch = scratch_doubles * sizeof(double);
+  if (scratch + 2 * tile > budget) return 0;
+  return (int)std::min<size_t>(GST_MAX_STAGES, (budget - scratch) / tile);
+}
+static size_t gst_smem(const RedCfg &rc, int nb, int stages, size_t scratch_doubles) {
+  return ((size_t)stages * rc.rows_per_block * nb + scratch_doubles) * sizeof(double);
+}
+
+// vnext = w - sum_i h[i,m] V_i ; partial2[b*nb + m] = |vnext|^2 over the chunk of block b
+static void gs_update_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vstride, int nvec,
+                          const double *h, const double *w, double *vnext, int n, int nb,
+                          double *partial2) {
+  const int st = nvec > 0 ? gst_stages(rc, nb, rc.threads) : 0;
+  if (st >= 2)
+    LAUNCH(ctx, k_gs_tma<true>, rc.nblocks, rc.threads + 32, gst_smem(rc, nb, st, rc.threads), V, vstride,
+           nvec, h, w, vnext, n, nb, rc.rpb, rc.rows_per_block, partial2, st);
+  else
+    LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, V, vstride, nvec, h, w, vnext, n, nb,
+           rc.rpb, rc.rows_per_block, partial2);
+}
+
 // h[0..nvec) = <V_i, w>, h[nvec] = <w, w>  (per member), deterministic
 static void mdot_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vstride,
                      int nvec, const double *w, int n, int nb, double *partial,
                      double *h) {
   const size_t smem = (size_t)(nvec + 1) * rc.threads * sizeof(double);
-  LAUNCH(ctx, k_mdot_b, rc.nblocks, rc.threads, smem, V, vstride, nvec, w, n, nb, rc.rpb,
-         rc.rows_per_block, partial);
+  const int st = nvec > 0 ? gst_stages(rc, nb, (size_t)(nvec + 1) * rc.threads) : 0;
+  if (st >= 2)
+    LAUNCH(ctx, k_gs_tma<false>, rc.nblocks, rc.threads + 32,
+           gst_smem(rc, nb, st, (size_t)(nvec + 1) * rc.threads), V, vstride, nvec, (const double *)nullptr, w,
+           (double *)nullptr, n, nb, rc.rpb, rc.rows_per_block, partial, st);
+  else
+    LAUNCH(ctx, k_mdot_b, rc.nblocks, rc.threads, smem, V, vstride, nvec, w, n, nb, rc.rpb,
+           rc.rows_per_block, partial);
   const int count = (nvec + 1) * nb;
   LAUNCH(ctx, k_reduce_partials2, cdiv(count, 32), 1024, 0, (const double *)partial, rc.nblocks,
          count, h);
@@ -348,6 +383,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
   if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
   if (const char *ev = getenv("DNSB_TMA_MIN_ROWS")) g_tma_min_rows = atoi(ev);
+  if (const char *ev = getenv("DNSB_GS_TMA")) g_gs_tma = atoi(ev);
   if (const char *ev = getenv("DNSB_TMA_ROWS")) g_tma_rows = std::min(SPT_ROWS, std::max(4, atoi(ev) & ~3));
   if (const char *ev = getenv("DNSB_TMA_STAGES")) g_tma_stages = std::min(SPT_MAX_STAGES, std::max(2, atoi(ev)));
   if (const char *ev = getenv("DNSB_DMMA")) g_dmma = atoi(ev);
@@ -371,6 +407,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
   // k_mdot_b keeps (nvec+1) x 256 partial sums in dynamic shared memory
   DNSB_CK(ctx, cudaFuncSetAttribute(k_mdot_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_gs_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_gs_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
 #define SPT_ATTR(E)                                                                                  \
   DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<true, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                     216 * 1024));                                                    \
@@ -1388,15 +1426,11 @@ static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
   const bool reorth = (nb == 1) || j >= 16;
   double *Vn = s->Vb.p + (size_t)(j + 1) * ntb;
   mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb, s->partial.p, s->gs.h);
-  LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
-         (const double *)s->gs.h, (const double *)s->w.p, Vn, ntot, nb, rc.rpb,
-         rc.rows_per_block, s->partial2.p);
+  gs_update_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->gs.h, s->w.p, Vn, ntot, nb, s->partial2.p);
   const double *unscaled = Vn;
   if (reorth) {
     mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, Vn, ntot, nb, s->partial.p, s->gh2.p);
-    LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)s->Vb.p, ntb, j + 1,
-           (const double *)s->gh2.p, (const double *)Vn, s->w.p, ntot, nb, rc.rpb,
-           rc.rows_per_block, s->partial2.p);
+    gs_update_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->gh2.p, Vn, s->w.p, ntot, nb, s->partial2.p);
     LAUNCH(ctx, k_axpby, cdiv((size_t)(j + 1) * nb, 256), 256, 0, 1.0, (const double *)s->gs.h, 1.0,
            (const double *)s->gh2.p, s->gs.h, (size_t)(j + 1) * nb);
     unscaled = s->w.p;
@@ -2212,12 +2246,8 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
     if (pass == 0)
       DNSB_CK(ctx, cudaMemcpyAsync(e->normout.p, e->gr.p + (size_t)k * nb, nb * sizeof(double),
                                    cudaMemcpyDeviceToDevice, ctx->stream));
-    LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)e->bq.p, ntb, k,
-           (const double *)e->gr.p, (const double *)w, w2, ntot, nb, rc.rpb, rc.rows_per_block,
-           e->normpart.p);
-    LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, (const double *)e->xq.p, ntb, k,
-           (const double *)e->gr.p, (const double *)d, d2, ntot, nb, rc.rpb, rc.rows_per_block,
-           e->partialh.p);
+    gs_update_dev(ctx, rc, e->bq.p, ntb, k, e->gr.p, w, w2, ntot, nb, e->normpart.p);
+    gs_update_dev(ctx, rc, e->xq.p, ntb, k, e->gr.p, d, d2, ntot, nb, e->partialh.p);
     std::swap(w, w2);
     std::swap(d, d2);
   }

@@ -198,3 +198,132 @@ k_spmv_tma(CsrDev A, const double *__restrict__ coef, const double *__restrict__
     if (lane == 0) spt_mbar_arrive(&empty[s]);
   }
 }
+
+// ---------------------------------------------------------------------------
+// Gram-Schmidt kernels of FGMRES with the basis vectors streamed by the TMA
+// engine: same block/thread mapping, partial-sum layout and summation order as
+// k_mdot_b / k_gs_update_b (dnsb_batched.cuh) -- bit-identical results -- but
+// the chunk [r0, r1) x nb of every basis vector (one contiguous block of
+// memory) arrives in a shared-memory ring through one bulk copy issued by a
+// producer thread, so that the bytes in flight per SM no longer depend on the
+// registers of the consumer threads (the register-pipelined kernels reach
+// about half of the HBM peak at 24 % occupancy).
+//   UPDATE = false:  partial[(b*(nvec+1) + i)*nb + m] = sum_chunk V_i*w, i = nvec: w*w
+//   UPDATE = true:   vnext = w - sum_i h[i,m] V_i ; partial[b*nb + m] = |vnext|^2 over the chunk
+// Block = rpb*nb consumer threads (thread = (rr, m)) + one producer warp;
+// requires nb even (16-byte bulk copies) and rows_per_block <= rpb*GST_RPT.
+// ---------------------------------------------------------------------------
+#define GST_RPT 16
+#define GST_H (GST_RPT / 2)
+#define GST_MAX_STAGES 4
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(288)
+k_gs_tma(const double *__restrict__ V, size_t vstride, int nvec, const double *__restrict__ h,
+         const double *__restrict__ w, double *__restrict__ vnext, int n, int nb, int rpb,
+         int rows_per_block, double *__restrict__ partial, int stages) {
+  extern __shared__ __align__(128) unsigned char gst_raw[];
+  __shared__ __align__(8) uint64_t full[GST_MAX_STAGES], empty[GST_MAX_STAGES];
+  const int nthr = rpb * nb;                 // consumer threads
+  const int ncw = nthr >> 5;                 // consumer warps (nthr is a multiple of 32)
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(n, r0 + rows_per_block);
+  const size_t tile_doubles = (size_t)rows_per_block * nb;
+  double *ring = reinterpret_cast<double *>(gst_raw);
+  double *sred = ring + (size_t)stages * tile_doubles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      spt_mbar_init(&full[s], 1);
+      spt_mbar_init(&empty[s], ncw);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  if ((int)threadIdx.x >= nthr) {
+    // ---- producer: one bulk copy per basis vector ----
+    if ((int)threadIdx.x == nthr) {
+      const uint32_t bytes = (uint32_t)((size_t)(r1 - r0) * nb * sizeof(double));
+      for (int i = 0; i < nvec; ++i) {
+        const int s = i % stages;
+        if (i >= stages) spt_mbar_wait(&empty[s], ((i / stages) - 1) & 1);
+        spt_mbar_expect(&full[s], bytes);
+        spt_bulk_g2s(ring + (size_t)s * tile_doubles, V + (size_t)i * vstride + (size_t)r0 * nb, bytes,
+                     &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int m = threadIdx.x % nb, rr = threadIdx.x / nb, lane = threadIdx.x & 31;
+  double wa[GST_H], wb[GST_H];
+#pragma unroll
+  for (int q = 0; q < GST_H; ++q) {
+    const int ra = r0 + rr + q * rpb, rb = r0 + rr + (GST_H + q) * rpb;
+    wa[q] = (ra < r1) ? w[(size_t)ra * nb + m] : 0.0;
+    wb[q] = (rb < r1) ? w[(size_t)rb * nb + m] : 0.0;
+  }
+  double hi = (UPDATE && nvec > 0) ? h[m] : 0.0;
+  for (int i = 0; i < nvec; ++i) {
+    const int s = i % stages;
+    const double hn = (UPDATE && i + 1 < nvec) ? h[(size_t)(i + 1) * nb + m] : 0.0;
+    spt_mbar_wait(&full[s], (i / stages) & 1);
+    const double *tile = ring + (size_t)s * tile_doubles + m;
+    double va[GST_H], vb[GST_H];
+#pragma unroll
+    for (int q = 0; q < GST_H; ++q) {
+      const int la = rr + q * rpb, lb = rr + (GST_H + q) * rpb;
+      va[q] = (r0 + la < r1) ? tile[(size_t)la * nb] : 0.0;
+      vb[q] = (r0 + lb < r1) ? tile[(size_t)lb * nb] : 0.0;
+    }
+    if (UPDATE) {
+#pragma unroll
+      for (int q = 0; q < GST_H; ++q) wa[q] -= hi * va[q];
+#pragma unroll
+      for (int q = 0; q < GST_H; ++q) wb[q] -= hi * vb[q];
+      hi = hn;
+    } else {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < GST_H; ++q) acc += va[q] * wa[q];
+#pragma unroll
+      for (int q = 0; q < GST_H; ++q) acc += vb[q] * wb[q];
+      sred[(size_t)i * nthr + threadIdx.x] = acc;
+    }
+    // the values have been consumed (the shared-memory reads are complete): hand the stage back
+    __syncwarp();
+    if (lane == 0) spt_mbar_arrive(&empty[s]);
+  }
+  double ww = 0.0;
+  if (UPDATE) {
+#pragma unroll
+    for (int q = 0; q < GST_H; ++q) {
+      const int ra = r0 + rr + q * rpb, rb = r0 + rr + (GST_H + q) * rpb;
+      if (ra < r1) vnext[(size_t)ra * nb + m] = wa[q];
+      if (rb < r1) vnext[(size_t)rb * nb + m] = wb[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < GST_H; ++q) ww += wa[q] * wa[q];
+#pragma unroll
+  for (int q = 0; q < GST_H; ++q) ww += wb[q] * wb[q];
+  sred[(size_t)(UPDATE ? 0 : nvec) * nthr + threadIdx.x] = ww;
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // consumers only
+  if (UPDATE) {
+    if (rr == 0) {
+      double s = 0.0;
+      for (int q = 0; q < rpb; ++q) s += sred[q * nb + m];
+      partial[(size_t)blockIdx.x * nb + m] = s;
+    }
+  } else {
+    for (int o = threadIdx.x; o < (nvec + 1) * nb; o += nthr) {
+      const int i = o / nb, mm = o % nb;
+      double s = 0.0;
+      for (int q = 0; q < rpb; ++q) s += sred[(size_t)i * nthr + q * nb + mm];
+      partial[((size_t)blockIdx.x * (nvec + 1) + i) * nb + mm] = s;
+    }
+  }
+}

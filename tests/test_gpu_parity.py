@@ -588,3 +588,33 @@ def test_schur_tf32_variant_meets_the_fp64_tolerance(cyl1):
         _lib.Context(0)
         del os.environ['DNSB_SCHUR_TF32']
     assert abs(int(np.max(its['1'])) - int(np.max(its['0']))) <= 1, its
+
+
+def test_tma_gram_schmidt_is_bit_identical(cyl1):
+    """k_gs_tma (basis vectors streamed through a shared-memory ring by bulk
+    copies) keeps the thread mapping and summation order of the
+    register-pipelined kernels: same iteration counts, bit-identical solution"""
+    import os
+    from dolfin_navier_scipy_b200 import _lib, lin_alg_utils as lau
+    femp, sm, rhsd = cyl1
+    dt = 1./512
+    F = (sm['M'] + .5*dt*sm['A']).tocsr()
+    ncols = 64
+    rng = np.random.default_rng(12)
+    b = sm['M']@rng.standard_normal((F.shape[0], ncols))
+    g = sm['J']@rng.standard_normal((F.shape[0], ncols))*1e-3
+    out = {}
+    try:
+        for flag in ('0', '1'):
+            os.environ['DNSB_GS_TMA'] = flag
+            ctx = _lib.Context(0)
+            op = lau.SadpntOperator(F, sm['J'], sm['JT'], ncols=ncols, ctx=ctx)
+            vp = op.solve(b, g, tol=1e-12, maxit=200)
+            out[flag] = (vp.copy(), op.last_iters.copy())
+            op.close()
+    finally:
+        os.environ['DNSB_GS_TMA'] = '1'
+        _lib.Context(0)
+        del os.environ['DNSB_GS_TMA']
+    assert np.array_equal(out['0'][1], out['1'][1])
+    assert np.array_equal(out['0'][0], out['1'][0])
