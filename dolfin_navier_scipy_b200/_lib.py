@@ -39,6 +39,8 @@ SIGNATURES = {
     'dnsb_csr_create': (_i, [_vp, _i, _i, c_int_p, c_int_p, c_dbl_p, c_dbl_p,
                              c_void_pp]),
     'dnsb_csr_destroy': (None, [_vp]),
+    'dnsb_assemble_stokes': (_i, [_vp, _d, _i, _i, c_int_p, _i, c_int_p,
+                                  c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]),
     'dnsb_spmm': (_i, [_vp, c_dbl_p, c_dbl_p, c_dbl_p, _i, _d, _d]),
     'dnsb_spmm_dev': (_i, [_vp, _vp, _vp, _vp, _i, _d, _d]),
     'dnsb_solver_create': (_i, [_vp, _vp, _vp, _vp, c_dbl_p, _i, _i, _i, _d,
@@ -310,6 +312,50 @@ class ConvDevice(object):
         self.ctx.check(self.ctx.lib.dnsb_convvec(self.ctx.h, _dp(u1), _dp(u2),
                                                  _dp(out), nb))
         return out
+
+    def assemble_stokes(self, Q, nu=1., gradvsymmtrc=True):
+        """M, A, J, JT, MP of `fem.assemble_stokes_operators` (no outflow
+        correction) assembled on the device: per-cell kernel + gather into the
+        fixed patterns (`dnsb_assemble_stokes`); zeros are kept"""
+        import scipy.sparse as sps
+        indptr, indices = self.pattern
+        mesh = self.V.mesh()
+        cn = self.V.cell_nodes.astype(np.int64)
+        c3 = mesh.cells.astype(np.int64)
+        nc = cn.shape[0]
+        NV, NQ = self.nvf, Q.dim()
+        vd = np.stack([2*cn, 2*cn + 1], axis=2).reshape(nc, 12)
+
+        def _pattern(rows, cols, ncols):
+            keys = (rows*ncols + cols).reshape(-1)
+            ukeys = np.unique(keys)
+            return ukeys, np.searchsorted(ukeys, keys).astype(np.int32)
+
+        def _csr(ukeys, nrows, ncols, vals):
+            r = ukeys // ncols
+            ip = np.zeros(nrows + 1, dtype=np.int64)
+            np.add.at(ip, r + 1, 1)
+            return sps.csr_matrix((vals, (ukeys % ncols).astype(np.int32),
+                                   np.cumsum(ip).astype(np.int32)),
+                                  shape=(nrows, ncols))
+        jk, jslots = _pattern(np.repeat(c3[:, :, None], 12, axis=2),
+                              np.repeat(vd[:, None, :], 3, axis=1), NV)
+        pk, pslots = _pattern(np.repeat(c3[:, :, None], 3, axis=2),
+                              np.repeat(c3[:, None, :], 3, axis=1), NQ)
+        mv, av = np.empty(indices.size), np.empty(indices.size)
+        jv, pv = np.empty(jk.size), np.empty(pk.size)
+        self.ctx.check(self.ctx.lib.dnsb_assemble_stokes(
+            self.ctx.h, float(nu), int(bool(gradvsymmtrc)), jk.size,
+            _ip(jslots), pk.size, _ip(pslots), _dp(mv), _dp(av), _dp(jv),
+            _dp(pv)))
+        # private copies of the pattern: callers compact the matrices in place
+        # (`eliminate_zeros`, `dts:80`)
+        M = sps.csr_matrix((mv, indices.copy(), indptr.copy()), shape=(NV, NV))
+        A = sps.csr_matrix((av, indices.copy(), indptr.copy()), shape=(NV, NV))
+        J = _csr(jk, NQ, NV, jv)
+        JT = J.T.tocsr()
+        JT.sort_indices()
+        return dict(M=M, A=A, J=J, JT=JT, MP=_csr(pk, NQ, NQ, pv))
 
     def convmats(self, u0):
         indptr, indices = self.pattern

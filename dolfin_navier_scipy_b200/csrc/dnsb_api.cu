@@ -349,7 +349,7 @@ static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
 // ===========================================================================
 // context
 // ===========================================================================
-static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7]) {
+static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7], double lam[7][3]) {
   const double s15 = std::sqrt(15.0);
   const double a1 = (6.0 - s15) / 21.0, a2 = (6.0 + s15) / 21.0;
   const double w1 = (155.0 - s15) / 1200.0, w2 = (155.0 + s15) / 1200.0;
@@ -360,6 +360,7 @@ static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7]
   for (int q = 0; q < 7; ++q) {
     const double l0 = qp[q][0], l1 = qp[q][1], l2 = qp[q][2];
     qw[q] = w[q];
+    lam[q][0] = l0; lam[q][1] = l1; lam[q][2] = l2;
     phi[q][0] = l0 * (2 * l0 - 1); phi[q][1] = l1 * (2 * l1 - 1);
     phi[q][2] = l2 * (2 * l2 - 1); phi[q][3] = 4 * l1 * l2;
     phi[q][4] = 4 * l0 * l2;       phi[q][5] = 4 * l0 * l1;
@@ -400,11 +401,12 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   ctx->cc = prop.major * 10 + prop.minor;
   ctx->mem_bytes = prop.totalGlobalMem;
   DNSB_CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  double phi[7][6], dphi[7][6][3], qw[7];
-  fill_tabulation(phi, dphi, qw);
+  double phi[7][6], dphi[7][6][3], qw[7], lam[7][3];
+  fill_tabulation(phi, dphi, qw, lam);
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_phi, phi, sizeof phi));
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_dphi, dphi, sizeof dphi));
   DNSB_CK(ctx, cudaMemcpyToSymbol(c_qw, qw, sizeof qw));
+  DNSB_CK(ctx, cudaMemcpyToSymbol(c_lam, lam, sizeof lam));
   // k_mdot_b keeps (nvec+1) x 256 partial sums in dynamic shared memory
   DNSB_CK(ctx, cudaFuncSetAttribute(k_mdot_b, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_gs_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -696,6 +698,83 @@ static int convmats_dev(dnsb_ctx *ctx, const double *u0, double *n1, double *n2,
          (const int *)ctx->cslot_src.p, (const double *)ctx->en1.p, (const double *)ctx->en2.p, n1, n2);
   if (f3) return convvec_dev(ctx, u0, nullptr, f3, 1);
   return 0;
+}
+
+// slot -> contributions for a per-cell element array of `per` entries: the caller gives, for every
+// HOST cell, the CSR slot of each of its `per` entries; the lists are built in device cell order
+static int slot_lists(dnsb_ctx *ctx, int per, int nslots, const int32_t *cell_slots, DBuf<int> &sptr,
+                      DBuf<int> &ssrc) {
+  const int ncell = ctx->ncell;
+  std::vector<int> sp(nslots + 1, 0), ss((size_t)per * ncell);
+  for (size_t k = 0; k < (size_t)per * ncell; ++k) {
+    DNSB_REQUIRE(ctx, cell_slots[k] >= 0 && cell_slots[k] < nslots, "cell slot out of range");
+    sp[cell_slots[k] + 1]++;
+  }
+  for (int k = 0; k < nslots; ++k) sp[k + 1] += sp[k];
+  std::vector<int> fill(sp.begin(), sp.end() - 1);
+  for (int q = 0; q < ncell; ++q) {
+    const int c = ctx->perm[q];
+    for (int e = 0; e < per; ++e) ss[fill[cell_slots[(size_t)c * per + e]]++] = q * per + e;
+  }
+  DNSB_CK(ctx, sptr.upload(sp.data(), sp.size(), ctx->stream));
+  DNSB_CK(ctx, ssrc.upload(ss.data(), ss.size(), ctx->stream));
+  return 0;
+}
+
+extern "C" int dnsb_assemble_stokes(dnsb_ctx *ctx, double nu, int symgrad, int jnnz,
+                                    const int32_t *jslots, int mpnnz, const int32_t *mpslots,
+                                    double *m_vals, double *a_vals, double *j_vals,
+                                    double *mp_vals) {
+  if (!ctx) return -2;
+  DNSB_REQUIRE(ctx, ctx->ncell > 0 && ctx->cnnz > 0, "set mesh and pattern first");
+  DNSB_REQUIRE(ctx, m_vals && a_vals, "null output");
+  DNSB_REQUIRE(ctx, (!j_vals || (jslots && jnnz > 0)) && (!mp_vals || (mpslots && mpnnz > 0)),
+               "slot lists of J / MP missing");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  const int ncell = ctx->ncell;
+  const size_t nnz = ctx->cnnz;
+  DBuf<double> ej, emp, dm, da, dj, dmp;
+  DBuf<int> jp, js, pp, ps;
+  int rc = 0;
+  do {
+    cudaError_t e;
+    if ((e = ctx->en1.alloc((size_t)36 * ncell)) != cudaSuccess || (e = ctx->en2.alloc((size_t)144 * ncell)) != cudaSuccess ||
+        (e = dm.alloc(nnz)) != cudaSuccess || (e = da.alloc(nnz)) != cudaSuccess ||
+        (j_vals && ((e = ej.alloc((size_t)36 * ncell)) != cudaSuccess || (e = dj.alloc(jnnz)) != cudaSuccess)) ||
+        (mp_vals && ((e = emp.alloc((size_t)9 * ncell)) != cudaSuccess || (e = dmp.alloc(mpnnz)) != cudaSuccess))) {
+      ctx->fail(std::string("assemble_stokes alloc: ") + cudaGetErrorString(e), __FILE__, __LINE__);
+      rc = -1;
+      break;
+    }
+    if (j_vals && (rc = slot_lists(ctx, 36, jnnz, jslots, jp, js))) break;
+    if (mp_vals && (rc = slot_lists(ctx, 9, mpnnz, mpslots, pp, ps))) break;
+    LAUNCH(ctx, k_stokes_elem, cdiv((size_t)ncell, CME_CELLS), 6 * CME_CELLS, 0, ncell,
+           (const double *)ctx->geom.p, nu, symgrad, ctx->en1.p, ctx->en2.p, j_vals ? ej.p : (double *)nullptr,
+           mp_vals ? emp.p : (double *)nullptr);
+    LAUNCH(ctx, k_convmats_gather, cdiv(nnz, 256), 256, 0, (int)nnz, ncell, (const int *)ctx->cslot_ptr.p,
+           (const int *)ctx->cslot_src.p, (const double *)ctx->en1.p, (const double *)ctx->en2.p, dm.p, da.p);
+    if (j_vals)
+      LAUNCH(ctx, k_slot_gather, cdiv((size_t)jnnz, 256), 256, 0, jnnz, (const int *)jp.p, (const int *)js.p,
+             (const double *)ej.p, dj.p);
+    if (mp_vals)
+      LAUNCH(ctx, k_slot_gather, cdiv((size_t)mpnnz, 256), 256, 0, mpnnz, (const int *)pp.p, (const int *)ps.p,
+             (const double *)emp.p, dmp.p);
+    cudaError_t ce = cudaMemcpyAsync(m_vals, dm.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(a_vals, da.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess && j_vals)
+      ce = cudaMemcpyAsync(j_vals, dj.p, (size_t)jnnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess && mp_vals)
+      ce = cudaMemcpyAsync(mp_vals, dmp.p, (size_t)mpnnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+      ctx->fail(std::string("assemble_stokes: ") + cudaGetErrorString(ce), __FILE__, __LINE__);
+      rc = -1;
+    }
+  } while (0);
+  ej.release(); emp.release(); dm.release(); da.release(); dj.release(); dmp.release();
+  jp.release(); js.release(); pp.release(); ps.release();
+  return rc;
 }
 
 extern "C" int dnsb_convmats(dnsb_ctx *ctx, const double *u0, double *n1_data,

@@ -12,6 +12,7 @@
 __constant__ double c_phi[7][6];       // phi_a(q)
 __constant__ double c_dphi[7][6][3];   // d phi_a / d lambda_i (q)
 __constant__ double c_qw[7];           // weights, sum = 1 (times area)
+__constant__ double c_lam[7][3];       // barycentric coordinates of the points (= P1 basis)
 
 struct CsrDev {
   int nrows, ncols, nnz;
@@ -359,6 +360,109 @@ k_convmats_elem(int ncell, const int *__restrict__ cn, const double *__restrict_
   double *o2 = EN2 + (size_t)cell0 * 144, *o1 = EN1 + (size_t)cell0 * 36;
   for (int i = threadIdx.x; i < nc * 144; i += 6 * CME_CELLS) o2[i] = sm[(i / 144) * CME_LD + i % 144];
   for (int i = threadIdx.x; i < nc * 36; i += 6 * CME_CELLS) o1[i] = sm[(i / 36) * CME_LD + 144 + i % 36];
+}
+
+// ---------------------------------------------------------------------------
+// Constant operators of the Taylor-Hood discretisation, per cell (SURVEY 8f-1;
+// reference dolfin_to_sparrays.py:236-275, get_stokessysmats): same CTA shape
+// and staging as k_convmats_elem.  Thread = (cell, local row n):
+//   EN1[cell*36 + n*6 + m]            = int phi_n phi_m                         (mass, per component)
+//   EN2[cell*144 + (2n+a)*12 + 2m+b]  = nu (d_ab grad phi_n.grad phi_m + d_a phi_m d_b phi_n)   (2 eps(u):grad(v))
+//                                       or 2 nu d_ab grad phi_n.grad phi_m      (symgrad == 0)
+//   EJ[cell*36 + k*12 + 2m+b]         = int lambda_k d_b phi_m      (k = n < 3: divergence rows)
+//   EMP[cell*9 + k*3 + l]             = int lambda_k lambda_l       (pressure mass)
+// The P2 vector blocks are summed into the fixed pattern by k_convmats_gather
+// (EN1 -> the a == b entries, like N1), EJ / EMP by k_slot_gather.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(6 * CME_CELLS, 2)
+k_stokes_elem(int ncell, const double *__restrict__ geom, double nu, int symgrad,
+              double *__restrict__ EN1, double *__restrict__ EN2, double *__restrict__ EJ,
+              double *__restrict__ EMP) {
+  __shared__ __align__(16) double sm[CME_CELLS * CME_LD];
+  const int cl = threadIdx.x % CME_CELLS, n = threadIdx.x / CME_CELLS;
+  const int cell0 = blockIdx.x * CME_CELLS;
+  const int nc = min(CME_CELLS, ncell - cell0);
+  const int cell = cell0 + min(cl, nc - 1);
+  const double g1x = geom[0 * ncell + cell], g1y = geom[1 * ncell + cell];
+  const double g2x = geom[2 * ncell + cell], g2y = geom[3 * ncell + cell];
+  const double detj = geom[4 * ncell + cell];
+  const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+  const double wdet = 0.5 * fabs(detj);
+  double mrow[6], a2[2][6][2], jrow[6][2], mp[3];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    mrow[k] = 0;
+    jrow[k][0] = jrow[k][1] = 0;
+    a2[0][k][0] = a2[0][k][1] = a2[1][k][0] = a2[1][k][1] = 0;
+  }
+  mp[0] = mp[1] = mp[2] = 0;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) {
+    double gx[6], gy[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      gx[a] = c_dphi[q][a][0] * g0x + c_dphi[q][a][1] * g1x + c_dphi[q][a][2] * g2x;
+      gy[a] = c_dphi[q][a][0] * g0y + c_dphi[q][a][1] * g1y + c_dphi[q][a][2] * g2y;
+    }
+    const double w = c_qw[q] * wdet;
+    const double wphi = w * c_phi[q][n];
+    const double wl = n < 3 ? w * c_lam[q][n] : 0.0;
+#pragma unroll
+    for (int mm = 0; mm < 6; ++mm) {
+      mrow[mm] += wphi * c_phi[q][mm];
+      const double kk = w * (gx[n] * gx[mm] + gy[n] * gy[mm]);
+      if (symgrad) {
+        // test (n,a), trial (m,b): d_ab grad.grad + d_a phi_m d_b phi_n
+        a2[0][mm][0] += kk + w * gx[mm] * gx[n];
+        a2[0][mm][1] += w * gx[mm] * gy[n];
+        a2[1][mm][0] += w * gy[mm] * gx[n];
+        a2[1][mm][1] += kk + w * gy[mm] * gy[n];
+      } else {
+        a2[0][mm][0] += 2.0 * kk;
+        a2[1][mm][1] += 2.0 * kk;
+      }
+      jrow[mm][0] += wl * gx[mm];
+      jrow[mm][1] += wl * gy[mm];
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) mp[l] += wl * c_lam[q][l];
+  }
+  double *row = sm + cl * CME_LD;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int mm = 0; mm < 6; ++mm)
+      *reinterpret_cast<double2 *>(row + (2 * n + a) * 12 + 2 * mm) =
+          make_double2(nu * a2[a][mm][0], nu * a2[a][mm][1]);
+#pragma unroll
+  for (int mm = 0; mm < 6; mm += 2)
+    *reinterpret_cast<double2 *>(row + 144 + n * 6 + mm) = make_double2(mrow[mm], mrow[mm + 1]);
+  if (n < 3 && cl < nc) {
+    if (EJ) {
+#pragma unroll
+      for (int mm = 0; mm < 6; ++mm)
+        *reinterpret_cast<double2 *>(EJ + (size_t)cell * 36 + n * 12 + 2 * mm) =
+            make_double2(jrow[mm][0], jrow[mm][1]);
+    }
+    if (EMP) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l) EMP[(size_t)cell * 9 + n * 3 + l] = mp[l];
+    }
+  }
+  __syncthreads();
+  double *o2 = EN2 + (size_t)cell0 * 144, *o1 = EN1 + (size_t)cell0 * 36;
+  for (int i = threadIdx.x; i < nc * 144; i += 6 * CME_CELLS) o2[i] = sm[(i / 144) * CME_LD + i % 144];
+  for (int i = threadIdx.x; i < nc * 36; i += 6 * CME_CELLS) o1[i] = sm[(i / 36) * CME_LD + 144 + i % 36];
+}
+
+// out[s] = sum of the element entries listed for slot s (ascending cell order: deterministic)
+__global__ void k_slot_gather(int nslots, const int *__restrict__ sptr, const int *__restrict__ ssrc,
+                              const double *__restrict__ E, double *__restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  double v = 0.0;
+  for (int k = sptr[s]; k < sptr[s + 1]; ++k) v += E[ssrc[k]];
+  out[s] = v;
 }
 
 // contributions of slot s: src = cell*144 + e, e = r*12 + c (r = 2n+a, c = 2m+b)

@@ -66,11 +66,14 @@ def expand_vp(vc=None, pc=None, V=None, Q=None, invinds=None,
 
 def get_stokessysmats(V, Q, nu=None, bccontrol=False, gradvsymmtrc=True,
                       outflowds=None,
-                      cbclist=None, cbds=None, cbshapefuns=None):
+                      cbclist=None, cbds=None, cbshapefuns=None, device=False):
     """M, A, JT, J, MP [, amatrob, bmatrob] -- `dts:167-322`
 
     ``outflowds`` / ``cbds`` are boolean masks over ``V.mesh().bnd_edge``
-    (the shim's stand-in for dolfin `ds` measures).
+    (the shim's stand-in for dolfin `ds` measures).  ``device=True`` (an
+    extension) assembles the cell integrals on the GPU (`dnsb_assemble_stokes`:
+    the per-cell machinery of the convection matrices); boundary integrals
+    stay on the host.
     """
     if nu is None:
         nu = 1
@@ -79,9 +82,19 @@ def get_stokessysmats(V, Q, nu=None, bccontrol=False, gradvsymmtrc=True,
         print('Note: The symmetric gradient is not corrected in the outflow')
     elif not gradvsymmtrc:
         print('we use the nonsymmetric velocity gradient')
-    stokesmats = fem.assemble_stokes_operators(V, Q, nu=nu,
-                                               gradvsymmtrc=gradvsymmtrc,
-                                               outflow_mask=outflowds)
+    if device:
+        from . import _lib
+        stokesmats = _lib.device_for(V).assemble_stokes(
+            Q, nu=nu, gradvsymmtrc=gradvsymmtrc)
+        if outflowds is not None and gradvsymmtrc and np.any(outflowds):
+            A = stokesmats['A'] - \
+                nu*fem._assemble_outflow_correction(V, outflowds)
+            A.sort_indices()
+            stokesmats['A'] = A.tocsr()
+    else:
+        stokesmats = fem.assemble_stokes_operators(V, Q, nu=nu,
+                                                   gradvsymmtrc=gradvsymmtrc,
+                                                   outflow_mask=outflowds)
     for key in ('M', 'A', 'J', 'JT', 'MP'):
         stokesmats[key].eliminate_zeros()      # `mat_dolfin2sparse`, dts:80
     if bccontrol:

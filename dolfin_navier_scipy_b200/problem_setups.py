@@ -351,6 +351,8 @@ def get_sysmats(problem='gen_bccont', scheme=None, ppin=None,
     ``scipy.sparse.csr_matrix`` objects exactly as in the reference; the
     uncondensed ones are kept under ``stokesmatsc['Afull'|'Mfull'|'Jfull']``
     for the device path and the drag/lift functional.
+    ``meshparams['assemble_on_device']`` (extension) assembles the cell
+    integrals of M, A, J, MP on the GPU (`dts.get_stokessysmats(device=True)`).
     """
     problemdict = dict(drivencavity=drivcav_fems,
                        cylinderwake=cyl_fems,
@@ -388,7 +390,9 @@ def get_sysmats(problem='gen_bccont', scheme=None, ppin=None,
                                        gradvsymmtrc=gradvsymmtrc,
                                        outflowds=outflowds,
                                        cbshapefuns=cbshapefuns,
-                                       bccontrol=bccontrol)
+                                       bccontrol=bccontrol,
+                                       device=bool(meshparams.get(
+                                           'assemble_on_device', False)))
     rhsd_vf = dict(fv=np.array(femp['fv'], dtype=float),
                    fp=np.array(femp['fp'], dtype=float))
 

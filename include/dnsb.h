@@ -67,6 +67,19 @@ int dnsb_set_conv_pattern(dnsb_ctx *ctx, const int32_t *indptr,
  * dolfin_to_sparrays.py:427-472 (get_convvec).  nb members, batched layout. */
 int dnsb_convvec(dnsb_ctx *ctx, const double *u1, const double *u2,
                  double *out, int nb);
+/* Constant operators of the Taylor-Hood discretisation assembled on the device
+ * with the per-cell machinery of K1b (replaces the dolfin
+ * assembles of dolfin_to_sparrays.py:243-275, get_stokessysmats): values of
+ * the mass matrix M and of A = nu*int 2 eps(u):grad(v) (symgrad != 0) or
+ * 2 nu int grad(u):grad(v) on the pattern of dnsb_set_conv_pattern (zeros
+ * kept); optionally J = int q div(u) (P1 x P2-vector) and the pressure mass
+ * MP on patterns of the caller: jslots[c*36 + k*12 + 2m+b] / mpslots[c*9 + k*3 + l]
+ * give the CSR slot of the element entries of (host) cell c.  j_vals / mp_vals
+ * may be NULL.  Boundary terms (outflow correction, Robin) stay on the host. */
+int dnsb_assemble_stokes(dnsb_ctx *ctx, double nu, int symgrad, int jnnz,
+                         const int32_t *jslots, int mpnnz, const int32_t *mpslots,
+                         double *m_vals, double *a_vals, double *j_vals,
+                         double *mp_vals);
 /* N1, N2 values in the fixed pattern and f3 = N(u0)u0;
  * dolfin_to_sparrays.py:325-376 (get_convmats).  Any output may be NULL. */
 int dnsb_convmats(dnsb_ctx *ctx, const double *u0, double *n1_data,

@@ -618,3 +618,32 @@ def test_tma_gram_schmidt_is_bit_identical(cyl1):
         del os.environ['DNSB_GS_TMA']
     assert np.array_equal(out['0'][1], out['1'][1])
     assert np.array_equal(out['0'][0], out['1'][0])
+
+
+@pytest.mark.parametrize('symm', [True, False])
+def test_device_assembly_of_the_constant_operators(ctx, symm):
+    """M, A, J, JT, MP assembled on the device (per-cell kernel +
+    gather into fixed patterns) against the host assembly of the FEM shim
+    (`dts:236-275`), cylinder mesh and a unit square"""
+    from dolfin_navier_scipy_b200 import fem, dolfin_to_sparrays as dts
+    for mesh in (fem.load_mesh('cylinder_1'), fem.unit_square_mesh(5, 3)):
+        V, Q = fem.VectorP2Space(mesh), fem.P1Space(mesh)
+        host = fem.assemble_stokes_operators(V, Q, nu=.37, gradvsymmtrc=symm)
+        from dolfin_navier_scipy_b200 import _lib
+        dev = _lib.device_for(V, ctx).assemble_stokes(Q, nu=.37,
+                                                      gradvsymmtrc=symm)
+        for key in ('M', 'A', 'J', 'JT', 'MP'):
+            h, d = host[key].tocsr(), dev[key].tocsr()
+            assert h.shape == d.shape
+            diff = abs(h - d)
+            assert diff.max() <= 1e-13*abs(h).max(), key
+    # through the reference-facing function, outflow correction included
+    mesh = fem.load_mesh('cylinder_1')
+    V, Q = fem.VectorP2Space(mesh), fem.P1Space(mesh)
+    mask = np.zeros(mesh.bnd_edge.shape[0], dtype=bool)
+    mask[::7] = True
+    a = dts.get_stokessysmats(V, Q, nu=1e-2, gradvsymmtrc=symm, outflowds=mask)
+    b = dts.get_stokessysmats(V, Q, nu=1e-2, gradvsymmtrc=symm, outflowds=mask,
+                              device=True)
+    for key in ('M', 'A', 'J', 'JT', 'MP'):
+        assert abs(a[key] - b[key]).max() <= 1e-13*abs(a[key]).max(), key
