@@ -338,10 +338,13 @@ class ConvDevice(object):
             return sps.csr_matrix((vals, (ukeys % ncols).astype(np.int32),
                                    np.cumsum(ip).astype(np.int32)),
                                   shape=(nrows, ncols))
-        jk, jslots = _pattern(np.repeat(c3[:, :, None], 12, axis=2),
-                              np.repeat(vd[:, None, :], 3, axis=1), NV)
-        pk, pslots = _pattern(np.repeat(c3[:, :, None], 3, axis=2),
-                              np.repeat(c3[:, None, :], 3, axis=1), NQ)
+        if getattr(self, '_stokes_slots', None) is None:   # once per mesh
+            self._stokes_slots = (
+                _pattern(np.repeat(c3[:, :, None], 12, axis=2),
+                         np.repeat(vd[:, None, :], 3, axis=1), NV) +
+                _pattern(np.repeat(c3[:, :, None], 3, axis=2),
+                         np.repeat(c3[:, None, :], 3, axis=1), NQ))
+        jk, jslots, pk, pslots = self._stokes_slots
         mv, av = np.empty(indices.size), np.empty(indices.size)
         jv, pv = np.empty(jk.size), np.empty(pk.size)
         self.ctx.check(self.ctx.lib.dnsb_assemble_stokes(
