@@ -374,6 +374,8 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         e2e_s = time.perf_counter() - t0
     U = Urep
+    st1 = integ.stats()      # counters of the last run
+    e2e_its = st1['iters']/float(max(st1['solves'], 1))
     te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -407,6 +409,8 @@ def run_ours(args, rank, world, local_rank):
                 clocks=clocks,
                 e2e=dict(value=e2e_value, unit=UNIT,
                          h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                         ms_per_step=1e3*float(te[0])/args.steps,
+                         fgmres_iters_per_step=e2e_its,
                          note='control-signal chunk H2D (host numpy), K steps, (v,p) '
                          'of every step D2H (async, pinned mirror, caller '
                          'numbering) through DeviceImex; host reads the last '
