@@ -241,6 +241,37 @@ class Csr(object):
             self.h = ctypes.c_void_p()
 
 
+def _key_pattern(rows, cols, ncols):
+    """sorted unique (row, col) keys of a pattern and, per element entry, its CSR slot"""
+    keys = (rows*ncols + cols).reshape(-1)
+    ukeys = np.unique(keys)
+    return ukeys, np.searchsorted(ukeys, keys).astype(np.int32)
+
+
+def _csr_from_keys(ukeys, nrows, ncols, vals):
+    import scipy.sparse as sps
+    r = ukeys // ncols
+    ip = np.zeros(nrows + 1, dtype=np.int64)
+    np.add.at(ip, r + 1, 1)
+    return sps.csr_matrix((vals, (ukeys % ncols).astype(np.int32),
+                           np.cumsum(ip).astype(np.int32)),
+                          shape=(nrows, ncols))
+
+
+def stokes_slot_patterns(cn, c3, NV, NQ):
+    """patterns of J (P1 x P2-vector) and MP (P1 x P1) from the connectivity:
+    ``(jkeys, jslots, pkeys, pslots)`` with ``jslots[c*36 + k*12 + 2m+b]`` /
+    ``pslots[c*9 + k*3 + l]`` the CSR slot of the element entries of cell c
+    (the layout `dnsb_assemble_stokes` expects)"""
+    cn, c3 = np.asarray(cn, dtype=np.int64), np.asarray(c3, dtype=np.int64)
+    nc = cn.shape[0]
+    vd = np.stack([2*cn, 2*cn + 1], axis=2).reshape(nc, 12)
+    return (_key_pattern(np.repeat(c3[:, :, None], 12, axis=2),
+                         np.repeat(vd[:, None, :], 3, axis=1), NV) +
+            _key_pattern(np.repeat(c3[:, :, None], 3, axis=2),
+                         np.repeat(c3[:, None, :], 3, axis=1), NQ))
+
+
 class ConvDevice(object):
     """mesh + convection kernels (K1a/K1b) bound to a P2 vector space
 
@@ -322,29 +353,11 @@ class ConvDevice(object):
         mesh = self.V.mesh()
         cn = self.V.cell_nodes.astype(np.int64)
         c3 = mesh.cells.astype(np.int64)
-        nc = cn.shape[0]
         NV, NQ = self.nvf, Q.dim()
-        vd = np.stack([2*cn, 2*cn + 1], axis=2).reshape(nc, 12)
-
-        def _pattern(rows, cols, ncols):
-            keys = (rows*ncols + cols).reshape(-1)
-            ukeys = np.unique(keys)
-            return ukeys, np.searchsorted(ukeys, keys).astype(np.int32)
-
-        def _csr(ukeys, nrows, ncols, vals):
-            r = ukeys // ncols
-            ip = np.zeros(nrows + 1, dtype=np.int64)
-            np.add.at(ip, r + 1, 1)
-            return sps.csr_matrix((vals, (ukeys % ncols).astype(np.int32),
-                                   np.cumsum(ip).astype(np.int32)),
-                                  shape=(nrows, ncols))
         if getattr(self, '_stokes_slots', None) is None:   # once per mesh
-            self._stokes_slots = (
-                _pattern(np.repeat(c3[:, :, None], 12, axis=2),
-                         np.repeat(vd[:, None, :], 3, axis=1), NV) +
-                _pattern(np.repeat(c3[:, :, None], 3, axis=2),
-                         np.repeat(c3[:, None, :], 3, axis=1), NQ))
+            self._stokes_slots = stokes_slot_patterns(cn, c3, NV, NQ)
         jk, jslots, pk, pslots = self._stokes_slots
+        _csr = _csr_from_keys
         mv, av = np.empty(indices.size), np.empty(indices.size)
         jv, pv = np.empty(jk.size), np.empty(pk.size)
         self.ctx.check(self.ctx.lib.dnsb_assemble_stokes(

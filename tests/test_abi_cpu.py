@@ -141,3 +141,31 @@ def test_missing_library_is_an_error(tmp_path):
     from dolfin_navier_scipy_b200 import _lib
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         _lib.load(str(tmp_path / 'libdnsb200.so'))
+
+
+def test_stokes_slot_patterns_reproduce_the_host_assembly():
+    """host side of the device assembly (`dnsb_assemble_stokes`): the patterns
+    of J and MP built from the connectivity equal the host shim's, and summing
+    per-cell element entries through the slots equals the COO assembly"""
+    mesh = fem.unit_square_mesh(4, 3)
+    V, Q = fem.VectorP2Space(mesh), fem.P1Space(mesh)
+    host = fem.assemble_stokes_operators(V, Q, nu=1.)
+    cn, c3 = V.cell_nodes.astype(np.int64), mesh.cells.astype(np.int64)
+    jk, jslots, pk, pslots = _lib.stokes_slot_patterns(cn, c3, V.dim(), Q.dim())
+    for keys, slots, per, ref in ((jk, jslots, 36, host['J']), (pk, pslots, 9, host['MP'])):
+        ref = ref.tocsr()
+        ref.sort_indices()
+        pat = _lib._csr_from_keys(keys, ref.shape[0], ref.shape[1], np.ones(keys.size))
+        assert np.array_equal(pat.indptr, ref.indptr)
+        assert np.array_equal(pat.indices, ref.indices)
+        assert slots.size == per*mesh.num_cells and slots.min() == 0 and slots.max() == keys.size - 1
+    # scatter of random element entries through the slots == COO assembly
+    rng = np.random.default_rng(5)
+    E = rng.standard_normal((mesh.num_cells, 3, 12))
+    vals = np.zeros(jk.size)
+    np.add.at(vals, jslots, E.ravel())
+    vd = np.stack([2*cn, 2*cn + 1], axis=2).reshape(-1, 12)
+    ref = fem._coo_to_csr(np.repeat(c3[:, :, None], 12, axis=2), np.repeat(vd[:, None, :], 3, axis=1), E,
+                          (Q.dim(), V.dim()))
+    got = _lib._csr_from_keys(jk, Q.dim(), V.dim(), vals)
+    assert abs(got - ref).max() < 1e-14
