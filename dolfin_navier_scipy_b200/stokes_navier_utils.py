@@ -56,8 +56,6 @@ def _reject_unsupported(diricontbcinds=None, closed_loop=False,
         raise NotImplementedError('Dirichlet control boundaries')
     if closed_loop:
         raise NotImplementedError('closed-loop feedback')
-    if paraviewoutput:
-        raise NotImplementedError('paraview output needs dolfin')
     if fvtvd is not None or use_custom_nonlinearity:
         raise NotImplementedError('state dependent Python callbacks cannot '
                                   'run inside the device loop')
@@ -133,13 +131,29 @@ def solve_steadystate_nse(A=None, J=None, JT=None, M=None,
     Same iteration as the reference; each linear system ``[[A+N, JT],[J, 0]]``
     goes to the device FGMRES (relative residual ``lin_tol``).
     """
-    _reject_unsupported(diricontbcinds=diricontbcinds,
-                        paraviewoutput=paraviewoutput)
+    _reject_unsupported(diricontbcinds=diricontbcinds)
     JT = J.T if JT is None else JT
     dbcinds, dbcvals = dts.unroll_dlfn_dbcs(diribcs, bcinds=dbcinds,
                                             bcvals=dbcvals)
     cnv = A.shape[0]
     norm_nwtnupd_list = []
+    # paraview files of the iterates (`snu:348-357`), written without dolfin
+    prvoutdict = dict(writeoutput=False)
+    if paraviewoutput:
+        from . import data_output_utils as dou
+        prvoutdict = dict(V=V, Q=Q, invinds=invinds, dbcinds=dbcinds,
+                          dbcvals=dbcvals, ppin=ppin, writeoutput=True,
+                          vfile=dou.PvdFile(vfileprfx + '__steadystates.pvd',
+                                            V, name='v'),
+                          pfile=dou.PvdFile(pfileprfx + '__steadystates.pvd',
+                                            Q, name='p'))
+    nprv = [0]
+
+    def _prvout(vp):
+        if prvoutdict['writeoutput']:
+            from . import data_output_utils as dou
+            dou.output_paraview(vp=vp, t=nprv[0], **prvoutdict)
+            nprv[0] += 1
 
     def _appbcs(vvec):
         return dts.append_bcs_vec(vvec, V=V, invinds=invinds,
@@ -160,6 +174,7 @@ def solve_steadystate_nse(A=None, J=None, JT=None, M=None,
         vp_k = _solve(A, fv)
         vp_k[cnv:] = -vp_k[cnv:]            # p was flipped for symmetry
         vel_k = vp_k[:cnv, ]
+        _prvout(vp_k)                       # `snu:412-416`
     else:
         vel_k = vel_start_nwtn[invinds, :]
         vp_k = np.vstack([vel_k, np.zeros((J.shape[0], 1))])
@@ -177,6 +192,7 @@ def solve_steadystate_nse(A=None, J=None, JT=None, M=None,
                          format(k+1, normpicupd))
         vel_k = vp_k[:cnv, ]
         vp_k[cnv:] = -vp_k[cnv:]
+        _prvout(vp_k)                       # `snu:472-473`
         if normpicupd < vel_pcrd_tol:
             break
 
@@ -191,6 +207,7 @@ def solve_steadystate_nse(A=None, J=None, JT=None, M=None,
         norm_nwtnupd_list.append(float(np.ravel(norm_nwtnupd)[0]))
         vel_k = vp_k[:cnv, ]
         vp_k[cnv:] = -vp_k[cnv:]
+        _prvout(vp_k)                       # `snu:514-516`
         if verbose:
             logging.info('Steady State NSE: Newton iteration: {0} -- norm of '
                          'update: {1}'.format(vel_newtk, norm_nwtnupd))
@@ -237,7 +254,8 @@ def solve_nse(A=None, M=None, J=None, JT=None,
               clearprvdata=False,
               get_datastring=None,
               data_prfx='',
-              paraviewoutput=False,
+              paraviewoutput=False, plttrange=None, prvoutpnts=None,
+              vfileprfx='', pfileprfx='',
               return_dictofvelstrs=False,
               return_dictofpstrs=False,
               treat_nonl_explicit=True, no_data_caching=True,
@@ -263,7 +281,7 @@ def solve_nse(A=None, M=None, J=None, JT=None,
     ``guess`` (initial-guess mode of ``dnsb_imex_run``), ``cheb_steps``.
     """
     _reject_unsupported(diricontbcinds=diricontbcinds, closed_loop=closed_loop,
-                        paraviewoutput=paraviewoutput, fvtvd=fvtvd,
+                        fvtvd=fvtvd,
                         use_custom_nonlinearity=use_custom_nonlinearity)
     if fv_tmdp is not None:
         raise DeprecationWarning()
@@ -287,6 +305,18 @@ def solve_nse(A=None, M=None, J=None, JT=None,
     def _appbcs(vvec):
         return dts.append_bcs_vec(vvec, V=V, invinds=invinds,
                                   bcinds=dbcinds, bcvals=dbcvals)
+
+    def _paraview_trajectory(vdict, pdict):
+        """`vfile << v, t` for the times in `plttrange` (all if None) --
+        `snu:817-821,1091-1098,1169-1196`, files `<prfx>__timestep.pvd`"""
+        from . import data_output_utils as dou
+        tfilter = None if plttrange is None else [float(t) for t in plttrange]
+        vfile = dou.PvdFile(vfileprfx + '__timestep.pvd', V, name='v')
+        pfile = dou.PvdFile(pfileprfx + '__timestep.pvd', Q, name='p')
+        for t in sorted(vdict.keys()):
+            dou.output_paraview(V=V, Q=Q, vc=vdict[t], pc=pdict.get(t), t=t,
+                                tfilter=tfilter, ppin=ppin, vfile=vfile,
+                                pfile=pfile)
 
     vgroups = (invinds//2, invinds % 2)
     krydict = dict(krylov='gmres', vgroups=vgroups,
@@ -321,7 +351,8 @@ def solve_nse(A=None, M=None, J=None, JT=None,
                 return fv + np.asarray(fvtd(t)).reshape(cnv, 1)
             fvc = None
         vp_dict = {}
-        want_traj = return_vp_dict or return_dictofvelstrs or return_y_list
+        want_traj = (return_vp_dict or return_dictofvelstrs or return_y_list
+                     or paraviewoutput)
 
         def _svpplz(vvec, pvec, time=None):
             vp_dict.update({float(time): dict(p=pvec, v=vvec)})
@@ -352,6 +383,10 @@ def solve_nse(A=None, M=None, J=None, JT=None,
                 savevp=_svpplz if want_traj else None,
                 check_ff_maxv=check_ff_maxv, tol=lin_tol, guess=guess,
                 cheb_steps=cheb_steps)
+
+        if paraviewoutput:
+            _paraview_trajectory({t: d['v'] for t, d in vp_dict.items()},
+                                 {t: d['p'] for t, d in vp_dict.items()})
 
         def _flag(thing):
             return (thing, ffflag) if check_ff else thing
@@ -508,6 +543,8 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         sweep.close()
     if op is not None:
         op.close()
+    if paraviewoutput:            # the last sweep (`snu:1563-1566`)
+        _paraview_trajectory(dictofvelstrs, dictofpstrs)
 
     if return_final_vp:
         return (_appbcs(v_old), p_old)

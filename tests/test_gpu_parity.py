@@ -647,3 +647,47 @@ def test_device_assembly_of_the_constant_operators(ctx, symm):
                               device=True)
     for key in ('M', 'A', 'J', 'JT', 'MP'):
         assert abs(a[key] - b[key]).max() <= 1e-13*abs(a[key]).max(), key
+
+
+def test_paraviewoutput_of_the_solvers(cyl1, ctx, tmp_path):
+    """`paraviewoutput=True` (`snu:817-821,1091-1098`, `snu:348-357`) writes
+    `<prfx>__timestep.pvd` / `__steadystates.pvd` without dolfin; the last
+    piece holds the returned velocity"""
+    import xml.etree.ElementTree as ET
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    femp, sm, rhsd = cyl1
+    V, Q = femp['V'], femp['Q']
+
+    def _last_piece(pvd, name, ncomp):
+        sets = ET.parse(pvd).getroot().find('Collection').findall('DataSet')
+        root = ET.parse(os.path.join(os.path.dirname(pvd), sets[-1].get('file'))).getroot()
+        arr = [a for a in root.iter('DataArray') if a.get('Name') == name][0]
+        return len(sets), np.array(arr.text.split(), dtype=float).reshape(-1, ncomp)
+
+    vprfx, pprfx = str(tmp_path / 'v'), str(tmp_path / 'p')
+    vfin, pfin = snu.solve_nse(t0=0., tE=4./512, Nts=4, start_ssstokes=True, return_final_vp=True,
+                               paraviewoutput=True, vfileprfx=vprfx, pfileprfx=pprfx, verbose=False,
+                               Q=Q, **soldict(femp, sm, rhsd))
+    nsets, v = _last_piece(vprfx + '__timestep.pvd', 'v', 3)
+    assert nsets == 5
+    vfull = np.asarray(vfin).reshape(-1)
+    if vfull.size != V.dim():
+        vfull = dts_full(vfull, femp)
+    assert np.allclose(v[:, 0], vfull[0::2], rtol=0, atol=1e-15)
+    assert np.allclose(v[:, 1], vfull[1::2], rtol=0, atol=1e-15)
+    _, p = _last_piece(pprfx + '__timestep.pvd', 'p', 1)
+    assert np.allclose(p[:, 0], np.asarray(pfin).reshape(-1), rtol=0, atol=1e-15)
+    # steady solver: Stokes + 1 Picard + 1 Newton iterate
+    sprfx = str(tmp_path / 's')
+    vss = snu.solve_steadystate_nse(vel_pcrd_stps=1, vel_nwtn_stps=1, vel_nwtn_tol=1., verbose=False,
+                                    paraviewoutput=True, vfileprfx=sprfx, pfileprfx=sprfx + 'p', Q=Q,
+                                    **soldict(femp, sm, rhsd))
+    nsets, v = _last_piece(sprfx + '__steadystates.pvd', 'v', 3)
+    assert nsets == 3
+    assert np.allclose(v[:, 0], np.asarray(vss).reshape(-1)[0::2], rtol=0, atol=1e-15)
+
+
+def dts_full(vinner, femp):
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    return dts.append_bcs_vec(vinner, V=femp['V'], invinds=femp['invinds'], bcinds=femp['dbcinds'],
+                              bcvals=femp['dbcvals']).reshape(-1)

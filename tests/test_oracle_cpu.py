@@ -249,3 +249,50 @@ def test_golden_dfg_numbers():
     assert abs(float(g['cd']) - lit[0]) < 2e-3
     assert abs(float(g['cl']) - lit[1]) < 2e-5
     assert abs(float(g['dp']) - lit[2]) < 5e-5
+
+
+def test_paraview_writer_without_dolfin(tmp_path):
+    """`data_output_utils.output_paraview` (`dou:14-71`): one .vtu piece per
+    call plus the .pvd collection; quadratic triangles for the velocity, the
+    values round-trip, `tfilter` selects the times like the reference"""
+    import xml.etree.ElementTree as ET
+    from dolfin_navier_scipy_b200 import data_output_utils as dou
+    from dolfin_navier_scipy_b200 import fem
+    mesh = fem.unit_square_mesh(3, 2)
+    V, Q = fem.VectorP2Space(mesh), fem.P1Space(mesh)
+    rng = np.random.default_rng(0)
+    inv = np.arange(4, V.dim())
+    bci, bcv = [0, 1, 2, 3], [.5, -1., 2., 0.]
+    prfx = str(tmp_path / 'run')
+    vfile = pfile = None
+    tfilter = [0., 2.]
+    written = {}
+    for t in (0., 1., 2.):
+        vc, pc = rng.standard_normal((inv.size, 1)), rng.standard_normal((Q.dim(), 1))
+        vfile, pfile = dou.output_paraview(V=V, Q=Q, fstring=prfx, invinds=inv, dbcinds=bci, dbcvals=bcv,
+                                           vc=vc, pc=pc, t=t, tfilter=tfilter, vfile=vfile, pfile=pfile)
+        written[t] = (vc, pc)
+    assert tfilter == []
+    coll = ET.parse(prfx + '_vel.pvd').getroot().find('Collection').findall('DataSet')
+    assert [float(d.get('timestep')) for d in coll] == [0., 2.]
+    root = ET.parse(str(tmp_path / coll[1].get('file'))).getroot()
+    piece = root.find('UnstructuredGrid').find('Piece')
+    assert int(piece.get('NumberOfPoints')) == V.dim()//2
+    assert int(piece.get('NumberOfCells')) == mesh.num_cells
+    arrays = {a.get('Name'): a for a in piece.iter('DataArray')}
+    assert set(arrays['types'].text.split()) == {'22'}
+    conn = np.array(arrays['connectivity'].text.split(), dtype=int).reshape(-1, 6)
+    xy = np.array(piece.find('Points').find('DataArray').text.split(), dtype=float).reshape(-1, 3)
+    # VTK order: node 3 of a cell is the midpoint of the edge (0, 1)
+    assert np.allclose(xy[conn[:, 3]], .5*(xy[conn[:, 0]] + xy[conn[:, 1]]))
+    assert np.allclose(xy[conn[:, 4]], .5*(xy[conn[:, 1]] + xy[conn[:, 2]]))
+    v = np.array(arrays['v'].text.split(), dtype=float).reshape(-1, 3)
+    full = np.zeros(V.dim())
+    full[inv] = written[2.][0][:, 0]
+    full[bci] = bcv
+    assert np.array_equal(v[:, 0], full[0::2]) and np.array_equal(v[:, 1], full[1::2])
+    proot = ET.parse(str(tmp_path / ET.parse(prfx + '_p.pvd').getroot().find('Collection')
+                         .findall('DataSet')[1].get('file'))).getroot()
+    parr = {a.get('Name'): a for a in proot.iter('DataArray')}
+    assert np.array_equal(np.array(parr['p'].text.split(), dtype=float), written[2.][1][:, 0])
+    assert set(parr['types'].text.split()) == {'5'}
