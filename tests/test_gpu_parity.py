@@ -287,6 +287,13 @@ def test_golden_dfg_steady_state_device(ctx):
     cd, cl = osnu.drag_lift(sm['Afull'], sm['JTfull'], femp['V'], v, p,
                             femp['ldsbcinds'])
     dp = femp['Q'].eval_at(p, (.15, .2)) - femp['Q'].eval_at(p, (.25, .2))
+    # the product's functional (`residual_checks`, convection term on the device)
+    from dolfin_navier_scipy_b200 import residual_checks as rck
+    ssres = rck.get_steady_state_res(V=femp['V'], gradvsymmtrc=True, outflowds=femp['outflowds'], nu=1e-3)
+    cd2, cl2 = rck.lift_drag_via_residual(ssres, v, p, femp['ldsbcinds'])
+    assert abs(cd2 - cd) < 1e-10*abs(cd) and abs(cl2 - cl) < 1e-10*abs(cl)
+    res = ssres(v, p)
+    assert np.linalg.norm(res[femp['invinds']]) < 1e-8*np.linalg.norm(sm['Afull']@v.reshape(-1))
     assert abs(-cd - float(g['cd'])) < 1e-6*abs(float(g['cd']))
     assert abs(-cl - float(g['cl'])) < 1e-6*abs(float(g['cl']))
     assert abs(dp - float(g['dp'])) < 1e-6*abs(float(g['dp']))
@@ -691,3 +698,28 @@ def dts_full(vinner, femp):
     from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
     return dts.append_bcs_vec(vinner, V=femp['V'], invinds=femp['invinds'], bcinds=femp['dbcinds'],
                               bcvals=femp['dbcvals']).reshape(-1)
+
+
+def test_imex_residual_of_an_ab2_step(cyl1, ctx):
+    """`residual_checks.get_imex_res` (`rck:59-103`) on a device CNAB run: the
+    Crank-Nicolson/AB2 residual of the third state vanishes on the inner dofs
+    (`tests/test_units_residuals.py:117-134`)"""
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from dolfin_navier_scipy_b200 import residual_checks as rck
+    femp, sm, rhsd = cyl1
+    dt = 1./512
+    vpd = snu.solve_nse(t0=0., tE=2*dt, Nts=2, start_ssstokes=True, return_vp_dict=True, verbose=False,
+                        **soldict(femp, sm, rhsd))
+    ts = sorted(vpd.keys())
+    assert len(ts) == 3
+    v0, vm, vE = (vpd[t]['v'] for t in ts)
+    crnires = rck.get_imex_res(V=femp['V'], nu=femp['nu'], gradvsymmtrc=True, outflowds=femp.get('outflowds'),
+                               explscheme='abtw')
+    res = crnires(vE, vpd[ts[2]]['p'], dt, lastvel=vm, othervel=v0)
+    inv = np.asarray(femp['invinds'])
+    scale = np.linalg.norm((sm['Mfull']@(vE - vm).reshape(-1))[inv])/dt
+    assert np.linalg.norm(res[inv]) < 1e-8*scale
+    # tested with a single basis function: the scalar form of the same residual
+    phi = np.zeros(femp['V'].dim())
+    phi[inv[7]] = 1.
+    assert crnires(vE, vpd[ts[2]]['p'], dt, lastvel=vm, othervel=v0, phi=phi) == pytest.approx(res[inv[7]])
