@@ -553,12 +553,21 @@ def roofline_of(kern, info, integ, args):
 def main():
     # the JSON line must be the only thing on stdout: library notes (e.g. the
     # reference's own "Note: ..." prints, `dts:236-252`) go to stderr
+    # -- at the file-descriptor level too: NCCL prints its version banner on
+    # fd 1 from C when the first communicator is created
     import contextlib
-    out = sys.stdout
-    with contextlib.redirect_stdout(sys.stderr):
-        line = _main()
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        with contextlib.redirect_stdout(sys.stderr):
+            line = _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     if line is not None:
-        print(json.dumps(line), file=out, flush=True)
+        print(json.dumps(line), flush=True)
 
 
 def _main():
