@@ -169,3 +169,26 @@ def test_stokes_slot_patterns_reproduce_the_host_assembly():
                           (Q.dim(), V.dim()))
     got = _lib._csr_from_keys(jk, Q.dim(), V.dim(), vals)
     assert abs(got - ref).max() < 1e-14
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours):
+    exactly one JSON line on stdout with the contract's keys; everything else
+    (library notes, worker output) goes to stderr"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2',
+                        '--warmup', '1', '--mesh', '1', '--members', '2'],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'cylinder-wake DoF*steps/s'
+    assert d['higher_is_better'] is True and d['value'] > 0 and d['steps'] == 2
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['value'] == d['value']
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in d['config']
