@@ -28,11 +28,25 @@ def saddle_matrix(amat, jmat, jmatT=None):
                       format='csc')
 
 
+class SadLU(object):
+    """the factorisation handed out with ``return_alu``: the reference CALLS
+    it on a stacked right-hand side (`time_int_utils.py:604-613`), so it is
+    a `scipy.sparse.linalg.factorized`-like callable"""
+
+    def __init__(self, kmat):
+        self.lu = spsla.splu(kmat)
+
+    def solve(self, rhs):
+        return self.lu.solve(rhs)
+
+    __call__ = solve
+
+
 def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
                      rhsp=None, sadlu=None, return_alu=False, **kw):
     NP, NV = jmat.shape
     if sadlu is None:
-        sadlu = spsla.splu(saddle_matrix(amat, jmat, jmatT))
+        sadlu = SadLU(saddle_matrix(amat, jmat, jmatT))
     rhsv = np.asarray(rhsv, dtype=float).reshape(NV, -1)
     if rhsp is None:
         rhsp = np.zeros((NP, rhsv.shape[1]))
