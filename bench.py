@@ -58,6 +58,8 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=12.)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-parity', action='store_true',
+                    help='skip the CPU-oracle check of the measured trajectory')
     return ap.parse_args()
 
 
@@ -213,6 +215,62 @@ def _cpu_member_worker(args):
     return n, time.perf_counter() - tic
 
 
+def _cpu_parity_worker(args):
+    """the oracle's CNAB (`oracle.tiu.cnab` = `tiu:23-145`, pinned to the
+    reference by tests/test_reference_pin.py) for ONE member of the measured
+    ensemble from the same initial state over the same steps; returns the
+    final (v, p).  Convection through the compiled cell loop."""
+    (N, nu, dt, nsteps, palpha, v0, p0) = args
+    sys.stdout = sys.stderr
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from oracle.cconv import CConv
+    from oracle.snu import append_bcs_vec
+    from oracle import tiu as otiu
+    femp, sm, rv, rb = dnsps.get_sysmats(
+        problem='cylinderwake', nu=1., bccontrol=True, scheme='TH',
+        meshparams=dict(refinement_level=N))
+    M, J = sm['M'], sm['J']
+    A = nu*sm['A'] + sm['Arob']/palpha
+    Brob = sm['Brob']/palpha
+    bdiff = np.asarray(Brob[:, :1] - Brob[:, 1:]).reshape(-1, 1)
+    fv = nu*(rb['fv'] + rv['fv'])
+    fp = rb['fp'] + rv['fp']
+    V, inv = femp['V'], femp['invinds']
+    cc = CConv(V)
+
+    def appndbcs(v):
+        return append_bcs_vec(v, V.dim(), inv, femp['dbcinds'], femp['dbcvals'])
+
+    def f_vdp(vfull):
+        return -cc.convvec(np.asarray(vfull).reshape(-1))[inv].reshape(-1, 1)
+    trange = dt*np.arange(nsteps + 1)
+    v, p, ff = otiu.cnab(trange=trange, inivel=v0.reshape(-1, 1),
+                         inip=p0.reshape(-1, 1), M=M, A=A, J=J, f_vdp=f_vdp,
+                         f_tdp=lambda t: fv + np.sin(t)*bdiff,
+                         g_tdp=lambda t: fp, appndbcs=appndbcs,
+                         savevp=lambda *a, **k: None)
+    return v, p
+
+
+def parity_check(job):
+    """rel. L2 error of the MEASURED trajectory's state (after the timed
+    steps) against the CPU oracle, for the first and the last member"""
+    import multiprocessing as mp
+    jobs = [(job['mesh'], float(job['nus'][k]), job['dt'], job['nsteps'], 1e-5,
+             job['v0'][:, k], job['p0'][:, k]) for k in range(len(job['nus']))]
+    with mp.get_context('spawn').Pool(len(jobs)) as pool:
+        res = pool.map(_cpu_parity_worker, jobs)
+    ev = [float(np.linalg.norm(job['vd'][:, k] - r[0].ravel())/np.linalg.norm(r[0]))
+          for k, r in enumerate(res)]
+    ep = [float(np.linalg.norm(job['pd'][:, k] - r[1].ravel())/np.linalg.norm(r[1]))
+          for k, r in enumerate(res)]
+    return dict(v_rel=max(ev), p_rel=max(ep), members=job['members'],
+                steps=job['nsteps'], tol_bar=1e-8,
+                against='oracle CNAB (tiu:23-145 restated, pinned to the '
+                'reference run) from the same initial state, state after '
+                'the timed steps')
+
+
 def cpu_reference(args, nworkers, seconds, maxsteps=10**9, nwarm=3):
     """all host cores: one member per worker process, Re spread over [60,150]"""
     import multiprocessing as mp
@@ -355,6 +413,17 @@ def run_ours(args, rank, world, local_rank):
     dev_ms_max, wall_ms_max = float(tt[0]), float(tt[1])
     units = (NV + NP)*args.members*world*args.steps
     value = units/(dev_ms_max*1e-3)
+    # state after spin-up + warm-up + timed steps: checked against the CPU
+    # oracle (first and last member of rank 0's shard) once the timing is over
+    parity_job = None
+    if rank == 0 and not args.no_parity:
+        Vd, Pd = integ.state()
+        sel = [0, nb - 1] if nb > 1 else [0]
+        parity_job = dict(mesh=args.mesh, dt=1./args.nts, nsteps=nwarm + args.steps,
+                          nus=[float(info['nus'][k]) for k in sel],
+                          members=[int(info['members'][0] + k) for k in sel],
+                          v0=v0[:, sel].copy(), p0=p0[:, sel].copy(),
+                          vd=Vd[:, sel].copy(), pd=Pd[:, sel].copy())
 
     # ---- e2e: through the public API with host buffers ----------------------
     # per step the host supplies the boundary-control signal (H2D, host numpy
@@ -422,8 +491,10 @@ def run_ours(args, rank, world, local_rank):
                 gpu_launches=int(launches),
                 wall_ms_per_step=wall_ms_max/args.steps,
                 solver=dict(fgmres_iters_per_step=st['iters']/max(st['solves'], 1),
-                            last_relres=st['last_relres'], finite=finite),
+                            max_relres=st['max_relres'],
+                            unconverged=st['unconverged'], finite=finite),
                 dofs_per_member=NV + NP, gram=gram)
+    line['_parity_job'] = parity_job
     if roofline is not None:
         line['roofline'] = roofline
         tot = sum(v[1] for v in kern.values())
@@ -584,8 +655,17 @@ def _main():
         dist.init_process_group('nccl', rank=rank, world_size=world,
                                 device_id=torch.device('cuda', local_rank))
     line = run_ours(args, rank, world, local_rank)
-    if rank == 0 and not args.no_cpu_baseline:
-        NV, NP = line['dofs_per_member'] - 0, 0
+    if world > 1:
+        # the CPU legs below run on rank 0 only: leave the process group first
+        # so that the other ranks exit instead of spinning in a NCCL barrier
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    job = line.pop('_parity_job', None)
+    if job is not None:
+        line['parity'] = parity_check(job)
+    if not args.no_cpu_baseline:
         res = cpu_reference(args, 1, seconds=args.cpu_seconds)
         n, t = res[0]
         line['cpu_baseline'] = dict(
@@ -593,10 +673,7 @@ def _main():
             kind='port',
             sample='1 member (Re=60), {0} CNAB steps in {1:.1f} s: SuperLU '
             'solve + compiled cell loop, factorisation excluded'.format(n, t))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return line if rank == 0 else None
+    return line
 
 
 if __name__ == '__main__':

@@ -85,7 +85,12 @@ SIGNATURES = {
     'dnsb_imex_stats': (_i, [_vp, ctypes.POINTER(_ll), ctypes.POINTER(_ll),
                              c_dbl_p]),
     'dnsb_imex_gram_dev': (_i, [_vp, _vp]),
+    'dnsb_imex_gram': (_i, [_vp, c_dbl_p]),
+    'dnsb_imex_unconverged': (_ll, [_vp]),
+    'dnsb_cnsweep_stats': (_i, [_vp, c_dbl_p, ctypes.POINTER(_ll)]),
 }
+
+E_NOT_CONVERGED = -3
 
 
 def load(path=None):
@@ -131,6 +136,11 @@ class DnsbError(RuntimeError):
     pass
 
 
+class NotConverged(DnsbError):
+    """an iterative solve stopped at ``maxit`` above ``tol`` (the reference's
+    sparse-LU solve cannot fail this way: never ignored silently)"""
+
+
 class Context(object):
     """one device + one stream (``dnsb_ctx``)"""
 
@@ -147,6 +157,8 @@ class Context(object):
         self._keep = []
 
     def check(self, rc):
+        if rc == E_NOT_CONVERGED:
+            raise NotConverged(self.lib.dnsb_last_error(self.h).decode())
         if rc != 0:
             raise DnsbError(self.lib.dnsb_last_error(self.h).decode())
 
@@ -532,12 +544,16 @@ class ImexEngine(object):
                                                         _dp(p0)))
 
     def run(self, nsteps, snap_stride=0, tol=1e-12, maxit=400, guess=16,
-            check_ff_maxv=1e8, ntimeslices=10):
+            check_ff_maxv=1e8, ntimeslices=10, allow_unconverged=False):
+        """raises `NotConverged` if a solve of the run stopped at ``maxit``
+        above ``tol`` (``allow_unconverged=True``: only `stats()` tells)"""
         ff = ctypes.c_int(0)
-        self.ctx.check(self.ctx.lib.dnsb_imex_run(
+        rc = self.ctx.lib.dnsb_imex_run(
             self.h, int(nsteps), int(snap_stride), float(tol), int(maxit),
             int(guess), float(check_ff_maxv), int(ntimeslices),
-            ctypes.byref(ff)))
+            ctypes.byref(ff))
+        if not (allow_unconverged and rc == E_NOT_CONVERGED):
+            self.ctx.check(rc)
         return ff.value
 
     def last_run_ms(self):
@@ -585,7 +601,16 @@ class ImexEngine(object):
         it, ns, rr = _ll(), _ll(), ctypes.c_double()
         self.ctx.check(self.ctx.lib.dnsb_imex_stats(
             self.h, ctypes.byref(it), ctypes.byref(ns), ctypes.byref(rr)))
-        return dict(iters=it.value, solves=ns.value, last_relres=rr.value)
+        unc = int(self.ctx.lib.dnsb_imex_unconverged(self.h))
+        return dict(iters=it.value, solves=ns.value, max_relres=rr.value,
+                    last_relres=rr.value, unconverged=unc)
+
+    def gram(self):
+        """local POD Gram matrix ``sum_m X_m^T M X_m`` as a numpy array"""
+        ns = self.ctx.lib.dnsb_imex_num_snapshots(self.h)
+        g = np.empty((ns, ns))
+        self.ctx.check(self.ctx.lib.dnsb_imex_gram(self.h, _dp(g)))
+        return g
 
     def gram_dev(self, g_dev_ptr):
         self.ctx.check(self.ctx.lib.dnsb_imex_gram_dev(
@@ -632,6 +657,12 @@ class CnSweep(object):
             _dp(p0), float(tol), int(maxit), _dp(vtraj), _dp(ptraj),
             ctypes.byref(nrm), ctypes.byref(its)))
         return vtraj, ptraj, nrm.value, its.value
+
+    def stats(self):
+        rr, unc = ctypes.c_double(0.), _ll(0)
+        self.ctx.check(self.ctx.lib.dnsb_cnsweep_stats(
+            self.h, ctypes.byref(rr), ctypes.byref(unc)))
+        return dict(max_relres=rr.value, unconverged=unc.value)
 
     def close(self):
         if self.h:

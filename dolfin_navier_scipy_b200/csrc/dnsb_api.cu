@@ -148,6 +148,9 @@ static cudaError_t upload_padded(DBuf<T> &b, const T *h, size_t count, size_t pa
 
 static int g_tma_stages = 2;
 static int g_tma_rows = 64;
+// dynamic shared memory the TMA-staged SpMV kernels opt in to (dnsb_ctx_create);
+// spt_plan never plans a ring beyond it
+static const size_t SPT_SMEM_OPTIN = 216 * 1024;
 static size_t spt_stage_bytes(int cap, bool h2) {
   const size_t off_ip = (size_t)cap * (h2 ? 20 : 12);
   return (off_ip + (SPT_ROWS + 4) * 4 + 127) & ~(size_t)127;
@@ -169,10 +172,10 @@ static SptPlan spt_plan(int nrows, const int32_t *indptr, bool h2) {
   // gather and row-sum phases); 228 KB per SM, 1 KB reserved + 1152 B static per CTA
   p.stages = g_tma_stages;
   p.ctas_per_sm = (int)std::min<size_t>(7, (size_t)233472 / (p.stages * p.stage_bytes + 2304));
-  if (p.ctas_per_sm < 1) {
+  if (p.ctas_per_sm < 1 || (size_t)p.stages * p.stage_bytes > SPT_SMEM_OPTIN) {
     p.ctas_per_sm = 1;
-    p.stages = (int)std::min<size_t>(SPT_MAX_STAGES, (size_t)220 * 1024 / p.stage_bytes);
-    if (p.stages < 2) p.stages = 0;
+    p.stages = (int)std::min<size_t>(SPT_MAX_STAGES, SPT_SMEM_OPTIN / p.stage_bytes);
+    if (p.stages < 2) p.stages = 0;   // tile span too long for a ring: k_spmm<8> serves this operator
   }
   p.smem = p.stages * p.stage_bytes;
   return p;
@@ -413,9 +416,9 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_gs_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
 #define SPT_ATTR(E)                                                                                  \
   DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<true, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                    216 * 1024));                                                    \
+                                    (int)SPT_SMEM_OPTIN));                                           \
   DNSB_CK(ctx, cudaFuncSetAttribute(k_spmv_tma<false, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                    216 * 1024));
+                                    (int)SPT_SMEM_OPTIN));
   SPT_ATTR(SPT_AXPBY) SPT_ATTR(SPT_CHEB_INIT) SPT_ATTR(SPT_CHEB_STEP) SPT_ATTR(SPT_CHEB_STEP_FIRST)
   SPT_ATTR(SPT_CHEB_STEP_LAST) SPT_ATTR(SPT_CHEB_STEP_ONLY)
 #undef SPT_ATTR
@@ -893,6 +896,7 @@ struct dnsb_solver {
   // GMRES scalars
   DBuf<double> gR, gcs, gsn, gg, gh, gh2, ginvh, gbnorm, gresid;
   DBuf<int> gdone, gits, gittot, gflags;
+  DBuf<double> grelmax;
   GmresState gs;
   int *h_flags = nullptr;   // pinned
   std::vector<MgLevel *> levels;    // Schur (pressure) hierarchy
@@ -910,7 +914,7 @@ struct dnsb_solver {
   std::vector<int> igraph_launches;
   double igraph_tol = -1.0;
   long long stat_iters = 0, stat_solves = 0, stat_launched = 0;
-  double stat_max_relres = 0;
+  long long stat_unconverged = 0;   // solves that stopped at maxit above tol
 };
 
 static void solver_drop_graphs(dnsb_solver *s);
@@ -1030,10 +1034,12 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
   DNSB_CK(ctx, s->gits.alloc(nb));
   DNSB_CK(ctx, s->gittot.alloc(nb));
   DNSB_CK(ctx, s->gflags.alloc(4));
+  DNSB_CK(ctx, s->grelmax.alloc(nb));
+  DNSB_CK(ctx, s->grelmax.zero(ctx->stream));
   s->gs.R = s->gR.p; s->gs.cs = s->gcs.p; s->gs.sn = s->gsn.p; s->gs.g = s->gg.p;
   s->gs.h = s->gh.p; s->gs.invh = s->ginvh.p; s->gs.bnorm = s->gbnorm.p;
   s->gs.resid = s->gresid.p; s->gs.done = s->gdone.p; s->gs.its = s->gits.p;
-  s->gs.ittot = s->gittot.p; s->gs.flags = s->gflags.p; s->gs.mr = mr;
+  s->gs.ittot = s->gittot.p; s->gs.flags = s->gflags.p; s->gs.relmax = s->grelmax.p; s->gs.mr = mr;
   DNSB_CK(ctx, cudaMallocHost((void **)&s->h_flags, 4 * sizeof(int)));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   DNSB_CK(ctx, cudaGetLastError());
@@ -1613,6 +1619,12 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
     }
     if (alldone || total >= maxit) break;
   }
+  if (s->h_flags[0] != 0) {
+    // stopped at maxit: the residual of the unfinished members enters the
+    // running maximum, the solve is counted (callers decide what to do)
+    LAUNCH(ctx, k_gmres_track_unconverged, 1, std::max(32, ((nb + 31) / 32) * 32), 0, s->gs, nb);
+    s->stat_unconverged += 1;
+  }
   // h_flags[1]: iteration at which the last member converged (<= total; the
   // difference are iterations launched between two convergence polls)
   const int needed = std::min(total, std::max(0, s->h_flags[1]));
@@ -1621,6 +1633,21 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
   s->stat_launched += total;
   s->stat_solves += 1;
   DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// max over members of the running maximum of the final relative residuals
+// since the last reset (NaN if any solve produced one); optionally reset
+static int solver_relmax(dnsb_solver *s, bool reset, double *out) {
+  dnsb_ctx *ctx = s->ctx;
+  std::vector<double> h(s->nb);
+  DNSB_CK(ctx, cudaMemcpyAsync(h.data(), s->grelmax.p, s->nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (reset) DNSB_CK(ctx, s->grelmax.zero(ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  double mx = 0.0;
+  for (int m = 0; m < s->nb; ++m)
+    if (!(h[m] <= mx)) mx = h[m];
+  *out = mx;
   return 0;
 }
 
@@ -1768,6 +1795,8 @@ struct dnsb_cnsweep {
   DBuf<double> n1, n2, f3;                // K1b outputs on the full convection pattern
   DBuf<double> vfull, fn, fc, b, x, xprev, xguess, y, dvec, mdv, lin, vtraj, ptraj, v, p;
   DBuf<double> npart, nout;
+  double max_relres = 0;      // of the last sweep (all step solves)
+  long long unconverged = 0;
 };
 
 extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double *mvals,
@@ -1899,6 +1928,8 @@ extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, 
          (const double *)nullptr, w->x.p + nv, (size_t)np);
   double norm_acc = 0.0;
   long long its0 = s->stat_iters;
+  const long long unc0 = s->stat_unconverged;
+  DNSB_CK(ctx, s->grelmax.zero(ctx->stream));
   for (int n = 1; n <= nsteps; ++n) {
     const double dt = dts[n - 1];
     const double *lin_n = w->lin.p + (size_t)n * nvf;
@@ -1957,6 +1988,22 @@ extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, 
   if (upd_norm) *upd_norm = norm_acc;
   if (iters_total) *iters_total = s->stat_iters - its0;
   DNSB_CK(ctx, cudaGetLastError());
+  if (solver_relmax(s, false, &w->max_relres)) return -1;
+  w->unconverged = s->stat_unconverged - unc0;
+  if (w->unconverged > 0) {
+    char msg[200];
+    snprintf(msg, sizeof msg, "FGMRES stopped at maxit=%d above tol=%.1e in %lld of the %d step solves of this sweep "
+             "(largest final relative residual %.3e)", maxit, tol, w->unconverged, nsteps, w->max_relres);
+    ctx->fail(msg, __FILE__, __LINE__);
+    return DNSB_E_NOT_CONVERGED;
+  }
+  return 0;
+}
+
+extern "C" int dnsb_cnsweep_stats(dnsb_cnsweep *w, double *max_relres, long long *unconverged) {
+  if (!w) return -2;
+  if (max_relres) *max_relres = w->max_relres;
+  if (unconverged) *unconverged = w->unconverged;
   return 0;
 }
 
@@ -2007,8 +2054,8 @@ struct dnsb_imex {
   int hist_len = 0, hist_cnt = 0, hist_pos = 0, hist_mode = 0;
   int pcnt = 0, pkeep = 0;
   DBuf<double> xh, bq, xq, gr, partialh, x0, pw0, pw1, pd0, pd1, pinv, normpart, normout;
-  double last_relres = 0;
-  long long run_iters = 0, run_solves = 0;
+  double last_relres = 0;   // max over ALL solves of the last run (every member, Heun solves included)
+  long long run_iters = 0, run_solves = 0, run_unconverged = 0;
   // snapshots: device store (device row order; input of the Gram matrix) and
   // a pinned host mirror in OUTPUT row order, filled by async D2H copies on
   // a second stream while the integration goes on
@@ -2478,8 +2525,14 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
     if (e->step == 0) { int rc = imex_snapshot(e); if (rc) return rc; }
   }
   const long long it0 = e->sl->stat_iters, ns0 = e->sl->stat_solves;
+  dnsb_solver *const run_solvers[3] = {e->sl, e->sp, e->sc};
+  long long unc0 = 0;
+  for (dnsb_solver *sv : run_solvers)
+    if (sv) {
+      unc0 += sv->stat_unconverged;
+      DNSB_CK(ctx, sv->grelmax.zero(ctx->stream));
+    }
   DNSB_CK(ctx, cudaEventRecord(e->ev0, ctx->stream));
-  bool solved = false;
   int done = 0;
   // ======================= start-up (Heun) step =============================
   if (e->step == 0 && e->scheme != 2) {
@@ -2583,7 +2636,6 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
       DNSB_CK(ctx, cudaMemcpyAsync(e->x0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     rc = solver_solve_dev(e->sl, e->b.p, e->x.p, tol, maxit, false);
     if (rc) return rc;
-    solved = true;
     e->p_stale = true;
     rc = imex_push_history(e, guess);
     if (rc) return rc;
@@ -2606,20 +2658,34 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
   DNSB_CK(ctx, cudaEventSynchronize(e->ev1));
   if (snap_stride > 0 && e->cstream) DNSB_CK(ctx, cudaStreamSynchronize(e->cstream));
   DNSB_CK(ctx, cudaEventElapsedTime(&e->last_run_ms, e->ev0, e->ev1));
-  // relative residual of the last solve (max over members)
+  // convergence of the run: the largest final relative residual over ALL
+  // solves and members (the device keeps the running maximum), and the number
+  // of solves that stopped at `maxit` above `tol`
   {
-    std::vector<double> res(nb), bn(nb);
-    DNSB_CK(ctx, cudaMemcpyAsync(res.data(), e->sl->gs.resid, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    DNSB_CK(ctx, cudaMemcpyAsync(bn.data(), e->sl->gs.bnorm, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    double mx = 0;
-    if (solved)
-      for (int m = 0; m < nb; ++m) mx = std::max(mx, bn[m] > 0 ? res[m] / bn[m] : 0.0);
+    double mx = 0.0;
+    long long unc = -unc0;
+    for (dnsb_solver *sv : run_solvers)
+      if (sv) {
+        double r = 0.0;
+        if (solver_relmax(sv, false, &r)) return -1;
+        if (!(r <= mx)) mx = r;
+        unc += sv->stat_unconverged;
+      }
     e->last_relres = mx;
+    e->run_unconverged = unc;
   }
   e->run_iters = e->sl->stat_iters - it0;
   e->run_solves = e->sl->stat_solves - ns0;
   DNSB_CK(ctx, cudaGetLastError());
+  if (e->run_unconverged > 0 && !blown) {
+    // the state is valid and can be read; the caller decides (the reference's
+    // exact LU solve cannot fail this way, so the default is to refuse)
+    char msg[200];
+    snprintf(msg, sizeof msg, "FGMRES stopped at maxit=%d above tol=%.1e in %lld solve(s) of this run "
+             "(largest final relative residual %.3e)", maxit, tol, e->run_unconverged, e->last_relres);
+    ctx->fail(msg, __FILE__, __LINE__);
+    return DNSB_E_NOT_CONVERGED;
+  }
   return 0;
 }
 
@@ -2713,6 +2779,8 @@ extern "C" int dnsb_imex_stats(dnsb_imex *e, long long *total_iters, long long *
   return 0;
 }
 
+extern "C" long long dnsb_imex_unconverged(dnsb_imex *e) { return e ? e->run_unconverged : -2; }
+
 // G[a,b] = sum_m sum_i X_a[i,m] * (M X_b)[i,m]
 __global__ void k_gram_partial(const double *__restrict__ X, size_t xstride,
                                const double *__restrict__ MX,
@@ -2735,7 +2803,30 @@ __global__ void k_gram_partial(const double *__restrict__ X, size_t xstride,
   if (threadIdx.x == 0) partial[(size_t)blockIdx.x * ns * ns + pair] = sred[0];
 }
 
-extern "C" int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev) {
+static int imex_gram_impl(dnsb_imex *e, double *g_dev);
+
+extern "C" int dnsb_imex_gram(dnsb_imex *e, double *g) {
+  if (!e) return -2;
+  dnsb_ctx *ctx = e->ctx;
+  DNSB_REQUIRE(ctx, g != nullptr && e->nsnap > 0, "no snapshots / null output");
+  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DBuf<double> gd;
+  DNSB_CK(ctx, gd.alloc((size_t)e->nsnap * e->nsnap));
+  int rc = imex_gram_impl(e, gd.p);
+  if (!rc) {
+    cudaError_t ce = cudaMemcpyAsync(g, gd.p, gd.n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    gd.release();
+    DNSB_CK(ctx, ce);
+    return 0;
+  }
+  gd.release();
+  return rc;
+}
+
+extern "C" int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev) { return imex_gram_impl(e, g_dev); }
+
+static int imex_gram_impl(dnsb_imex *e, double *g_dev) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, g_dev != nullptr && e->nsnap > 0, "no snapshots / null output");

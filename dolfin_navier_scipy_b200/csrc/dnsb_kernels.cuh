@@ -689,8 +689,23 @@ struct GmresState {
   int *its;         // nb  iterations in the current cycle
   int *ittot;       // nb  total iterations of the solve
   int *flags;       // [0]: number of members not yet done
+  double *relmax;   // nb  -- running max over solves of the final |r|/|b| (NaN sticks)
   int mr;
 };
+
+// relmax[m] = max(relmax[m], rel) with NaN kept (a NaN residual must surface)
+__device__ __forceinline__ void gmres_track(GmresState &S, int m, double res) {
+  const double bn = S.bnorm[m];
+  const double rel = bn > 0.0 ? res / bn : (res > 0.0 ? res : 0.0);
+  const double old = S.relmax[m];
+  if (!(rel <= old)) S.relmax[m] = rel;
+}
+
+// members that hit maxit without reaching tol: their last residual counts
+__global__ void k_gmres_track_unconverged(GmresState S, int nb) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < nb && !S.done[m]) gmres_track(S, m, S.resid[m]);
+}
 
 // start of a cycle: beta = |r| from partials; V0 scale = 1/beta
 __global__ void k_gmres_begin(GmresState S, const double *__restrict__ partial,
@@ -707,6 +722,7 @@ __global__ void k_gmres_begin(GmresState S, const double *__restrict__ partial,
     const bool fin = !(beta > tol * S.bnorm[m]);   // also catches NaN -> done
     S.done[m] = fin ? 1 : 0;
     S.invh[m] = fin ? 0.0 : 1.0 / beta;
+    if (fin) gmres_track(S, m, beta);
   }
   __syncthreads();
   if (m == 0) {
@@ -803,6 +819,7 @@ k_gmres_givens(GmresState S, const double *__restrict__ partial2,
       const bool fin = !(res > tol * S.bnorm[m]) || !(hn > 0.0);
       S.done[m] = fin ? 1 : 0;
       S.invh[m] = fin ? 0.0 : 1.0 / hn;
+      if (fin) gmres_track(S, m, res);
     }
   }
   __syncthreads();

@@ -52,13 +52,27 @@ class SadpntOperator(object):
             cache.setdefault('hierarchy', self.info['hierarchy'])
             cache.setdefault('vhierarchy', self.info['vhierarchy'])
 
-    def solve(self, rhsv, rhsp=None, x0=None, tol=1e-12, maxit=800):
+    def solve(self, rhsv, rhsp=None, x0=None, tol=1e-12, maxit=800,
+              allow_unconverged=False):
+        """FGMRES to the relative residual ``tol``.  The solve replaces an
+        exact sparse LU: if any column stops at ``maxit`` above ``tol`` (or
+        produces a NaN) `_lib.NotConverged` is raised unless
+        ``allow_unconverged`` -- the iterate is then in ``self.last_vp``."""
         rhsv = np.asarray(rhsv, dtype=float).reshape(self.NV, self.ncols)
         if rhsp is not None:
             rhsp = np.asarray(rhsp, dtype=float).reshape(self.NP, self.ncols)
         vp, iters, relres = self.solver.solve(rhsv, rhsp, x0=x0, tol=tol,
                                               maxit=maxit)
-        self.last_iters, self.last_relres = iters, relres
+        self.last_iters, self.last_relres, self.last_vp = iters, relres, vp
+        bad = ~(relres <= tol)
+        if bad.any() and not allow_unconverged:
+            raise _lib.NotConverged(
+                'FGMRES stopped after {0} iterations above tol={1:.1e} for '
+                '{2} of {3} right-hand sides (largest relative residual '
+                '{4:.3e})'.format(int(iters.max()), tol, int(bad.sum()),
+                                  relres.size, float(np.nanmax(relres))
+                                  if not np.isnan(relres).all() else
+                                  float('nan')))
         return vp
 
     def update_values(self, vals):

@@ -287,6 +287,20 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         raise DeprecationWarning()
     if nsects != 1 or addfullsweep:
         raise NotImplementedError('time sections (`nsects`)')
+    # argument combinations are checked BEFORE any device work
+    if lin_vel_point is None:
+        if time_int_scheme not in ('cnab', 'sbdf2'):
+            raise ValueError("`time_int_scheme` must be 'cnab' or 'sbdf2' "
+                             "(`snu:1199-1202`), got {0!r}".
+                             format(time_int_scheme))
+        if not treat_nonl_explicit:
+            raise NotImplementedError(
+                'IMEX -> Newton hand-off inside one call is broken at HEAD '
+                '(SURVEY.md 8c): run the IMEX integration with '
+                '`return_dictofvelstrs=True` first and call again with '
+                '`lin_vel_point=<that dict>, treat_nonl_explicit=False`')
+        if stokes_flow:
+            raise NotImplementedError('stokes_flow in the IMEX branch')
     if trange is None:
         trange = np.linspace(t0, tE, int(Nts) + 1)
     trange = np.asarray(trange, dtype=float)
@@ -341,8 +355,6 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         vel_nwtn_stps, vel_pcrd_stps = 1, 0
 
     if lin_vel_point is None:       # ---- semi-explicit integration ---------
-        if stokes_flow:
-            raise NotImplementedError('stokes_flow in the IMEX branch')
         if fvtd is None:
             f_tdp = None
             fvc = fv
@@ -356,7 +368,7 @@ def solve_nse(A=None, M=None, J=None, JT=None,
 
         def _svpplz(vvec, pvec, time=None):
             vp_dict.update({float(time): dict(p=pvec, v=vvec)})
-        scheme = dict(cnab='cnab', sbdf2='sbdf2')[time_int_scheme]
+        scheme = time_int_scheme
         if f_tdp is None:
             # constant rhs: hand it over as `fv` (no sampling needed)
             integ = tiu.DeviceImex(M, A, J, V, invinds, dbcinds, dbcvals,
@@ -390,10 +402,6 @@ def solve_nse(A=None, M=None, J=None, JT=None,
 
         def _flag(thing):
             return (thing, ffflag) if check_ff else thing
-        if not treat_nonl_explicit:
-            raise NotImplementedError(
-                'IMEX -> Newton hand-off inside one call is broken at HEAD '
-                '(SURVEY.md 8c); call again with `lin_vel_point=<dict>`')
         if return_vp_dict:
             return _flag(vp_dict)
         elif return_final_vp:

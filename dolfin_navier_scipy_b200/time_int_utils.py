@@ -211,6 +211,10 @@ class DeviceImex(object):
     def stats(self):
         return self.engine.stats()
 
+    def gram(self):
+        """POD snapshot Gram matrix ``sum_m X_m^T M X_m`` of this shard (numpy)"""
+        return self.engine.gram()
+
     def close(self):
         self.engine.close()
         for s in self.solvers:
@@ -239,7 +243,16 @@ def _run_imex(scheme, trange=None, inivel=None, inip=None, M=None, A=None,
     B = U = None
     if f_tdp is not None:
         B, U = lowrank_forcing(f_tdp, trange, NV)
-    fp = np.zeros((NP, 1)) if g_tdp is None else np.asarray(g_tdp(trange[0]))
+    fp = np.zeros((NP, 1)) if g_tdp is None else \
+        np.asarray(g_tdp(trange[0]), dtype=float).reshape(NP, 1)
+    if g_tdp is not None:
+        # the reference evaluates `g_tdp(ctime)` every step (`tiu:120,337,391`);
+        # the device loop holds ONE continuity right-hand side
+        for t in trange[1:]:
+            if not np.array_equal(np.asarray(g_tdp(t), dtype=float).
+                                  reshape(NP, 1), fp):
+                raise NotImplementedError(
+                    'time dependent continuity right-hand side `g_tdp`')
     integ = DeviceImex(M, A, J, V, invinds, dbcinds, dbcvals, dt,
                        scheme=scheme, nus=(1.,), fv=fv0, fp=fp, ctx=ctx,
                        cheb_steps=cheb_steps)

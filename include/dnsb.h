@@ -10,8 +10,11 @@
  * Batched ("ensemble") layout: a vector of n entries for nb members is stored
  * member-fastest, x[i*nb + m].  nb = 1 is a plain vector.
  *
- * Return value: 0 = ok, < 0 = error (message via dnsb_last_error).  Nothing
- * throws across the ABI.  One context = one device + one stream; a context is
+ * Return value: 0 = ok, < 0 = error (message via dnsb_last_error);
+ * DNSB_E_NOT_CONVERGED: an iterative solve stopped at `maxit` above `tol` --
+ * the outputs / the state are valid and can be read, the caller decides (the
+ * reference's sparse-LU solve cannot fail this way).  Nothing throws across
+ * the ABI.  One context = one device + one stream; a context is
  * not thread-safe.
  */
 #ifndef DNSB_H
@@ -23,6 +26,8 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define DNSB_E_NOT_CONVERGED (-3)
 
 typedef struct dnsb_ctx dnsb_ctx;
 typedef struct dnsb_csr dnsb_csr;       /* CSR pattern + 1..2 value arrays on the device */
@@ -220,15 +225,22 @@ int dnsb_imex_set_output_order(dnsb_imex *e, const int32_t *vmap, const int32_t 
 int dnsb_imex_reserve_snapshots(dnsb_imex *e, int nsnap);
 int dnsb_imex_snapshots_host(dnsb_imex *e, const double **ptr, int *nsnap);
 /* solver statistics of the last run: total FGMRES iterations (max over
- * members per solve, summed over the loop solves), number of loop solves,
- * relative residual of the last solve (max over members) */
+ * members per solve, summed over the loop solves), number of loop solves, and
+ * the LARGEST final relative residual over all solves of the run (every
+ * member, start-up solves included; NaN if a solve produced one).
+ * dnsb_imex_run returns DNSB_E_NOT_CONVERGED when a solve of the run stopped
+ * at maxit above tol (unless the blow-up guard fired, which is reported through
+ * ffflag like time_int_utils.py:94-103); dnsb_imex_unconverged = how many. */
 int dnsb_imex_stats(dnsb_imex *e, long long *total_iters, long long *nsolves,
                     double *max_relres);
+long long dnsb_imex_unconverged(dnsb_imex *e);
 /* local POD Gram matrix  G = sum_m X_m^T M X_m  (nsnap x nsnap, row-major)
  * written to DEVICE memory g_dev (so that torch.distributed / NCCL can
  * all-reduce it in place) -- stokes_navier_utils.py:136-143 is the only
  * Gram-like op of the reference. */
 int dnsb_imex_gram_dev(dnsb_imex *e, double *g_dev);
+/* the same into HOST memory g (nsnap*nsnap doubles) */
+int dnsb_imex_gram(dnsb_imex *e, double *g);
 
 /* ---- device-resident Picard/Newton + Crank-Nicolson sweep -------------------
  * One sweep of stokes_navier_utils.py:1402-1566 over the whole time grid:
@@ -259,6 +271,10 @@ int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, int picard,
                      const double *linpoint, const double *v0, const double *p0,
                      double tol, int maxit, double *vtraj, double *ptraj,
                      double *upd_norm, long long *iters_total);
+/* largest final relative residual over the step solves of the last sweep and
+ * the number of them that stopped at maxit above tol (then dnsb_cnsweep_run
+ * returned DNSB_E_NOT_CONVERGED; the trajectories were still written) */
+int dnsb_cnsweep_stats(dnsb_cnsweep *w, double *max_relres, long long *unconverged);
 
 #ifdef __cplusplus
 }

@@ -723,3 +723,290 @@ def test_imex_residual_of_an_ab2_step(cyl1, ctx):
     phi = np.zeros(femp['V'].dim())
     phi[inv[7]] = 1.
     assert crnires(vE, vpd[ts[2]]['p'], dt, lastvel=vm, othervel=v0, phi=phi) == pytest.approx(res[inv[7]])
+
+
+# ---------------------------------------------------------------------------
+# reference-RUN fixtures (tests/golden/ref_*.npz: outputs of the reference's
+# own code, written by tests/golden/make_reference_golden.py)
+# ---------------------------------------------------------------------------
+def _dfg_lvl1():
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    return dnsps.get_sysmats(
+        problem='gen_bccont', nu=1e-3, charvel=.2, scheme='TH', mergerhs=True,
+        meshparams=dict(strtomeshfile='mesh/karman2D-rotcyl_lvl1.xml.gz',
+                        movingwallcntrl=False,
+                        strtophysicalregions='mesh/karman2D-rotcyl_lvl1_'
+                        'facet_region.xml.gz',
+                        strtobcsobs='mesh/karman2D-rotcyl-bm_geo_cntrlbc.json'))
+
+
+@pytest.mark.parametrize('scheme', ['cnab', 'sbdf2'])
+def test_reference_run_imex_device(cyl1, ctx, scheme):
+    """`snu.solve_nse` -> `tiu.cnab` / `tiu.sbdftwo` as run by the reference
+    itself: v and p at the start-up, Heun, first multistep and later steps"""
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    femp, sm, rhsd = cyl1
+    g = np.load(os.path.join(GOLD, 'ref_%s_cyl1_re60.npz' % scheme))
+    got = snu.solve_nse(t0=0., tE=16./512, Nts=16, start_ssstokes=True,
+                        return_vp_dict=True, time_int_scheme=scheme,
+                        **soldict(femp, sm, rhsd))
+    for j, t in enumerate(g['t']):
+        assert _rel(got[float(t)]['v'], g['v'][:, j:j+1]) < 1e-8, (scheme, t)
+        assert _rel(got[float(t)]['p'], g['p'][:, j:j+1]) < 1e-8, (scheme, t)
+
+
+def test_reference_run_robin_control_ensemble_device(ctx):
+    """cfg 5 on cylinder_1 against the reference's own runs of
+    `tests/time_dep_nse_bcrob.py:26-34` (A + Arob/alpha, sin(t)(B1-B2)/alpha)
+    for Re = 60, 105, 150: the three trajectories as ONE batched ensemble"""
+    from dolfin_navier_scipy_b200 import ensemble as ens
+    g = np.load(os.path.join(GOLD, 'ref_bcrob_cyl1.npz'))
+    nsteps, dt = 16, 1./512
+    integ, info = ens.cylinder_ensemble(N=1, Res=(60., 150.), nmembers=3,
+                                        dt=dt, ntimes=nsteps + 1, ctx=ctx)
+    assert np.allclose(info['Re'], g['Re'])
+    inv = np.asarray(info['femp']['invinds'])
+    # the reference starts every member from its own Stokes state; state at t1
+    # (first fixture column) is the earliest one stored for all members, so
+    # start from the stored initial values of a separate oracle-free source:
+    # the fixture of step 1 cannot seed a multistep run -- solve the Stokes
+    # problems on the device instead (`start_ssstokes`, snu:903-908)
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    sm, femp = info['sm'], info['femp']
+    v0 = np.zeros((info['NV'], 3))
+    p0 = np.zeros((info['NP'], 3))
+    for m, nu in enumerate(info['nus']):
+        Am = (nu*sm['A'] + info['Arob']).tocsr()
+        fvm = nu*info['B'][:, :1]
+        vp = lau.solve_sadpnt_smw(amat=Am, jmat=sm['J'], jmatT=sm['JT'],
+                                  rhsv=fvm, rhsp=info['fp'], krylov='gmres',
+                                  vgroups=(inv//2, inv % 2),
+                                  mass_diag=sm['M'].diagonal(),
+                                  krpslvprms=dict(tol=1e-13, maxiter=2000))
+        v0[:, m] = vp[:info['NV'], 0]
+        p0[:, m:m+1] = snu.get_pfromv(
+            v=v0[:, m:m+1], V=femp['V'], M=sm['M'], A=sm['M'], J=sm['J'],
+            fv=fvm, fp=info['fp'], dbcinds=femp['dbcinds'],
+            dbcvals=femp['dbcvals'], invinds=inv)
+    integ.set_state(v0, p0)
+    integ.run(nsteps, snap_stride=1, tol=1e-12)
+    vs, ps = integ.snapshots()
+    integ.close()
+    for j, k in enumerate(g['keep']):
+        for m in range(3):
+            assert _rel(vs[k, :, m], g['v'][inv, j, m]) < 1e-8, (k, m)
+            assert _rel(ps[k, :, m], g['p'][:, j, m]) < 1e-8, (k, m)
+
+
+def test_reference_run_newton_cn_device(ctx):
+    """Picard + Newton sweeps with the trapezoidal rule as run by the
+    reference (`snu:1304-1587`): velocity AND pressure of every step"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    g = np.load(os.path.join(GOLD, 'ref_newtoncn_cyl1_re100.npz'))
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=100,
+                                       scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=1))
+    sd = soldict(femp, sm, rhsd, t0=0., tE=6./512, Nts=6, start_ssstokes=True)
+    traj = snu.solve_nse(return_dictofvelstrs=True, **sd)
+    vd, pd = snu.solve_nse(lin_vel_point=traj, treat_nonl_explicit=False,
+                           vel_pcrd_stps=1, vel_nwtn_stps=2,
+                           return_dictofvelstrs=True, return_dictofpstrs=True,
+                           verbose=False, **sd)
+    for k, t in enumerate(g['t']):
+        assert _rel(vd[float(t)], g['v'][:, k:k+1]) < 1e-8, t
+        assert _rel(pd[float(t)], g['p'][:, k:k+1]) < 1e-8, t
+
+
+def test_reference_run_steady_state_device(cyl1, ctx):
+    """`snu.solve_steadystate_nse` (DFG 2D-1 and cylinder_1), `snu.get_pfromv`
+    and `snu.get_v_conv_conts` as returned by the reference"""
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    g = np.load(os.path.join(GOLD, 'ref_dfg2d1_lvl1.npz'))
+    femp, sm, rhsd = _dfg_lvl1()
+    v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False,
+                                     **soldict(femp, sm, rhsd))
+    assert _rel(v, g['v']) < 1e-8 and _rel(p, g['p']) < 1e-8
+    femp, sm, rhsd = cyl1
+    g = np.load(os.path.join(GOLD, 'ref_steady_cyl1_re60.npz'))
+    sd = soldict(femp, sm, rhsd)
+    v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False, **sd)
+    assert _rel(v, g['v']) < 1e-8 and _rel(p, g['p']) < 1e-8
+    inv = femp['invinds']
+    pfv = snu.get_pfromv(v=g['v'][inv], V=femp['V'], M=sm['M'], A=sm['A'],
+                         J=sm['J'], fv=rhsd['fv'], invinds=inv,
+                         dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'])
+    assert _rel(pfv, g['pfromv']) < 1e-8
+    cm, rc, rbc = snu.get_v_conv_conts(
+        vvec=g['v'], V=femp['V'], invinds=inv, dbcinds=femp['dbcinds'],
+        dbcvals=femp['dbcvals'])
+    assert _rel(cm@g['w'], g['newton_mat_w']) < 1e-12
+    assert _rel(rc, g['newton_rhs_con']) < 1e-12
+    assert _rel(rbc, g['newton_rhs_bc']) < 1e-12
+    pm, none, pbc = snu.get_v_conv_conts(
+        vvec=g['v'], V=femp['V'], invinds=inv, dbcinds=femp['dbcinds'],
+        dbcvals=femp['dbcvals'], Picard=True)
+    assert none is None
+    assert _rel(pm@g['w'], g['picard_mat_w']) < 1e-12
+    assert _rel(pbc, g['picard_rhs_bc']) < 1e-12
+
+
+def test_reference_run_semi_implicit_euler_device(cyl1, ctx):
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    femp, sm, rhsd = cyl1
+    g = np.load(os.path.join(GOLD, 'ref_sie_cyl1_re60.npz'))
+    trange = np.linspace(0., 12./512, 13)
+    got = tiu.semi_implicit_euler(iniv=g['v'][:, :1], jmat=sm['J'],
+                                  mmat=sm['M'], amat=sm['A'], trange=trange,
+                                  fp=rhsd['fp'], V=femp['V'],
+                                  invinds=femp['invinds'],
+                                  dbcinds=femp['dbcinds'],
+                                  dbcvals=femp['dbcvals'], fv=rhsd['fv'])
+    for j, k in enumerate((0, 1, 6, 12)):
+        assert _rel(got[k], g['v'][:, j:j+1]) < 1e-8, k
+
+
+# ---------------------------------------------------------------------------
+# the BENCHMARKED workload at its own size: cylinder_4 (28 970 + 3 836 DoFs)
+# ---------------------------------------------------------------------------
+def _bcrob_soldict(level, Re, palpha=1e-5):
+    """`tests/time_dep_nse_bcrob.py:14-34` on the host shim's operators"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    femp, sm, rv, rb = dnsps.get_sysmats(
+        problem='cylinderwake', Re=Re, bccontrol=True, scheme='TH',
+        meshparams=dict(refinement_level=level))
+    Brob = sm['Brob']/palpha
+    bdiff = np.asarray(Brob[:, :1] - Brob[:, 1:]).reshape(-1, 1)
+    return dict(A=sm['A'] + sm['Arob']/palpha, M=sm['M'], J=sm['J'],
+                JT=sm['JT'], fv=rb['fv'] + rv['fv'], fp=rb['fp'] + rv['fp'],
+                fvtd=lambda t: np.sin(t)*bdiff, V=femp['V'],
+                invinds=femp['invinds'], dbcinds=femp['dbcinds'],
+                dbcvals=femp['dbcvals'])
+
+
+def _oracle_member(args):
+    level, Re, nsteps, dt = args
+    from oracle import snu as osnu
+    out = osnu.solve_nse(t0=0., tE=nsteps*dt, Nts=nsteps, start_ssstokes=True,
+                         return_vp_dict=True, **_bcrob_soldict(level, Re))
+    ts = sorted(out.keys())
+    return (np.hstack([out[t]['v'] for t in ts]),
+            np.hstack([out[t]['p'] for t in ts]))
+
+
+def test_bench_workload_parity_per_step_cylinder4(ctx):
+    """BASELINE config 5 as benchmarked: Robin-control ensemble on cylinder_4,
+    8 members across Re 60..150, sin(t) control, CNAB dt = 1/2048, 16 steps.
+    Velocity and pressure of EVERY step and member against the oracle's CNAB
+    (`tiu:104-143` with `A + Arob/alpha`), rel. L2 error <= 1e-8; then the POD
+    Gram matrix of the device (`dnsb_imex_gram`) against numpy."""
+    from dolfin_navier_scipy_b200 import ensemble as ens
+    nb, nsteps, dt = 8, 16, 1./2048
+    integ, info = ens.cylinder_ensemble(N=4, Res=(60., 150.), nmembers=nb,
+                                        dt=dt, ntimes=nsteps + 1, ctx=ctx)
+    inv = np.asarray(info['femp']['invinds'])
+    import multiprocessing as mp
+    jobs = [(4, float(Re), nsteps, dt) for Re in info['Re']]
+    with mp.get_context('spawn').Pool(min(nb, os.cpu_count() or 1)) as pool:
+        ref = pool.map(_oracle_member, jobs)
+    v0 = np.hstack([r[0][inv, :1] for r in ref])
+    p0 = np.hstack([r[1][:, :1] for r in ref])
+    integ.set_state(v0, p0)
+    integ.run(nsteps, snap_stride=1, tol=1e-12)
+    vs, ps = integ.snapshots()
+    st = integ.stats()
+    assert st['max_relres'] <= 1e-12
+    worst = 0.
+    for k in range(1, nsteps + 1):
+        for m in range(nb):
+            ev = _rel(vs[k, :, m], ref[m][0][inv, k])
+            ep = _rel(ps[k, :, m], ref[m][1][:, k])
+            worst = max(worst, ev, ep)
+            assert ev < 1e-8 and ep < 1e-8, (k, m, ev, ep)
+    print('cylinder_4 ensemble: worst rel. error over steps/members', worst)
+    # ---- POD snapshot Gram matrix G = sum_m X_m^T M X_m ----------------------
+    G = integ.gram()
+    M = info['sm']['M']
+    Gn = np.zeros_like(G)
+    for m in range(nb):
+        X = vs[:, :, m].T
+        Gn += X.T@(M@X)
+    assert G.shape == (nsteps + 1, nsteps + 1)
+    assert np.linalg.norm(G - Gn) <= 1e-12*np.linalg.norm(Gn)
+    assert np.array_equal(G, integ.gram())          # deterministic
+    integ.close()
+
+
+def test_newton_cn_sweeps_cylinder4_with_pressure(ctx):
+    """BASELINE config 3 on its own mesh: cylinder_4, Re = 100, Picard +
+    Newton sweeps with Crank-Nicolson about the IMEX trajectory; velocity and
+    pressure of every step against the oracle (`snu:1304-1587`)"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from oracle import snu as osnu
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=100,
+                                       scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=4))
+    nsteps = 4
+    sd = soldict(femp, sm, rhsd, t0=0., tE=nsteps/2048., Nts=nsteps)
+    o0 = osnu.solve_nse(start_ssstokes=True, return_vp_dict=True, **sd)
+    t0 = sorted(o0.keys())[0]
+    ini = dict(iniv=o0[t0]['v'], inip=o0[t0]['p'])
+    otraj = {t: d['v'] for t, d in o0.items()}
+    oref = osnu.solve_nse(lin_vel_point=otraj, treat_nonl_explicit=False,
+                          vel_pcrd_stps=1, vel_nwtn_stps=1,
+                          return_dictofvelstrs=True, **dict(sd, **ini))
+    ovf, opf = osnu.solve_nse(lin_vel_point=otraj, treat_nonl_explicit=False,
+                              vel_pcrd_stps=1, vel_nwtn_stps=1,
+                              return_final_vp=True, **dict(sd, **ini))
+    traj = snu.solve_nse(return_dictofvelstrs=True, **dict(sd, **ini))
+    for t in sorted(otraj.keys()):
+        assert _rel(traj[float(t)], otraj[t]) < 1e-8, t
+    vd, pd = snu.solve_nse(lin_vel_point=traj, treat_nonl_explicit=False,
+                           vel_pcrd_stps=1, vel_nwtn_stps=1,
+                           return_dictofvelstrs=True, return_dictofpstrs=True,
+                           verbose=False, **dict(sd, **ini))
+    for t in sorted(oref.keys()):
+        assert _rel(vd[float(t)], oref[t]) < 1e-8, t
+    tE = sorted(oref.keys())[-1]
+    assert _rel(vd[float(tE)], ovf) < 1e-8
+    assert _rel(pd[float(tE)], opf) < 1e-8
+
+
+def test_unconverged_solves_are_reported(cyl1, ctx):
+    """the FGMRES solve stands in for an exact sparse LU: stopping at `maxit`
+    above `tol` must never pass silently (single solves, the IMEX loop, the
+    Newton/CN sweep)"""
+    from dolfin_navier_scipy_b200 import _lib, lin_alg_utils as lau
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    femp, sm, rhsd = cyl1
+    F = (sm['M'] + .5/512*sm['A']).tocsr()
+    b = sm['M']@np.random.default_rng(8).standard_normal((F.shape[0], 1))
+    op = lau.SadpntOperator(F, sm['J'], sm['JT'])
+    with pytest.raises(_lib.NotConverged):
+        op.solve(b, tol=1e-12, maxit=1)
+    vp = op.solve(b, tol=1e-12, maxit=1, allow_unconverged=True)
+    assert op.last_relres.max() > 1e-12 and np.all(np.isfinite(vp))
+    op.solve(b, tol=1e-12, maxit=200)
+    assert op.last_relres.max() <= 1e-12
+    op.close()
+    with pytest.raises(_lib.NotConverged):
+        lau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b,
+                             krylov='gmres',
+                             krpslvprms=dict(tol=1e-12, maxiter=1))
+    # IMEX loop: guess=0 (previous solution) needs several iterations per step
+    inv = femp['invinds']
+    integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv,
+                           femp['dbcinds'], femp['dbcvals'], 1./512,
+                           fv=rhsd['fv'], fp=rhsd['fp'])
+    integ.set_state(np.zeros((inv.size, 1)), np.zeros((sm['J'].shape[0], 1)))
+    with pytest.raises(_lib.NotConverged):
+        integ.run(4, tol=1e-12, maxit=1, guess=0)
+    st = integ.stats()
+    assert st['unconverged'] >= 1 and st['max_relres'] > 1e-12
+    integ.run(4, tol=1e-12, maxit=1, guess=0, allow_unconverged=True)
+    integ.run(4, tol=1e-12, maxit=200, guess=0)
+    st = integ.stats()
+    assert st['unconverged'] == 0 and 0 < st['max_relres'] <= 1e-12
+    integ.close()

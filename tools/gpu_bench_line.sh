@@ -6,7 +6,7 @@ python - <<PY
 import json
 try:
     d=json.load(open("gpurun_out/bench_$label.json"))
-    print("== $label", "value %.4g"%d["value"], "ms/step %.3f"%d["ms_per_step"], "e2e %.4g"%d["e2e"]["value"], "its", d["solver"]["fgmres_iters_per_step"], "relres %.2e"%d["solver"]["last_relres"], "launches", d["gpu_launches"])
+    print("== $label", "value %.4g"%d["value"], "ms/step %.3f"%d["ms_per_step"], "e2e %.4g"%d["e2e"]["value"], "its", d["solver"]["fgmres_iters_per_step"], "relres %.2e"%d["solver"]["max_relres"], "launches", d["gpu_launches"])
 except Exception as ex:
     print("== $label FAILED", ex); print(open("gpurun_out/bench_$label.json").read()[-800:])
 PY
