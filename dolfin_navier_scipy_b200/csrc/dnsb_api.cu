@@ -239,6 +239,7 @@ static int g_dense_ctas_per_sm = 2;
 static int g_graphs = 1;
 static int g_schur_tf32 = 0;   // 1: dense Schur inverse applied in 3xTF32 (fp32 copy), see dnsb_dense.cuh
 static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur solve
+static int g_proj_passes = 1;   // Gram-Schmidt passes when a correction joins the projection space
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
 static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
   const long total = (long)nrows * nb;
@@ -395,6 +396,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
+  if (const char *ev = getenv("DNSB_PROJ_PASSES")) g_proj_passes = std::min(2, std::max(1, atoi(ev)));
   if (const char *ev = getenv("DNSB_DENSE_CTAS_PER_SM")) g_dense_ctas_per_sm = std::max(1, atoi(ev));
   *out = ctx;   // returned even on failure so that the message can be read
   DNSB_CK(ctx, cudaSetDevice(device));
@@ -2053,6 +2055,7 @@ struct dnsb_imex {
   // `keep` raw solutions for the rebuild when the space is full
   int hist_len = 0, hist_cnt = 0, hist_pos = 0, hist_mode = 0;
   int pcnt = 0, pkeep = 0;
+  long long pring = 0;   // projection space full: slot pring % hist_len is the oldest pair
   DBuf<double> xh, bq, xq, gr, partialh, x0, pw0, pw1, pd0, pd1, pinv, normpart, normout;
   double last_relres = 0;   // max over ALL solves of the last run (every member, Heun solves included)
   long long run_iters = 0, run_solves = 0, run_unconverged = 0;
@@ -2352,10 +2355,15 @@ __global__ void k_inv_norm(const double *__restrict__ n2, const double *__restri
   inv[m] = (v > eps * ref[m] && v > 0.0) ? 1.0 / sqrt(v) : 0.0;
 }
 
-// append the direction d (ntb, destroyed) to the projection space; `npass`
+// add the direction d (ntb, destroyed) to the projection space; `npass`
 // Gram-Schmidt passes: the image of a correction x - x0 is orthogonal to the
 // space already (up to the solver tolerance), one pass cleans it; a raw
-// solution (rebuild) lies almost inside the space and needs two
+// solution lies almost inside the space and needs two.
+// While the space has free slots the pair is appended; once it is full the
+// pair REPLACES the oldest one (ring): the remaining pairs stay orthonormal and
+// consistent (K xq_i = bq_i), so nothing has to be rebuilt -- the new image is
+// orthogonalised against all slots with the coefficient of the slot that is
+// being replaced set to zero.
 static int proj_add(dnsb_imex *e, double *d, int npass) {
   dnsb_ctx *ctx = e->ctx;
   const int nb = e->nb, ntot = e->nv + e->np;
@@ -2365,13 +2373,17 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
   RedCfg rc = red_cfg(ctx, ntot, nb);
   double *w = e->pw0.p, *w2 = e->pw1.p, *d2 = e->pd1.p;
   spmm_dev(ctx, sl->K, coef, d, nullptr, w, nb, 1.0, 0.0);
-  const int k = e->pcnt;
+  const bool full = e->pcnt >= e->hist_len;
+  const int k = full ? e->hist_len : e->pcnt;          // vectors to orthogonalise against
+  const int slot = full ? e->pring % e->hist_len : k;  // where the new pair goes
   // |K d|^2 before the orthogonalisation (reference for the breakdown test)
   for (int pass = 0; pass < npass && k > 0; ++pass) {
     mdot_dev(ctx, rc, e->bq.p, ntb, k, w, ntot, nb, e->partialh.p, e->gr.p);
     if (pass == 0)
       DNSB_CK(ctx, cudaMemcpyAsync(e->normout.p, e->gr.p + (size_t)k * nb, nb * sizeof(double),
                                    cudaMemcpyDeviceToDevice, ctx->stream));
+    if (full)
+      DNSB_CK(ctx, cudaMemsetAsync(e->gr.p + (size_t)slot * nb, 0, nb * sizeof(double), ctx->stream));
     gs_update_dev(ctx, rc, e->bq.p, ntb, k, e->gr.p, w, w2, ntot, nb, e->normpart.p);
     gs_update_dev(ctx, rc, e->xq.p, ntb, k, e->gr.p, d, d2, ntot, nb, e->partialh.p);
     std::swap(w, w2);
@@ -2390,10 +2402,11 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
   LAUNCH(ctx, k_inv_norm, cdiv(nb, 64), 64, 0, (const double *)(e->pinv.p + nb),
          (const double *)e->normout.p, e->pinv.p, nb, 1e-26);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)w, (const double *)e->pinv.p,
-         e->bq.p + (size_t)k * ntb, (size_t)ntot, nb);
+         e->bq.p + (size_t)slot * ntb, (size_t)ntot, nb);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)d, (const double *)e->pinv.p,
-         e->xq.p + (size_t)k * ntb, (size_t)ntot, nb);
-  e->pcnt = k + 1;
+         e->xq.p + (size_t)slot * ntb, (size_t)ntot, nb);
+  if (full) e->pring++;
+  else e->pcnt = k + 1;
   return 0;
 }
 
@@ -2411,32 +2424,15 @@ static int imex_push_history(dnsb_imex *e, int guess) {
     e->hist_cnt++;
     return 0;
   }
-  // ring of raw solutions (for the rebuild)
-  const int K = e->pkeep;
-  DNSB_CK(ctx, cudaMemcpyAsync(e->xh.p + (size_t)(e->hist_pos % K) * ntb, e->x.p, ntb * sizeof(double),
-                               cudaMemcpyDeviceToDevice, ctx->stream));
-  e->hist_pos++;
   e->hist_cnt++;
-  if (e->pcnt < e->hist_len) {
-    // new direction: the correction x - x0 (or x itself while the space is empty)
-    if (e->pcnt == 0)
-      DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    else
-      LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
-             (const double *)e->x0.p, e->pd0.p, ntb);
-    return proj_add(e, e->pd0.p, e->pcnt == 0 ? 2 : 1);
+  // new direction: the correction x - x0 (or x itself while the space is empty)
+  if (e->pcnt == 0) {
+    DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return proj_add(e, e->pd0.p, 2);
   }
-  // space full: rebuild it from the last K raw solutions, oldest first
-  e->pcnt = 0;
-  const int have = std::min(K, e->hist_cnt);
-  for (int q = have; q >= 1; --q) {
-    const int slot = (e->hist_pos - q) % K;
-    DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->xh.p + (size_t)slot * ntb, ntb * sizeof(double),
-                                 cudaMemcpyDeviceToDevice, ctx->stream));
-    int rc = proj_add(e, e->pd0.p, 2);
-    if (rc) return rc;
-  }
-  return 0;
+  LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
+         (const double *)e->x0.p, e->pd0.p, ntb);
+  return proj_add(e, e->pd0.p, g_proj_passes);
 }
 
 // |v_m| > maxv or NaN for any member?  (time_int_utils.py:94-103)
@@ -2476,9 +2472,13 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
     const int mode = guess >= 2 ? 2 : 1;
     if (e->hist_len != L || e->hist_mode != mode) {
       e->hist_len = L; e->hist_cnt = 0; e->hist_pos = 0; e->hist_mode = mode; e->pcnt = 0;
-      e->pkeep = std::max(2, L / 2);
-      DNSB_CK(ctx, e->xh.alloc(ntb * (mode == 2 ? e->pkeep : L)));
-      DNSB_CK(ctx, e->xh.zero(ctx->stream));
+      e->pring = 0;
+      if (mode == 1) {
+        DNSB_CK(ctx, e->xh.alloc(ntb * L));
+        DNSB_CK(ctx, e->xh.zero(ctx->stream));
+      } else {
+        e->xh.release();
+      }
       if (mode == 2) {
         RedCfg rc = red_cfg(ctx, nv + np, nb);
         DNSB_CK(ctx, e->bq.alloc(ntb * L));

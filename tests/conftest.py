@@ -28,3 +28,15 @@ def soldict(femp, sm, rhsd, **kw):
              dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'])
     d.update(kw)
     return d
+
+
+@pytest.fixture(scope='session')
+def cyl1_re30():
+    """cylinder wake on the coarsest mesh at Re=30: the steady Picard/Newton
+    systems of this Reynolds number are inside the envelope of the device's
+    iterative solve on this mesh (at Re=60 the element Peclet number of the
+    unstabilised Galerkin convection is too large: `NotConverged`)"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    return dnsps.get_sysmats(problem='cylinderwake', Re=30, scheme='TH',
+                             mergerhs=True,
+                             meshparams=dict(refinement_level=1))

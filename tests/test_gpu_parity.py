@@ -656,7 +656,7 @@ def test_device_assembly_of_the_constant_operators(ctx, symm):
         assert abs(a[key] - b[key]).max() <= 1e-13*abs(a[key]).max(), key
 
 
-def test_paraviewoutput_of_the_solvers(cyl1, ctx, tmp_path):
+def test_paraviewoutput_of_the_solvers(cyl1, cyl1_re30, ctx, tmp_path):
     """`paraviewoutput=True` (`snu:817-821,1091-1098`, `snu:348-357`) writes
     `<prfx>__timestep.pvd` / `__steadystates.pvd` without dolfin; the last
     piece holds the returned velocity"""
@@ -688,7 +688,7 @@ def test_paraviewoutput_of_the_solvers(cyl1, ctx, tmp_path):
     sprfx = str(tmp_path / 's')
     vss = snu.solve_steadystate_nse(vel_pcrd_stps=1, vel_nwtn_stps=1, vel_nwtn_tol=1., verbose=False,
                                     paraviewoutput=True, vfileprfx=sprfx, pfileprfx=sprfx + 'p', Q=Q,
-                                    **soldict(femp, sm, rhsd))
+                                    **soldict(*cyl1_re30))
     nsets, v = _last_piece(sprfx + '__steadystates.pvd', 'v', 3)
     assert nsets == 3
     assert np.allclose(v[:, 0], np.asarray(vss).reshape(-1)[0::2], rtol=0, atol=1e-15)
@@ -819,7 +819,7 @@ def test_reference_run_newton_cn_device(ctx):
         assert _rel(pd[float(t)], g['p'][:, k:k+1]) < 1e-8, t
 
 
-def test_reference_run_steady_state_device(cyl1, ctx):
+def test_reference_run_steady_state_device(cyl1_re30, ctx):
     """`snu.solve_steadystate_nse` (DFG 2D-1 and cylinder_1), `snu.get_pfromv`
     and `snu.get_v_conv_conts` as returned by the reference"""
     from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
@@ -828,8 +828,8 @@ def test_reference_run_steady_state_device(cyl1, ctx):
     v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False,
                                      **soldict(femp, sm, rhsd))
     assert _rel(v, g['v']) < 1e-8 and _rel(p, g['p']) < 1e-8
-    femp, sm, rhsd = cyl1
-    g = np.load(os.path.join(GOLD, 'ref_steady_cyl1_re60.npz'))
+    femp, sm, rhsd = cyl1_re30
+    g = np.load(os.path.join(GOLD, 'ref_steady_cyl1_re30.npz'))
     sd = soldict(femp, sm, rhsd)
     v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False, **sd)
     assert _rel(v, g['v']) < 1e-8 and _rel(p, g['p']) < 1e-8
@@ -1010,3 +1010,18 @@ def test_unconverged_solves_are_reported(cyl1, ctx):
     st = integ.stats()
     assert st['unconverged'] == 0 and 0 < st['max_relres'] <= 1e-12
     integ.close()
+
+
+def test_steady_solver_outside_its_envelope_fails_loudly(cyl1, ctx):
+    """cylinder_1 at Re = 60: the unstabilised Galerkin convection has element
+    Peclet numbers (eigenvalues of D^-1 F at 0.8 +- 3i) on which the Jacobi-
+    Chebyshev smoothed V-cycle is no contraction; the Oseen solve stagnates.
+    The reference's sparse LU does not care -- the device path must say so
+    instead of handing back an unconverged iterate."""
+    from dolfin_navier_scipy_b200 import _lib
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    femp, sm, rhsd = cyl1
+    with pytest.raises(_lib.NotConverged):
+        snu.solve_steadystate_nse(vel_pcrd_stps=1, vel_nwtn_stps=1,
+                                  vel_nwtn_tol=1., verbose=False,
+                                  **soldict(femp, sm, rhsd))

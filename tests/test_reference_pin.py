@@ -110,7 +110,7 @@ def test_oracle_newton_cn_equals_reference_run():
     assert _rel(pfin, g['p'][:, -1:]) <= TOL
 
 
-def test_oracle_steady_state_equals_reference_run(cyl1):
+def test_oracle_steady_state_equals_reference_run(cyl1_re30):
     from dolfin_navier_scipy_b200 import problem_setups as dnsps
     from oracle import snu as osnu
     g = _gold('ref_dfg2d1_lvl1.npz')
@@ -130,8 +130,8 @@ def test_oracle_steady_state_equals_reference_run(cyl1):
     assert len(g['nwtnupd_norms']) == 0 and len(nrms) == 3
     assert nrms[-1] < 5e-15 <= nrms[-2]
 
-    femp, sm, rhsd = cyl1
-    g = _gold('ref_steady_cyl1_re60.npz')
+    femp, sm, rhsd = cyl1_re30
+    g = _gold('ref_steady_cyl1_re30.npz')
     sd = soldict(femp, sm, rhsd)
     v, p = osnu.solve_steadystate_nse(return_vp=True, **sd)
     assert _rel(v, g['v']) <= TOL and _rel(p, g['p']) <= TOL
