@@ -51,7 +51,7 @@ def parse():
     ap.add_argument('--spinup', type=int, default=16,
                     help='untimed steps before the W warm-up steps: the solver recycles the last 16 '
                          'solutions for its initial guesses; a run reaches that operating point after 16 steps')
-    ap.add_argument('--schur-precision', default='f64', choices=['f64', 'tf32x3', 'tf32x2', 'tf32'],
+    ap.add_argument('--schur-precision', default='tc', choices=['f64', 'tf32x3', 'tf32x2', 'tf32', 'tc'],
                     help='dense Schur block of the preconditioner: fp64 (default) or 3xTF32 '
                          '(fp32 copy of the inverse; FGMRES residuals stay fp64)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
@@ -354,7 +354,11 @@ def run_ours(args, rank, world, local_rank):
     from dolfin_navier_scipy_b200 import ensemble as ens
 
     torch.cuda.set_device(local_rank)
-    if args.schur_precision != 'f64':      # read when the context is created
+    if args.schur_precision == 'tc':       # read when the context is created
+        os.environ['DNSB_SCHUR_TC'] = '1'
+    elif args.schur_precision == 'f64':
+        os.environ['DNSB_SCHUR_TC'] = '0'
+    else:
         os.environ['DNSB_SCHUR_TF32'] = dict(tf32x3='1', tf32x2='2', tf32='3')[args.schur_precision]
     ctx = _lib.default_context(local_rank)
     nmembers = args.members*world
@@ -543,6 +547,8 @@ def kernel_bytes(name, info, integ):
         return 12.*J.nnz + 4.*(n + 1) + 8.*npp*nb + 32.*n*nb
     if name.startswith(('k_dense_gemm', 'k_dense_dmma')):
         return 8.*npp*npp + 16.*npp*nb
+    if name.startswith('k_schur_tc'):
+        return 4.*npp*npp + 8.*npp*nb
     if name.startswith('k_scale_member'):
         return 16.*(n + npp)*nb
     if name.startswith('k_convvec'):
@@ -608,6 +614,17 @@ def roofline_of(kern, info, integ, args):
                                   tf32_tflops=3*2.*npp*npp*nb/(m*1e-3/c)/1e12,
                                   note='3xTF32 mma.sync (fp32 copy of the inverse), '
                                   'preconditioner block only; FGMRES residuals fp64')
+    tc = [k for k in kern if k.strip('()').startswith('k_schur_tc')]
+    if tc:
+        c, m = kern[tc[0]]
+        byts = 4.*npp*npp + 8.*npp*nb
+        out['dense_schur'] = dict(kernel=tc[0], mean_us=1e3*m/c, bytes_per_launch=byts,
+                                  achieved_gbs=byts/(m*1e-3/c)/1e9,
+                                  frac_of_hbm_peak=byts/(m*1e-3/c)/1e9/peak,
+                                  tf32_tflops=2.*npp*npp*nb/(m*1e-3/c)/1e12,
+                                  note='tcgen05.mma kind::tf32 (TMA-fed, TMEM accumulators) on '
+                                  'a TF32-rounded fp32 copy of the inverse: HBM bound; '
+                                  'preconditioner block only, FGMRES bases/residuals fp64')
     dn = [k for k in kern if k.strip('()').startswith(('k_dense_gemm', 'k_dense_dmma'))]
     if dn:
         c, m = kern[dn[0]]

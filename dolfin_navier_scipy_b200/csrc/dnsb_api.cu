@@ -15,6 +15,7 @@
 #include "dnsb_batched.cuh"
 #include "dnsb_dense.cuh"
 #include "dnsb_stream.cuh"
+#include "dnsb_tc.cuh"
 
 #define DNSB_VERSION 100
 
@@ -239,7 +240,10 @@ static int g_dense_ctas_per_sm = 2;
 static int g_graphs = 1;
 static int g_schur_tf32 = 0;   // 1: dense Schur inverse applied in 3xTF32 (fp32 copy), see dnsb_dense.cuh
 static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur solve
-static int g_proj_passes = 1;   // Gram-Schmidt passes when a correction joins the projection space
+// 1: dense Schur block on the tcgen05 tensor cores (TF32 operands from an fp32 copy of the inverse,
+// fp32 accumulation in TMEM; dnsb_tc.cuh).  Preconditioner block only: FGMRES stays fp64.
+static int g_schur_tc = 1;
+static const int TC_SMEM_OPTIN = 208 * 1024;
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
 static inline int spb_gpc(dnsb_ctx *ctx, int nrows, int nb) {
   const long total = (long)nrows * nb;
@@ -393,10 +397,10 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_TMA_STAGES")) g_tma_stages = std::min(SPT_MAX_STAGES, std::max(2, atoi(ev)));
   if (const char *ev = getenv("DNSB_DMMA")) g_dmma = atoi(ev);
   if (const char *ev = getenv("DNSB_SCHUR_TF32")) g_schur_tf32 = atoi(ev);
+  if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
-  if (const char *ev = getenv("DNSB_PROJ_PASSES")) g_proj_passes = std::min(2, std::max(1, atoi(ev)));
   if (const char *ev = getenv("DNSB_DENSE_CTAS_PER_SM")) g_dense_ctas_per_sm = std::max(1, atoi(ev));
   *out = ctx;   // returned even on failure so that the message can be read
   DNSB_CK(ctx, cudaSetDevice(device));
@@ -428,6 +432,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_schur_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_OPTIN));
   return 0;
 }
 
@@ -876,6 +881,8 @@ struct MgLevel {
   DBuf<double> gpart;        // split-K partial sums of the dense solve
   DBuf<float> dinv_f32, x_f32;   // fp32 copies for the optional TF32 variant (DNSB_SCHUR_TF32)
   int ldf = 0;
+  TcPlan tc;                     // tcgen05 variant (DNSB_SCHUR_TC): tensor maps, split-K shape
+  DBuf<float> xt, tcpart;        // K-major fp32 copy of X (NP x ldx), split-K partial tiles
   DBuf<double> dinv_own;     // n*nb Jacobi (owned)
   const double *dinv = nullptr;
   DBuf<double> b, x, r, d0, d1, t;   // n*nb work vectors
@@ -1061,9 +1068,67 @@ static void dense_split(dnsb_ctx *ctx, int n, int nb, int *tn, DenseSplit *sp) {
   sp->maxseg = 2 + sp->upc / sp->ksteps;
 }
 
+// ---- tcgen05 dense Schur block: tensor maps + split-K shape ------------------
+typedef CUresult (*dnsb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                         const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                         const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static dnsb_encode_tiled_fn tc_encode_fn() {
+  static dnsb_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (dnsb_encode_tiled_fn)p;
+  }
+  return fn;
+}
+// a 2-D fp32 tensor (rows x cols, leading dimension ld floats) seen by TMA in boxes of
+// box_rows x TC_BK with the 128-byte swizzle the UMMA descriptors expect; out-of-range = 0
+static bool tc_map_2d(CUtensorMap *map, const float *base, int rows, int cols, int ld, int box_rows) {
+  dnsb_encode_tiled_fn enc = tc_encode_fn();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// needs L->dinv_f32 (n x ldf); returns cudaSuccess with tc.ok = false when the block does not qualify
+static cudaError_t tc_setup(dnsb_ctx *ctx, MgLevel *L, int n, int nb) {
+  TcPlan &p = L->tc;
+  p.ok = false;
+  if (ctx->cc < 100 || nb < 8 || nb > 256 || n < TC_BM) return cudaSuccess;   // nb < 8: k_dense_gemv (fp64, D-bandwidth bound)
+  p.np_ = (nb + 15) & ~15;
+  p.kblocks = (n + TC_BK - 1) / TC_BK;
+  p.mtiles = (n + TC_BM - 1) / TC_BM;
+  p.splits = std::max(1, std::min(p.kblocks, ctx->sm_count / p.mtiles));
+  p.kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
+  p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+  const size_t a_bytes = (size_t)TC_BM * TC_BK * 4;
+  const size_t b_bytes = (((size_t)p.np_ * TC_BK * 4) + 1023) & ~(size_t)1023;
+  p.stages = (int)std::min<size_t>(TC_MAX_STAGES, ((size_t)TC_SMEM_OPTIN - 1024) / (a_bytes + b_bytes));
+  if (p.stages < 2) return cudaSuccess;
+  p.smem = (size_t)p.stages * (a_bytes + b_bytes) + 1024;
+  p.ldx = (n + 3) & ~3;
+  cudaError_t e;
+  if ((e = L->xt.alloc((size_t)p.np_ * p.ldx)) != cudaSuccess) return e;
+  if ((e = L->xt.zero(ctx->stream)) != cudaSuccess) return e;
+  if ((e = L->tcpart.alloc((size_t)p.splits * p.mtiles * TC_BM * p.np_)) != cudaSuccess) return e;
+  // D: TF32-rounded fp32 copy in packed, pre-swizzled 128 x 32 tiles
+  if ((e = L->dinv_f32.alloc((size_t)p.mtiles * p.kblocks * TC_BM * TC_BK)) != cudaSuccess) return e;
+  LAUNCH(ctx, k_tc_pack_d, cdiv(L->dinv_f32.n, 256), 256, 0, (const double *)L->dinv_dense.p, L->dinv_f32.p, n,
+         p.mtiles, p.kblocks);
+  p.ok = tc_map_2d(&p.mapB, L->xt.p, p.np_, n, p.ldx, p.np_);
+  return cudaSuccess;
+}
+
 static void level_free(MgLevel *L) {
   if (!L) return;
-  L->dinv_dense.release(); L->gpart.release(); L->dinv_f32.release(); L->x_f32.release(); L->dinv_own.release(); L->b.release(); L->x.release();
+  L->dinv_dense.release(); L->gpart.release(); L->dinv_f32.release(); L->x_f32.release(); L->xt.release(); L->tcpart.release(); L->dinv_own.release(); L->b.release(); L->x.release();
   L->r.release(); L->d0.release(); L->d1.release(); L->t.release();
   delete L;
 }
@@ -1125,6 +1190,13 @@ static int solver_add_level(dnsb_solver *s, int block, dnsb_csr *amat, dnsb_csr 
             (e = L->x_f32.alloc((size_t)nexpect * s->nb)) == cudaSuccess)
           LAUNCH(ctx, k_f64_to_f32, cdiv((size_t)nexpect * L->ldf, 256), 256, 0, (const double *)L->dinv_dense.p,
                  L->dinv_f32.p, (size_t)nexpect, (size_t)nexpect, (size_t)L->ldf);
+      }
+    }
+    if (e == cudaSuccess && g_schur_tc && !g_schur_tf32) {
+      e = tc_setup(ctx, L, nexpect, s->nb);
+      if (e == cudaSuccess && !L->tc.ok) {   // block does not qualify: the fp64 kernels serve it
+        DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        L->dinv_f32.release(); L->xt.release(); L->tcpart.release();
       }
     }
     if (e != cudaSuccess) { level_free(L); DNSB_CK(ctx, e); }
@@ -1226,6 +1298,17 @@ static int dense_apply(dnsb_solver *s, MgLevel *L, const double *x,
   const int n = L->n, nb = s->nb;
   const double *ad = with_mass ? s->mp_dinv.p : nullptr;
   const double *as = with_mass ? s->mp_scale.p : nullptr;
+  if (L->tc.ok) {
+    const TcPlan &p = L->tc;
+    int tmem_cols = 32;
+    while (tmem_cols < p.np_) tmem_cols *= 2;
+    LAUNCH(ctx, k_tc_pack_x, dim3(cdiv(p.ldx, 32), cdiv(nb, 32)), 256, 0, x, L->xt.p, n, nb, p.ldx);
+    LAUNCH(ctx, k_schur_tc, dim3(p.mtiles, p.splits), TC_THREADS, p.smem, (const float *)L->dinv_f32.p, p.mapB, L->tcpart.p, p.np_,
+           p.kblocks, p.kb_per_split, p.stages, tmem_cols);
+    LAUNCH(ctx, k_tc_epilogue, cdiv((size_t)n * nb, 256), 256, 0, (const float *)L->tcpart.p, p.splits,
+           (size_t)p.mtiles * TC_BM * p.np_, p.np_, x, y, n, nb, alpha, ad, as);
+    return 0;
+  }
   if (nb <= 1)
     LAUNCH(ctx, k_dense_gemv<1>, cdiv((size_t)n * 32, 256), 256, 0, L->dinv_dense.p, x, y, n, nb, alpha, ad, as);
   else if (nb <= 2)
@@ -1239,7 +1322,7 @@ static int dense_apply(dnsb_solver *s, MgLevel *L, const double *x,
     DenseSplit sp;
     dense_split(ctx, n, nb, &tn, &sp);
     const dim3 grid(sp.nctas, cdiv(nb, tn));
-    if (L->dinv_f32.p && tn == 64) {
+    if (g_schur_tf32 && L->dinv_f32.p && L->x_f32.p && tn == 64) {
       LAUNCH(ctx, k_f64_to_f32, cdiv((size_t)n * nb, 256), 256, 0, x, L->x_f32.p, (size_t)n, (size_t)nb, (size_t)nb);
 const float *df_ = L->dinv_f32.p, *xf_ = L->x_f32.p;
       if (g_schur_tf32 == 1)
@@ -2055,7 +2138,6 @@ struct dnsb_imex {
   // `keep` raw solutions for the rebuild when the space is full
   int hist_len = 0, hist_cnt = 0, hist_pos = 0, hist_mode = 0;
   int pcnt = 0, pkeep = 0;
-  long long pring = 0;   // projection space full: slot pring % hist_len is the oldest pair
   DBuf<double> xh, bq, xq, gr, partialh, x0, pw0, pw1, pd0, pd1, pinv, normpart, normout;
   double last_relres = 0;   // max over ALL solves of the last run (every member, Heun solves included)
   long long run_iters = 0, run_solves = 0, run_unconverged = 0;
@@ -2355,15 +2437,10 @@ __global__ void k_inv_norm(const double *__restrict__ n2, const double *__restri
   inv[m] = (v > eps * ref[m] && v > 0.0) ? 1.0 / sqrt(v) : 0.0;
 }
 
-// add the direction d (ntb, destroyed) to the projection space; `npass`
+// append the direction d (ntb, destroyed) to the projection space; `npass`
 // Gram-Schmidt passes: the image of a correction x - x0 is orthogonal to the
 // space already (up to the solver tolerance), one pass cleans it; a raw
-// solution lies almost inside the space and needs two.
-// While the space has free slots the pair is appended; once it is full the
-// pair REPLACES the oldest one (ring): the remaining pairs stay orthonormal and
-// consistent (K xq_i = bq_i), so nothing has to be rebuilt -- the new image is
-// orthogonalised against all slots with the coefficient of the slot that is
-// being replaced set to zero.
+// solution (rebuild) lies almost inside the space and needs two
 static int proj_add(dnsb_imex *e, double *d, int npass) {
   dnsb_ctx *ctx = e->ctx;
   const int nb = e->nb, ntot = e->nv + e->np;
@@ -2373,17 +2450,13 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
   RedCfg rc = red_cfg(ctx, ntot, nb);
   double *w = e->pw0.p, *w2 = e->pw1.p, *d2 = e->pd1.p;
   spmm_dev(ctx, sl->K, coef, d, nullptr, w, nb, 1.0, 0.0);
-  const bool full = e->pcnt >= e->hist_len;
-  const int k = full ? e->hist_len : e->pcnt;          // vectors to orthogonalise against
-  const int slot = full ? e->pring % e->hist_len : k;  // where the new pair goes
+  const int k = e->pcnt;
   // |K d|^2 before the orthogonalisation (reference for the breakdown test)
   for (int pass = 0; pass < npass && k > 0; ++pass) {
     mdot_dev(ctx, rc, e->bq.p, ntb, k, w, ntot, nb, e->partialh.p, e->gr.p);
     if (pass == 0)
       DNSB_CK(ctx, cudaMemcpyAsync(e->normout.p, e->gr.p + (size_t)k * nb, nb * sizeof(double),
                                    cudaMemcpyDeviceToDevice, ctx->stream));
-    if (full)
-      DNSB_CK(ctx, cudaMemsetAsync(e->gr.p + (size_t)slot * nb, 0, nb * sizeof(double), ctx->stream));
     gs_update_dev(ctx, rc, e->bq.p, ntb, k, e->gr.p, w, w2, ntot, nb, e->normpart.p);
     gs_update_dev(ctx, rc, e->xq.p, ntb, k, e->gr.p, d, d2, ntot, nb, e->partialh.p);
     std::swap(w, w2);
@@ -2402,11 +2475,10 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
   LAUNCH(ctx, k_inv_norm, cdiv(nb, 64), 64, 0, (const double *)(e->pinv.p + nb),
          (const double *)e->normout.p, e->pinv.p, nb, 1e-26);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)w, (const double *)e->pinv.p,
-         e->bq.p + (size_t)slot * ntb, (size_t)ntot, nb);
+         e->bq.p + (size_t)k * ntb, (size_t)ntot, nb);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)d, (const double *)e->pinv.p,
-         e->xq.p + (size_t)slot * ntb, (size_t)ntot, nb);
-  if (full) e->pring++;
-  else e->pcnt = k + 1;
+         e->xq.p + (size_t)k * ntb, (size_t)ntot, nb);
+  e->pcnt = k + 1;
   return 0;
 }
 
@@ -2424,15 +2496,32 @@ static int imex_push_history(dnsb_imex *e, int guess) {
     e->hist_cnt++;
     return 0;
   }
+  // ring of raw solutions (for the rebuild)
+  const int K = e->pkeep;
+  DNSB_CK(ctx, cudaMemcpyAsync(e->xh.p + (size_t)(e->hist_pos % K) * ntb, e->x.p, ntb * sizeof(double),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+  e->hist_pos++;
   e->hist_cnt++;
-  // new direction: the correction x - x0 (or x itself while the space is empty)
-  if (e->pcnt == 0) {
-    DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    return proj_add(e, e->pd0.p, 2);
+  if (e->pcnt < e->hist_len) {
+    // new direction: the correction x - x0 (or x itself while the space is empty)
+    if (e->pcnt == 0)
+      DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+      LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
+             (const double *)e->x0.p, e->pd0.p, ntb);
+    return proj_add(e, e->pd0.p, e->pcnt == 0 ? 2 : 1);
   }
-  LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
-         (const double *)e->x0.p, e->pd0.p, ntb);
-  return proj_add(e, e->pd0.p, g_proj_passes);
+  // space full: rebuild it from the last K raw solutions, oldest first
+  e->pcnt = 0;
+  const int have = std::min(K, e->hist_cnt);
+  for (int q = have; q >= 1; --q) {
+    const int slot = (e->hist_pos - q) % K;
+    DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->xh.p + (size_t)slot * ntb, ntb * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    int rc = proj_add(e, e->pd0.p, 2);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 // |v_m| > maxv or NaN for any member?  (time_int_utils.py:94-103)
@@ -2472,13 +2561,9 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
     const int mode = guess >= 2 ? 2 : 1;
     if (e->hist_len != L || e->hist_mode != mode) {
       e->hist_len = L; e->hist_cnt = 0; e->hist_pos = 0; e->hist_mode = mode; e->pcnt = 0;
-      e->pring = 0;
-      if (mode == 1) {
-        DNSB_CK(ctx, e->xh.alloc(ntb * L));
-        DNSB_CK(ctx, e->xh.zero(ctx->stream));
-      } else {
-        e->xh.release();
-      }
+      e->pkeep = std::max(2, L / 2);
+      DNSB_CK(ctx, e->xh.alloc(ntb * (mode == 2 ? e->pkeep : L)));
+      DNSB_CK(ctx, e->xh.zero(ctx->stream));
       if (mode == 2) {
         RedCfg rc = red_cfg(ctx, nv + np, nb);
         DNSB_CK(ctx, e->bq.alloc(ntb * L));

@@ -1025,3 +1025,111 @@ def test_steady_solver_outside_its_envelope_fails_loudly(cyl1, ctx):
         snu.solve_steadystate_nse(vel_pcrd_stps=1, vel_nwtn_stps=1,
                                   vel_nwtn_tol=1., verbose=False,
                                   **soldict(femp, sm, rhsd))
+
+
+def _ctx_with_env(name, value):
+    """a context created under an environment switch (read at creation)"""
+    from dolfin_navier_scipy_b200 import _lib
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return _lib.Context(0)
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.fixture
+def tc_ctx():
+    """the tcgen05 Schur block (the default for nb >= 8) switched on explicitly"""
+    return _ctx_with_env('DNSB_SCHUR_TC', '1')
+
+
+@pytest.fixture
+def f64_ctx():
+    """every block of the preconditioner in fp64 (DNSB_SCHUR_TC=0)"""
+    return _ctx_with_env('DNSB_SCHUR_TC', '0')
+
+
+@pytest.mark.parametrize('ncols', [64, 24, 8])
+def test_schur_tensor_core_block_against_numpy(cyl1, tc_ctx, ncols):
+    """k_schur_tc (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulators): the
+    pressure part of one preconditioner application, z_p = -D r_p, against the
+    fp64 product with the same inverse.  TF32 operands: rel. error of a few
+    1e-4 (and NOT 1e-16: the fp64 path would hide a dispatch mistake)"""
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    femp, sm, rhsd = cyl1
+    F = (sm['M'] + .5/512*sm['A']).tocsr()
+    NP, NV = sm['J'].shape
+    op = lau.SadpntOperator(F, sm['J'], sm['JT'], ncols=ncols, ctx=tc_ctx)
+    levels, dense = op.info['hierarchy']
+    assert len(levels) == 0 and dense.shape == (NP, NP) and NP % 128 != 0
+    rng = np.random.default_rng(ncols)
+    R = rng.standard_normal((NV + NP, ncols))
+    Z = op.solver.apply_prec(R)
+    ref = -dense@R[NV:]
+    # forward error bound of a product with both operands rounded to TF32
+    # (unit round-off 2^-11 each) and fp32 accumulation: |err| <= 2^-10 |D||x|
+    bound = 2.**-10*(np.abs(dense)@np.abs(R[NV:]))
+    for m in range(ncols):
+        err = _rel(Z[NV:, m], ref[:, m])
+        assert 1e-9 < err < 1e-2, (m, err)
+        assert np.linalg.norm(Z[NV:, m] - ref[:, m]) <= np.linalg.norm(bound[:, m]), m
+    # rows beyond a 128-row tile and K beyond a 32-column block are zero-filled
+    # by TMA: a right-hand side concentrated on the last rows must come through
+    R2 = np.zeros_like(R)
+    R2[-3:, :] = rng.standard_normal((3, ncols))
+    Z2 = op.solver.apply_prec(R2)
+    ref2 = -dense@R2[NV:]
+    assert _rel(Z2[NV:], ref2) < 1e-2
+    op.close()
+
+
+def test_schur_tensor_core_block_keeps_iterations_and_parity(cyl1, tc_ctx, f64_ctx):
+    """the TF32 tensor-core block is a preconditioner detail: same FGMRES
+    iteration counts (+-1), the solution meets the fp64 tolerance against LU,
+    and a CNAB run stays within 1e-8 of the oracle per step"""
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle.lau import solve_sadpnt_smw as olu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    dt = 1./512
+    F = (sm['M'] + .5*dt*sm['A']).tocsr()
+    ncols = 64
+    rng = np.random.default_rng(21)
+    b = sm['M']@rng.standard_normal((F.shape[0], ncols))
+    g = sm['J']@rng.standard_normal((F.shape[0], ncols))*1e-3
+    ref = olu(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b, rhsp=g)
+    NV = F.shape[0]
+    its = {}
+    for name, c in (('f64', f64_ctx), ('tc', tc_ctx)):
+        op = lau.SadpntOperator(F, sm['J'], sm['JT'], ncols=ncols, ctx=c)
+        vp = op.solve(b, g, tol=1e-12, maxit=200)
+        its[name] = int(op.last_iters.max())
+        for k in range(ncols):
+            assert _rel(vp[:NV, k], ref[:NV, k]) < 1e-9, (name, k)
+            assert _rel(vp[NV:, k], ref[NV:, k]) < 1e-8, (name, k)
+        op.close()
+    assert abs(its['tc'] - its['f64']) <= 1, its
+    # CNAB, 3 members, per-step parity
+    inv = femp['invinds']
+    sd = soldict(femp, sm, rhsd)
+    nsteps = 8
+    o = osnu.solve_nse(t0=0, tE=nsteps*dt, Nts=nsteps, start_ssstokes=True,
+                       return_vp_dict=True, **sd)
+    ts = sorted(o.keys())
+    integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv,
+                           femp['dbcinds'], femp['dbcvals'], dt,
+                           nus=np.ones(16), fv=rhsd['fv'], fp=rhsd['fp'],
+                           ctx=tc_ctx)
+    integ.set_state(o[ts[0]]['v'][inv], o[ts[0]]['p'])
+    integ.run(nsteps, snap_stride=1, tol=1e-12)
+    vs, ps = integ.snapshots()
+    integ.close()
+    for k in range(1, nsteps + 1):
+        for m in (0, 15):
+            assert _rel(vs[k, :, m], o[ts[k]]['v'][inv, 0]) < 1e-8, (k, m)
+            assert _rel(ps[k, :, m], o[ts[k]]['p'][:, 0]) < 1e-8, (k, m)
