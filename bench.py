@@ -535,8 +535,12 @@ def kernel_bytes(name, info, integ):
     name = name.strip('()')
     if name.startswith('k_cheb_step'):
         flags = name.split('<')[1].rstrip('>').split(', ')
-        first, last = flags[1] == 'true', flags[2] == 'true'
+        tiled = name.startswith('k_cheb_step_tile')        # <FIRST, LAST>, packed entries
+        first, last = (flags[0] == 'true', flags[1] == 'true') if tiled \
+            else (flags[1] == 'true', flags[2] == 'true')
         passes = 7 - (1 if first else 0) - (2 if last else 0)
+        if tiled:    # 4 values + 1 offset per column of a row pair: 18 B per CSR entry
+            return 18.*nnzF + 4.*(n + 1) + 8.*passes*n*nb
         return 20.*nnzF + 4.*(n + 1) + 8.*passes*n*nb
     if name.startswith('k_spmm'):
         # the block matrix K = [F JT; J 0] (two value arrays): gather + store

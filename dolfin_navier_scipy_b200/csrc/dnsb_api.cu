@@ -16,6 +16,7 @@
 #include "dnsb_dense.cuh"
 #include "dnsb_stream.cuh"
 #include "dnsb_tc.cuh"
+#include "dnsb_tile.cuh"
 
 #define DNSB_VERSION 100
 
@@ -125,6 +126,16 @@ struct dnsb_csr {
   bool has2 = false;
   int npair_rows = 0;   // leading rows that pair up (2k, 2k+1) with identical column lists
   SptPlan spt;          // TMA-staged row tiles (dnsb_stream.cuh)
+  TilePlan tile;        // fully staged batched Chebyshev step (dnsb_tile.cuh), built by tile_setup
+  DBuf<int> t_uptr, t_rptr, t_runs, t_pidx;
+  DBuf<double> t_pval;
+  TileDev tile_view() const {
+    TileDev t;
+    t.indptr = indptr.p; t.uptr = t_uptr.p; t.rptr = t_rptr.p; t.runs = t_runs.p; t.pidx = t_pidx.p; t.pval = t_pval.p;
+    t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap;
+    { const char *ev = getenv("DNSB_TILE_DBG"); t.dbg = ev ? atoi(ev) : 0; }
+    return t;
+  }
   // host copies (setup only: assembling the block matrix K, diagonal positions)
   std::vector<int> h_indptr, h_indices;
   std::vector<double> h_v1, h_v2;
@@ -221,8 +232,75 @@ static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
   return 0;
 }
 
+static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
+static const int TILE_SMEM_OPTIN = 220 * 1024;
+// tiles of TILE_RP row pairs: unique x rows, tile-local gather offsets, pair-interleaved values.
+// Needs the host copies of the matrix (two value arrays, all rows paired).
+static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
+  TilePlan &p = m->tile;
+  p.ok = false;
+  if (!g_tile || !m->has2 || m->npair_rows != m->nrows || m->nrows < 2 || m->h_indptr.empty() ||
+      m->h_v2.empty() || ctx->cc < 100)
+    return 0;
+  const int np = m->nrows / 2;
+  const std::vector<int> &ip = m->h_indptr, &ix = m->h_indices;
+  p.npairs = np;
+  p.ntiles = (np + TILE_RP - 1) / TILE_RP;
+  const size_t npe = (size_t)m->nnz / 2;
+  std::vector<int> uptr(p.ntiles + 1, 0), rptr(p.ntiles + 1, 0), runs, ucols, pidx(npe + 8, 0);
+  std::vector<double> pval((npe + 8) * 4, 0.0);
+  std::vector<int> slot(m->ncols, -1);
+  p.umax = 0; p.cap = 0;
+  for (int t = 0; t < p.ntiles; ++t) {
+    const int p0 = t * TILE_RP, p1 = std::min(np, p0 + TILE_RP);
+    // unique columns of the tile, ascending; consecutive columns form one run (one bulk copy)
+    ucols.clear();
+    for (int q = p0; q < p1; ++q)
+      for (int k = ip[2 * q]; k < ip[2 * q + 1]; ++k)
+        if (slot[ix[k]] < 0) { slot[ix[k]] = 0; ucols.push_back(ix[k]); }
+    std::sort(ucols.begin(), ucols.end());
+    for (size_t u = 0; u < ucols.size(); ++u) {
+      slot[ucols[u]] = (int)u;
+      if (u == 0 || ucols[u] != ucols[u - 1] + 1) {
+        runs.push_back(ucols[u]); runs.push_back(1); runs.push_back((int)u);
+      } else {
+        runs[runs.size() - 2] += 1;
+      }
+    }
+    for (int q = p0; q < p1; ++q) {
+      const int L = ip[2 * q + 1] - ip[2 * q];
+      const size_t e0 = (size_t)ip[2 * q] / 2;
+      for (int k = 0; k < L; ++k) {
+        const int ka = ip[2 * q] + k, kb = ka + L;
+        pidx[e0 + k] = slot[ix[ka]] * TILE_ROWB;
+        pval[(e0 + k) * 4 + 0] = m->h_v1[ka]; pval[(e0 + k) * 4 + 1] = m->h_v2[ka];
+        pval[(e0 + k) * 4 + 2] = m->h_v1[kb]; pval[(e0 + k) * 4 + 3] = m->h_v2[kb];
+      }
+    }
+    for (size_t u = 0; u < ucols.size(); ++u) slot[ucols[u]] = -1;
+    uptr[t + 1] = uptr[t] + (int)ucols.size();
+    rptr[t + 1] = (int)(runs.size() / 3);
+    p.umax = std::max(p.umax, (int)ucols.size());
+    const int pe0 = ip[2 * p0] / 2, pe1 = ip[2 * p1] / 2;
+    p.cap = std::max(p.cap, ((pe1 + 3) & ~3) - (pe0 & ~3));
+  }
+  const size_t off_val = (size_t)p.umax * TILE_ROWB;
+  p.stage_bytes = (off_val + (size_t)p.cap * 36 + 127) & ~(size_t)127;
+  p.smem = TILE_STAGES * p.stage_bytes;
+  if (p.smem > (size_t)TILE_SMEM_OPTIN) return 0;   // neighbourhoods too large for the ring: row-pair kernels
+  if (runs.empty()) return 0;
+  DNSB_CK(ctx, m->t_uptr.upload(uptr.data(), uptr.size(), ctx->stream));
+  DNSB_CK(ctx, m->t_rptr.upload(rptr.data(), rptr.size(), ctx->stream));
+  DNSB_CK(ctx, m->t_runs.upload(runs.data(), runs.size(), ctx->stream));
+  DNSB_CK(ctx, m->t_pidx.upload(pidx.data(), pidx.size(), ctx->stream));
+  DNSB_CK(ctx, m->t_pval.upload(pval.data(), pval.size(), ctx->stream));
+  p.ok = true;
+  return 0;
+}
+
 static void csr_free(dnsb_csr *m) {
   if (!m) return;
+  m->t_uptr.release(); m->t_rptr.release(); m->t_runs.release(); m->t_pidx.release(); m->t_pval.release();
   m->indptr.release(); m->indices.release(); m->v1.release(); m->v2.release();
   delete m;
 }
@@ -398,6 +476,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_DMMA")) g_dmma = atoi(ev);
   if (const char *ev = getenv("DNSB_SCHUR_TF32")) g_schur_tf32 = atoi(ev);
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
+  if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
@@ -433,6 +512,10 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_schur_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   return 0;
 }
 
@@ -999,6 +1082,7 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
     DNSB_CK(ctx, s->coef.upload(coef, nb, ctx->stream));
     s->has_coef = true;
   }
+  if (nb == TILE_NB && coef && !fmat->tile.ok) { int rc = tile_setup(ctx, fmat); if (rc) return rc; }
   std::vector<int> dp;
   { int rc = find_diagpos(ctx, fmat, dp); if (rc) return rc; }
   DNSB_CK(ctx, s->diagpos.upload(dp.data(), dp.size(), ctx->stream));
@@ -1419,7 +1503,17 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
       else if (last) LAUNCH(ctx, (k_cheb_step_p2<HAS2, false, true>), grid_, SPB_THREADS, 0, CHEB_ARGS_R);      \
       else LAUNCH(ctx, (k_cheb_step_p2<HAS2, false, false>), grid_, SPB_THREADS, 0, CHEB_ARGS_R);               \
     } while (0)
-      if (has2) CHEB_DISPATCH_R(true);
+      if (has2 && nb == TILE_NB && A->tile.ok) {
+        // everything staged by TMA (dnsb_tile.cuh): persistent CTAs, one per SM
+        const unsigned grid_ = std::min(A->tile.ntiles, ctx->sm_count);
+        const TileDev tv = A->tile_view();
+#define CHEB_ARGS_T tv, coef, (const double *)dc, dinv, res, dn, z, c1, c2
+        if (first && last) LAUNCH(ctx, (k_cheb_step_tile<true, true>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_T);
+        else if (first) LAUNCH(ctx, (k_cheb_step_tile<true, false>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_T);
+        else if (last) LAUNCH(ctx, (k_cheb_step_tile<false, true>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_T);
+        else LAUNCH(ctx, (k_cheb_step_tile<false, false>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_T);
+#undef CHEB_ARGS_T
+      } else if (has2) CHEB_DISPATCH_R(true);
       else CHEB_DISPATCH_R(false);
 #undef CHEB_DISPATCH_R
 #undef CHEB_ARGS_R
@@ -1798,6 +1892,7 @@ extern "C" int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1) {
                                ctx->stream));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));   // host buffer is borrowed
   std::copy(vals1, vals1 + F->nnz, F->h_v1.begin());
+  F->tile.ok = false;   // packed copies of the values are stale: the row-pair kernels serve this matrix
   LAUNCH(ctx, k_copy_f_into_k, cdiv((size_t)F->nrows * 32, 256), 256, 0, F->view(),
          (const int *)s->K->indptr.p, s->K->v1.p);
   const size_t nvb = (size_t)s->nv * s->nb;

@@ -462,6 +462,18 @@ k_cheb_step_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restr
 // are handled (csr->npair_rows / 2, verified on the host when the matrix is
 // created); the sums run in CSR order per row: bit-identical results.
 // ---------------------------------------------------------------------------
+// Explicit fused operations shared by the row-pair kernels and the TMA-staged tile kernel
+// (dnsb_tile.cuh): both evaluate EXACTLY the same sequence of roundings, whatever the compiler
+// would choose to contract, so that the two paths are bit-identical.
+//   acc += (a.x + c*a.y) * x
+__device__ __forceinline__ double spp_acc(double acc, double c, double2 a, double x) {
+  return __fma_rn(__fma_rn(c, a.y, a.x), x, acc);
+}
+//   dd = c1*dold + (c2*dinv)*r
+__device__ __forceinline__ double spp_dir(double c1, double dold, double c2, double dinv, double r) {
+  return __fma_rn(__dmul_rn(c2, dinv), r, __dmul_rn(c1, dold));
+}
+
 #ifndef SPP_CAP
 #define SPP_CAP 192
 #endif
@@ -529,10 +541,10 @@ spp_rowdots(const CsrDev &A, double2 cm, const double2 *__restrict__ xm, int nb2
       const double2 x0 = xm[soff[k]], x1 = xm[soff[k + 1]];
       if (HAS2) {
         const double2 a0 = sv2[k], a1 = sv2[k + 1], b0 = sv2[k + L], b1 = sv2[k + 1 + L];
-        ax += (a0.x + cm.x * a0.y) * x0.x;  ay += (a0.x + cm.y * a0.y) * x0.y;
-        bx += (b0.x + cm.x * b0.y) * x0.x;  by += (b0.x + cm.y * b0.y) * x0.y;
-        ax += (a1.x + cm.x * a1.y) * x1.x;  ay += (a1.x + cm.y * a1.y) * x1.y;
-        bx += (b1.x + cm.x * b1.y) * x1.x;  by += (b1.x + cm.y * b1.y) * x1.y;
+        ax = spp_acc(ax, cm.x, a0, x0.x);  ay = spp_acc(ay, cm.y, a0, x0.y);
+        bx = spp_acc(bx, cm.x, b0, x0.x);  by = spp_acc(by, cm.y, b0, x0.y);
+        ax = spp_acc(ax, cm.x, a1, x1.x);  ay = spp_acc(ay, cm.y, a1, x1.y);
+        bx = spp_acc(bx, cm.x, b1, x1.x);  by = spp_acc(by, cm.y, b1, x1.y);
       } else {
         const double a0 = sv1[k], a1 = sv1[k + 1], b0 = sv1[k + L], b1 = sv1[k + 1 + L];
         ax += a0 * x0.x;  ay += a0 * x0.y;  bx += b0 * x0.x;  by += b0 * x0.y;
@@ -543,8 +555,8 @@ spp_rowdots(const CsrDev &A, double2 cm, const double2 *__restrict__ xm, int nb2
       const double2 xv = xm[soff[k]];
       if (HAS2) {
         const double2 a = sv2[k], b = sv2[k + L];
-        ax += (a.x + cm.x * a.y) * xv.x;  ay += (a.x + cm.y * a.y) * xv.y;
-        bx += (b.x + cm.x * b.y) * xv.x;  by += (b.x + cm.y * b.y) * xv.y;
+        ax = spp_acc(ax, cm.x, a, xv.x);  ay = spp_acc(ay, cm.y, a, xv.y);
+        bx = spp_acc(bx, cm.x, b, xv.x);  by = spp_acc(by, cm.y, b, xv.y);
       } else {
         const double a = sv1[k], b = sv1[k + L];
         ax += a * xv.x;  ay += a * xv.y;  bx += b * xv.x;  by += b * xv.y;
@@ -629,8 +641,8 @@ k_cheb_step_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restr
   const double2 za = FIRST ? zero : z[sa_], zb = FIRST ? zero : z[sb_];
   if (valid) {
     const double rax = ra.x - a.x, ray = ra.y - a.y, rbx = rb.x - b.x, rby = rb.y - b.y;
-    const double dax = c1 * oa.x + c2 * da.x * rax, day = c1 * oa.y + c2 * da.y * ray;
-    const double dbx = c1 * ob.x + c2 * db.x * rbx, dby = c1 * ob.y + c2 * db.y * rby;
+    const double dax = spp_dir(c1, oa.x, c2, da.x, rax), day = spp_dir(c1, oa.y, c2, da.y, ray);
+    const double dbx = spp_dir(c1, ob.x, c2, db.x, rbx), dby = spp_dir(c1, ob.y, c2, db.y, rby);
     if (!LAST) {
       res[ta_] = make_double2(rax, ray);
       res[tb_] = make_double2(rbx, rby);

@@ -1133,3 +1133,35 @@ def test_schur_tensor_core_block_keeps_iterations_and_parity(cyl1, tc_ctx, f64_c
         for m in (0, 15):
             assert _rel(vs[k, :, m], o[ts[k]]['v'][inv, 0]) < 1e-8, (k, m)
             assert _rel(ps[k, :, m], o[ts[k]]['p'][:, 0]) < 1e-8, (k, m)
+
+
+def test_tiled_chebyshev_is_bit_identical(cyl1):
+    """k_cheb_step_tile (matrix entries, update operands and the unique x rows
+    of a tile all staged by TMA bulk copies, gathers from shared memory) keeps
+    the summation order of the row-pair kernel: a 64-member ensemble run is
+    bit-identical with DNSB_TILE=0 and =1, iteration counts included"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    nu0 = femp['nu']
+    A0 = sm['A']/nu0
+    nus = nu0*np.linspace(.5, 2., 64)
+    dt, nsteps = 1./512, 6
+    v0 = osnu.solve_nse(t0=0, tE=dt, Nts=1, start_ssstokes=True,
+                        return_vp_dict=True, **soldict(femp, sm, rhsd))[0.0]
+    out = {}
+    for flag in ('0', '1'):
+        c = _ctx_with_env('DNSB_TILE', flag)
+        integ = tiu.DeviceImex(sm['M'], A0, sm['J'], femp['V'], inv,
+                               femp['dbcinds'], femp['dbcvals'], dt, nus=nus,
+                               fp=rhsd['fp'], ctx=c)
+        U = np.broadcast_to((nus/nu0)[None, None, :], (nsteps + 1, 1, 64))
+        integ.set_forcing(rhsd['fv'], U)
+        integ.set_state(v0['v'][inv], v0['p'])
+        integ.run(nsteps, tol=1e-12)
+        out[flag] = integ.state() + (integ.stats()['iters'],)
+        integ.close()
+    assert out['0'][2] == out['1'][2]
+    assert np.array_equal(out['0'][0], out['1'][0])
+    assert np.array_equal(out['0'][1], out['1'][1])
