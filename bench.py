@@ -58,6 +58,10 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=12.)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-profile', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true',
+                    help='skip the secondary records (configs 1, 3, 4, dt = 1/512)')
+    ap.add_argument('--no-strong', action='store_true',
+                    help='N > 1: skip the strong-scaling record (64 members split over the GPUs)')
     ap.add_argument('--no-parity', action='store_true',
                     help='skip the CPU-oracle check of the measured trajectory')
     return ap.parse_args()
@@ -345,6 +349,217 @@ def workload_config(args, members_total, world):
 
 
 # --------------------------------------------------------------------------
+# secondary records: the other BASELINE configs, device + CPU + parity each
+# --------------------------------------------------------------------------
+def _cpu_single_worker(args):
+    """oracle CNAB (`tiu:23-145`) for ONE plain cylinder-wake trajectory;
+    returns (final v, final p, seconds per loop step)"""
+    (N, Re, dt, nsteps, v0, p0) = args
+    sys.stdout = sys.stderr
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from oracle.cconv import CConv
+    from oracle.snu import append_bcs_vec
+    from oracle import tiu as otiu
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=Re, scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=N))
+    V, inv = femp['V'], femp['invinds']
+    cc = CConv(V)
+    stamps = []
+
+    def appndbcs(v):
+        return append_bcs_vec(v, V.dim(), inv, femp['dbcinds'], femp['dbcvals'])
+
+    def f_vdp(vfull):
+        return -cc.convvec(np.asarray(vfull).reshape(-1))[inv].reshape(-1, 1)
+
+    def savevp(v, p, time=None):
+        stamps.append(__import__('time').perf_counter())
+    trange = dt*np.arange(nsteps + 1)
+    v, p, ff = otiu.cnab(trange=trange, inivel=v0.reshape(-1, 1), inip=p0.reshape(-1, 1),
+                         M=sm['M'], A=sm['A'], J=sm['J'], f_vdp=f_vdp, f_tdp=lambda t: rhsd['fv'],
+                         g_tdp=lambda t: rhsd['fp'], appndbcs=appndbcs, savevp=savevp)
+    # loop steps only (the LU factorisation sits between stamps 1 and 2)
+    per = (stamps[-1] - stamps[3])/max(len(stamps) - 4, 1) if len(stamps) > 5 else float('nan')
+    return v, p, per
+
+
+def _cpu_sweep_worker(args):
+    """oracle Picard + Newton sweeps with the trapezoidal rule (`snu:1304-1587`)"""
+    (N, Re, dt, nsteps, iniv, inip) = args
+    sys.stdout = sys.stderr
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from oracle import snu as osnu
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=Re, scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=N))
+    sd = dict(A=sm['A'], M=sm['M'], J=sm['J'], JT=sm['JT'], fv=rhsd['fv'], fp=rhsd['fp'], V=femp['V'],
+              invinds=femp['invinds'], dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'],
+              t0=0., tE=nsteps*dt, Nts=nsteps, iniv=iniv, inip=inip)
+    traj = osnu.solve_nse(return_dictofvelstrs=True, **sd)
+    t0 = time.perf_counter()
+    v, p = osnu.solve_nse(lin_vel_point=traj, treat_nonl_explicit=False, vel_pcrd_stps=1, vel_nwtn_stps=1,
+                          return_final_vp=True, **sd)
+    return v, p, (time.perf_counter() - t0)/(2.*nsteps)
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(np.ravel(a) - np.ravel(b))/np.linalg.norm(b))
+
+
+def ensemble_initial_state(info, nb):
+    """steady Stokes solution (`start_ssstokes`, snu:903-908) for the mean
+    viscosity, shared by the members of the shard; solved on the device
+    (velocity AMG + LSC Schur FGMRES)"""
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    sm, inv = info['sm'], np.asarray(info['femp']['invinds'])
+    NV = info['NV']
+    numean = float(np.mean(info['nus']))
+    Ast = numean*sm['A'] if info['Arob'] is None else \
+        numean*sm['A'] + info['Arob']
+    vp = lau.solve_sadpnt_smw(amat=Ast, jmat=sm['J'], jmatT=sm['JT'],
+                              rhsv=numean*info['B'][:, :1], rhsp=info['fp'],
+                              krylov='gmres', vgroups=(inv//2, inv % 2),
+                              mass_diag=sm['M'].diagonal(),
+                              krpslvprms=dict(tol=1e-10, maxiter=1500))
+    return np.repeat(vp[:NV], nb, axis=1), np.repeat(-vp[NV:], nb, axis=1)
+
+
+def secondary_records(args, ctx):
+    """BASELINE configs 1/3 (single trajectory, IMEX), 3 (Newton/CN sweeps), 4
+    (Krylov tolerance of `tests/time_dep_nse_krylov.py:4-7`) on cylinder_4 at
+    Re = 100, dt = 1/2048, and the headline ensemble at the reference script's
+    dt = 1/512 -- each with the device time, the CPU oracle's time on one host
+    core for the same work and the rel. L2 error against it."""
+    import multiprocessing as mp
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from dolfin_navier_scipy_b200 import ensemble as ens
+    N, Re, dt = args.mesh, 100., 1./args.nts
+    out = []
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=Re, scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=N))
+    inv = np.asarray(femp['invinds'])
+    NP, NV = sm['J'].shape
+    vp = lau.solve_sadpnt_smw(amat=sm['A'], jmat=sm['J'], jmatT=sm['JT'], rhsv=rhsd['fv'], rhsp=rhsd['fp'],
+                              krylov='gmres', vgroups=(inv//2, inv % 2), mass_diag=sm['M'].diagonal(),
+                              krpslvprms=dict(tol=1e-11, maxiter=1500))
+    v0 = vp[:NV]
+    p0 = snu.get_pfromv(v=v0, V=femp['V'], M=sm['M'], A=sm['M'], J=sm['J'], fv=rhsd['fv'], fp=rhsd['fp'],
+                        dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'], invinds=inv)
+    pool = mp.get_context('spawn').Pool(2)
+    nsingle, nsweep, nsweep_long = 48, 2, 24
+    vfull0 = snu.dts.append_bcs_vec(v0, V=femp['V'], invinds=inv, bcinds=femp['dbcinds'],
+                                    bcvals=femp['dbcvals'])
+    cpu_single = pool.apply_async(_cpu_single_worker, ((N, Re, dt, nsingle, v0, p0),))
+    cpu_sweep = pool.apply_async(_cpu_sweep_worker, ((N, Re, dt, nsweep, vfull0, p0),))
+    # ---- configs 1/3, IMEX part: one trajectory, tol 1e-12 and the Krylov tolerance 1e-3 ----
+    for tol, name in ((args.tol, 'single trajectory CNAB (configs 1/3, IMEX)'),
+                      (1e-3, 'single trajectory CNAB, Krylov tol 1e-3 (config 4, '
+                       'tests/time_dep_nse_krylov.py:4-7)')):
+        integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv, femp['dbcinds'], femp['dbcvals'],
+                               dt, fv=rhsd['fv'], fp=rhsd['fp'], ctx=ctx)
+        integ.set_state(v0, p0)
+        integ.run(nsingle, tol=tol, ntimeslices=0)
+        vd, pd = integ.state()
+        st0 = integ.stats()
+        integ.run(200, tol=tol, ntimeslices=0)      # throughput: later in the same trajectory
+        ms = integ.engine.last_run_ms()/200.
+        st = integ.stats()
+        integ.close()
+        out.append(dict(name=name, mesh='cylinder_%d' % N, Re=Re, dt='1/%d' % args.nts, tol=tol,
+                        dofs=NV + NP, ms_per_step=ms, value=(NV + NP)/(ms*1e-3), unit=UNIT,
+                        fgmres_iters_per_step=st['iters']/float(max(st['solves'], 1)),
+                        max_relres=max(st0['max_relres'], st['max_relres']), _vd=vd, _pd=pd))
+    # ---- config 3: Picard + Newton sweep with Crank-Nicolson ----
+    # parity on a short sweep (the CPU needs 1.5 s per sweep step), throughput on a longer one,
+    # timed around dnsb_cnsweep_run (upload of the linearisation trajectory, the device-resident
+    # sweep, download of the new trajectory); the host set-up of the solver is reported beside it
+    from dolfin_navier_scipy_b200 import _lib
+    sweep_calls = []
+    _run = _lib.CnSweep.run
+
+    def timed_run(self, *a, **k):
+        t = time.perf_counter()
+        res = _run(self, *a, **k)
+        sweep_calls.append(time.perf_counter() - t)
+        return res
+    sd = dict(A=sm['A'], M=sm['M'], J=sm['J'], JT=sm['JT'], fv=rhsd['fv'], fp=rhsd['fp'], V=femp['V'],
+              invinds=inv, dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'], t0=0., iniv=vfull0, inip=p0)
+    swkw = dict(treat_nonl_explicit=False, vel_pcrd_stps=1, vel_nwtn_stps=1, verbose=False)
+    traj = snu.solve_nse(return_dictofvelstrs=True, tE=nsweep*dt, Nts=nsweep, **sd)
+    vs, ps = snu.solve_nse(lin_vel_point=traj, return_final_vp=True, tE=nsweep*dt, Nts=nsweep,
+                           **dict(sd, **swkw))
+    trajl = snu.solve_nse(return_dictofvelstrs=True, tE=nsweep_long*dt, Nts=nsweep_long, **sd)
+    its = []
+    _lib.CnSweep.run = timed_run
+    try:
+        t0 = time.perf_counter()
+        snu.solve_nse(lin_vel_point=trajl, return_final_vp=True, tE=nsweep_long*dt, Nts=nsweep_long,
+                      krpslvprms=dict(convstatsl=its), **dict(sd, **swkw))
+        sweep_total = time.perf_counter() - t0
+    finally:
+        _lib.CnSweep.run = _run
+    sweep_ms = 1e3*sum(sweep_calls)/(len(sweep_calls)*nsweep_long)
+    # ---- CPU legs and parity ----
+    vo, po, per = cpu_single.get()
+    for k in (0, 1):
+        r = out[k]
+        vd, pd = r.pop('_vd'), r.pop('_pd')
+        r['cpu'] = dict(ms_per_step=1e3*per, cores=1, kind='port',
+                        sample='%d CNAB steps, SuperLU solve + compiled cell loop' % nsingle)
+        r['speedup_vs_1_core'] = 1e3*per/r['ms_per_step']
+        r['parity'] = dict(v_rel=_rel(vd, vo), p_rel=_rel(pd, po), steps=nsingle,
+                           note='relative residual 1e-3 (the reference script\'s setting): the recycled guesses already '
+                           'meet it, FGMRES does no iteration and the trajectory drifts -- a like-for-like timing, '
+                           'not a usable tolerance' if k else
+                           'bar 1e-8')
+    vso, pso, sper = cpu_sweep.get()
+    pool.close()
+    out.append(dict(name='Picard + Newton sweep with Crank-Nicolson (config 3, snu:1304-1587)',
+                    mesh='cylinder_%d' % N, Re=Re, dt='1/%d' % args.nts, steps=nsweep_long, sweeps=2,
+                    ms_per_sweep_step=sweep_ms,
+                    fgmres_iters_per_step=float(np.mean(its)) if its else None,
+                    call_seconds_with_host_setup=sweep_total,
+                    cpu=dict(ms_per_sweep_step=1e3*sper, cores=1, kind='port',
+                             sample='2 sweeps x %d steps: K1b in numpy + SuperLU factorisation '
+                             'per step' % nsweep),
+                    speedup_vs_1_core=1e3*sper/sweep_ms,
+                    parity=dict(v_rel=_rel(vs, vso), p_rel=_rel(ps, pso), steps=nsweep,
+                                note='final state of the short sweep, bar 1e-8')))
+    # ---- the headline ensemble at the reference script's step size ----
+    # dt = 1/512 (tests/time_dep_nse_bcrob.py:66 is written for cylinder_2); on cylinder_4 the
+    # explicit convection blows up there for the members of highest Re (SURVEY 8d: "halve dt until
+    # check_ff stays 0"): the record names the largest power-of-two step that integrates all members
+    nb = args.members
+    for nts in (512, 1024):
+        integ, info = ens.cylinder_ensemble(N=N, nmembers=nb, dt=1./nts, ntimes=200, ctx=ctx,
+                                            cheb_steps=args.cheb, schur_poly=args.schur_poly,
+                                            coarse_max=args.coarse_max)
+        NVe, NPe = info['NV'], info['NP']
+        integ.set_state(*ensemble_initial_state(info, nb))
+        rec = dict(name='headline ensemble at dt = 1/%d' % nts, members=nb)
+        try:
+            ff = integ.run(120, tol=args.tol, check_ff_maxv=1e8, ntimeslices=10)
+            if ff:
+                rec['blow_up'] = 'check_ff guard (tiu:94-103) tripped within 120 steps'
+            else:
+                integ.run(40, tol=args.tol, ntimeslices=0)
+                ms = integ.engine.last_run_ms()/40.
+                st = integ.stats()
+                rec.update(ms_per_step=ms, value=(NVe + NPe)*nb/(ms*1e-3), unit=UNIT,
+                           fgmres_iters_per_step=st['iters']/float(max(st['solves'], 1)),
+                           max_relres=st['max_relres'])
+        except Exception as ex:
+            rec['blow_up'] = repr(ex)[:200]
+        integ.close()
+        out.append(rec)
+        if 'ms_per_step' in rec:
+            break
+    return out
+
+
+# --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
@@ -368,21 +583,7 @@ def run_ours(args, rank, world, local_rank):
         dt=1./args.nts, ntimes=ntimes, ctx=ctx, cheb_steps=args.cheb,
         schur_poly=args.schur_poly, coarse_max=args.coarse_max)
     NV, NP, nb = info['NV'], info['NP'], integ.nb
-    # initial state: steady Stokes solution (`start_ssstokes`, snu:903-908) for
-    # the mean viscosity, shared by the members of the shard; solved on the
-    # device (velocity AMG + lumped Schur FGMRES)
-    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
-    sm, inv = info['sm'], np.asarray(info['femp']['invinds'])
-    numean = float(np.mean(info['nus']))
-    Ast = numean*sm['A'] if info['Arob'] is None else \
-        numean*sm['A'] + info['Arob']
-    vp = lau.solve_sadpnt_smw(amat=Ast, jmat=sm['J'], jmatT=sm['JT'],
-                              rhsv=numean*info['B'][:, :1], rhsp=info['fp'],
-                              krylov='gmres', vgroups=(inv//2, inv % 2),
-                              mass_diag=sm['M'].diagonal(),
-                              krpslvprms=dict(tol=1e-10, maxiter=1500))
-    v0 = np.repeat(vp[:NV], nb, axis=1)
-    p0 = np.repeat(-vp[NV:], nb, axis=1)
+    v0, p0 = ensemble_initial_state(info, nb)
     runkw = dict(tol=args.tol, guess=args.guess, ntimeslices=0, maxit=400)
 
     def barrier():
@@ -475,6 +676,31 @@ def run_ours(args, rank, world, local_rank):
     gram = dict(ns=int(G.shape[0]), trace=float(torch.trace(G)),
                 symmetric=bool(torch.allclose(G, G.T, rtol=1e-10, atol=0)))
 
+    # ---- strong scaling: the 64-member ensemble of BASELINE config 5 split over the GPUs ----
+    strong = None
+    if world > 1 and not args.no_strong and args.members % world == 0:
+        integ.close()
+        sint, sinfo = ens.cylinder_ensemble(
+            N=args.mesh, nmembers=args.members, rank=rank, world=world,
+            dt=1./args.nts, ntimes=ntimes, ctx=ctx, cheb_steps=args.cheb,
+            schur_poly=args.schur_poly, coarse_max=args.coarse_max)
+        sint.set_state(*ensemble_initial_state(sinfo, sint.nb))
+        sint.run(nwarm, **runkw)
+        barrier()
+        sint.run(args.steps, **runkw)
+        sms = sint.engine.last_run_ms()
+        barrier()
+        sst = sint.stats()
+        ts = torch.tensor([sms, sst['iters']/float(max(sst['solves'], 1))], dtype=torch.float64, device='cuda')
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = dict(scaling='strong', members_total=args.members, members_per_gpu=sint.nb,
+                      ms_per_step=float(ts[0])/args.steps,
+                      value=(NV + NP)*args.members*args.steps/(float(ts[0])*1e-3), unit=UNIT,
+                      fgmres_iters_per_step_max_over_ranks=float(ts[1]),
+                      note='the SAME 64 members as at N = 1, %d per GPU; device time, max over ranks; '
+                      'parallel efficiency = value / (N x the N = 1 value)' % sint.nb)
+        sint.close()
+
     if rank != 0:
         return None
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world,
@@ -499,6 +725,13 @@ def run_ours(args, rank, world, local_rank):
                             unconverged=st['unconverged'], finite=finite),
                 dofs_per_member=NV + NP, gram=gram)
     line['_parity_job'] = parity_job
+    if strong is not None:
+        line['strong'] = strong
+    if world == 1 and not args.no_secondary:
+        try:
+            line['secondary'] = secondary_records(args, ctx)
+        except Exception as ex:      # the headline must survive a failing side record
+            line['secondary'] = dict(error=repr(ex))
     if roofline is not None:
         line['roofline'] = roofline
         tot = sum(v[1] for v in kern.values())

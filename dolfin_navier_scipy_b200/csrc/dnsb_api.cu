@@ -1824,8 +1824,10 @@ static int solver_relmax(dnsb_solver *s, bool reset, double *out) {
   if (reset) DNSB_CK(ctx, s->grelmax.zero(ctx->stream));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   double mx = 0.0;
-  for (int m = 0; m < s->nb; ++m)
-    if (!(h[m] <= mx)) mx = h[m];
+  for (int m = 0; m < s->nb; ++m) {
+    if (h[m] != h[m]) { mx = h[m]; break; }   // NaN wins
+    if (h[m] > mx) mx = h[m];
+  }
   *out = mx;
   return 0;
 }
@@ -2848,7 +2850,7 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
       if (sv) {
         double r = 0.0;
         if (solver_relmax(sv, false, &r)) return -1;
-        if (!(r <= mx)) mx = r;
+        if (mx == mx && !(r <= mx)) mx = r;
         unc += sv->stat_unconverged;
       }
     e->last_relres = mx;
@@ -2857,6 +2859,14 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
   e->run_iters = e->sl->stat_iters - it0;
   e->run_solves = e->sl->stat_solves - ns0;
   DNSB_CK(ctx, cudaGetLastError());
+  if (e->last_relres != e->last_relres && !blown) {
+    // inf/NaN right-hand sides "converge" trivially (NaN compares false): a blown-up member with
+    // the guard of time_int_utils.py:94-103 switched off (ntimeslices = 0) must not pass silently
+    ctx->fail("a solve of this run had a non-finite residual: the state of at least one member has blown up "
+              "(run with the blow-up guard, ntimeslices > 0, to get the reference's ffflag instead)",
+              __FILE__, __LINE__);
+    return DNSB_E_NOT_CONVERGED;
+  }
   if (e->run_unconverged > 0 && !blown) {
     // the state is valid and can be read; the caller decides (the reference's
     // exact LU solve cannot fail this way, so the default is to refuse)

@@ -698,7 +698,7 @@ __device__ __forceinline__ void gmres_track(GmresState &S, int m, double res) {
   const double bn = S.bnorm[m];
   const double rel = bn > 0.0 ? res / bn : (res > 0.0 ? res : 0.0);
   const double old = S.relmax[m];
-  if (!(rel <= old)) S.relmax[m] = rel;
+  if (old == old && !(rel <= old)) S.relmax[m] = rel;   // a NaN, once recorded, stays
 }
 
 // members that hit maxit without reaching tol: their last residual counts

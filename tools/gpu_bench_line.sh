@@ -1,7 +1,7 @@
 #!/bin/bash
 # one-line summary of a bench run: tools/gpu_bench_line.sh <label> [bench args...]
 label=$1; shift
-timeout 300 python bench.py --no-cpu-baseline --no-profile "$@" 2>&1 | tail -1 > gpurun_out/bench_$label.json
+timeout 300 python bench.py --no-cpu-baseline --no-profile --no-secondary --no-parity "$@" 2>&1 | tail -1 > gpurun_out/bench_$label.json
 python - <<PY
 import json
 try:
