@@ -88,6 +88,7 @@ SIGNATURES = {
     'dnsb_imex_gram': (_i, [_vp, c_dbl_p]),
     'dnsb_imex_unconverged': (_ll, [_vp]),
     'dnsb_cnsweep_stats': (_i, [_vp, c_dbl_p, ctypes.POINTER(_ll)]),
+    'dnsb_cnsweep_set_guess': (_i, [_vp, _i]),
 }
 
 E_NOT_CONVERGED = -3
@@ -657,6 +658,12 @@ class CnSweep(object):
             _dp(p0), float(tol), int(maxit), _dp(vtraj), _dp(ptraj),
             ctypes.byref(nrm), ctypes.byref(its)))
         return vtraj, ptraj, nrm.value, its.value
+
+    def set_guess(self, krylovini):
+        """``'old'``: previous solution, ``'upd'`` / None: extrapolation
+        (`snu:1493-1503`)"""
+        mode = dict(old=0, upd=1)[krylovini or 'upd']
+        self.ctx.check(self.ctx.lib.dnsb_cnsweep_set_guess(self.h, mode))
 
     def stats(self):
         rr, unc = ctypes.c_double(0.), _ll(0)

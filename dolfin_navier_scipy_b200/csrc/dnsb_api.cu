@@ -1979,6 +1979,7 @@ struct dnsb_cnsweep {
   DBuf<double> npart, nout;
   double max_relres = 0;      // of the last sweep (all step solves)
   long long unconverged = 0;
+  int guess_mode = 1;         // 0: previous solution ('old'), 1: linear extrapolation ('upd')
 };
 
 extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double *mvals,
@@ -2135,7 +2136,7 @@ extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, 
     DNSB_CK(ctx, cudaMemcpyAsync(w->b.p + nv, w->fp.p, np * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     // initial guess: linear extrapolation 2 x_{n-1} - x_{n-2} of the saddle
     // solutions (the reference's `krylovini='upd'`, snu:1496-1501)
-    if (n >= 3 && dts[n - 1] == dts[n - 2]) {
+    if (w->guess_mode == 1 && n >= 3 && dts[n - 1] == dts[n - 2]) {
       LAUNCH(ctx, k_axpby, cdiv((size_t)(nv + np), 256), 256, 0, 2.0, (const double *)w->x.p, -1.0,
              (const double *)w->xprev.p, w->xguess.p, (size_t)(nv + np));
       DNSB_CK(ctx, cudaMemcpyAsync(w->xprev.p, w->x.p, (nv + np) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -2179,6 +2180,13 @@ extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, 
     ctx->fail(msg, __FILE__, __LINE__);
     return DNSB_E_NOT_CONVERGED;
   }
+  return 0;
+}
+
+extern "C" int dnsb_cnsweep_set_guess(dnsb_cnsweep *w, int mode) {
+  if (!w) return -2;
+  DNSB_REQUIRE(w->ctx, mode == 0 || mode == 1, "guess mode: 0 (previous solution) or 1 (extrapolation)");
+  w->guess_mode = mode;
   return 0;
 }
 

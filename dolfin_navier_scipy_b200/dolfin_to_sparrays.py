@@ -20,35 +20,68 @@ __all__ = ['unroll_dlfn_dbcs', 'get_stokessysmats', 'get_convmats',
            'append_bcs_vec', 'expand_vp', 'setget_rhs']
 
 
+class _Dirichlet(object):
+    """index maps of one Dirichlet condensation
+
+    ``n`` full unknowns split into prescribed positions (``idx``, value
+    ``val``; a position listed twice keeps its LAST value, `dts:534-535`) and
+    the free ones (``free``, ascending).  The three things every helper below
+    needs follow from that: the lifting ``g`` (boundary values, zero elsewhere),
+    restriction to the free rows/columns and the load ``-(A g)[free]``.
+    """
+
+    def __init__(self, n, idx=(), val=(), free=None):
+        self.n = int(n)
+        self.idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        self.val = np.asarray(val, dtype=float).reshape(-1)
+        if free is None:
+            mask = np.ones(self.n, dtype=bool)
+            mask[self.idx] = False
+            free = np.flatnonzero(mask).astype(np.int32)
+        self.free = free
+
+    @staticmethod
+    def flat(groups_idx, groups_val):
+        """``[[i..], [j..]], [[a..], [b..]]`` -> one index and one value list"""
+        if groups_idx is None or len(groups_idx) == 0:
+            return [], []
+        if isinstance(groups_idx[0], (list, np.ndarray)):
+            return ([i for grp in groups_idx for i in grp],
+                    [v for grp in groups_val for v in grp])
+        return groups_idx, groups_val
+
+    def lifting(self):
+        g = np.zeros((self.n, 1))
+        g[self.idx, 0] = self.val          # fancy assignment: last write wins
+        return g
+
+    def load(self, mat, rows=True):
+        """``-(mat g)``, restricted to the free rows if ``rows``"""
+        f = -(mat@self.lifting())
+        return f[self.free, :] if rows else f
+
+
 def unroll_dlfn_dbcs(diribclist, bcinds=None, bcvals=None):
     """flatten (lists of) Dirichlet indices/values (`dts:27-46`)"""
     if diribclist is not None:
         raise NotImplementedError('dolfin DirichletBC objects need dolfin; '
                                   'pass `dbcinds`/`dbcvals`')
-    urbcinds, urbcvals = [], []
-    if bcinds is None or len(bcinds) == 0:
-        pass
-    elif not isinstance(bcinds[0], (list, np.ndarray)):
-        urbcinds, urbcvals = bcinds, bcvals
-    else:
-        for k, cbci in enumerate(bcinds):
-            urbcinds.extend(cbci)
-            urbcvals.extend(bcvals[k])
-    return urbcinds, urbcvals
+    return _Dirichlet.flat(bcinds, bcvals)
 
 
 def append_bcs_vec(vvec, V=None, vdim=None,
                    bcinds=None, bcvals=None,
                    invinds=None, diribcs=None, **kwargs):
-    """append boundary values to a vector of inner nodes (`dts:49-64`)"""
-    if vdim is None:
-        vdim = V.dim()
-    vwbcs = np.full((vdim, 1), np.nan)
-    cbcinds, cbcvals = unroll_dlfn_dbcs(diribcs, bcinds=bcinds, bcvals=bcvals)
-    vwbcs[invinds] = np.asarray(vvec).reshape(-1, 1)
-    if len(cbcinds) > 0:
-        vwbcs[cbcinds, 0] = cbcvals
-    return vwbcs
+    """append boundary values to a vector of inner nodes (`dts:49-64`)
+
+    Positions that are neither inner nor prescribed come back as NaN, like in
+    the reference."""
+    idx, val = unroll_dlfn_dbcs(diribcs, bcinds=bcinds, bcvals=bcvals)
+    full = np.full((V.dim() if vdim is None else vdim, 1), np.nan)
+    full[invinds] = np.asarray(vvec).reshape(-1, 1)
+    if len(idx) > 0:
+        full[np.asarray(idx), 0] = val
+    return full
 
 
 def expand_vp(vc=None, pc=None, V=None, Q=None, invinds=None,
@@ -129,75 +162,60 @@ def condense_sysmatsbybcs(stms, velbcs=None, dbcinds=None, dbcvals=None,
                           invinds=None,
                           mergerhs=False, rhsdict=None, ret_unrolled=False,
                           get_rhs_only=False):
-    """resolve the Dirichlet BCs, condense to the inner nodes (`dts:475-573`)"""
+    """resolve the Dirichlet BCs, condense to the inner nodes (`dts:475-573`)
+
+    Returns ``(stokesmatsc, rhsvecsbc, invinds, bcinds, bcvals)`` [or the
+    unrolled tuple / only the right-hand sides] with the reference's meaning.
+    """
     if velbcs is not None:
         raise NotImplementedError('dolfin DirichletBC objects need dolfin')
-    bcinds, bcvals = dbcinds, dbcvals
-    nv = stms['A'].shape[0]
-    if invinds is None:
-        invinds = np.setdiff1d(np.arange(nv), bcinds).astype(np.int32)
-    auxu = np.zeros((nv, 1))
-    if len(bcinds) > 0:
-        auxu[bcinds, 0] = bcvals
-    fvbc = - stms['A'] * auxu
-    fpbc = - stms['J'] * auxu
-    fvbc = fvbc[invinds, :]
-    if get_rhs_only:
-        if mergerhs:
-            return {'fv': rhsdict['fv'][invinds, :] + fvbc,
-                    'fp': rhsdict['fp'] + fpbc}
-        else:
-            return {'fv': fvbc, 'fp': fpbc}
-    Mc = stms['M'][invinds, :][:, invinds]
-    Ac = stms['A'][invinds, :][:, invinds]
-    Jc = stms['J'][:, invinds]
-    JTc = stms['JT'][invinds, :]
-    bcvals = auxu[bcinds]
-    stokesmatsc = {'M': Mc, 'A': Ac, 'JT': JTc, 'J': Jc, 'MP': stms['MP']}
+    dbc = _Dirichlet(stms['A'].shape[0], dbcinds, dbcvals, free=invinds)
+    rhs = {'fv': dbc.load(stms['A']), 'fp': dbc.load(stms['J'], rows=False)}
     if mergerhs:
-        rhsvecsbc = {'fv': rhsdict['fv'][invinds, :] + fvbc,
-                     'fp': rhsdict['fp'] + fpbc}
-    else:
-        rhsvecsbc = {'fv': fvbc, 'fp': fpbc}
+        rhs = {'fv': rhsdict['fv'][dbc.free, :] + rhs['fv'],
+               'fp': rhsdict['fp'] + rhs['fp']}
+    if get_rhs_only:
+        return rhs
+    fr = dbc.free
+    mats = {'M': stms['M'][fr, :][:, fr], 'A': stms['A'][fr, :][:, fr],
+            'JT': stms['JT'][fr, :], 'J': stms['J'][:, fr], 'MP': stms['MP']}
     if ret_unrolled:
-        return (Mc, Ac, JTc, Jc, stms['MP'], rhsvecsbc['fv'], rhsvecsbc['fp'],
-                invinds)
-    else:
-        return stokesmatsc, rhsvecsbc, invinds, bcinds, bcvals
+        return (mats['M'], mats['A'], mats['JT'], mats['J'], mats['MP'],
+                rhs['fv'], rhs['fp'], fr)
+    return mats, rhs, fr, dbcinds, dbc.lifting()[dbcinds]
 
 
 def condense_velmatsbybcs(A, velbcs=None, return_bcinfo=False,
                           invinds=None, dbcinds=None, dbcvals=None,
                           vwithbcs=None, get_rhs_only=False,
                           columnsonly=False):
-    """condense a velocity matrix, rhs contribution of the BCs (`dts:576-642`)"""
-    bcinds = None
+    """condense a velocity matrix, rhs contribution of the BCs (`dts:576-642`)
+
+    The boundary data come either as index/value lists or as a full vector
+    ``vwithbcs`` whose inner part is ignored.  ``columnsonly``: ``A`` acts on
+    full velocities but its rows are something else (e.g. ``J``).
+    """
+    ncols = A.shape[1] if columnsonly else A.shape[0]
     if vwithbcs is not None:
-        bcsv = np.copy(vwithbcs)
-        bcsv[invinds] = 0
+        lift = np.array(vwithbcs, dtype=float).reshape(ncols, -1)
+        lift[invinds] = 0.
+        dbc = _Dirichlet(ncols, free=invinds)
+        load_full = -(A@lift)
+        bnd = None
     else:
-        nv = A.shape[0] if not columnsonly else A.shape[1]
-        bcinds, bcvals = unroll_dlfn_dbcs(velbcs, bcinds=dbcinds,
-                                          bcvals=dbcvals)
-        bcsv = np.zeros((nv, 1))
-        if len(bcinds) > 0:
-            bcsv[bcinds, 0] = bcvals
-    fvbc = - A * bcsv
-    if invinds is None:
-        ininds = np.setdiff1d(np.arange(nv), bcinds).astype(np.int32)
-    else:
-        ininds = invinds
+        bnd, val = unroll_dlfn_dbcs(velbcs, bcinds=dbcinds, bcvals=dbcvals)
+        dbc = _Dirichlet(ncols, bnd, val, free=invinds)
+        load_full = dbc.load(A, rows=False)
+    fr = dbc.free
     if get_rhs_only:
-        return fvbc[ininds, :]
+        return load_full[fr, :]
     if columnsonly:
-        Ac = A[:, ininds]
+        Ac, load = A[:, fr], load_full
     else:
-        Ac = A[ininds, :][:, ininds]
-        fvbc = fvbc[ininds, :]
+        Ac, load = A[fr, :][:, fr], load_full[fr, :]
     if return_bcinfo:
-        return Ac, fvbc, dict(ininds=ininds, bcinds=bcinds)
-    else:
-        return Ac, fvbc
+        return Ac, load, dict(ininds=fr, bcinds=bnd)
+    return Ac, load
 
 
 def _full_velocity(V, u0_vec, invinds, dbcinds, dbcvals):

@@ -83,6 +83,41 @@ class SadpntOperator(object):
         self.solver.close()
 
 
+def _solve_smw(amat, jmat, rhsv, jmatT, rhsp, umat, vmat, krylov, krpslvprms,
+               vgroups, mass_diag, cache):
+    """``[[amat + umat vmat, jmatT], [jmat, 0]] x = b`` by Sherman-Morrison-
+    Woodbury (the `smw` of the reference's `solve_sadpnt_smw`, call site
+    `snu:1505-1512`): with ``K = [[amat, jmatT], [jmat, 0]]`` and the padded
+    factors ``U = [umat; 0]``, ``V = [vmat, 0]``,
+
+        x = y - Z (I + V Z)^-1 V y,    K y = b,   K Z = U,
+
+    one batched device solve for the ``1 + rank`` columns of ``[b, U]``."""
+    NP, NV = jmat.shape
+    U = np.asarray(umat.todense() if sps.issparse(umat) else umat,
+                   dtype=float).reshape(NV, -1)
+    V = sps.csr_matrix(vmat) if sps.issparse(vmat) else \
+        np.asarray(vmat, dtype=float).reshape(-1, NV)
+    rhsv = np.asarray(rhsv, dtype=float).reshape(NV, -1)
+    nrhs, rank = rhsv.shape[1], U.shape[1]
+    bp = np.zeros((NP, nrhs)) if rhsp is None else \
+        np.asarray(rhsp, dtype=float).reshape(NP, nrhs)
+    op = SadpntOperator(sps.csr_matrix(amat), sps.csr_matrix(jmat), jmatT,
+                        ncols=nrhs + rank, vgroups=vgroups,
+                        mass_diag=mass_diag, cache=cache)
+    tol = krpslvprms.get('tol', 1e-12) if krylov is not None else 1e-12
+    maxit = krpslvprms.get('maxiter', 800) if krylov is not None else 800
+    try:
+        sol = op.solve(np.hstack([rhsv, U]),
+                       np.hstack([bp, np.zeros((NP, rank))]), tol=tol,
+                       maxit=maxit)
+    finally:
+        op.close()
+    y, Z = sol[:, :nrhs], sol[:, nrhs:]
+    small = np.eye(rank) + V@Z[:NV]
+    return y - Z@np.linalg.solve(small, V@y[:NV])
+
+
 def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
                      rhsp=None, umat=None, vmat=None, krylov=None,
                      krpslvprms={}, krplsprms={}, return_alu=False,
@@ -100,11 +135,15 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
     unknowns for the vector AMG), ``mass_diag`` (diagonal of the velocity mass
     matrix for the LSC Schur approximation of stiffness dominated systems),
     ``cache`` (dict that carries the host-side hierarchies through a
-    Picard/Newton sequence).  Low-rank updates (``umat``,
-    ``vmat``) and ``decouplevp`` are outside the hot path and not supported.
+    Picard/Newton sequence).  Low-rank updates ``amat + umat @ vmat`` go
+    through the Sherman-Morrison-Woodbury formula on one batched device solve;
+    ``decouplevp`` (a different algorithm, off the hot path) is not supported.
     """
-    if umat is not None or vmat is not None:
-        raise NotImplementedError('Sherman-Morrison-Woodbury updates')
+    if (umat is None) != (vmat is None):
+        raise ValueError('`umat` and `vmat` come together')
+    if umat is not None:
+        return _solve_smw(amat, jmat, rhsv, jmatT, rhsp, umat, vmat, krylov,
+                          krpslvprms, vgroups, mass_diag, cache)
     if decouplevp:
         raise NotImplementedError('decoupled v/p solves')
     NP, NV = jmat.shape

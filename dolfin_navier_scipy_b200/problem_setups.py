@@ -354,86 +354,69 @@ def get_sysmats(problem='gen_bccont', scheme=None, ppin=None,
     ``meshparams['assemble_on_device']`` (extension) assembles the cell
     integrals of M, A, J, MP on the GPU (`dts.get_stokessysmats(device=True)`).
     """
-    problemdict = dict(drivencavity=drivcav_fems,
-                       cylinderwake=cyl_fems,
-                       gen_bccont=gen_bccont_fems)
-    meshparams = dict(meshparams)
-    if problem == 'cylinderwake' or problem == 'gen_bccont':
-        meshparams.update(dict(inflowvel=charvel))
+    # ---- which geometry, with which mesh arguments ---------------------------
+    geo = dict(meshparams)
+    if problem in ('cylinderwake', 'gen_bccont', 'cylinder_rot'):
+        geo['inflowvel'] = charvel
     if problem == 'drivencavity':
-        meshparams = dict(N=meshparams['N'])
-    if problem == 'cylinder_rot':
-        problemfem = gen_bccont_fems
-        meshparams.update(dict(movingwallcntrl=True))
-        meshparams.update(dict(inflowvel=charvel))
+        builder, geo = drivcav_fems, dict(N=geo['N'])
+    elif problem == 'cylinder_rot':
+        builder = gen_bccont_fems
+        geo['movingwallcntrl'] = True
+    elif problem == 'cylinderwake':
+        builder = cyl_fems
+    elif problem == 'gen_bccont':
+        builder = gen_bccont_fems
     else:
-        problemfem = problemdict[problem]
-
-    femp = problemfem(scheme=scheme, bccontrol=bccontrol, **meshparams)
+        raise KeyError(problem)
+    femp = builder(scheme=scheme, bccontrol=bccontrol, **geo)
     if onlymesh:
         return femp
 
-    if Re is not None:
-        nu = charvel*femp['charlen']/Re
-    else:
-        Re = charvel*femp['charlen']/nu
+    # ---- Reynolds number <-> viscosity (`dnsps:138-141`) ---------------------
+    scale = charvel*femp['charlen']
+    nu, Re = (scale/Re, Re) if Re is not None else (nu, scale/nu)
 
-    if bccontrol:
-        cbshapefuns = femp['contrbcsshapefuns']
-        cbmasks = femp.get('contrbcsmasks', femp.get('cntrbcsds'))
-    else:
-        cbshapefuns, cbmasks = None, None
-    outflowds = femp.get('outflowds', None)
+    # ---- uncondensed operators ----------------------------------------------
+    full = dts.get_stokessysmats(
+        femp['V'], femp['Q'], nu, gradvsymmtrc=gradvsymmtrc,
+        outflowds=femp.get('outflowds', None), bccontrol=bccontrol,
+        cbshapefuns=femp['contrbcsshapefuns'] if bccontrol else None,
+        cbds=femp.get('contrbcsmasks', femp.get('cntrbcsds'))
+        if bccontrol else None,
+        device=bool(geo.get('assemble_on_device', False)))
+    body = dict(fv=np.array(femp['fv'], dtype=float),
+                fp=np.array(femp['fp'], dtype=float))
 
-    stokesmats = dts.get_stokessysmats(femp['V'], femp['Q'], nu,
-                                       cbds=cbmasks,
-                                       gradvsymmtrc=gradvsymmtrc,
-                                       outflowds=outflowds,
-                                       cbshapefuns=cbshapefuns,
-                                       bccontrol=bccontrol,
-                                       device=bool(meshparams.get(
-                                           'assemble_on_device', False)))
-    rhsd_vf = dict(fv=np.array(femp['fv'], dtype=float),
-                   fp=np.array(femp['fp'], dtype=float))
-
+    # ---- pressure pin (`dnsps:171-184`) --------------------------------------
     if problem == 'cylinderwake':
-        logging.debug('cylinderwake: pressure need not be pinned')
-        if ppin is not None:
+        if ppin is not None:      # outflow boundary: p is fixed by the do-nothing condition
             raise UserWarning('pinning the p will give wrong results')
-    elif ppin is None:
-        logging.debug('pressure is not pinned - ' +
-                      '`J` may be singular for internal flow')
     elif ppin == -1:
-        stokesmats['J'] = stokesmats['J'][:-1, :][:, :]
-        stokesmats['JT'] = stokesmats['JT'][:, :-1][:, :]
-        rhsd_vf['fp'] = rhsd_vf['fp'][:-1, :]
+        full['J'], full['JT'] = full['J'][:-1, :], full['JT'][:, :-1]
+        body['fp'] = body['fp'][:-1, :]
         logging.info('pressure pinned at last dof `-1`')
-    else:
+    elif ppin is not None:
         raise NotImplementedError('Cannot pin `p` other than at `-1`')
-
-    (stokesmatsc, rhsd_stbc, invinds, _, _) = \
-        dts.condense_sysmatsbybcs(stokesmats, dbcinds=femp['dbcinds'],
-                                  dbcvals=femp['dbcvals'])
-    stokesmatsc.update({'Jfull': stokesmats['J'], 'Afull': stokesmats['A'],
-                        'Mfull': stokesmats['M'], 'JTfull': stokesmats['JT']})
-
-    rhsd_vfrc = dict(fp=rhsd_vf['fp'], fv=rhsd_vf['fv'][invinds, ])
-    if bccontrol:
-        Arob, fvrob = dts.condense_velmatsbybcs(stokesmats['amatrob'],
-                                                dbcinds=femp['dbcinds'],
-                                                dbcvals=femp['dbcvals'])
-        if np.linalg.norm(fvrob) > 1e-15:
-            raise UserWarning('diri and control bc must not intersect')
-        Brob = stokesmats['bmatrob'][invinds, :]
-        stokesmatsc.update({'Brob': Brob, 'Arob': Arob})
-
-    femp.update({'invinds': invinds, 'ppin': ppin})
-    femp.update({'nu': nu})
-    femp.update({'Re': Re})
-
-    if mergerhs:
-        rhsd = dict(fv=rhsd_vfrc['fv']+rhsd_stbc['fv'],
-                    fp=rhsd_vfrc['fp']+rhsd_stbc['fp'])
-        return femp, stokesmatsc, rhsd
     else:
-        return femp, stokesmatsc, rhsd_vfrc, rhsd_stbc
+        logging.debug('pressure is not pinned - `J` may be singular for '
+                      'internal flow')
+
+    # ---- Dirichlet condensation ----------------------------------------------
+    inner_mats, bc_rhs, inner, _, _ = dts.condense_sysmatsbybcs(
+        full, dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'])
+    for key in ('J', 'A', 'M', 'JT'):
+        inner_mats[key + 'full'] = full[key]
+    if bccontrol:
+        arob, arob_load = dts.condense_velmatsbybcs(
+            full['amatrob'], dbcinds=femp['dbcinds'], dbcvals=femp['dbcvals'])
+        if np.linalg.norm(arob_load) > 1e-15:
+            raise UserWarning('diri and control bc must not intersect')
+        inner_mats['Arob'], inner_mats['Brob'] = arob, full['bmatrob'][inner, :]
+    femp.update(invinds=inner, ppin=ppin, nu=nu, Re=Re)
+
+    body_inner = dict(fv=body['fv'][inner, ], fp=body['fp'])
+    if mergerhs:
+        return femp, inner_mats, dict(fv=body_inner['fv'] + bc_rhs['fv'],
+                                      fp=body_inner['fp'] + bc_rhs['fp'])
+    return femp, inner_mats, body_inner, bc_rhs

@@ -49,16 +49,9 @@ def m_innerproduct(M, v1, v2=None):
     return np.dot(v1.T, M*v2)
 
 
-def _reject_unsupported(diricontbcinds=None, closed_loop=False,
-                        paraviewoutput=False, fvtvd=None,
-                        use_custom_nonlinearity=False, **kw):
+def _reject_unsupported(diricontbcinds=None, **kw):
     if diricontbcinds not in (None, []):
         raise NotImplementedError('Dirichlet control boundaries')
-    if closed_loop:
-        raise NotImplementedError('closed-loop feedback')
-    if fvtvd is not None or use_custom_nonlinearity:
-        raise NotImplementedError('state dependent Python callbacks cannot '
-                                  'run inside the device loop')
 
 
 def get_v_conv_conts(vvec=None, V=None,
@@ -246,6 +239,10 @@ def solve_nse(A=None, M=None, J=None, JT=None,
               N=None, nu=None,
               ppin=None,
               closed_loop=False,
+              static_feedback=False,
+              dynamic_feedback=False, dyn_fb_dict={},
+              dyn_fb_disc='trapezoidal',
+              b_mat=None,
               vel_nwtn_stps=20, vel_nwtn_tol=5e-15,
               nsects=1, loc_nwtn_tol=5e-15, loc_pcrd_stps=True,
               addfullsweep=False,
@@ -280,13 +277,17 @@ def solve_nse(A=None, M=None, J=None, JT=None,
     an IMEX run).  Extra keywords: ``lin_tol`` (FGMRES relative residual),
     ``guess`` (initial-guess mode of ``dnsb_imex_run``), ``cheb_steps``.
     """
-    _reject_unsupported(diricontbcinds=diricontbcinds, closed_loop=closed_loop,
-                        fvtvd=fvtvd,
-                        use_custom_nonlinearity=use_custom_nonlinearity)
+    _reject_unsupported(diricontbcinds=diricontbcinds)
     if fv_tmdp is not None:
         raise DeprecationWarning()
     if nsects != 1 or addfullsweep:
-        raise NotImplementedError('time sections (`nsects`)')
+        # dead at HEAD: the second section looks its linearisation point up in
+        # the dict of the first one and dies with `KeyError: None`
+        # (`snu:1425-1431`; tests/test_reference_pin.py::
+        # test_live_reference_time_sections_are_broken_at_head)
+        raise NotImplementedError(
+            'time sections (`nsects` > 1, `addfullsweep`) fail in the '
+            'reference itself (`KeyError` at `stokes_navier_utils.py:1428`)')
     # argument combinations are checked BEFORE any device work
     if lin_vel_point is None:
         if time_int_scheme not in ('cnab', 'sbdf2'):
@@ -368,8 +369,51 @@ def solve_nse(A=None, M=None, J=None, JT=None,
 
         def _svpplz(vvec, pvec, time=None):
             vp_dict.update({float(time): dict(p=pvec, v=vvec)})
+        # ---- opaque callbacks: per-step host hop (`snu:1129-1140,1207-1247`) --
+        if fvtvd is not None or use_custom_nonlinearity or closed_loop:
+            if use_custom_nonlinearity:
+                def nonlvfunc(vfull):      # minus: it goes to the rhs (`snu:1131`)
+                    return -custom_nonlinear_vel_function(vfull)
+            else:
+                def nonlvfunc(vfull):
+                    return -dts.get_convvec(V=V, u0_vec=vfull, invinds=invinds)
+            dynamic_rhs = None
+            if closed_loop and dynamic_feedback:
+                if dyn_fb_disc != 'AB2':
+                    # `snu:1212-1222` builds `implicit_dynamic_rhs` for the
+                    # trapezoidal observer but never hands it to the integrator
+                    raise NotImplementedError(
+                        "dyn_fb_disc={0!r}: only 'AB2' reaches the integrator "
+                        "at HEAD (`snu:1224-1234`)".format(dyn_fb_disc))
+                dfb = dyn_fb_dict
+                observer = tiu.get_heunab_lti(hb=dfb['hb'], ha=dfb['ha'],
+                                              hc=dfb['hc'], inihx=dfb['inihx'],
+                                              drift=dfb['drift'])
+
+                def dynamic_rhs(t, vc=None, memory={}, mode=None):
+                    curu, memory = observer(t, vc=cv_mat.dot(vc),
+                                            memory=memory, mode=mode)
+                    return b_mat.dot(curu), memory
+            elif closed_loop and static_feedback:
+                raise NotImplementedError('static feedback enters through the '
+                                          'Newton sweeps (`snu:1367-1383`)')
+            timintsc = dict(cnab=tiu.cnab, sbdf2=tiu.sbdftwo)[time_int_scheme]
+            v_end, p_end, ffflag = timintsc(
+                trange=trange, inivel=iniv, inip=inip, M=M, A=A, J=J,
+                scalep=-1., f_vdp=nonlvfunc, f_tvdp=fvtvd,
+                f_tdp=(lambda t: fv) if fvtd is None else
+                (lambda t: fv + np.asarray(fvtd(t)).reshape(cnv, 1)),
+                g_tdp=lambda t: fp, dynamic_rhs=dynamic_rhs,
+                appndbcs=lambda vvec, bcs: _appbcs(vvec), savevp=_svpplz,
+                check_ff_maxv=check_ff_maxv, tol=lin_tol)
+            f_tdp = fvc = None
+            hosthop_done = True
+        else:
+            hosthop_done = False
         scheme = time_int_scheme
-        if f_tdp is None:
+        if hosthop_done:
+            pass
+        elif f_tdp is None:
             # constant rhs: hand it over as `fv` (no sampling needed)
             integ = tiu.DeviceImex(M, A, J, V, invinds, dbcinds, dbcvals,
                                    trange[1] - trange[0], scheme=scheme,
@@ -494,6 +538,7 @@ def solve_nse(A=None, M=None, J=None, JT=None,
         dev.bind()
         sweep = _lib.CnSweep(op.solver, mmat, Mv, Av, src, convpos, invinds,
                              bci, bcv, fv, fp, nvf)
+        sweep.set_guess(krpslvprms.get('krylovini', None))
     while newtk < vel_nwtn_stps and norm_nwtnupd > vel_nwtn_tol:
         if vel_pcrd_stps > 0:
             vel_pcrd_stps -= 1

@@ -19,7 +19,7 @@ from . import _lib
 from . import hostsetup
 
 __all__ = ['cnab', 'sbdftwo', 'semi_implicit_euler', 'DeviceImex',
-           'lowrank_forcing']
+           'lowrank_forcing', 'get_heunab_lti', 'get_heuntrpz_lti']
 
 _THETA = dict(cnab=.5, sbdf2=2./3, imexeuler=1.)
 
@@ -278,19 +278,103 @@ def _run_imex(scheme, trange=None, inivel=None, inip=None, M=None, A=None,
     return v_n, p_n, ffflag
 
 
+def _needs_host_hop(kw):
+    """opaque callbacks (`tiu:23-38`: ``f_vdp``, ``f_tvdp``, ``dynamic_rhs``,
+    ``getbcs`` / ``applybcs``) cannot run inside the CUDA loop"""
+    if callable(kw.get('f_vdp', 'convection')) or \
+            kw.get('f_vdp', 'convection') is None:
+        return True
+    if any(kw.get(k) is not None for k in ('f_tvdp', 'dynamic_rhs', 'getbcs',
+                                           'applybcs')):
+        return True
+    return kw.get('V') is None
+
+
 def cnab(**kw):
-    """Crank-Nicolson/Adams-Bashforth on the device -- `tiu:23-145`
+    """Crank-Nicolson/Adams-Bashforth -- `tiu:23-145`
 
     ``cnab(trange=, inivel=, inip=, M=, A=, J=, f_tdp=, g_tdp=, V=, invinds=,
-    dbcinds=, dbcvals=, savevp=, check_ff_maxv=, ntimeslices=)`` returns
-    ``(v_n, p_n, ffflag)`` like the reference.
+    dbcinds=, dbcvals=, savevp=, check_ff_maxv=, ntimeslices=)`` runs the whole
+    loop on the device (the convection is the P2 form of ``V``) and returns
+    ``(v_n, p_n, ffflag)`` like the reference.  With the reference's callback
+    arguments (``f_vdp`` callable or ``None`` = no nonlinearity, ``f_tvdp``,
+    ``dynamic_rhs``, ``getbcs``/``applybcs``/``appndbcs``) the loop runs on the
+    host with every solve on the device (`hosthop.imex_with_callbacks`).
     """
+    if _needs_host_hop(kw):
+        from . import hosthop
+        return hosthop.imex_with_callbacks('cnab', **kw)
     return _run_imex('cnab', **kw)
 
 
 def sbdftwo(**kw):
-    """SBDF2 on the device -- `tiu:260-355`"""
+    """SBDF2 -- `tiu:260-355` (device loop or host hop like `cnab`)"""
+    if _needs_host_hop(kw):
+        from . import hosthop
+        return hosthop.imex_with_callbacks('sbdf2', **kw)
     return _run_imex('sbdf2', **kw)
+
+
+def get_heunab_lti(hb=None, ha=None, hc=None, inihx=None, drift=None):
+    """Heun/AB2 discretisation of a linear observer ``hx' = ha hx + hb y +
+    drift(t)``, ``u = hc hx`` as a ``dynamic_rhs`` callback (`tiu:148-198`)
+
+    The returned function is called by the integrators with
+    ``mode in {'init', 'heunpred', 'heuncorr', 'abtwo'}`` and threads its state
+    through ``memory`` exactly like the reference's.
+    """
+    def f(x, y, t):
+        return ha@x + hb@y + drift(t)
+
+    def observer(t, vc=None, memory={}, mode='abtwo'):
+        if mode == 'init':
+            memory.update(lastt=t, lasthx=inihx)
+            return hc@inihx, memory
+        h = t - memory['lastt']
+        if mode == 'heunpred':                 # explicit Euler from the start value
+            rate = f(inihx, vc, memory['lastt'])
+            x = inihx + h*rate
+            memory.update(lastrhs=rate, hphx=x)
+        elif mode == 'heuncorr':               # trapezoidal average of the two rates
+            x = inihx + .5*h*(f(memory['hphx'], vc, t) + memory['lastrhs'])
+            memory.update(lastt=t, lasthx=x, lastdt=h)
+        else:                                  # AB2 on a (possibly) varying step
+            rate = f(memory['lasthx'], vc, memory['lastt'])
+            x = memory['lasthx'] + 1.5*h*rate \
+                - .5*memory['lastdt']*memory['lastrhs']
+            memory.update(lastt=t, lasthx=x, lastrhs=rate, lastdt=h)
+        return hc@x, memory
+    return observer
+
+
+def get_heuntrpz_lti(hb=None, ha=None, hc=None, inihx=None, drift=None,
+                     constdt=None):
+    """Heun / implicit trapezoidal discretisation of the same observer on a
+    uniform grid (`tiu:201-257`): ``(I - dt/2 ha) x+ = x + dt/2 (ha x + r + r-)``
+    with ``r = hb y + drift(t)``"""
+    if constdt is None:
+        raise NotImplementedError()
+    dt = constdt
+    step = np.linalg.inv(np.eye(ha.shape[0]) - .5*dt*ha)
+
+    def observer(t, vc=None, memory={}, mode='abtwo'):
+        if mode == 'init':
+            memory.update(lastt=t, lasthx=inihx)
+            return hc@inihx, memory
+        r = hb@vc + drift(t)
+        if mode == 'heunpred':
+            x = inihx + dt*(ha@inihx + r)
+            memory.update(lastrhs=r, lasthx=inihx, hphx=x)
+        elif mode == 'heuncorr':
+            x = inihx + .5*dt*(ha@(memory['hphx'] + memory['lasthx'])
+                               + r + memory['lastrhs'])
+            memory.update(lastt=t, hchx=x)
+        else:
+            x0 = memory['lasthx']
+            x = step@(x0 + .5*dt*(ha@x0 + r + memory['lastrhs']))
+            memory.update(lasthx=x, lastrhs=r)
+        return hc@x, memory
+    return observer
 
 
 def semi_implicit_euler(iniv=None, jmat=None, mmat=None, amat=None, rhsv=None,
@@ -305,8 +389,12 @@ def semi_implicit_euler(iniv=None, jmat=None, mmat=None, amat=None, rhsv=None,
     ``data_trange``.
     """
     if rhsv is not None:
-        raise NotImplementedError('opaque `rhsv(t, v)` callbacks cannot run '
-                                  'on the device; pass `fv`/`fvtd`')
+        # the reference's interface: an opaque right-hand side, per-step host hop
+        from . import hosthop
+        return hosthop.euler_with_callbacks(
+            iniv=iniv, jmat=jmat, mmat=mmat, amat=amat, rhsv=rhsv,
+            trange=trange, data_trange=data_trange, fp=fp,
+            **{k: v for k, v in kw.items() if k in ('tol', 'maxit', 'ctx')})
     trange = np.asarray(trange, dtype=float)
     NP, NV = jmat.shape
     integ = DeviceImex(mmat, amat, jmat, V, invinds, dbcinds, dbcvals,

@@ -271,6 +271,10 @@ int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, int picard,
                      const double *linpoint, const double *v0, const double *p0,
                      double tol, int maxit, double *vtraj, double *ptraj,
                      double *upd_norm, long long *iters_total);
+/* initial guess of the step solves: 0 = the previous step's solution
+ * (`krylovini='old'`, stokes_navier_utils.py:1493-1495), 1 = linear
+ * extrapolation of the last two (`'upd'`, :1496-1501; the default) */
+int dnsb_cnsweep_set_guess(dnsb_cnsweep *w, int mode);
 /* largest final relative residual over the step solves of the last sweep and
  * the number of them that stopped at maxit above tol (then dnsb_cnsweep_run
  * returned DNSB_E_NOT_CONVERGED; the trajectories were still written) */

@@ -257,9 +257,55 @@ def golden_sie(run):
                         v=np.hstack([vl[k] for k in (0, 1, 6, 12)]))
 
 
+def golden_callbacks(run):
+    """`tiu.cnab` / `tiu.sbdftwo` with the reference's callback interface
+    (custom ``f_vdp``, ``f_tvdp``, an AB2 observer as ``dynamic_rhs``) and
+    `tiu.semi_implicit_euler` with its opaque ``rhsv(t, v)``"""
+    import callback_cases as cbc
+    from oracle import convection as oconv
+    femp, sm, rhsd = cyl(1, 60)
+    tiu, dts = run.ref['tiu'], run.ref['dts']
+    sd = rh.as_spmatrix(soldict(femp, sm, rhsd))
+    inv = femp['invinds']
+    NV = inv.size
+    gold = np.load(os.path.join(HERE, 'ref_cnab_cyl1_re60.npz'))
+    iniv, inip = gold['v'][inv, :1], gold['p'][:, :1]
+
+    def conv_inner(vfull):
+        return oconv.convvec(femp['V'], np.ravel(vfull))[inv].reshape(-1, 1)
+
+    def appndbcs(vvec, bcs):
+        return dts.append_bcs_vec(vvec, vdim=femp['V'].dim(), invinds=inv,
+                                  bcinds=[femp['dbcinds'], []],
+                                  bcvals=[femp['dbcvals'], bcs])
+    trange = np.linspace(0., 10./512, 11)
+    res = {}
+    for name, integ in (('cnab', tiu.cnab), ('sbdf2', tiu.sbdftwo)):
+        kw = cbc.callback_kwargs(sd['M'], inv, conv_inner, tiu.get_heunab_lti,
+                                 NV)
+        if name == 'sbdf2':        # `tiu:260-268` has no `f_tvdp`: fold it in
+            ftv, dyn = kw.pop('f_tvdp'), kw['dynamic_rhs']
+
+            def dynamic_rhs(t, vc=None, memory={}, mode=None, _d=dyn, _f=ftv):
+                val, memory = _d(t, vc=vc, memory=memory, mode=mode)
+                return val + _f(t, vc), memory
+            kw['dynamic_rhs'] = dynamic_rhs
+        v, p, ff = integ(trange=trange, inivel=iniv, inip=inip, bcs_ini=[],
+                         M=sd['M'], A=sd['A'], J=sd['J'],
+                         f_tdp=lambda t: sd['fv'], g_tdp=lambda t: sd['fp'],
+                         scalep=-1., getbcs=lambda *a, **k: [],
+                         applybcs=lambda bcs: (0., 0., 0.), appndbcs=appndbcs,
+                         savevp=lambda *a, **k: None, dynamic_rhs_memory={},
+                         check_ff_maxv=1e8, verbose=False, **kw)
+        res['v_' + name], res['p_' + name] = v, p
+    np.savez_compressed(os.path.join(HERE, 'ref_callbacks_cyl1_re60.npz'),
+                        iniv=iniv, inip=inip, t=trange, **res)
+
+
 if __name__ == '__main__':
     run = RefRun()
     try:
+        golden_callbacks(run)
         golden_imex(run)
         golden_bcrob(run)
         golden_newton_cn(run)

@@ -1165,3 +1165,128 @@ def test_tiled_chebyshev_is_bit_identical(cyl1):
     assert out['0'][2] == out['1'][2]
     assert np.array_equal(out['0'][0], out['1'][0])
     assert np.array_equal(out['0'][1], out['1'][1])
+
+
+# ---------------------------------------------------------------------------
+# the reference's callback interface: per-step host hop, device solves
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('scheme', ['cnab', 'sbdf2'])
+def test_reference_run_callbacks_device(cyl1, ctx, scheme):
+    """`tiu.cnab` / `tiu.sbdftwo` with a custom ``f_vdp``, ``f_tvdp(t, v)`` and
+    an AB2 observer as ``dynamic_rhs`` against what the reference returned for
+    the same callbacks (`tests/golden/ref_callbacks_cyl1_re60.npz`)"""
+    import callback_cases as cbc
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    femp, sm, rhsd = cyl1
+    g = np.load(os.path.join(GOLD, 'ref_callbacks_cyl1_re60.npz'))
+    inv = femp['invinds']
+
+    def conv_inner(vfull):          # the device kernel K1a
+        return dts.get_convvec(V=femp['V'], u0_vec=np.ravel(vfull), invinds=inv)
+    kw = cbc.callback_kwargs(sm['M'], inv, conv_inner, tiu.get_heunab_lti,
+                             inv.size)
+    integ = dict(cnab=tiu.cnab, sbdf2=tiu.sbdftwo)[scheme]
+    v, p, ff = integ(trange=g['t'], inivel=g['iniv'], inip=g['inip'],
+                     M=sm['M'], A=sm['A'], J=sm['J'],
+                     f_tdp=lambda t: rhsd['fv'], g_tdp=lambda t: rhsd['fp'],
+                     scalep=-1.,
+                     appndbcs=lambda vv, bcs: dts_full(vv, femp).reshape(-1, 1),
+                     check_ff_maxv=1e8, **kw)
+    assert ff == 0
+    assert _rel(v, g['v_' + scheme]) < 1e-8
+    assert _rel(p, g['p_' + scheme]) < 1e-8
+
+
+def test_solve_nse_with_callbacks_and_output_feedback(cyl1, ctx):
+    """`snu.solve_nse(fvtvd=, closed_loop=True, dynamic_feedback=True,
+    dyn_fb_disc='AB2', b_mat=, cv_mat=)` (`snu:1129-1140,1224-1247`) routes
+    through the host hop: equals a direct `tiu.cnab` call with the same
+    callbacks, and `semi_implicit_euler` takes the reference's ``rhsv(t, v)``"""
+    import callback_cases as cbc
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    femp, sm, rhsd = cyl1
+    g = np.load(os.path.join(GOLD, 'ref_callbacks_cyl1_re60.npz'))
+    inv = femp['invinds']
+    om = cbc.observer_matrices(inv.size, sm['M'])
+
+    def fvtvd(t, vc):
+        return .2*np.sin(40.*t)*(sm['M']@np.asarray(vc).reshape(-1, 1))
+    trange = g['t'][:7]
+    iniv_full = dts_full(g['iniv'], femp).reshape(-1, 1)
+    v1, p1 = snu.solve_nse(
+        trange=trange, iniv=iniv_full, inip=g['inip'], fvtvd=fvtvd,
+        closed_loop=True, dynamic_feedback=True, dyn_fb_disc='AB2',
+        dyn_fb_dict=dict(ha=om['ha'], hb=om['hb'], hc=om['hc'],
+                         inihx=om['inihx'], drift=om['drift']),
+        b_mat=om['bmat'], cv_mat=om['cmat'], return_final_vp=True,
+        **soldict(femp, sm, rhsd))
+    observer = tiu.get_heunab_lti(hb=om['hb'], ha=om['ha'], hc=om['hc'],
+                                  inihx=om['inihx'], drift=om['drift'])
+
+    def dynamic_rhs(t, vc=None, memory={}, mode=None):
+        u, memory = observer(t, vc=om['cmat']@vc, memory=memory, mode=mode)
+        return om['bmat']@u, memory
+    v2, p2, _ = tiu.cnab(
+        trange=trange, inivel=g['iniv'], inip=g['inip'], M=sm['M'], A=sm['A'],
+        J=sm['J'], f_tdp=lambda t: rhsd['fv'], g_tdp=lambda t: rhsd['fp'],
+        f_vdp=lambda vf: -dts.get_convvec(V=femp['V'], u0_vec=np.ravel(vf),
+                                          invinds=inv),
+        f_tvdp=fvtvd, dynamic_rhs=dynamic_rhs, dynamic_rhs_memory={},
+        appndbcs=lambda vv, bcs: dts_full(vv, femp).reshape(-1, 1))
+    assert _rel(v1, v2) < 1e-9 and _rel(p1, p2) < 1e-8
+    # opaque rhsv(t, v) of `tiu.semi_implicit_euler` against the reference run
+    gs = np.load(os.path.join(GOLD, 'ref_sie_cyl1_re60.npz'))
+
+    def rhsv(t, v):
+        return rhsd['fv'] - dts.get_convvec(
+            V=femp['V'], u0_vec=dts_full(v, femp), invinds=inv)
+    got = tiu.semi_implicit_euler(iniv=gs['v'][:, :1], jmat=sm['J'],
+                                  mmat=sm['M'], amat=sm['A'], rhsv=rhsv,
+                                  trange=np.linspace(0., 12./512, 13),
+                                  fp=rhsd['fp'])
+    for j, k in enumerate((0, 1, 6, 12)):
+        assert _rel(got[k], gs['v'][:, j:j+1]) < 1e-8, k
+
+
+def test_low_rank_update_and_krylovini(cyl1, ctx):
+    """`lau.solve_sadpnt_smw(umat=, vmat=)` (Sherman-Morrison-Woodbury,
+    `snu:1505-1512`) against a direct solve of the updated matrix, and the
+    `krylovini` initial-guess modes of the Newton sweeps (`snu:1493-1503`)"""
+    import scipy.sparse.linalg as spsla
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import stokes_navier_utils as snu
+    femp, sm, rhsd = cyl1
+    F = (sm['M'] + .5/512*sm['A']).tocsr()
+    NP, NV = sm['J'].shape
+    rng = np.random.default_rng(9)
+    U = np.asarray(sm['M']@rng.standard_normal((NV, 3)))
+    V = rng.standard_normal((3, NV))/NV
+    b = np.asarray(sm['M']@rng.standard_normal((NV, 1)))
+    got = lau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=b,
+                               umat=U, vmat=V)
+    K = sps.bmat([[F + sps.csr_matrix(U@V), sm['J'].T], [sm['J'], None]],
+                 format='csc')
+    ref = spsla.spsolve(K, np.vstack([b, np.zeros((NP, 1))]).ravel())
+    assert _rel(got[:NV, 0], ref[:NV]) < 1e-9
+    assert _rel(got[NV:, 0], ref[NV:]) < 1e-8
+    # krylovini: same sweep result, previous-solution guesses need more iterations
+    femp, sm, rhsd = dnsps.get_sysmats(problem='cylinderwake', Re=100,
+                                       scheme='TH', mergerhs=True,
+                                       meshparams=dict(refinement_level=1))
+    g = np.load(os.path.join(GOLD, 'ref_newtoncn_cyl1_re100.npz'))
+    sd = soldict(femp, sm, rhsd, t0=0., tE=6./512, Nts=6, start_ssstokes=True)
+    traj = snu.solve_nse(return_dictofvelstrs=True, **sd)
+    its = {}
+    for mode in ('old', 'upd'):
+        st = []
+        vd = snu.solve_nse(lin_vel_point=traj, treat_nonl_explicit=False,
+                           vel_pcrd_stps=1, vel_nwtn_stps=2, verbose=False,
+                           return_dictofvelstrs=True, krylov='Gmres',
+                           krpslvprms=dict(krylovini=mode, convstatsl=st), **sd)
+        its[mode] = np.mean(st)
+        assert _rel(vd[float(g['t'][-1])], g['v'][:, -1:]) < 1e-8, mode
+    assert its['upd'] < its['old']

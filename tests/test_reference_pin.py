@@ -240,3 +240,105 @@ def test_fixtures_are_what_the_reference_returns_today(cyl1, tmp_path):
     for j, k in enumerate(g['keep']):
         assert np.array_equal(got[ts[k]]['v'], g['v'][:, j:j+1])
         assert np.array_equal(got[ts[k]]['p'], g['p'][:, j:j+1])
+
+
+# ---------------------------------------------------------------------------
+# callback interface (host logic of the product, no GPU: the device solves are
+# replaced by the LU oracle) and the observer discretisations
+# ---------------------------------------------------------------------------
+class _LuWarmSolver(object):
+    """stands in for `hosthop._WarmSolver` (device FGMRES) on a CPU-only box"""
+
+    def __init__(self, F, J, **kw):
+        from oracle.lau import SadLU, saddle_matrix
+        self.lu = SadLU(saddle_matrix(F, J))
+        self.nv = F.shape[0]
+
+    def __call__(self, rhsv, rhsp):
+        vp = self.lu.solve(np.vstack([np.asarray(rhsv).reshape(-1, 1),
+                                      np.asarray(rhsp).reshape(-1, 1)]))
+        return vp[:self.nv].reshape(-1, 1), vp[self.nv:].reshape(-1, 1)
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize('scheme', ['cnab', 'sbdf2'])
+def test_host_hop_loop_equals_reference_run_with_callbacks(cyl1, scheme,
+                                                           monkeypatch):
+    """`hosthop.imex_with_callbacks` (custom ``f_vdp``, ``f_tvdp``, AB2
+    observer as ``dynamic_rhs``) reproduces what the reference's `tiu.cnab` /
+    `tiu.sbdftwo` returned for the same callbacks"""
+    import callback_cases as cbc
+    from dolfin_navier_scipy_b200 import hosthop
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import convection as oconv
+    from oracle.snu import append_bcs_vec
+    monkeypatch.setattr(hosthop, '_WarmSolver', _LuWarmSolver)
+    femp, sm, rhsd = cyl1
+    g = _gold('ref_callbacks_cyl1_re60.npz')
+    inv = femp['invinds']
+
+    def conv_inner(vfull):
+        return oconv.convvec(femp['V'], np.ravel(vfull))[inv].reshape(-1, 1)
+    kw = cbc.callback_kwargs(sm['M'], inv, conv_inner, tiu.get_heunab_lti,
+                             inv.size)
+    v, p, ff = hosthop.imex_with_callbacks(
+        scheme, trange=g['t'], inivel=g['iniv'], inip=g['inip'], M=sm['M'],
+        A=sm['A'], J=sm['J'], f_tdp=lambda t: rhsd['fv'],
+        g_tdp=lambda t: rhsd['fp'], scalep=-1.,
+        appndbcs=lambda vv, bcs: append_bcs_vec(vv, femp['V'].dim(), inv,
+                                                femp['dbcinds'],
+                                                femp['dbcvals']),
+        check_ff_maxv=1e8, **kw)
+    assert ff == 0
+    assert _rel(v, g['v_' + scheme]) <= 1e-12
+    assert _rel(p, g['p_' + scheme]) <= 1e-10
+
+
+@needs_ref
+def test_observer_discretisations_equal_the_reference():
+    """`tiu.get_heunab_lti` / `get_heuntrpz_lti` (`tiu:148-257`): same outputs
+    and the same memory trail as the reference's closures, mode by mode"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    ref = rh.load()['tiu']
+    rng = np.random.default_rng(3)
+    ha = -2.*np.eye(4) + rng.standard_normal((4, 4))
+    hb, hc = rng.standard_normal((4, 2)), rng.standard_normal((3, 4))
+    x0 = rng.standard_normal((4, 1))
+    kw = dict(hb=hb, ha=ha, hc=hc, inihx=x0,
+              drift=lambda t: np.full((4, 1), np.sin(t)))
+    ts = np.linspace(0., .5, 6)
+    ys = [rng.standard_normal((2, 1)) for _ in ts]
+    for mine, theirs, extra in (
+            (tiu.get_heunab_lti, ref.get_heunab_lti, {}),
+            (tiu.get_heuntrpz_lti, ref.get_heuntrpz_lti,
+             dict(constdt=ts[1] - ts[0]))):
+        a, b = mine(**dict(kw, **extra)), theirs(**dict(kw, **extra))
+        ma, mb = {}, {}
+        seq = [(ts[0], 'init'), (ts[1], 'heunpred'), (ts[1], 'heuncorr')] + \
+            [(t, 'abtwo') for t in ts[2:]]
+        for k, (t, mode) in enumerate(seq):
+            ua, ma = a(t, vc=ys[min(k, 5)], memory=ma, mode=mode)
+            ub, mb = b(t, vc=ys[min(k, 5)], memory=mb, mode=mode)
+            assert np.allclose(ua, ub, rtol=1e-14, atol=0), (mode, k)
+            assert set(ma.keys()) == set(mb.keys())
+
+
+@needs_ref
+def test_live_reference_time_sections_are_broken_at_head(tmp_path):
+    """`nsects` > 1 (`snu:1076-1087`): the reference's second time section dies
+    with `KeyError: None` (`snu:1425-1431`) -- the product's
+    `NotImplementedError` for `nsects`/`addfullsweep` mirrors a dead path"""
+    ref = rh.load()
+    femp, sm, rhsd = _cyl(1, 100)
+    sd = rh.as_spmatrix(soldict(femp, sm, rhsd, t0=0., tE=8./512, Nts=8,
+                                start_ssstokes=True))
+    kw = dict(verbose=False, paraviewoutput=False)
+    traj = ref['snu'].solve_nse(return_dictofvelstrs=True,
+                                data_prfx=str(tmp_path/'a'), **kw, **sd)
+    with pytest.raises(KeyError):
+        ref['snu'].solve_nse(lin_vel_point=traj, treat_nonl_explicit=False,
+                             vel_pcrd_stps=1, vel_nwtn_stps=2, nsects=2,
+                             return_dictofvelstrs=True,
+                             data_prfx=str(tmp_path/'b'), **kw, **sd)
