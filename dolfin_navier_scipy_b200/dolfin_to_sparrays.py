@@ -16,6 +16,7 @@ import scipy.sparse as sps
 from . import fem
 
 __all__ = ['unroll_dlfn_dbcs', 'get_stokessysmats', 'get_convmats',
+           'ass_convmat_asmatquad',
            'get_convvec', 'condense_sysmatsbybcs', 'condense_velmatsbybcs',
            'append_bcs_vec', 'expand_vp', 'setget_rhs']
 
@@ -216,6 +217,63 @@ def condense_velmatsbybcs(A, velbcs=None, return_bcinfo=False,
     if return_bcinfo:
         return Ac, load, dict(ininds=fr, bcinds=bnd)
     return Ac, load
+
+
+def ass_convmat_asmatquad(W=None, invindsw=None):
+    """the convection as a quadratic form: ``H`` with ``N(v)v = H (v kron v)``
+    on the inner nodes (`dts:86-164`; 2D, as there)
+
+    The reference assembles, per inner scalar basis function ``phi_i``, the two
+    matrices ``int phi_j d_x phi_i phi_k`` and ``int phi_j d_y phi_i phi_k``
+    with dolfin and shuffles them into place; here the third-order element
+    tensor ``T[k, j, i, d] = int phi_k phi_j d_d phi_i`` is computed for all
+    cells at once (7-point rule, exact for the degree-5 integrand) and
+    scattered into the same layout:
+
+        H[pos(2k + c),  b*NVi + pos(2j + d)] += T[k, j, i, d],   b = pos(2i + c)
+
+    for both components ``c`` (``pos`` = position in ``invindsw``; as in the
+    reference ``invindsw`` must list the x and y dof of every inner node next
+    to each other).  Shape ``(NVi, NVi**2)``, csc -- a set-up routine for
+    reduced-order models on small meshes (864 entries per cell before merging).
+    """
+    inv = np.asarray(invindsw, dtype=np.int64)
+    nvi = inv.size
+    if nvi % 2 or not (np.all(inv[0::2] % 2 == 0) and
+                       np.all(inv[1::2] == inv[0::2] + 1)):
+        raise ValueError('`invindsw` must hold the (x, y) dof pair of every '
+                         'inner node (`dts:102-103`)')
+    pos = -np.ones(W.dim(), dtype=np.int64)
+    pos[inv] = np.arange(nvi)
+    mesh = W.mesh()
+    cn = mesh.p2_cell_nodes().astype(np.int64)                 # (nc, 6)
+    gl, detj = mesh.geometry()                                 # grad lambda (nc, 3, 2)
+    phi = fem.p2_basis(fem.TRI_QP)                             # (nq, 6)
+    dphi = np.einsum('qar,crd->cqad', fem.p2_dbasis(fem.TRI_QP), gl)
+    wq = fem.TRI_QW[None, :]*(.5*np.abs(detj))[:, None]
+    # T[c, k, j, i, d] = sum_q w phi_k phi_j d_d phi_i
+    T = np.einsum('cq,qk,qj,cqid->ckjid', wq, phi, phi, dphi)
+    rows, cols, vals = [], [], []
+    k_, j_, i_ = (cn[:, :, None, None], cn[:, None, :, None],
+                  cn[:, None, None, :])
+    for c in (0, 1):
+        prow = pos[2*k_ + c]
+        pb = pos[2*i_ + c]
+        for d in (0, 1):
+            pcol = pos[2*j_ + d]
+            keep = (prow >= 0) & (pb >= 0) & (pcol >= 0)
+            keep = np.broadcast_to(keep, T.shape[:4])
+            rr = np.broadcast_to(prow, T.shape[:4])[keep]
+            cc = (np.broadcast_to(pb, T.shape[:4])[keep]*nvi
+                  + np.broadcast_to(pcol, T.shape[:4])[keep])
+            rows.append(rr)
+            cols.append(cc)
+            vals.append(T[..., d][keep])
+    hmat = sps.coo_matrix((np.concatenate(vals),
+                           (np.concatenate(rows), np.concatenate(cols))),
+                          shape=(nvi, nvi*nvi)).tocsc()
+    hmat.eliminate_zeros()
+    return hmat
 
 
 def _full_velocity(V, u0_vec, invinds, dbcinds, dbcvals):

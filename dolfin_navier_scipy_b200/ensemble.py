@@ -13,7 +13,7 @@ from . import problem_setups as dnsps
 from . import time_int_utils as tiu
 
 __all__ = ['cylinder_ensemble', 'shard_members', 'gram_allreduce',
-           'allreduce_gram']
+           'allreduce_gram', 'pod_from_gram', 'pod_modes']
 
 
 def shard_members(nmembers, rank, world):
@@ -94,3 +94,30 @@ def gram_allreduce(integ, group=None):
     torch.cuda.synchronize(dev)
     integ.engine.gram_dev(G.data_ptr())
     return allreduce_gram(G, group)
+
+
+def pod_from_gram(G, energy=0.9999, kmax=None):
+    """method of snapshots on the (all-reduced) Gram matrix
+    ``G = sum_m X_m^T M X_m``: eigenvalues (descending), the temporal modes
+    ``W`` (ns x r, scaled so that the spatial modes ``Phi_m = X_m W`` satisfy
+    ``sum_m Phi_m^T M Phi_m = I``) and the rank ``r`` that captures ``energy``
+    of the trace.  ``G`` is tiny (ns x ns): plain host ``eigh``."""
+    G = np.asarray(G.cpu() if hasattr(G, 'cpu') else G, dtype=float)
+    lam, Q = np.linalg.eigh(.5*(G + G.T))
+    lam, Q = lam[::-1], Q[:, ::-1]
+    lam = np.maximum(lam, 0.)
+    frac = np.cumsum(lam)/max(lam.sum(), 1e-300)
+    r = int(np.searchsorted(frac, energy) + 1)
+    r = min(r, int(np.sum(lam > 1e-14*lam[0])))
+    if kmax is not None:
+        r = min(r, kmax)
+    W = Q[:, :r]/np.sqrt(lam[:r])[None, :]
+    return lam, W, r
+
+
+def pod_modes(snapshots, W):
+    """spatial POD modes of every member: ``snapshots`` (ns, NV, nb) as
+    returned by `DeviceImex.snapshots()[0]`, ``W`` from `pod_from_gram` ->
+    (NV, r, nb).  The reduced coordinates of member ``m`` at snapshot ``s``
+    are ``(W^T G)[:, s]`` -- shared by all members by construction."""
+    return np.einsum('snm,sr->nrm', np.asarray(snapshots), W)

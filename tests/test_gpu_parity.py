@@ -203,7 +203,7 @@ def test_ensemble_members_equal_single_runs(cyl1, ctx):
         ref = osnu.solve_nse(t0=0, tE=nsteps*dt, Nts=nsteps, iniv=v0[0.0]['v'],
                              inip=v0[0.0]['p'], return_final_vp=True, **sd)
         assert _rel(V[:, m:m+1], ref[0]) < 1e-8, m
-        assert _rel(P[:, m:m+1], ref[1]) < 1e-7, m
+        assert _rel(P[:, m:m+1], ref[1]) < 1e-8, m
 
 
 # ---------------------------------------------------------------------------
@@ -283,7 +283,7 @@ def test_golden_dfg_steady_state_device(ctx):
     v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False,
                                      **soldict(femp, sm, rhsd))
     assert _rel(v, g['v']) < 1e-8
-    assert _rel(p, g['p']) < 1e-7
+    assert _rel(p, g['p']) < 1e-8
     cd, cl = osnu.drag_lift(sm['Afull'], sm['JTfull'], femp['V'], v, p,
                             femp['ldsbcinds'])
     dp = femp['Q'].eval_at(p, (.15, .2)) - femp['Q'].eval_at(p, (.25, .2))
@@ -494,7 +494,7 @@ def test_cnab_with_multilevel_schur_hierarchy(cyl1, ctx):
         integ.close()
         for m in (0, nb - 1):
             assert _rel(V[:, m:m+1], ref[0]) < 1e-8, (nb, m)
-            assert _rel(P[:, m:m+1], ref[1]) < 1e-7, (nb, m)
+            assert _rel(P[:, m:m+1], ref[1]) < 1e-8, (nb, m)
 
 
 @pytest.fixture
@@ -1290,3 +1290,41 @@ def test_low_rank_update_and_krylovini(cyl1, ctx):
         its[mode] = np.mean(st)
         assert _rel(vd[float(g['t'][-1])], g['v'][:, -1:]) < 1e-8, mode
     assert its['upd'] < its['old']
+
+
+@pytest.mark.parametrize('switch', ['DNSB_CONV_COLOURS=1', 'DNSB_GRAPHS=0',
+                                    'DNSB_DMMA=0', 'DNSB_PAIR=0',
+                                    'DNSB_ROWPAIR=0', 'DNSB_GS_TMA=0',
+                                    'DNSB_TILE=0', 'DNSB_SCHUR_TC=0'])
+def test_every_tuning_switch_gives_the_same_trajectory(cyl1, ctx, switch):
+    """the environment switches select kernel VARIANTS of the same arithmetic
+    (coloured scatter vs gather assembly -- the form `north_star` names --,
+    graphs on/off, DFMA vs DMMA, member/row pairing, TMA staging, fp64 vs
+    tensor-core Schur block): a 64-member CNAB run under each of them agrees
+    with the default path to 1e-9 and with the LU oracle to 1e-8"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    dt, nsteps = 1./512, 5
+    sd = soldict(femp, sm, rhsd)
+    o = osnu.solve_nse(t0=0, tE=nsteps*dt, Nts=nsteps, start_ssstokes=True,
+                       return_vp_dict=True, **sd)
+    ts = sorted(o.keys())
+    name, val = switch.split('=')
+    out = {}
+    for label, c in (('default', ctx), (switch, _ctx_with_env(name, val))):
+        integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv,
+                               femp['dbcinds'], femp['dbcvals'], dt,
+                               nus=np.ones(64), fv=rhsd['fv'], fp=rhsd['fp'],
+                               ctx=c)
+        integ.set_state(o[ts[0]]['v'][inv], o[ts[0]]['p'])
+        integ.run(nsteps, tol=1e-12)
+        out[label] = integ.state()
+        integ.close()
+    v, p = out[switch]
+    assert _rel(v, out['default'][0]) < 1e-9
+    assert _rel(p, out['default'][1]) < 1e-9
+    for m in (0, 63):
+        assert _rel(v[:, m], o[ts[-1]]['v'][inv, 0]) < 1e-8
+        assert _rel(p[:, m], o[ts[-1]]['p'][:, 0]) < 1e-8

@@ -296,3 +296,50 @@ def test_paraview_writer_without_dolfin(tmp_path):
     parr = {a.get('Name'): a for a in proot.iter('DataArray')}
     assert np.array_equal(np.array(parr['p'].text.split(), dtype=float), written[2.][1][:, 0])
     assert set(parr['types'].text.split()) == {'5'}
+
+
+def test_convection_as_quadratic_form(cyl1):
+    """`dts.ass_convmat_asmatquad` (`dts:86-164`): ``H (v kron v) = N(v) v`` on
+    the inner nodes for fields that vanish on the Dirichlet boundary"""
+    import scipy.sparse as sps
+    from dolfin_navier_scipy_b200 import dolfin_to_sparrays as dts
+    from dolfin_navier_scipy_b200 import fem
+    from oracle import convection as oconv
+    mesh = fem.unit_square_mesh(4, 3)
+    V = fem.VectorP2Space(mesh)
+    xy = np.asarray(V.tabulate_dof_coordinates())
+    inner = (xy[:, 0] > 1e-12) & (xy[:, 0] < 1 - 1e-12) & \
+        (xy[:, 1] > 1e-12) & (xy[:, 1] < 1 - 1e-12)
+    inv = np.flatnonzero(inner).astype(np.int32)
+    H = dts.ass_convmat_asmatquad(W=V, invindsw=inv)
+    assert H.shape == (inv.size, inv.size**2) and sps.issparse(H)
+    rng = np.random.default_rng(8)
+    for _ in range(2):
+        vi = rng.standard_normal(inv.size)
+        vfull = np.zeros(V.dim())
+        vfull[inv] = vi
+        ref = oconv.convvec(V, vfull)[inv]
+        got = H@np.kron(vi, vi)
+        assert np.linalg.norm(got - ref) <= 1e-12*np.linalg.norm(ref)
+    with pytest.raises(ValueError):
+        dts.ass_convmat_asmatquad(W=V, invindsw=inv[1:-1])
+
+
+def test_pod_from_gram_gives_orthonormal_modes():
+    from dolfin_navier_scipy_b200 import ensemble as ens
+    rng = np.random.default_rng(4)
+    ns, nv, nb = 9, 40, 3
+    A = rng.standard_normal((nv, nv))
+    M = A@A.T + nv*np.eye(nv)
+    low = rng.standard_normal((nv, 4, nb))
+    X = np.einsum('nkm,sk->snm', low, rng.standard_normal((ns, 4)))   # rank 4
+    G = sum(X[:, :, m]@M@X[:, :, m].T for m in range(nb))
+    lam, W, r = ens.pod_from_gram(G, energy=1 - 1e-12)
+    assert r == 4 and np.all(np.diff(lam) <= 1e-9*lam[0])
+    Phi = ens.pod_modes(X, W)
+    gram = sum(Phi[:, :, m].T@M@Phi[:, :, m] for m in range(nb))
+    assert np.allclose(gram, np.eye(r), atol=1e-9)
+    # the rank-r reconstruction reproduces the snapshots
+    coeff = W.T@G                      # (r, ns)
+    for m in range(nb):
+        assert np.allclose(Phi[:, :, m]@coeff, X[:, :, m].T, atol=1e-8)
