@@ -87,14 +87,14 @@ static size_t gst_smem(const RedCfg &rc, int nb, int stages, size_t scratch_doub
 // vnext = w - sum_i h[i,m] V_i ; partial2[b*nb + m] = |vnext|^2 over the chunk of block b
 static void gs_update_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vstride, int nvec,
                           const double *h, const double *w, double *vnext, int n, int nb,
-                          double *partial2) {
+                          double *partial2, const double *scale = nullptr) {
   const int st = nvec > 0 ? gst_stages(rc, nb, rc.threads) : 0;
   if (st >= 2)
     LAUNCH(ctx, k_gs_tma<true>, rc.nblocks, rc.threads + 32, gst_smem(rc, nb, st, rc.threads), V, vstride,
-           nvec, h, w, vnext, n, nb, rc.rpb, rc.rows_per_block, partial2, st);
+           nvec, h, w, vnext, n, nb, rc.rpb, rc.rows_per_block, partial2, st, scale);
   else
     LAUNCH(ctx, k_gs_update_b, rc.nblocks, rc.threads, rc.smem, V, vstride, nvec, h, w, vnext, n, nb,
-           rc.rpb, rc.rows_per_block, partial2);
+           rc.rpb, rc.rows_per_block, partial2, scale);
 }
 
 // h[0..nvec) = <V_i, w>, h[nvec] = <w, w>  (per member), deterministic
@@ -106,7 +106,7 @@ static void mdot_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vs
   if (st >= 2)
     LAUNCH(ctx, k_gs_tma<false>, rc.nblocks, rc.threads + 32,
            gst_smem(rc, nb, st, (size_t)(nvec + 1) * rc.threads), V, vstride, nvec, (const double *)nullptr, w,
-           (double *)nullptr, n, nb, rc.rpb, rc.rows_per_block, partial, st);
+           (double *)nullptr, n, nb, rc.rpb, rc.rows_per_block, partial, st, (const double *)nullptr);
   else
     LAUNCH(ctx, k_mdot_b, rc.nblocks, rc.threads, smem, V, vstride, nvec, w, n, nb, rc.rpb,
            rc.rows_per_block, partial);
@@ -232,6 +232,7 @@ static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
   return 0;
 }
 
+static int g_gs_pyth = 1;   // norm of the orthogonalised Arnoldi vector from Pythagoras (batches, columns < 16)
 static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
 static const int TILE_SMEM_OPTIN = 220 * 1024;
 // tiles of TILE_RP row pairs: unique x rows, tile-local gather offsets, pair-interleaved values.
@@ -477,6 +478,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TF32")) g_schur_tf32 = atoi(ev);
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
+  if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
@@ -1005,6 +1007,12 @@ struct dnsb_solver {
   std::vector<cudaGraphExec_t> igraph;
   std::vector<int> igraph_launches;
   double igraph_tol = -1.0;
+  // Pythagorean norm in the Arnoldi step: only for solves that are expected to be SHORT (the
+  // previous solve of this solver took <= 8 iterations: the time loop with recycled guesses).
+  // Classical Gram-Schmidt loses orthogonality as a long solve converges, and then |h|^2 is no
+  // measure of |V h|^2 any more (a 25-iteration solve from a zero guess ended at 1e-8 instead of
+  // 1e-12); the graphs of a solver are captured for one variant and dropped when it changes
+  bool use_pyth = false, igraph_pyth = false;
   long long stat_iters = 0, stat_solves = 0, stat_launched = 0;
   long long stat_unconverged = 0;   // solves that stopped at maxit above tol
 };
@@ -1690,6 +1698,15 @@ static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
   const bool reorth = (nb == 1) || j >= 16;
   double *Vn = s->Vb.p + (size_t)(j + 1) * ntb;
   mdot_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->w.p, ntot, nb, s->partial.p, s->gs.h);
+  if (!reorth && s->use_pyth) {
+    // one pass less and no scalar glue: the norm of the orthogonalised vector from Pythagoras,
+    // Givens first, then the update writes the NORMALISED vector (no k_scale_member pass, no
+    // reduction of 586 partial norms inside the one-CTA Givens kernel)
+    LAUNCH(ctx, k_gmres_givens, 1, 1024, 0, s->gs, (const double *)nullptr, 0, nb, j, tol, 1);
+    gs_update_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->gs.h, s->w.p, Vn, ntot, nb, s->partial2.p,
+                  (const double *)s->gs.invh);
+    return 0;
+  }
   gs_update_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->gs.h, s->w.p, Vn, ntot, nb, s->partial2.p);
   const double *unscaled = Vn;
   if (reorth) {
@@ -1699,7 +1716,7 @@ static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
            (const double *)s->gh2.p, s->gs.h, (size_t)(j + 1) * nb);
     unscaled = s->w.p;
   }
-  LAUNCH(ctx, k_gmres_givens, 1, 1024, 0, s->gs, (const double *)s->partial2.p, rc.nblocks, nb, j, tol);
+  LAUNCH(ctx, k_gmres_givens, 1, 1024, 0, s->gs, (const double *)s->partial2.p, rc.nblocks, nb, j, tol, 0);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, unscaled, (const double *)s->gs.invh, Vn,
          (size_t)ntot, nb);
   return 0;
@@ -1715,9 +1732,10 @@ static void solver_drop_graphs(dnsb_solver *s) {
 static int gmres_iteration(dnsb_solver *s, int j, double tol) {
   dnsb_ctx *ctx = s->ctx;
   if (!g_graphs || ctx->prof) return gmres_iteration_launch(s, j, tol);
-  if (s->igraph.empty() || s->igraph_tol != tol) {
+  if (s->igraph.empty() || s->igraph_tol != tol || s->igraph_pyth != s->use_pyth) {
     solver_drop_graphs(s);
     s->igraph_tol = tol;
+    s->igraph_pyth = s->use_pyth;
   }
   if (!s->igraph[j]) {
     const long long l0 = ctx->launches;
@@ -1766,6 +1784,7 @@ static int solver_solve_dev(dnsb_solver *s, const double *b, double *x, double t
   int total = 0;
   bool first = true;
   int expect = s->expect_its;
+  s->use_pyth = g_gs_pyth && nb > 1 && expect >= 1 && expect <= 8;
   while (true) {
     double *V0 = s->Vb.p;
     if (zero_guess && first)

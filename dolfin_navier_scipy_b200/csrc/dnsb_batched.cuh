@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256, 2)
 k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
               const double *__restrict__ h, const double *__restrict__ w,
               double *__restrict__ vnext, int n, int nb, int rpb, int rows_per_block,
-              double *__restrict__ partial2) {
+              double *__restrict__ partial2, const double *__restrict__ scale) {
   extern __shared__ double sred[];   // blockDim
   const int m = threadIdx.x % nb, rr = threadIdx.x / nb;
   const int r0 = blockIdx.x * rows_per_block;
@@ -289,12 +289,15 @@ k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
     hi = hn;
   }
   double nrm = 0.0;
+  // scale != null: the norm is known already (Pythagoras, k_gmres_givens): write the normalised vector
+  const double sc = scale ? scale[m] : 1.0;
 #pragma unroll
   for (int q = 0; q < GS_H; ++q) {
     const int ra = r0 + rr + q * rpb, rb = r0 + rr + (GS_H + q) * rpb;
-    if (ra < r1) vnext[(size_t)ra * nb + m] = wa[q];
-    if (rb < r1) vnext[(size_t)rb * nb + m] = wb[q];
+    if (ra < r1) vnext[(size_t)ra * nb + m] = scale ? wa[q] * sc : wa[q];
+    if (rb < r1) vnext[(size_t)rb * nb + m] = scale ? wb[q] * sc : wb[q];
   }
+  if (scale) return;
 #pragma unroll
   for (int q = 0; q < GS_H; ++q) nrm += wa[q] * wa[q];
 #pragma unroll

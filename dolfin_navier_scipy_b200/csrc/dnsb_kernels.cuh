@@ -753,10 +753,27 @@ __global__ void k_set_bnorm(GmresState S, const double *__restrict__ partial,
 // does the scalar work of member m.
 __global__ void __launch_bounds__(1024)
 k_gmres_givens(GmresState S, const double *__restrict__ partial2,
-               int nblocks, int nb, int j, double tol) {
+               int nblocks, int nb, int j, double tol, int pyth) {
   __shared__ double sp[32][33];
   __shared__ double snorm[1024];
-  {
+  if (pyth) {
+    // |w - V h|^2 = |w|^2 - |h|^2 (V orthonormal): h[0..j] and <w, w> = h[j+1] come from ONE pass
+    // over the basis (k_mdot / k_gs_tma<false>), so the update kernel can write the normalised vector
+    // directly and needs no reduction of its own.  The cancellation only bites when w lies in the
+    // span already (|w_orth| < 1e-6 |w|), i.e. when the member has converged; the Arnoldi relation
+    // K Z = V H stays exact whatever number is used as h_{j+1,j}, because V_{j+1} is scaled with it.
+    // The difference is floored at 1e-8 |w|^2: above the floor its relative error is < 1e-7; below
+    // it the vector is under-normalised, which makes the residual estimate pessimistic, never
+    // optimistic (no false convergence).
+    const int c = threadIdx.x;
+    if (c < nb) {
+      const double ww = S.h[(size_t)(j + 1) * nb + c];
+      double s = ww;
+      for (int i = 0; i <= j; ++i) { const double hi = S.h[(size_t)i * nb + c]; s -= hi * hi; }
+      snorm[c] = fmax(s, 1e-8 * ww);
+    }
+    __syncthreads();
+  } else {
     const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
     for (int m0 = 0; m0 < nb; m0 += 32) {
       const int c = m0 + cx;

@@ -221,7 +221,7 @@ template <bool UPDATE>
 __global__ void __launch_bounds__(288)
 k_gs_tma(const double *__restrict__ V, size_t vstride, int nvec, const double *__restrict__ h,
          const double *__restrict__ w, double *__restrict__ vnext, int n, int nb, int rpb,
-         int rows_per_block, double *__restrict__ partial, int stages) {
+         int rows_per_block, double *__restrict__ partial, int stages, const double *__restrict__ scale) {
   extern __shared__ __align__(128) unsigned char gst_raw[];
   __shared__ __align__(8) uint64_t full[GST_MAX_STAGES], empty[GST_MAX_STAGES];
   const int nthr = rpb * nb;                 // consumer threads
@@ -299,12 +299,16 @@ k_gs_tma(const double *__restrict__ V, size_t vstride, int nvec, const double *_
   }
   double ww = 0.0;
   if (UPDATE) {
+    // scale != null: the norm is known already (Pythagoras, k_gmres_givens): the normalised
+    // vector is written directly and no partial norms are needed
+    const double sc = scale ? scale[m] : 1.0;
 #pragma unroll
     for (int q = 0; q < GST_H; ++q) {
       const int ra = r0 + rr + q * rpb, rb = r0 + rr + (GST_H + q) * rpb;
-      if (ra < r1) vnext[(size_t)ra * nb + m] = wa[q];
-      if (rb < r1) vnext[(size_t)rb * nb + m] = wb[q];
+      if (ra < r1) vnext[(size_t)ra * nb + m] = scale ? wa[q] * sc : wa[q];
+      if (rb < r1) vnext[(size_t)rb * nb + m] = scale ? wb[q] * sc : wb[q];
     }
+    if (scale) return;
   }
 #pragma unroll
   for (int q = 0; q < GST_H; ++q) ww += wa[q] * wa[q];

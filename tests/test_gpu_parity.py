@@ -1295,7 +1295,8 @@ def test_low_rank_update_and_krylovini(cyl1, ctx):
 @pytest.mark.parametrize('switch', ['DNSB_CONV_COLOURS=1', 'DNSB_GRAPHS=0',
                                     'DNSB_DMMA=0', 'DNSB_PAIR=0',
                                     'DNSB_ROWPAIR=0', 'DNSB_GS_TMA=0',
-                                    'DNSB_TILE=0', 'DNSB_SCHUR_TC=0'])
+                                    'DNSB_TILE=0', 'DNSB_SCHUR_TC=0',
+                                    'DNSB_GS_PYTH=0'])
 def test_every_tuning_switch_gives_the_same_trajectory(cyl1, ctx, switch):
     """the environment switches select kernel VARIANTS of the same arithmetic
     (coloured scatter vs gather assembly -- the form `north_star` names --,
