@@ -772,6 +772,8 @@ def kernel_bytes(name, info, integ):
         first, last = (flags[0] == 'true', flags[1] == 'true') if tiled \
             else (flags[1] == 'true', flags[2] == 'true')
         passes = 7 - (1 if first else 0) - (2 if last else 0)
+        if name.startswith('k_cheb_step_tilef'):   # fp32 smoother: 4 floats + 1 offset per pair entry
+            return 10.*nnzF + 4.*(n + 1) + 4.*passes*n*nb + (4.*n*nb if last else 0.)
         if tiled:    # 4 values + 1 offset per column of a row pair: 18 B per CSR entry
             return 18.*nnzF + 4.*(n + 1) + 8.*passes*n*nb
         return 20.*nnzF + 4.*(n + 1) + 8.*passes*n*nb

@@ -127,13 +127,23 @@ struct dnsb_csr {
   int npair_rows = 0;   // leading rows that pair up (2k, 2k+1) with identical column lists
   SptPlan spt;          // TMA-staged row tiles (dnsb_stream.cuh)
   TilePlan tile;        // fully staged batched Chebyshev step (dnsb_tile.cuh), built by tile_setup
-  DBuf<int> t_uptr, t_rptr, t_runs, t_pidx;
+  DBuf<int> t_uptr, t_rptr, t_runs, t_pidx, t_pidxf, t_truns;
+  DBuf<int4> t_tdesc, t_pdesc;
+  int t_rmax = 0;
   DBuf<double> t_pval;
+  DBuf<float> t_pvalf;       // fp32 copy of the packed entries (smoother inside the preconditioner)
+  TileDevF tile_view_f() const {
+    TileDevF t;
+    t.indptr = indptr.p; t.uptr = t_uptr.p; t.rptr = t_rptr.p; t.runs = t_runs.p; t.pidx = t_pidxf.p; t.pval = t_pvalf.p;
+    t.tdesc = t_tdesc.p; t.truns = t_truns.p; t.pdesc = t_pdesc.p; t.rmax = t_rmax;
+    t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap;
+    return t;
+  }
   TileDev tile_view() const {
     TileDev t;
     t.indptr = indptr.p; t.uptr = t_uptr.p; t.rptr = t_rptr.p; t.runs = t_runs.p; t.pidx = t_pidx.p; t.pval = t_pval.p;
+    t.tdesc = t_tdesc.p; t.truns = t_truns.p; t.pdesc = t_pdesc.p; t.rmax = t_rmax;
     t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap;
-    { const char *ev = getenv("DNSB_TILE_DBG"); t.dbg = ev ? atoi(ev) : 0; }
     return t;
   }
   // host copies (setup only: assembling the block matrix K, diagonal positions)
@@ -232,6 +242,7 @@ static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
   return 0;
 }
 
+static int g_cheb_f32 = 1;  // fp32 work vectors of the Chebyshev smoother inside the preconditioner (tile path)
 static int g_gs_pyth = 1;   // norm of the orthogonalised Arnoldi vector from Pythagoras (batches, columns < 16)
 static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
 static const int TILE_SMEM_OPTIN = 220 * 1024;
@@ -290,11 +301,41 @@ static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
   p.smem = TILE_STAGES * p.stage_bytes;
   if (p.smem > (size_t)TILE_SMEM_OPTIN) return 0;   // neighbourhoods too large for the ring: row-pair kernels
   if (runs.empty()) return 0;
+  {
+    // per-tile descriptors and a fixed-stride copy of the run lists (addresses known without a lookup),
+    // per-pair descriptors (offset into the staged entries, row length)
+    int rmax = 0;
+    for (int t = 0; t < p.ntiles; ++t) rmax = std::max(rmax, rptr[t + 1] - rptr[t]);
+    if (rmax > 32) return 0;   // one run per producer lane
+    std::vector<int4> tdesc(p.ntiles), pdesc(np);
+    std::vector<int> truns((size_t)p.ntiles * rmax * 3, 0);
+    for (int t = 0; t < p.ntiles; ++t) {
+      const int p0 = t * TILE_RP, p1 = std::min(np, p0 + TILE_RP);
+      const int pe0 = ip[2 * p0] / 2, pe1 = ip[2 * p1] / 2;
+      const int a0 = pe0 & ~3, a1 = (pe1 + 3) & ~3;
+      tdesc[t] = make_int4(a0, a1 - a0, uptr[t + 1] - uptr[t], rptr[t + 1] - rptr[t]);
+      for (int r = rptr[t]; r < rptr[t + 1]; ++r)
+        for (int c = 0; c < 3; ++c) truns[((size_t)t * rmax + (r - rptr[t])) * 3 + c] = runs[3 * r + c];
+      for (int q = p0; q < p1; ++q) pdesc[q] = make_int4(ip[2 * q] / 2 - a0, ip[2 * q + 1] - ip[2 * q], 0, 0);
+    }
+    m->t_rmax = rmax;
+    DNSB_CK(ctx, m->t_tdesc.upload(tdesc.data(), tdesc.size(), ctx->stream));
+    DNSB_CK(ctx, m->t_pdesc.upload(pdesc.data(), pdesc.size(), ctx->stream));
+    DNSB_CK(ctx, m->t_truns.upload(truns.data(), truns.size(), ctx->stream));
+  }
   DNSB_CK(ctx, m->t_uptr.upload(uptr.data(), uptr.size(), ctx->stream));
   DNSB_CK(ctx, m->t_rptr.upload(rptr.data(), rptr.size(), ctx->stream));
   DNSB_CK(ctx, m->t_runs.upload(runs.data(), runs.size(), ctx->stream));
   DNSB_CK(ctx, m->t_pidx.upload(pidx.data(), pidx.size(), ctx->stream));
   DNSB_CK(ctx, m->t_pval.upload(pval.data(), pval.size(), ctx->stream));
+  {
+    std::vector<float> pvalf(pval.size());
+    std::vector<int> pidxf(pidx.size());
+    for (size_t q = 0; q < pval.size(); ++q) pvalf[q] = (float)pval[q];
+    for (size_t q = 0; q < pidx.size(); ++q) pidxf[q] = pidx[q] / 2;   // rows of 256 instead of 512 bytes
+    DNSB_CK(ctx, m->t_pvalf.upload(pvalf.data(), pvalf.size(), ctx->stream));
+    DNSB_CK(ctx, m->t_pidxf.upload(pidxf.data(), pidxf.size(), ctx->stream));
+  }
   p.ok = true;
   return 0;
 }
@@ -302,6 +343,7 @@ static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
 static void csr_free(dnsb_csr *m) {
   if (!m) return;
   m->t_uptr.release(); m->t_rptr.release(); m->t_runs.release(); m->t_pidx.release(); m->t_pval.release();
+  m->t_pidxf.release(); m->t_pvalf.release(); m->t_truns.release(); m->t_tdesc.release(); m->t_pdesc.release();
   m->indptr.release(); m->indices.release(); m->v1.release(); m->v2.release();
   delete m;
 }
@@ -479,6 +521,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
+  if (const char *ev = getenv("DNSB_CHEB_F32")) g_cheb_f32 = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
@@ -518,6 +561,10 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   return 0;
 }
 
@@ -985,6 +1032,7 @@ struct dnsb_solver {
   DBuf<int> diagpos;
   DBuf<double> Vb, Zb, w;  // Krylov bases
   DBuf<double> cres, cd0, cd1;   // Chebyshev work (nv*nb)
+  DBuf<float> cf_res, cf_d0, cf_d1, cf_z, cf_dinv;   // the same in fp32 (DNSB_CHEB_F32, tile path)
   DBuf<double> partial, partial2, red;
   RedCfg rc;
   // GMRES scalars
@@ -1091,6 +1139,7 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
     s->has_coef = true;
   }
   if (nb == TILE_NB && coef && !fmat->tile.ok) { int rc = tile_setup(ctx, fmat); if (rc) return rc; }
+  const bool want_f32 = g_cheb_f32 && nb == TILE_NB && coef && fmat->tile.ok;
   std::vector<int> dp;
   { int rc = find_diagpos(ctx, fmat, dp); if (rc) return rc; }
   DNSB_CK(ctx, s->diagpos.upload(dp.data(), dp.size(), ctx->stream));
@@ -1098,6 +1147,11 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
   DNSB_CK(ctx, s->dinv.alloc(nvb));
   LAUNCH(ctx, k_diag_inv, cdiv(nvb, 256), 256, 0, fmat->view(), s->diagpos.p,
          s->has_coef ? s->coef.p : nullptr, s->dinv.p, nb);
+  if (want_f32) {
+    DNSB_CK(ctx, s->cf_res.alloc(nvb)); DNSB_CK(ctx, s->cf_d0.alloc(nvb)); DNSB_CK(ctx, s->cf_d1.alloc(nvb));
+    DNSB_CK(ctx, s->cf_z.alloc(nvb)); DNSB_CK(ctx, s->cf_dinv.alloc(nvb));
+    LAUNCH(ctx, k_f64_to_f32, cdiv(nvb, 256), 256, 0, (const double *)s->dinv.p, s->cf_dinv.p, (size_t)1, nvb, nvb);
+  }
   {
     MgLevel *V0 = new (std::nothrow) MgLevel();
     DNSB_REQUIRE(ctx, V0 != nullptr, "out of host memory");
@@ -1234,6 +1288,7 @@ extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   csr_free(s->K);
   s->coef.release(); s->dinv.release(); s->diagpos.release();
   s->Vb.release(); s->Zb.release(); s->w.release();
+  s->cf_res.release(); s->cf_d0.release(); s->cf_d1.release(); s->cf_z.release(); s->cf_dinv.release();
   s->cres.release(); s->cd0.release(); s->cd1.release();
   s->partial.release(); s->partial2.release(); s->red.release();
   s->gR.release(); s->gcs.release(); s->gsn.release(); s->gg.release(); s->gh.release(); s->gh2.release();
@@ -1457,6 +1512,29 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
   const bool pair = pair_ok(A, nb) && (!C || pair_ok(C, nb));
   // all rows pair up (both components of every node are unknowns)?
   const bool rowpair = pair && rowpairs_of(A, nb) * 2 == n;
+  if (g_cheb_f32 && C && A == s->F && s->cf_res.p && rowpair && has2 && nb == TILE_NB && A->tile.ok && k >= 2 &&
+      rowpairs_of(C, nb) * 2 == n) {
+    // fp32 smoother (dnsb_tile.cuh): fp64 in (r, zc), fp64 out (z), work vectors and matrix values fp32
+    LAUNCH(ctx, k_cheb_init_p2f, spp_grid(n / 2, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
+           (const float2 *)s->cf_dinv.p, (float2 *)s->cf_res.p, (float2 *)s->cf_d0.p, nb, n / 2, (float)(1.0 / theta));
+    float *dcf = s->cf_d0.p, *dnf = s->cf_d1.p;
+    const unsigned grid_ = std::min(A->tile.ntiles, ctx->sm_count);
+    const TileDevF tv = A->tile_view_f();
+    for (int i = 0; i + 1 < k; ++i) {
+      const double rho_n = 1.0 / (2.0 * sigma - rho);
+      const float c1 = (float)(rho_n * rho), c2 = (float)(2.0 * rho_n / delta);
+      const bool first = i == 0, last = i + 2 == k;
+#define CHEB_ARGS_F tv, coef, (const float *)dcf, (const float *)s->cf_dinv.p, s->cf_res.p, dnf, s->cf_z.p, z, c1, c2
+      if (first && last) LAUNCH(ctx, (k_cheb_step_tilef<true, true>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
+      else if (first) LAUNCH(ctx, (k_cheb_step_tilef<true, false>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
+      else if (last) LAUNCH(ctx, (k_cheb_step_tilef<false, true>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
+      else LAUNCH(ctx, (k_cheb_step_tilef<false, false>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
+#undef CHEB_ARGS_F
+      std::swap(dcf, dnf);
+      rho = rho_n;
+    }
+    return;
+  }
   if (C) {
     if (pair && rowpairs_of(C, nb) * 2 == n)
       LAUNCH(ctx, k_cheb_init_p2, spp_grid(n / 2, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),

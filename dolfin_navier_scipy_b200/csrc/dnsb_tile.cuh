@@ -58,8 +58,11 @@ struct TileDev {
   const int *runs;          // per run: first column, number of columns, first slot in the x tile
   const int *pidx;          // per pair-entry: byte offset of the x row inside the tile
   const double *pval;       // per pair-entry: (a.v1, a.v2, b.v1, b.v2)
+  const int4 *tdesc;        // per tile: first staged pair-entry (aligned), number staged, unique x rows, runs
+  const int *truns;         // per tile `rmax` runs x (first column, columns, first slot), fixed stride
+  const int4 *pdesc;        // per row pair: (offset into the staged entries, entries per row, 0, 0)
+  int rmax;
   int ntiles, npairs, umax, cap;
-  int dbg;   // timing experiments only (DNSB_TILE_DBG): 1 = no x copies, 2 = no gather loop, 4 = no entry copies
 };
 
 __device__ __forceinline__ uint32_t tl_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,36 +121,47 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == TILE_RP) {
-    // ---- producer warp ----
+    // ---- producer warp: the descriptor and the runs of the NEXT tile are loaded (one independent
+    // round trip each, fixed addresses) while the copies of the current one are issued -- the loop
+    // used to pay three dependent global round trips per tile (indptr -> run list -> addresses), which
+    // bounded the whole kernel at ~2 us per tile whatever the number of bytes
     int it = 0;
-    for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
+    int t = blockIdx.x;
+    int4 dsc = make_int4(0, 0, 0, 0);
+    int rc = 0, rl = 0, rs = 0;
+    if (t < T.ntiles) {
+      dsc = T.tdesc[t];
+      if (lane < T.rmax) {
+        const int *rr = T.truns + ((size_t)t * T.rmax + lane) * 3;
+        rc = rr[0]; rl = rr[1]; rs = rr[2];
+      }
+    }
+    for (; t < T.ntiles; t += gridDim.x, ++it) {
       const int s = it % TILE_STAGES;
+      const int tn = t + gridDim.x;
+      int4 ndsc = dsc;
+      int nrc = 0, nrl = 0, nrs = 0;
+      if (tn < T.ntiles) {
+        ndsc = T.tdesc[tn];
+        if (lane < T.rmax) {
+          const int *rr = T.truns + ((size_t)tn * T.rmax + lane) * 3;
+          nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
+        }
+      }
       if (it >= TILE_STAGES) {
         if (lane == 0) tl_mbar_wait(&empty[s], ((it / TILE_STAGES) - 1) & 1);
         __syncwarp();
       }
-      const int p0 = t * TILE_RP, p1 = min(T.npairs, p0 + TILE_RP);
-      const int pe0 = T.indptr[2 * p0] >> 1, pe1 = T.indptr[2 * p1] >> 1;
-      const int a0 = pe0 & ~3, a1 = (pe1 + 3) & ~3;
-      const int nu = T.uptr[t + 1] - T.uptr[t];
       unsigned char *st = tl_raw + (size_t)s * stage_bytes;
       if (lane == 0) {
-        tl_mbar_expect(&full[s], ((T.dbg & 1) ? 0u : (uint32_t)nu * TILE_ROWB) +
-                                     ((T.dbg & 4) ? 0u : (uint32_t)(a1 - a0) * 36));
-        if (!(T.dbg & 4)) {
-          tl_bulk(st + off_val, T.pval + (size_t)a0 * 4, (uint32_t)(a1 - a0) * 32, &full[s]);
-          tl_bulk(st + off_idx, T.pidx + a0, (uint32_t)(a1 - a0) * 4, &full[s]);
-        }
+        tl_mbar_expect(&full[s], (uint32_t)dsc.z * TILE_ROWB + (uint32_t)dsc.y * 36);
+        tl_bulk(st + off_val, T.pval + (size_t)dsc.x * 4, (uint32_t)dsc.y * 32, &full[s]);
+        tl_bulk(st + off_idx, T.pidx + dsc.x, (uint32_t)dsc.y * 4, &full[s]);
       }
       __syncwarp();
-      if (T.dbg & 1) continue;
-      // the unique columns of a tile (Hilbert-ordered mesh nodes) form a few runs of consecutive
-      // rows of x: one bulk copy per run (the TMA engine is slow on many small copies)
-      const int r0 = T.rptr[t], nr = T.rptr[t + 1] - r0;
-      for (int r = lane; r < nr; r += 32) {
-        const int col = T.runs[3 * (r0 + r)], len = T.runs[3 * (r0 + r) + 1], sl = T.runs[3 * (r0 + r) + 2];
-        tl_bulk(st + (size_t)sl * TILE_ROWB, d + (size_t)col * TILE_NB, (uint32_t)len * TILE_ROWB, &full[s]);
-      }
+      if (lane < dsc.w)
+        tl_bulk(st + (size_t)rs * TILE_ROWB, d + (size_t)rc * TILE_NB, (uint32_t)rl * TILE_ROWB, &full[s]);
+      dsc = ndsc; rc = nrc; rl = nrl; rs = nrs;
     }
     return;
   }
@@ -157,10 +171,11 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
   const double2 zero = make_double2(0.0, 0.0);
   // update operands of the warp's own two rows (coalesced, addresses known up front): loaded
   // ONE TILE AHEAD into registers, so that their DRAM latency overlaps the previous tile
-  struct Ops { double2 ra, rb, oa, ob, da, db, za, zb; };
+  struct Ops { double2 ra, rb, oa, ob, da, db, za, zb; int4 pd; };
   auto load_ops = [&](int tile) {
     Ops o;
     const int q = min(tile * TILE_RP + warp, T.npairs - 1);
+    o.pd = T.pdesc[q];
     const size_t ia = (size_t)(2 * q) * (TILE_NB / 2) + lane, ib = ia + TILE_NB / 2;
     o.ra = reinterpret_cast<const double2 *>(res)[ia];  o.rb = reinterpret_cast<const double2 *>(res)[ib];
     o.oa = reinterpret_cast<const double2 *>(d)[ia];    o.ob = reinterpret_cast<const double2 *>(d)[ib];
@@ -176,9 +191,7 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
     const int p0 = t * TILE_RP;
     const int rp = p0 + warp;
     const bool have = rp < T.npairs;
-    const int tpe0 = T.indptr[2 * p0] >> 1;
-    const int k0 = have ? (T.indptr[2 * rp] >> 1) : 0;
-    const int L = have ? (T.indptr[2 * rp + 1] - T.indptr[2 * rp]) : 0;
+    const int kb = cur.pd.x, L = have ? cur.pd.y : 0;   // came with the operands, one tile ahead
     const size_t ta = (size_t)(2 * (have ? rp : 0)) * (TILE_NB / 2) + lane, tb = ta + TILE_NB / 2;
     const int tn = t + gridDim.x;
     Ops nxt = cur;
@@ -186,13 +199,11 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
     tl_mbar_wait(&full[s], (it / TILE_STAGES) & 1);
     const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
     if (have) {
-      const int kb = k0 - (tpe0 & ~3);
       const double2 *sval = reinterpret_cast<const double2 *>(st + off_val) + (size_t)kb * 2;
       const int *sidx = reinterpret_cast<const int *>(st + off_idx) + kb;
       const unsigned char *xt = st + (size_t)lane * 16;
       double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
       int k = 0;
-      if (T.dbg & 2) k = L;
       for (; k + 2 <= L; k += 2) {
         const int o0 = sidx[k], o1 = sidx[k + 1];
         const double2 x0 = *reinterpret_cast<const double2 *>(xt + o0);
@@ -230,5 +241,200 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
       if (lane == 0) tl_mbar_arrive(&empty[s]);
     }
     cur = nxt;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 variant of the same kernel for the SMOOTHER INSIDE THE PRECONDITIONER.
+// The Jacobi-Chebyshev iteration on the velocity block is a polynomial
+// approximation of F^-1 that is accurate to a few per cent; it is applied inside
+// a flexible GMRES whose bases, residuals and stopping test are fp64 (like the
+// tensor-core Schur block, dnsb_tc.cuh).  Carrying its work vectors (res, d, z,
+// dinv) and the matrix values in fp32 halves every byte the kernel moves -- DRAM
+// operands, the L2 refetch of the x tile, the shared-memory gathers -- and the
+// model of the solver (tools/solver_model.py) shows unchanged iteration counts.
+// The last step writes z in fp64 (the preconditioned vector Z_j of FGMRES).
+//   rows of x: 256 bytes (64 floats); packed entry: 4 floats + byte offset.
+// ---------------------------------------------------------------------------
+#define TILE_ROWBF (TILE_NB * 4)
+
+struct TileDevF {
+  const int *indptr, *uptr, *rptr, *runs;
+  const int *pidx;          // byte offset of the x row inside the fp32 tile
+  const float *pval;        // (a.v1, a.v2, b.v1, b.v2) as floats
+  const int4 *tdesc;
+  const int *truns;
+  const int4 *pdesc;
+  int rmax;
+  int ntiles, npairs, umax, cap;
+};
+
+template <bool FIRST, bool LAST>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__restrict__ d,
+                  const float *__restrict__ dinv, float *res, float *__restrict__ dn, float *zf,
+                  double *__restrict__ zout, float c1, float c2) {
+  extern __shared__ __align__(128) unsigned char tl_raw[];
+  __shared__ __align__(8) uint64_t full[TILE_STAGES], empty[TILE_STAGES];
+  const size_t off_val = (size_t)T.umax * TILE_ROWBF;
+  const size_t off_idx = off_val + (size_t)T.cap * 16;
+  const size_t stage_bytes = (off_idx + (size_t)T.cap * 4 + 127) & ~(size_t)127;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TILE_STAGES; ++s) {
+      tl_mbar_init(&full[s], 1);
+      tl_mbar_init(&empty[s], TILE_RP);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == TILE_RP) {
+    // ---- producer warp: the descriptor and the runs of the NEXT tile are loaded (one independent
+    // round trip each, fixed addresses) while the copies of the current one are issued -- the loop
+    // used to pay three dependent global round trips per tile (indptr -> run list -> addresses), which
+    // bounded the whole kernel at ~2 us per tile whatever the number of bytes
+    int it = 0;
+    int t = blockIdx.x;
+    int4 dsc = make_int4(0, 0, 0, 0);
+    int rc = 0, rl = 0, rs = 0;
+    if (t < T.ntiles) {
+      dsc = T.tdesc[t];
+      if (lane < T.rmax) {
+        const int *rr = T.truns + ((size_t)t * T.rmax + lane) * 3;
+        rc = rr[0]; rl = rr[1]; rs = rr[2];
+      }
+    }
+    for (; t < T.ntiles; t += gridDim.x, ++it) {
+      const int s = it % TILE_STAGES;
+      const int tn = t + gridDim.x;
+      int4 ndsc = dsc;
+      int nrc = 0, nrl = 0, nrs = 0;
+      if (tn < T.ntiles) {
+        ndsc = T.tdesc[tn];
+        if (lane < T.rmax) {
+          const int *rr = T.truns + ((size_t)tn * T.rmax + lane) * 3;
+          nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
+        }
+      }
+      if (it >= TILE_STAGES) {
+        if (lane == 0) tl_mbar_wait(&empty[s], ((it / TILE_STAGES) - 1) & 1);
+        __syncwarp();
+      }
+      unsigned char *st = tl_raw + (size_t)s * stage_bytes;
+      if (lane == 0) {
+        tl_mbar_expect(&full[s], (uint32_t)dsc.z * TILE_ROWBF + (uint32_t)dsc.y * 20);
+        tl_bulk(st + off_val, T.pval + (size_t)dsc.x * 4, (uint32_t)dsc.y * 16, &full[s]);
+        tl_bulk(st + off_idx, T.pidx + dsc.x, (uint32_t)dsc.y * 4, &full[s]);
+      }
+      __syncwarp();
+      if (lane < dsc.w)
+        tl_bulk(st + (size_t)rs * TILE_ROWBF, d + (size_t)rc * TILE_NB, (uint32_t)rl * TILE_ROWBF, &full[s]);
+      dsc = ndsc; rc = nrc; rl = nrl; rs = nrs;
+    }
+    return;
+  }
+
+  const double2 cmd = reinterpret_cast<const double2 *>(coef)[lane];
+  const float2 cm = make_float2((float)cmd.x, (float)cmd.y);
+  const float2 zero = make_float2(0.f, 0.f);
+  struct Ops { float2 ra, rb, oa, ob, da, db, za, zb; int4 pd; };
+  auto load_ops = [&](int tile) {
+    Ops o;
+    const int q = min(tile * TILE_RP + warp, T.npairs - 1);
+    o.pd = T.pdesc[q];
+    const size_t ia = (size_t)(2 * q) * (TILE_NB / 2) + lane, ib = ia + TILE_NB / 2;
+    o.ra = reinterpret_cast<const float2 *>(res)[ia];  o.rb = reinterpret_cast<const float2 *>(res)[ib];
+    o.oa = reinterpret_cast<const float2 *>(d)[ia];    o.ob = reinterpret_cast<const float2 *>(d)[ib];
+    o.da = reinterpret_cast<const float2 *>(dinv)[ia]; o.db = reinterpret_cast<const float2 *>(dinv)[ib];
+    o.za = FIRST ? zero : reinterpret_cast<const float2 *>(zf)[ia];
+    o.zb = FIRST ? zero : reinterpret_cast<const float2 *>(zf)[ib];
+    return o;
+  };
+  Ops cur = load_ops(min((int)blockIdx.x, T.ntiles - 1));
+  int it = 0;
+  for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
+    const int s = it % TILE_STAGES;
+    const int p0 = t * TILE_RP;
+    const int rp = p0 + warp;
+    const bool have = rp < T.npairs;
+    const int kb = cur.pd.x, L = have ? cur.pd.y : 0;   // came with the operands, one tile ahead
+    const size_t ta = (size_t)(2 * (have ? rp : 0)) * (TILE_NB / 2) + lane, tb = ta + TILE_NB / 2;
+    const int tn = t + gridDim.x;
+    Ops nxt = cur;
+    if (tn < T.ntiles) nxt = load_ops(tn);
+    tl_mbar_wait(&full[s], (it / TILE_STAGES) & 1);
+    const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
+    if (have) {
+      const float4 *sval = reinterpret_cast<const float4 *>(st + off_val) + kb;
+      const int *sidx = reinterpret_cast<const int *>(st + off_idx) + kb;
+      const unsigned char *xt = st + (size_t)lane * 8;
+      float ax = 0.f, ay = 0.f, bx = 0.f, by = 0.f;
+      int k = 0;
+      for (; k + 2 <= L; k += 2) {
+        const int o0 = sidx[k], o1 = sidx[k + 1];
+        const float2 x0 = *reinterpret_cast<const float2 *>(xt + o0);
+        const float2 x1 = *reinterpret_cast<const float2 *>(xt + o1);
+        const float4 e0 = sval[k], e1 = sval[k + 1];
+        ax = fmaf(fmaf(cm.x, e0.y, e0.x), x0.x, ax);  ay = fmaf(fmaf(cm.y, e0.y, e0.x), x0.y, ay);
+        bx = fmaf(fmaf(cm.x, e0.w, e0.z), x0.x, bx);  by = fmaf(fmaf(cm.y, e0.w, e0.z), x0.y, by);
+        ax = fmaf(fmaf(cm.x, e1.y, e1.x), x1.x, ax);  ay = fmaf(fmaf(cm.y, e1.y, e1.x), x1.y, ay);
+        bx = fmaf(fmaf(cm.x, e1.w, e1.z), x1.x, bx);  by = fmaf(fmaf(cm.y, e1.w, e1.z), x1.y, by);
+      }
+      for (; k < L; ++k) {
+        const float2 xv = *reinterpret_cast<const float2 *>(xt + sidx[k]);
+        const float4 e = sval[k];
+        ax = fmaf(fmaf(cm.x, e.y, e.x), xv.x, ax);  ay = fmaf(fmaf(cm.y, e.y, e.x), xv.y, ay);
+        bx = fmaf(fmaf(cm.x, e.w, e.z), xv.x, bx);  by = fmaf(fmaf(cm.y, e.w, e.z), xv.y, by);
+      }
+      __syncwarp();
+      if (lane == 0) tl_mbar_arrive(&empty[s]);
+      const float rax = cur.ra.x - ax, ray = cur.ra.y - ay, rbx = cur.rb.x - bx, rby = cur.rb.y - by;
+      const float dax = fmaf(c2 * cur.da.x, rax, c1 * cur.oa.x), day = fmaf(c2 * cur.da.y, ray, c1 * cur.oa.y);
+      const float dbx = fmaf(c2 * cur.db.x, rbx, c1 * cur.ob.x), dby = fmaf(c2 * cur.db.y, rby, c1 * cur.ob.y);
+      if (!LAST) {
+        reinterpret_cast<float2 *>(res)[ta] = make_float2(rax, ray);
+        reinterpret_cast<float2 *>(res)[tb] = make_float2(rbx, rby);
+        reinterpret_cast<float2 *>(dn)[ta] = make_float2(dax, day);
+        reinterpret_cast<float2 *>(dn)[tb] = make_float2(dbx, dby);
+      }
+      const float zax = (FIRST ? cur.oa.x : cur.za.x) + dax, zay = (FIRST ? cur.oa.y : cur.za.y) + day;
+      const float zbx = (FIRST ? cur.ob.x : cur.zb.x) + dbx, zby = (FIRST ? cur.ob.y : cur.zb.y) + dby;
+      if (LAST) {
+        reinterpret_cast<double2 *>(zout)[ta] = make_double2((double)zax, (double)zay);
+        reinterpret_cast<double2 *>(zout)[tb] = make_double2((double)zbx, (double)zby);
+      } else {
+        reinterpret_cast<float2 *>(zf)[ta] = make_float2(zax, zay);
+        reinterpret_cast<float2 *>(zf)[tb] = make_float2(zbx, zby);
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) tl_mbar_arrive(&empty[s]);
+    }
+    cur = nxt;
+  }
+}
+
+// Chebyshev start in fp32 storage (fp64 inputs): res = rv - JT*zp ; d = dinv*res/theta.
+// Same row-pair mapping as k_cheb_init_p2 (thread = 2 rows x 2 members).
+__global__ void __launch_bounds__(SPB_THREADS)
+k_cheb_init_p2f(CsrDev A, const double2 *__restrict__ zp, const double2 *__restrict__ rv,
+                const float2 *__restrict__ dinv, float2 *__restrict__ res, float2 *__restrict__ d,
+                int nb, int npairs, float inv_theta) {
+  SPP_MAP(false)
+  const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
+  const double2 ra = rv[sa_], rb = rv[sb_];
+  const float2 da = dinv[sa_], db = dinv[sb_];
+  double2 a, b;
+  spp_rowdots<false>(A, make_double2(0.0, 0.0), zp + mp, nb2, rp, valid, wp0, wp1, lane, sv2, sv1,
+                     soff, a, b);
+  if (valid) {
+    const float rax = (float)(ra.x - a.x), ray = (float)(ra.y - a.y);
+    const float rbx = (float)(rb.x - b.x), rby = (float)(rb.y - b.y);
+    res[ta_] = make_float2(rax, ray);
+    res[tb_] = make_float2(rbx, rby);
+    d[ta_] = make_float2(da.x * rax * inv_theta, da.y * ray * inv_theta);
+    d[tb_] = make_float2(db.x * rbx * inv_theta, db.y * rby * inv_theta);
   }
 }

@@ -1027,18 +1027,21 @@ def test_steady_solver_outside_its_envelope_fails_loudly(cyl1, ctx):
                                   **soldict(femp, sm, rhsd))
 
 
-def _ctx_with_env(name, value):
-    """a context created under an environment switch (read at creation)"""
+def _ctx_with_env(name, value, **more):
+    """a context created under environment switches (read at creation)"""
     from dolfin_navier_scipy_b200 import _lib
-    old = os.environ.get(name)
-    os.environ[name] = value
+    env = dict(more)
+    env[name] = value
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         return _lib.Context(0)
     finally:
-        if old is None:
-            del os.environ[name]
-        else:
-            os.environ[name] = old
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
 
 
 @pytest.fixture
@@ -1152,7 +1155,7 @@ def test_tiled_chebyshev_is_bit_identical(cyl1):
                         return_vp_dict=True, **soldict(femp, sm, rhsd))[0.0]
     out = {}
     for flag in ('0', '1'):
-        c = _ctx_with_env('DNSB_TILE', flag)
+        c = _ctx_with_env('DNSB_TILE', flag, DNSB_CHEB_F32='0')   # the fp64 tile kernel
         integ = tiu.DeviceImex(sm['M'], A0, sm['J'], femp['V'], inv,
                                femp['dbcinds'], femp['dbcvals'], dt, nus=nus,
                                fp=rhsd['fp'], ctx=c)
@@ -1296,7 +1299,7 @@ def test_low_rank_update_and_krylovini(cyl1, ctx):
                                     'DNSB_DMMA=0', 'DNSB_PAIR=0',
                                     'DNSB_ROWPAIR=0', 'DNSB_GS_TMA=0',
                                     'DNSB_TILE=0', 'DNSB_SCHUR_TC=0',
-                                    'DNSB_GS_PYTH=0'])
+                                    'DNSB_GS_PYTH=0', 'DNSB_CHEB_F32=0'])
 def test_every_tuning_switch_gives_the_same_trajectory(cyl1, ctx, switch):
     """the environment switches select kernel VARIANTS of the same arithmetic
     (coloured scatter vs gather assembly -- the form `north_star` names --,
