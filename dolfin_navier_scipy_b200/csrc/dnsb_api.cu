@@ -251,14 +251,13 @@ static const int TILE_SMEM_OPTIN = 220 * 1024;
 static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
   TilePlan &p = m->tile;
   p.ok = false;
-  if (!g_tile || !m->has2 || m->npair_rows != m->nrows || m->nrows < 2 || m->h_indptr.empty() ||
-      m->h_v2.empty() || ctx->cc < 100)
+  if (!g_tile || !m->has2 || m->npair_rows < 2 || m->h_indptr.empty() || m->h_v2.empty() || ctx->cc < 100)
     return 0;
-  const int np = m->nrows / 2;
+  const int np = m->npair_rows / 2;   // leading paired rows (all of F; the velocity rows of K)
   const std::vector<int> &ip = m->h_indptr, &ix = m->h_indices;
   p.npairs = np;
   p.ntiles = (np + TILE_RP - 1) / TILE_RP;
-  const size_t npe = (size_t)m->nnz / 2;
+  const size_t npe = (size_t)m->h_indptr[2 * np] / 2;
   std::vector<int> uptr(p.ntiles + 1, 0), rptr(p.ntiles + 1, 0), runs, ucols, pidx(npe + 8, 0);
   std::vector<double> pval((npe + 8) * 4, 0.0);
   std::vector<int> slot(m->ncols, -1);
@@ -431,7 +430,21 @@ static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
     const bool h2 = A->has2 && coef;
     const int npairs = rowpairs_of(A, nb);
     const int row_begin = 2 * npairs;
-    if (npairs > 0 && row_begin < A->nrows) {
+    if (h2 && nb == TILE_NB && A->tile.ok && A->tile.npairs == npairs) {
+      // TMA-staged tiles for the paired rows (dnsb_tile.cuh), the member-pair kernel for the tail
+      // (running the tail -- the long divergence rows of K, 13 us alone -- on a second stream beside
+      // the persistent tile kernel was measured: 1.470 instead of 1.451 ms/step, the tile kernel's
+      // shared memory leaves no room for a second resident CTA)
+      const unsigned grid_ = std::min(A->tile.ntiles, ctx->sm_count);
+      const TileDev tv = A->tile_view();
+      if (beta != 0.0)
+        LAUNCH(ctx, k_spmm_tile<true>, grid_, TILE_THREADS, A->tile.smem, tv, coef, x, z, y, alpha, beta);
+      else
+        LAUNCH(ctx, k_spmm_tile<false>, grid_, TILE_THREADS, A->tile.smem, tv, coef, x, z, y, alpha, beta);
+      if (row_begin < A->nrows)
+        LAUNCH(ctx, k_spmm_b2<true>, spb2_grid(A->nrows - row_begin, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
+               D2C(z), D2(y), nb, row_begin, alpha, beta);
+    } else if (npairs > 0 && row_begin < A->nrows) {
       // paired rows and a tail of single rows (K = [F JT; J 0]) in one launch
       const unsigned tb = spb2_grid(A->nrows - row_begin, nb);
       const unsigned grid = tb + spp_grid(npairs, nb);
@@ -561,6 +574,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_spmm_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_spmm_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
@@ -1130,6 +1145,7 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
     int rc = csr_build(ctx, ntot, ntot, ip.data(), ix.data(), a1.data(),
                        fmat->has2 ? a2.data() : nullptr, &s->K);
     if (rc) return rc;
+    if (nb == TILE_NB && coef) { int rct = tile_setup(ctx, s->K); if (rct) return rct; }
     // the block matrix is only needed on the device
     std::vector<int>().swap(s->K->h_indptr); std::vector<int>().swap(s->K->h_indices);
     std::vector<double>().swap(s->K->h_v1); std::vector<double>().swap(s->K->h_v2);
@@ -1992,6 +2008,7 @@ extern "C" int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1) {
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));   // host buffer is borrowed
   std::copy(vals1, vals1 + F->nnz, F->h_v1.begin());
   F->tile.ok = false;   // packed copies of the values are stale: the row-pair kernels serve this matrix
+  s->K->tile.ok = false;
   LAUNCH(ctx, k_copy_f_into_k, cdiv((size_t)F->nrows * 32, 256), 256, 0, F->view(),
          (const int *)s->K->indptr.p, s->K->v1.p);
   const size_t nvb = (size_t)s->nv * s->nb;

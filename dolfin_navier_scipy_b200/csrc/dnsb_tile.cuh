@@ -438,3 +438,137 @@ k_cheb_init_p2f(CsrDev A, const double2 *__restrict__ zp, const double2 *__restr
     d[tb_] = make_float2(db.x * rbx * inv_theta, db.y * rby * inv_theta);
   }
 }
+
+// ---------------------------------------------------------------------------
+// y = alpha*A*x + beta*z on the PAIRED rows of A with the same staging (fp64,
+// same summation order as k_spmm_p2 / k_spmm_k2: bit-identical).  Used for the
+// saddle-point matrix K = [F JT; J 0]: the unique rows of x of a tile include the
+// pressure rows the gradient block refers to; the unpaired divergence rows are
+// served by k_spmm_b2 as before.
+// ---------------------------------------------------------------------------
+template <bool HASZ>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ x,
+            const double *z, double *y, double alpha, double beta) {
+  extern __shared__ __align__(128) unsigned char tl_raw[];
+  __shared__ __align__(8) uint64_t full[TILE_STAGES], empty[TILE_STAGES];
+  const size_t off_val = (size_t)T.umax * TILE_ROWB;
+  const size_t off_idx = off_val + (size_t)T.cap * 32;
+  const size_t stage_bytes = (off_idx + (size_t)T.cap * 4 + 127) & ~(size_t)127;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TILE_STAGES; ++s) {
+      tl_mbar_init(&full[s], 1);
+      tl_mbar_init(&empty[s], TILE_RP);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double *d = x;   // the producer below streams rows of `d`
+
+  if (warp == TILE_RP) {
+    int it = 0;
+    int t = blockIdx.x;
+    int4 dsc = make_int4(0, 0, 0, 0);
+    int rc = 0, rl = 0, rs = 0;
+    if (t < T.ntiles) {
+      dsc = T.tdesc[t];
+      if (lane < T.rmax) {
+        const int *rr = T.truns + ((size_t)t * T.rmax + lane) * 3;
+        rc = rr[0]; rl = rr[1]; rs = rr[2];
+      }
+    }
+    for (; t < T.ntiles; t += gridDim.x, ++it) {
+      const int s = it % TILE_STAGES;
+      const int tn = t + gridDim.x;
+      int4 ndsc = dsc;
+      int nrc = 0, nrl = 0, nrs = 0;
+      if (tn < T.ntiles) {
+        ndsc = T.tdesc[tn];
+        if (lane < T.rmax) {
+          const int *rr = T.truns + ((size_t)tn * T.rmax + lane) * 3;
+          nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
+        }
+      }
+      if (it >= TILE_STAGES) {
+        if (lane == 0) tl_mbar_wait(&empty[s], ((it / TILE_STAGES) - 1) & 1);
+        __syncwarp();
+      }
+      unsigned char *st = tl_raw + (size_t)s * stage_bytes;
+      if (lane == 0) {
+        tl_mbar_expect(&full[s], (uint32_t)dsc.z * TILE_ROWB + (uint32_t)dsc.y * 36);
+        tl_bulk(st + off_val, T.pval + (size_t)dsc.x * 4, (uint32_t)dsc.y * 32, &full[s]);
+        tl_bulk(st + off_idx, T.pidx + dsc.x, (uint32_t)dsc.y * 4, &full[s]);
+      }
+      __syncwarp();
+      if (lane < dsc.w)
+        tl_bulk(st + (size_t)rs * TILE_ROWB, d + (size_t)rc * TILE_NB, (uint32_t)rl * TILE_ROWB, &full[s]);
+      dsc = ndsc; rc = nrc; rl = nrl; rs = nrs;
+    }
+    return;
+  }
+
+  const double2 cm = reinterpret_cast<const double2 *>(coef)[lane];
+  const double2 zero = make_double2(0.0, 0.0);
+  struct Ops { double2 za, zb; int4 pd; };
+  auto load_ops = [&](int tile) {
+    Ops o;
+    const int q = min(tile * TILE_RP + warp, T.npairs - 1);
+    o.pd = T.pdesc[q];
+    const size_t ia = (size_t)(2 * q) * (TILE_NB / 2) + lane, ib = ia + TILE_NB / 2;
+    o.za = HASZ ? reinterpret_cast<const double2 *>(z)[ia] : zero;
+    o.zb = HASZ ? reinterpret_cast<const double2 *>(z)[ib] : zero;
+    return o;
+  };
+  Ops cur = load_ops(min((int)blockIdx.x, T.ntiles - 1));
+  int it = 0;
+  for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
+    const int s = it % TILE_STAGES;
+    const int rp = t * TILE_RP + warp;
+    const bool have = rp < T.npairs;
+    const int kb = cur.pd.x, L = have ? cur.pd.y : 0;
+    const size_t ta = (size_t)(2 * (have ? rp : 0)) * (TILE_NB / 2) + lane, tb = ta + TILE_NB / 2;
+    const int tn = t + gridDim.x;
+    Ops nxt = cur;
+    if (tn < T.ntiles) nxt = load_ops(tn);
+    tl_mbar_wait(&full[s], (it / TILE_STAGES) & 1);
+    const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
+    if (have) {
+      const double2 *sval = reinterpret_cast<const double2 *>(st + off_val) + (size_t)kb * 2;
+      const int *sidx = reinterpret_cast<const int *>(st + off_idx) + kb;
+      const unsigned char *xt = st + (size_t)lane * 16;
+      double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+      int k = 0;
+      for (; k + 2 <= L; k += 2) {
+        const int o0 = sidx[k], o1 = sidx[k + 1];
+        const double2 x0 = *reinterpret_cast<const double2 *>(xt + o0);
+        const double2 x1 = *reinterpret_cast<const double2 *>(xt + o1);
+        const double2 a0 = sval[2 * k], b0 = sval[2 * k + 1], a1 = sval[2 * k + 2], b1 = sval[2 * k + 3];
+        ax = spp_acc(ax, cm.x, a0, x0.x);  ay = spp_acc(ay, cm.y, a0, x0.y);
+        bx = spp_acc(bx, cm.x, b0, x0.x);  by = spp_acc(by, cm.y, b0, x0.y);
+        ax = spp_acc(ax, cm.x, a1, x1.x);  ay = spp_acc(ay, cm.y, a1, x1.y);
+        bx = spp_acc(bx, cm.x, b1, x1.x);  by = spp_acc(by, cm.y, b1, x1.y);
+      }
+      for (; k < L; ++k) {
+        const double2 xv = *reinterpret_cast<const double2 *>(xt + sidx[k]);
+        const double2 a = sval[2 * k], b = sval[2 * k + 1];
+        ax = spp_acc(ax, cm.x, a, xv.x);  ay = spp_acc(ay, cm.y, a, xv.y);
+        bx = spp_acc(bx, cm.x, b, xv.x);  by = spp_acc(by, cm.y, b, xv.y);
+      }
+      __syncwarp();
+      if (lane == 0) tl_mbar_arrive(&empty[s]);
+      if (HASZ) {
+        reinterpret_cast<double2 *>(y)[ta] = make_double2(alpha * ax + beta * cur.za.x, alpha * ay + beta * cur.za.y);
+        reinterpret_cast<double2 *>(y)[tb] = make_double2(alpha * bx + beta * cur.zb.x, alpha * by + beta * cur.zb.y);
+      } else {
+        reinterpret_cast<double2 *>(y)[ta] = make_double2(alpha * ax, alpha * ay);
+        reinterpret_cast<double2 *>(y)[tb] = make_double2(alpha * bx, alpha * by);
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) tl_mbar_arrive(&empty[s]);
+    }
+    cur = nxt;
+  }
+}
