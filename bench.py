@@ -757,9 +757,10 @@ def _kname(name):
         .replace('k_cheb_step_b', 'k_cheb_step')
 
 
-def kernel_bytes(name, info, integ):
+def kernel_bytes(name, info, integ, mean_work=0.):
     """ALGORITHMIC bytes of one launch; None if the
-    kernel has no fixed byte count (depends on the Krylov column)"""
+    kernel has no fixed byte count.  ``mean_work``: average number of basis
+    vectors a Gram-Schmidt launch read (reported by the library's profiler)"""
     nb = integ.nb
     host = integ._host
     nnzF, n = host['M'].nnz, host['M'].shape[0]
@@ -777,11 +778,24 @@ def kernel_bytes(name, info, integ):
         if tiled:    # 4 values + 1 offset per column of a row pair: 18 B per CSR entry
             return 18.*nnzF + 4.*(n + 1) + 8.*passes*n*nb
         return 20.*nnzF + 4.*(n + 1) + 8.*passes*n*nb
+    if name.startswith('k_spmm_b2'):
+        # the unpaired divergence rows J of K beside k_spmm_tile: entries, gather of x_v, y_p out
+        return 20.*J.nnz + 4.*(npp + 1) + 8.*(n + npp)*nb
     if name.startswith('k_spmm'):
         # the block matrix K = [F JT; J 0] (two value arrays): gather + store
         nnzK = nnzF + 2*J.nnz
         nt = n + npp
         return 20.*nnzK + 4.*(nt + 1) + 16.*nt*nb
+    if name.startswith('k_spmm_tile'):
+        # paired rows of K = [F JT]: packed entries (18 B per CSR entry) + x in, y out
+        return 18.*(nnzF + J.nnz) + 8.*(n + npp)*nb + 8.*n*nb
+    if name.startswith('k_gs_tma<false>') or name.startswith('k_mdot_b'):
+        return 8.*(n + npp)*nb*(mean_work + 1.)           # basis vectors + w
+    if name.startswith('k_gs_tma<true>') or name.startswith('k_gs_update_b'):
+        return 8.*(n + npp)*nb*(mean_work + 2.)           # basis vectors + w in, vnext out
+    if name.startswith('k_cheb_init_p2f'):
+        # JT entries, zp and rv (fp64) in, dinv (fp32) in, res and d (fp32) out
+        return 12.*J.nnz + 4.*(n + 1) + 8.*npp*nb + 20.*n*nb
     if name.startswith('k_cheb_init'):
         return 12.*J.nnz + 4.*(n + 1) + 8.*npp*nb + 32.*n*nb
     if name.startswith(('k_dense_gemm', 'k_dense_dmma')):
@@ -806,8 +820,9 @@ def roofline_of(kern, info, integ, args):
     # template instantiations of one kernel (FIRST/LAST variants of the
     # Chebyshev step) are one kernel family: launches, time and bytes add up
     fam = {}
+    work = getattr(integ.ctx, 'last_work', {})
     for name, (cnt, ms) in kern.items():
-        b = kernel_bytes(name, info, integ)
+        b = kernel_bytes(name, info, integ, work.get(name, 0)/float(max(cnt, 1)))
         base = name.strip('()')
         if b is None or base.startswith('k_dense_'):
             continue
@@ -817,6 +832,11 @@ def roofline_of(kern, info, integ, args):
         f['bytes'] += cnt*b
         f['names'].append((base, cnt))
     key = max(fam.items(), key=lambda kv: kv[1]['ms'])[0]
+    families = [dict(kernel=k, launches=v['cnt'], mean_us=1e3*v['ms']/v['cnt'],
+                     bytes_per_launch=v['bytes']/v['cnt'],
+                     achieved_gbs=v['bytes']/(v['ms']*1e-3)/1e9,
+                     frac=v['bytes']/(v['ms']*1e-3)/1e9/peak)
+                for k, v in sorted(fam.items(), key=lambda kv: -kv[1]['ms'])]
     f = fam[key]
     cnt, ms = f['cnt'], f['ms']
     bytes_ = f['bytes']/cnt
@@ -842,6 +862,8 @@ def roofline_of(kern, info, integ, args):
                achieved=ach, peak=peak,
                peak_source=which, unit='GB/s', frac=ach/peak, traffic=traffic,
                launches=cnt, mean_us=dur*1e6, bytes_per_launch=bytes_)
+    # every HBM-class kernel family of the step, largest first (same arithmetic as the headline entry)
+    out['families'] = families
     # where the step goes: the six largest kernels of the timed region by summed event time
     tot_ms = sum(ms for _, ms in kern.values()) or 1.
     out['kernel_shares'] = [dict(kernel=k.strip('()'), launches=c, mean_us=1e3*m/c, share=m/tot_ms)

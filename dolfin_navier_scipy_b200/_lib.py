@@ -183,15 +183,17 @@ class Context(object):
         self.check(self.lib.dnsb_profile_begin(self.h, int(max_records)))
 
     def profile_end(self):
-        """{kernel: (count, total_ms)} measured with CUDA events"""
+        """{kernel: (count, total_ms)} measured with CUDA events; the summed
+        per-launch work some kernels report is kept in ``self.last_work``"""
         buf = ctypes.create_string_buffer(1 << 16)
         n = self.lib.dnsb_profile_end(self.h, buf, len(buf))
         if n < 0:
             self.check(n)
-        out = {}
+        out, self.last_work = {}, {}
         for line in buf.value.decode().splitlines():
-            name, cnt, ms = line.rsplit(' ', 2)
+            name, cnt, ms, work = line.rsplit(' ', 3)
             out[name] = (int(cnt), float(ms))
+            self.last_work[name] = int(work)
         return out
 
     def close(self):

@@ -36,8 +36,9 @@
     kern<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__);                \
     if (pr_) {                                                                 \
       cudaEventRecord(pe1_, c_->stream);                                       \
-      c_->recs.push_back(ProfRec{#kern, pe0_, pe1_});                          \
+      c_->recs.push_back(ProfRec{#kern, pe0_, pe1_, c_->next_work});           \
     }                                                                          \
+    c_->next_work = 0;                                                         \
     c_->launches++;                                                            \
   } while (0)
 
@@ -89,6 +90,7 @@ static void gs_update_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size
                           const double *h, const double *w, double *vnext, int n, int nb,
                           double *partial2, const double *scale = nullptr) {
   const int st = nvec > 0 ? gst_stages(rc, nb, rc.threads) : 0;
+  ctx->next_work = nvec;
   if (st >= 2)
     LAUNCH(ctx, k_gs_tma<true>, rc.nblocks, rc.threads + 32, gst_smem(rc, nb, st, rc.threads), V, vstride,
            nvec, h, w, vnext, n, nb, rc.rpb, rc.rows_per_block, partial2, st, scale);
@@ -103,6 +105,7 @@ static void mdot_dev(dnsb_ctx *ctx, const RedCfg &rc, const double *V, size_t vs
                      double *h) {
   const size_t smem = (size_t)(nvec + 1) * rc.threads * sizeof(double);
   const int st = nvec > 0 ? gst_stages(rc, nb, (size_t)(nvec + 1) * rc.threads) : 0;
+  ctx->next_work = nvec;
   if (st >= 2)
     LAUNCH(ctx, k_gs_tma<false>, rc.nblocks, rc.threads + 32,
            gst_smem(rc, nb, st, (size_t)(nvec + 1) * rc.threads), V, vstride, nvec, (const double *)nullptr, w,
@@ -570,6 +573,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_dense_tf32_streamk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TFM_SMEM_BYTES));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_schur_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_gmres_givens, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
@@ -634,14 +638,14 @@ extern "C" int dnsb_profile_end(dnsb_ctx *ctx, char *buf, int buflen) {
   ctx->prof = false;
   std::vector<std::string> names;
   std::vector<double> tot;
-  std::vector<long long> cnt;
+  std::vector<long long> cnt, work;
   for (ProfRec &r : ctx->recs) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
     size_t k = 0;
     for (; k < names.size(); ++k) if (names[k] == r.name) break;
-    if (k == names.size()) { names.push_back(r.name); tot.push_back(0.0); cnt.push_back(0); }
-    tot[k] += ms; cnt[k] += 1;
+    if (k == names.size()) { names.push_back(r.name); tot.push_back(0.0); cnt.push_back(0); work.push_back(0); }
+    tot[k] += ms; cnt[k] += 1; work[k] += r.work;
     cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
   ctx->recs.clear();
@@ -651,7 +655,7 @@ extern "C" int dnsb_profile_end(dnsb_ctx *ctx, char *buf, int buflen) {
   std::string out;
   char line[256];
   for (size_t k : order) {
-    snprintf(line, sizeof line, "%s %lld %.6f\n", names[k].c_str(), cnt[k], tot[k]);
+    snprintf(line, sizeof line, "%s %lld %.6f %lld\n", names[k].c_str(), cnt[k], tot[k], work[k]);
     out += line;
   }
   if (buf && buflen > 0) {
@@ -1796,7 +1800,11 @@ static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
     // one pass less and no scalar glue: the norm of the orthogonalised vector from Pythagoras,
     // Givens first, then the update writes the NORMALISED vector (no k_scale_member pass, no
     // reduction of 586 partial norms inside the one-CTA Givens kernel)
-    LAUNCH(ctx, k_gmres_givens, 1, 1024, 0, s->gs, (const double *)nullptr, 0, nb, j, tol, 1);
+    {
+      const size_t gsm = (size_t)3 * (j + 2) * nb * sizeof(double);
+      const int staged = gsm <= 96 * 1024;
+      LAUNCH(ctx, k_gmres_givens, 1, 1024, staged ? gsm : 0, s->gs, (const double *)nullptr, 0, nb, j, tol, 1, staged);
+    }
     gs_update_dev(ctx, rc, s->Vb.p, ntb, j + 1, s->gs.h, s->w.p, Vn, ntot, nb, s->partial2.p,
                   (const double *)s->gs.invh);
     return 0;
@@ -1810,7 +1818,11 @@ static int gmres_iteration_launch(dnsb_solver *s, int j, double tol) {
            (const double *)s->gh2.p, s->gs.h, (size_t)(j + 1) * nb);
     unscaled = s->w.p;
   }
-  LAUNCH(ctx, k_gmres_givens, 1, 1024, 0, s->gs, (const double *)s->partial2.p, rc.nblocks, nb, j, tol, 0);
+  {
+    const size_t gsm = (size_t)3 * (j + 2) * nb * sizeof(double);
+    const int staged = gsm <= 96 * 1024;
+    LAUNCH(ctx, k_gmres_givens, 1, 1024, staged ? gsm : 0, s->gs, (const double *)s->partial2.p, rc.nblocks, nb, j, tol, 0, staged);
+  }
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, unscaled, (const double *)s->gs.invh, Vn,
          (size_t)ntot, nb);
   return 0;

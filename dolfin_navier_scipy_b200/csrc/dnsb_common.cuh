@@ -66,6 +66,7 @@ struct DBuf {
 struct ProfRec {
   const char *name;
   cudaEvent_t e0, e1;
+  long long work;   // caller-defined size of the launch (e.g. basis vectors of a Gram-Schmidt pass), or 0
 };
 
 struct dnsb_ctx {
@@ -80,6 +81,7 @@ struct dnsb_ctx {
   size_t mem_bytes = 0;
   std::string err;
   long long launches = 0;
+  long long next_work = 0;   // recorded with the next profiled launch, then reset
 
   // ---- mesh / convection data (cells permuted into colour order) ----------
   int ncell = 0, nnodes = 0, ncolours = 0;

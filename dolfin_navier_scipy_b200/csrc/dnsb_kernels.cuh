@@ -753,7 +753,7 @@ __global__ void k_set_bnorm(GmresState S, const double *__restrict__ partial,
 // does the scalar work of member m.
 __global__ void __launch_bounds__(1024)
 k_gmres_givens(GmresState S, const double *__restrict__ partial2,
-               int nblocks, int nb, int j, double tol, int pyth) {
+               int nblocks, int nb, int j, double tol, int pyth, int staged) {
   __shared__ double sp[32][33];
   __shared__ double snorm[1024];
   if (pyth) {
@@ -799,23 +799,33 @@ k_gmres_givens(GmresState S, const double *__restrict__ partial2,
     }
   }
   int m = threadIdx.x;
+  // the rotations and the new column of every member, staged once (coalesced over members, all
+  // loads of the block in flight together) instead of 3 dependent global loads per (member, i)
+  // (staged == 0: the arrays do not fit the shared-memory window -- read them in place)
+  extern __shared__ double sgiv[];   // cs | sn | h : (j + 2) * nb each (h: j + 1 entries used)
+  const double *scs = S.cs, *ssn = S.sn, *sh = S.h;
+  if (staged) {
+    double *wcs = sgiv, *wsn = sgiv + (size_t)(j + 2) * nb, *wh = wsn + (size_t)(j + 2) * nb;
+    for (int t = threadIdx.x; t < j * nb; t += blockDim.x) { wcs[t] = S.cs[t]; wsn[t] = S.sn[t]; }
+    for (int t = threadIdx.x; t < (j + 1) * nb; t += blockDim.x) wh[t] = S.h[t];
+    scs = wcs; ssn = wsn; sh = wh;
+  }
+  __syncthreads();
+  int active = 0, myit = 0;
   if (m < nb) {
     if (S.done[m]) {
       S.invh[m] = 0.0;
+      myit = S.ittot[m];
     } else {
       const double s = snorm[m];
       const double hn = sqrt(s);
       const int mr = S.mr;
-      // the loads of (c, s, h) do not alias the stores to R: let them pipeline
-      const double *__restrict__ pcs = S.cs;
-      const double *__restrict__ psn = S.sn;
-      const double *__restrict__ ph = S.h;
       double *__restrict__ pR = S.R;
-      double hprev = ph[m];   // h[0]
+      double hprev = sh[m];   // h[0]
 #pragma unroll 4
       for (int i = 0; i < j; ++i) {
-        const double c = pcs[(size_t)i * nb + m], sn = psn[(size_t)i * nb + m];
-        const double hnext = ph[(size_t)(i + 1) * nb + m];
+        const double c = scs[(size_t)i * nb + m], sn = ssn[(size_t)i * nb + m];
+        const double hnext = sh[(size_t)(i + 1) * nb + m];
         const double t = c * hprev + sn * hnext;
         hprev = -sn * hprev + c * hnext;
         pR[((size_t)i * mr + j) * nb + m] = t;
@@ -832,22 +842,25 @@ k_gmres_givens(GmresState S, const double *__restrict__ partial2,
       const double res = fabs(sn * gj);
       S.resid[m] = res;
       S.its[m] = j + 1;
-      S.ittot[m] += 1;
+      myit = S.ittot[m] + 1;
+      S.ittot[m] = myit;
       const bool fin = !(res > tol * S.bnorm[m]) || !(hn > 0.0);
       S.done[m] = fin ? 1 : 0;
       S.invh[m] = fin ? 0.0 : 1.0 / hn;
       if (fin) gmres_track(S, m, res);
+      active = fin ? 0 : 1;
     }
   }
+  // members still iterating and the largest iteration count: block-wide, no serial loop over members
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
   __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int cnt = 0, mx = 0;
-    for (int k = 0; k < nb; ++k) {
-      cnt += S.done[k] ? 0 : 1;
-      mx = max(mx, S.ittot[k]);
-    }
+  const int cnt = __syncthreads_count(active);
+  if (m < nb) atomicMax(&s_max, myit);
+  __syncthreads();
+  if (threadIdx.x == 0) {
     S.flags[0] = cnt;
-    S.flags[1] = mx;   // iterations actually needed so far (max over members)
+    S.flags[1] = s_max;   // iterations actually needed so far (max over members)
   }
 }
 

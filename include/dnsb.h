@@ -48,8 +48,10 @@ long long dnsb_launch_count(dnsb_ctx *ctx);
 void dnsb_launch_count_reset(dnsb_ctx *ctx);
 
 /* per-kernel device timing with CUDA events on the context's stream: begin
- * records up to `max_records` launches, end writes "kernel count total_ms"
- * lines (sorted by time) into buf and returns the bytes needed. */
+ * records up to `max_records` launches, end writes "kernel count total_ms work"
+ * lines (sorted by time) into buf and returns the bytes needed; `work` is the
+ * sum of a per-launch size some kernels report (Gram-Schmidt: basis vectors
+ * read), so that their average algorithmic bytes can be computed. */
 int dnsb_profile_begin(dnsb_ctx *ctx, int max_records);
 int dnsb_profile_end(dnsb_ctx *ctx, char *buf, int buflen);
 
