@@ -781,14 +781,14 @@ def kernel_bytes(name, info, integ, mean_work=0.):
     if name.startswith('k_spmm_b2'):
         # the unpaired divergence rows J of K beside k_spmm_tile: entries, gather of x_v, y_p out
         return 20.*J.nnz + 4.*(npp + 1) + 8.*(n + npp)*nb
+    if name.startswith('k_spmm_tile'):
+        # paired rows of K = [F JT]: packed entries (18 B per CSR entry) + x in, y out
+        return 18.*(nnzF + J.nnz) + 8.*(n + npp)*nb + 8.*n*nb
     if name.startswith('k_spmm'):
         # the block matrix K = [F JT; J 0] (two value arrays): gather + store
         nnzK = nnzF + 2*J.nnz
         nt = n + npp
         return 20.*nnzK + 4.*(nt + 1) + 16.*nt*nb
-    if name.startswith('k_spmm_tile'):
-        # paired rows of K = [F JT]: packed entries (18 B per CSR entry) + x in, y out
-        return 18.*(nnzF + J.nnz) + 8.*(n + npp)*nb + 8.*n*nb
     if name.startswith('k_gs_tma<false>') or name.startswith('k_mdot_b'):
         return 8.*(n + npp)*nb*(mean_work + 1.)           # basis vectors + w
     if name.startswith('k_gs_tma<true>') or name.startswith('k_gs_update_b'):
