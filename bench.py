@@ -44,7 +44,7 @@ def parse():
     ap.add_argument('--mesh', type=int, default=4)
     ap.add_argument('--nts', type=int, default=2048, help='steps per time unit')
     ap.add_argument('--tol', type=float, default=1e-12)
-    ap.add_argument('--guess', type=int, default=16)
+    ap.add_argument('--guess', type=int, default=24)
     ap.add_argument('--cheb', type=int, default=4)
     ap.add_argument('--schur-poly', type=int, default=2)
     ap.add_argument('--coarse-max', type=int, default=4096)

@@ -246,6 +246,9 @@ static int csr_build(dnsb_ctx *ctx, int nrows, int ncols, const int32_t *indptr,
 }
 
 static int g_cheb_f32 = 1;  // fp32 work vectors of the Chebyshev smoother inside the preconditioner (tile path)
+static int g_proj_t = 1;   // projection space: directions kept raw + a small triangular factor per member
+static int g_pkeep = 0;    // raw solutions the projection space is rebuilt from (0: half of its size)
+static int g_tail_warps = 8;   // warps of k_spmm_tile that serve the unpaired tail rows (0: separate k_spmm_b2 launch)
 static int g_gs_pyth = 1;   // norm of the orthogonalised Arnoldi vector from Pythagoras (batches, columns < 16)
 static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
 static const int TILE_SMEM_OPTIN = 220 * 1024;
@@ -440,11 +443,15 @@ static void spmm_dev(dnsb_ctx *ctx, const dnsb_csr *A, const double *coef,
       // shared memory leaves no room for a second resident CTA)
       const unsigned grid_ = std::min(A->tile.ntiles, ctx->sm_count);
       const TileDev tv = A->tile_view();
+      const int ntw = row_begin < A->nrows ? g_tail_warps : 0;
+      const int threads_ = TILE_THREADS + 32 * ntw;
       if (beta != 0.0)
-        LAUNCH(ctx, k_spmm_tile<true>, grid_, TILE_THREADS, A->tile.smem, tv, coef, x, z, y, alpha, beta);
+        LAUNCH(ctx, k_spmm_tile<true>, grid_, threads_, A->tile.smem, tv, coef, x, z, y, alpha, beta, A->view(),
+               row_begin);
       else
-        LAUNCH(ctx, k_spmm_tile<false>, grid_, TILE_THREADS, A->tile.smem, tv, coef, x, z, y, alpha, beta);
-      if (row_begin < A->nrows)
+        LAUNCH(ctx, k_spmm_tile<false>, grid_, threads_, A->tile.smem, tv, coef, x, z, y, alpha, beta, A->view(),
+               row_begin);
+      if (row_begin < A->nrows && ntw == 0)
         LAUNCH(ctx, k_spmm_b2<true>, spb2_grid(A->nrows - row_begin, nb), SPB_THREADS, 0, A->view(), coef, D2C(x),
                D2C(z), D2(y), nb, row_begin, alpha, beta);
     } else if (npairs > 0 && row_begin < A->nrows) {
@@ -537,6 +544,9 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
+  if (const char *ev = getenv("DNSB_TAIL_WARPS")) g_tail_warps = std::max(0, std::min(TILE_TAIL_WARPS_MAX, atoi(ev)));
+  if (const char *ev = getenv("DNSB_PKEEP")) g_pkeep = atoi(ev);
+  if (const char *ev = getenv("DNSB_PROJ_T")) g_proj_t = atoi(ev);
   if (const char *ev = getenv("DNSB_CHEB_F32")) g_cheb_f32 = atoi(ev);
   if (const char *ev = getenv("DNSB_CONV_COLOURS")) g_conv_colours = atoi(ev);
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
@@ -1312,7 +1322,7 @@ extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   s->cres.release(); s->cd0.release(); s->cd1.release();
   s->partial.release(); s->partial2.release(); s->red.release();
   s->gR.release(); s->gcs.release(); s->gsn.release(); s->gg.release(); s->gh.release(); s->gh2.release();
-  s->ginvh.release(); s->gbnorm.release(); s->gresid.release();
+  s->ginvh.release(); s->gbnorm.release(); s->gresid.release(); s->grelmax.release();
   s->gdone.release(); s->gits.release(); s->gittot.release(); s->gflags.release();
   s->mp_dinv.release(); s->mp_scale.release(); s->sb.release(); s->sx.release();
   s->lsc_dinv.release(); s->lsc_t1.release(); s->lsc_t2.release(); s->lsc_p1.release(); s->lsc_p2.release();
@@ -2370,6 +2380,8 @@ struct dnsb_imex {
   int hist_len = 0, hist_cnt = 0, hist_pos = 0, hist_mode = 0;
   int pcnt = 0, pkeep = 0;
   DBuf<double> xh, bq, xq, gr, partialh, x0, pw0, pw1, pd0, pd1, pinv, normpart, normout;
+  DBuf<double> ptri, py, pgsum;   // implicit form of the projection space (see imex_guess)
+  bool proj_t = false;
   double last_relres = 0;   // max over ALL solves of the last run (every member, Heun solves included)
   long long run_iters = 0, run_solves = 0, run_unconverged = 0;
   // snapshots: device store (device row order; input of the Gram matrix) and
@@ -2485,6 +2497,7 @@ extern "C" void dnsb_imex_destroy(dnsb_imex *e) {
   e->b.release(); e->x.release(); e->xh.release(); e->bq.release(); e->xq.release(); e->x0.release();
   e->pw0.release(); e->pw1.release(); e->pd0.release(); e->pd1.release(); e->pinv.release();
   e->gr.release(); e->partialh.release(); e->snaps.release();
+  e->ptri.release(); e->py.release(); e->pgsum.release();
   e->normpart.release(); e->normout.release();
   delete e;
 }
@@ -2631,6 +2644,32 @@ static int imex_snapshot(dnsb_imex *e) {
 // small the new information is.  On cylinder_4, dt = 1/2048, eight pairs put
 // the initial residual at ~1e-11 |b| (previous solution: 1e-3, linear
 // extrapolation: 4e-6): the FGMRES then needs 1-3 iterations instead of 20.
+// Implicit form (DNSB_PROJ_T=1, default): only the images bq_i are orthonormalised; the directions stay
+// as they were handed in (D_i) and a small upper-triangular factor per member records the combination,
+//   xq_j = sum_{i<=j} T[i][j] D_i,   x0 = sum_i (T c)_i D_i,   c = bq^T b.
+// Every Gram-Schmidt pass over the xq side disappears (a third of the vector reads of proj_add).
+// y[i] = sum_{j=i..k-1} T[i][j] c[j]
+__global__ void k_proj_tri_apply(const double *__restrict__ T, const double *__restrict__ c,
+                                 double *__restrict__ y, int k, int L, int nb) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k * nb) return;
+  const int i = t / nb, m = t % nb;
+  double s = 0.0;
+  for (int j = i; j < k; ++j) s += T[((size_t)i * L + j) * nb + m] * c[(size_t)j * nb + m];
+  y[t] = s;
+}
+// column k of T after the direction D_k was cleaned with the coefficients g (sum over the passes) and
+// normalised with inv:  T[i][k] = -inv * sum_{j=i..k-1} T[i][j] g[j],  T[k][k] = inv
+__global__ void k_proj_tri_column(double *__restrict__ T, const double *__restrict__ g,
+                                  const double *__restrict__ inv, int k, int L, int nb) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (k + 1) * nb) return;
+  const int i = t / nb, m = t % nb;
+  if (i == k) { T[((size_t)k * L + k) * nb + m] = inv[m]; return; }
+  double s = 0.0;
+  for (int j = i; j < k; ++j) s += T[((size_t)i * L + j) * nb + m] * g[(size_t)j * nb + m];
+  T[((size_t)i * L + k) * nb + m] = -inv[m] * s;
+}
 static int imex_guess(dnsb_imex *e, int guess, double *x) {
   dnsb_ctx *ctx = e->ctx;
   const int nb = e->nb;
@@ -2654,7 +2693,13 @@ static int imex_guess(dnsb_imex *e, int guess, double *x) {
   RedCfg rc = red_cfg(ctx, ntot, nb);
   mdot_dev(ctx, rc, e->bq.p, ntb, e->pcnt, e->b.p, ntot, nb, e->partialh.p, e->gr.p);
   DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
-  LAUNCH(ctx, k_gmres_update_x, cdiv(ntb, 256), 256, 0, e->xq.p, ntb, e->pcnt, e->gr.p, x,
+  const double *cf = e->gr.p;
+  if (e->proj_t) {
+    LAUNCH(ctx, k_proj_tri_apply, cdiv((size_t)e->pcnt * nb, 128), 128, 0, (const double *)e->ptri.p,
+           (const double *)e->gr.p, e->py.p, e->pcnt, L, nb);
+    cf = e->py.p;
+  }
+  LAUNCH(ctx, k_gmres_update_x, cdiv(ntb, 256), 256, 0, e->xq.p, ntb, e->pcnt, cf, x,
          (size_t)ntot, nb);
   return 0;
 }
@@ -2689,9 +2734,18 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
       DNSB_CK(ctx, cudaMemcpyAsync(e->normout.p, e->gr.p + (size_t)k * nb, nb * sizeof(double),
                                    cudaMemcpyDeviceToDevice, ctx->stream));
     gs_update_dev(ctx, rc, e->bq.p, ntb, k, e->gr.p, w, w2, ntot, nb, e->normpart.p);
-    gs_update_dev(ctx, rc, e->xq.p, ntb, k, e->gr.p, d, d2, ntot, nb, e->partialh.p);
+    if (e->proj_t) {
+      if (pass == 0)
+        DNSB_CK(ctx, cudaMemcpyAsync(e->pgsum.p, e->gr.p, (size_t)k * nb * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+      else
+        LAUNCH(ctx, k_axpby, cdiv((size_t)k * nb, 256), 256, 0, 1.0, (const double *)e->pgsum.p, 1.0,
+               (const double *)e->gr.p, e->pgsum.p, (size_t)k * nb);
+    } else {
+      gs_update_dev(ctx, rc, e->xq.p, ntb, k, e->gr.p, d, d2, ntot, nb, e->partialh.p);
+      std::swap(d, d2);
+    }
     std::swap(w, w2);
-    std::swap(d, d2);
   }
   if (k == 0) {
     LAUNCH(ctx, k_dot1, rc.nblocks, rc.threads, rc.smem, (const double *)w, (const double *)w, ntot, nb,
@@ -2707,8 +2761,17 @@ static int proj_add(dnsb_imex *e, double *d, int npass) {
          (const double *)e->normout.p, e->pinv.p, nb, 1e-26);
   LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)w, (const double *)e->pinv.p,
          e->bq.p + (size_t)k * ntb, (size_t)ntot, nb);
-  LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)d, (const double *)e->pinv.p,
-         e->xq.p + (size_t)k * ntb, (size_t)ntot, nb);
+  if (e->proj_t) {
+    // the direction itself is the new column of D (the caller may have built it in place)
+    if (d != e->xq.p + (size_t)k * ntb)
+      DNSB_CK(ctx, cudaMemcpyAsync(e->xq.p + (size_t)k * ntb, d, ntb * sizeof(double), cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+    LAUNCH(ctx, k_proj_tri_column, cdiv((size_t)(k + 1) * nb, 128), 128, 0, e->ptri.p, (const double *)e->pgsum.p,
+           (const double *)e->pinv.p, k, e->hist_len, nb);
+  } else {
+    LAUNCH(ctx, k_scale_member, cdiv(ntb, 256), 256, 0, (const double *)d, (const double *)e->pinv.p,
+           e->xq.p + (size_t)k * ntb, (size_t)ntot, nb);
+  }
   e->pcnt = k + 1;
   return 0;
 }
@@ -2735,21 +2798,23 @@ static int imex_push_history(dnsb_imex *e, int guess) {
   e->hist_cnt++;
   if (e->pcnt < e->hist_len) {
     // new direction: the correction x - x0 (or x itself while the space is empty)
+    double *dir = e->proj_t ? e->xq.p + (size_t)e->pcnt * ntb : e->pd0.p;
     if (e->pcnt == 0)
-      DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      DNSB_CK(ctx, cudaMemcpyAsync(dir, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     else
       LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
-             (const double *)e->x0.p, e->pd0.p, ntb);
-    return proj_add(e, e->pd0.p, e->pcnt == 0 ? 2 : 1);
+             (const double *)e->x0.p, dir, ntb);
+    return proj_add(e, dir, e->pcnt == 0 ? 2 : 1);
   }
   // space full: rebuild it from the last K raw solutions, oldest first
   e->pcnt = 0;
   const int have = std::min(K, e->hist_cnt);
   for (int q = have; q >= 1; --q) {
     const int slot = (e->hist_pos - q) % K;
-    DNSB_CK(ctx, cudaMemcpyAsync(e->pd0.p, e->xh.p + (size_t)slot * ntb, ntb * sizeof(double),
+    double *dir = e->proj_t ? e->xq.p + (size_t)e->pcnt * ntb : e->pd0.p;
+    DNSB_CK(ctx, cudaMemcpyAsync(dir, e->xh.p + (size_t)slot * ntb, ntb * sizeof(double),
                                  cudaMemcpyDeviceToDevice, ctx->stream));
-    int rc = proj_add(e, e->pd0.p, 2);
+    int rc = proj_add(e, dir, 2);
     if (rc) return rc;
   }
   return 0;
@@ -2792,7 +2857,7 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
     const int mode = guess >= 2 ? 2 : 1;
     if (e->hist_len != L || e->hist_mode != mode) {
       e->hist_len = L; e->hist_cnt = 0; e->hist_pos = 0; e->hist_mode = mode; e->pcnt = 0;
-      e->pkeep = std::max(2, L / 2);
+      e->pkeep = g_pkeep > 0 ? std::max(1, std::min(g_pkeep, L)) : std::max(2, std::min(8, L / 2));
       DNSB_CK(ctx, e->xh.alloc(ntb * (mode == 2 ? e->pkeep : L)));
       DNSB_CK(ctx, e->xh.zero(ctx->stream));
       if (mode == 2) {
@@ -2805,6 +2870,13 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
         DNSB_CK(ctx, e->pw0.alloc(ntb)); DNSB_CK(ctx, e->pw1.alloc(ntb));
         DNSB_CK(ctx, e->pd0.alloc(ntb)); DNSB_CK(ctx, e->pd1.alloc(ntb));
         DNSB_CK(ctx, e->pinv.alloc(2 * (size_t)nb));
+        e->proj_t = g_proj_t != 0;
+        if (e->proj_t) {
+          DNSB_CK(ctx, e->ptri.alloc((size_t)L * L * nb));
+          DNSB_CK(ctx, e->ptri.zero(ctx->stream));
+          DNSB_CK(ctx, e->py.alloc((size_t)L * nb));
+          DNSB_CK(ctx, e->pgsum.alloc((size_t)L * nb));
+        }
       }
     }
   }

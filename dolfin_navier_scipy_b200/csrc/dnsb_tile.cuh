@@ -446,10 +446,17 @@ k_cheb_init_p2f(CsrDev A, const double2 *__restrict__ zp, const double2 *__restr
 // pressure rows the gradient block refers to; the unpaired divergence rows are
 // served by k_spmm_b2 as before.
 // ---------------------------------------------------------------------------
+// Warps beyond the producer (launch with TILE_THREADS + 32*ntw threads) serve the UNPAIRED tail rows of
+// the matrix (the divergence rows J of K) beside the tile pipeline: a warp per row, lane = member pair, the
+// row's entries loaded by the lanes and handed round with shuffles, 8 gathers from global memory in
+// flight, sums in CSR order (bit-identical to k_spmm_b2).  They use no shared memory, so they fit next
+// to the ring; a separate tail kernel could neither share the SM with the persistent tile CTA (its
+// staging buffers) nor overlap on a second stream.
+#define TILE_TAIL_WARPS_MAX 12
 template <bool HASZ>
-__global__ void __launch_bounds__(TILE_THREADS, 1)
+__global__ void __launch_bounds__(TILE_THREADS + 32 * TILE_TAIL_WARPS_MAX, 1)
 k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ x,
-            const double *z, double *y, double alpha, double beta) {
+            const double *z, double *y, double alpha, double beta, CsrDev A, int row_begin) {
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_STAGES], empty[TILE_STAGES];
   const size_t off_val = (size_t)T.umax * TILE_ROWB;
@@ -511,6 +518,49 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
 
   const double2 cm = reinterpret_cast<const double2 *>(coef)[lane];
   const double2 zero = make_double2(0.0, 0.0);
+  if (warp > TILE_RP) {
+    const int tw = warp - TILE_RP - 1, ntw = (int)(blockDim.x >> 5) - TILE_RP - 1;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x);
+    for (int row = row_begin + blockIdx.x * ntw + tw; row < A.nrows; row += gridDim.x * ntw) {
+      const int k0 = A.indptr[row], k1 = A.indptr[row + 1];
+      double ax = 0.0, ay = 0.0;
+      for (int base = k0; base < k1; base += 32) {
+        const int cnt = min(32, k1 - base);
+        int col = 0;
+        double v1 = 0.0, v2 = 0.0;
+        if (lane < cnt) {
+          col = A.indices[base + lane];
+          v1 = A.v1[base + lane];
+          v2 = A.v2[base + lane];
+        }
+        for (int k = 0; k < cnt; k += 8) {
+          double2 xs[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = __shfl_sync(0xffffffffu, col, (k + u) & 31);
+            xs[u] = (k + u < cnt) ? x2[(size_t)c * (TILE_NB / 2) + lane] : zero;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double a1 = __shfl_sync(0xffffffffu, v1, (k + u) & 31);
+            const double a2 = __shfl_sync(0xffffffffu, v2, (k + u) & 31);
+            if (k + u < cnt) {
+              ax = __fma_rn(__fma_rn(cm.x, a2, a1), xs[u].x, ax);
+              ay = __fma_rn(__fma_rn(cm.y, a2, a1), xs[u].y, ay);
+            }
+          }
+        }
+      }
+      const size_t t = (size_t)row * (TILE_NB / 2) + lane;
+      if (HASZ) {
+        const double2 zin = reinterpret_cast<const double2 *>(z)[t];
+        reinterpret_cast<double2 *>(y)[t] = make_double2(alpha * ax + beta * zin.x, alpha * ay + beta * zin.y);
+      } else {
+        reinterpret_cast<double2 *>(y)[t] = make_double2(alpha * ax, alpha * ay);
+      }
+    }
+    return;
+  }
   struct Ops { double2 za, zb; int4 pd; };
   auto load_ops = [&](int tile) {
     Ops o;

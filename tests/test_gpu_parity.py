@@ -1295,11 +1295,47 @@ def test_low_rank_update_and_krylovini(cyl1, ctx):
     assert its['upd'] < its['old']
 
 
+def test_projection_space_forms_agree_across_rebuilds(cyl1, ctx):
+    """the recycled-solution space in its implicit form (raw directions + a
+    triangular factor per member, DNSB_PROJ_T=1, default) against the explicit
+    form (both sides orthogonalised): a short space (6 pairs, rebuilt from 3
+    raw solutions every few steps) over 24 steps gives the same trajectory,
+    the same iteration count within 10 %, and the LU oracle's states"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    from oracle import snu as osnu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    dt, nsteps = 1./512, 24
+    sd = soldict(femp, sm, rhsd)
+    o = osnu.solve_nse(t0=0, tE=nsteps*dt, Nts=nsteps, start_ssstokes=True,
+                       return_vp_dict=True, **sd)
+    ts = sorted(o.keys())
+    out = {}
+    for label, c in (('implicit', ctx),
+                     ('explicit', _ctx_with_env('DNSB_PROJ_T', '0'))):
+        integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv,
+                               femp['dbcinds'], femp['dbcvals'], dt,
+                               nus=np.ones(64), fv=rhsd['fv'], fp=rhsd['fp'],
+                               ctx=c)
+        integ.set_state(o[ts[0]]['v'][inv], o[ts[0]]['p'])
+        integ.run(nsteps, tol=1e-12, guess=6)
+        out[label] = integ.state() + (integ.stats()['iters'],)
+        integ.close()
+    v, p, its = out['implicit']
+    assert _rel(v, out['explicit'][0]) < 1e-9
+    assert _rel(p, out['explicit'][1]) < 1e-9
+    assert abs(its - out['explicit'][2]) <= 0.1*out['explicit'][2] + 1
+    for m in (0, 63):
+        assert _rel(v[:, m], o[ts[-1]]['v'][inv, 0]) < 1e-8
+        assert _rel(p[:, m], o[ts[-1]]['p'][:, 0]) < 1e-8
+
+
 @pytest.mark.parametrize('switch', ['DNSB_CONV_COLOURS=1', 'DNSB_GRAPHS=0',
                                     'DNSB_DMMA=0', 'DNSB_PAIR=0',
                                     'DNSB_ROWPAIR=0', 'DNSB_GS_TMA=0',
                                     'DNSB_TILE=0', 'DNSB_SCHUR_TC=0',
-                                    'DNSB_GS_PYTH=0', 'DNSB_CHEB_F32=0'])
+                                    'DNSB_GS_PYTH=0', 'DNSB_CHEB_F32=0',
+                                    'DNSB_PROJ_T=0', 'DNSB_TAIL_WARPS=0'])
 def test_every_tuning_switch_gives_the_same_trajectory(cyl1, ctx, switch):
     """the environment switches select kernel VARIANTS of the same arithmetic
     (coloured scatter vs gather assembly -- the form `north_star` names --,
