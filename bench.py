@@ -783,7 +783,9 @@ def kernel_bytes(name, info, integ, mean_work=0.):
         return 20.*J.nnz + 4.*(npp + 1) + 8.*(n + npp)*nb
     if name.startswith('k_spmm_tile'):
         # paired rows of K = [F JT]: packed entries (18 B per CSR entry) + x in, y out
-        return 18.*(nnzF + J.nnz) + 8.*(n + npp)*nb + 8.*n*nb
+        # + the unpaired rows J served by the kernel's tail warps: entries, y_p out
+        return 18.*(nnzF + J.nnz) + 8.*(n + npp)*nb + 8.*n*nb \
+            + 20.*J.nnz + 4.*(npp + 1) + 8.*npp*nb
     if name.startswith('k_spmm'):
         # the block matrix K = [F JT; J 0] (two value arrays): gather + store
         nnzK = nnzF + 2*J.nnz

@@ -2670,6 +2670,26 @@ __global__ void k_proj_tri_column(double *__restrict__ T, const double *__restri
   for (int j = i; j < k; ++j) s += T[((size_t)i * L + j) * nb + m] * g[(size_t)j * nb + m];
   T[((size_t)i * L + k) * nb + m] = -inv[m] * s;
 }
+// x = x0 = sum_i y[i,m] D_i   (the guess and the copy the new direction is measured from, one pass)
+__global__ void k_proj_guess(const double *__restrict__ D, size_t dstride, int nvec, const double *__restrict__ y,
+                             double *__restrict__ x, double *__restrict__ x0, size_t n, int nb) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * nb) return;
+  const int m = (int)(idx % nb);
+  double s = 0.0;
+  for (int i = 0; i < nvec; ++i) s += y[(size_t)i * nb + m] * D[(size_t)i * dstride + idx];
+  x[idx] = s;
+  x0[idx] = s;
+}
+// d = x - x0 and keep = x  (new direction + the ring of raw solutions, one pass)
+__global__ void k_proj_dir(const double *__restrict__ x, const double *__restrict__ x0, double *__restrict__ d,
+                           double *__restrict__ keep, size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const double v = x[idx];
+  d[idx] = v - x0[idx];
+  keep[idx] = v;
+}
 static int imex_guess(dnsb_imex *e, int guess, double *x) {
   dnsb_ctx *ctx = e->ctx;
   const int nb = e->nb;
@@ -2692,16 +2712,16 @@ static int imex_guess(dnsb_imex *e, int guess, double *x) {
   if (e->pcnt == 0) return 1;
   RedCfg rc = red_cfg(ctx, ntot, nb);
   mdot_dev(ctx, rc, e->bq.p, ntb, e->pcnt, e->b.p, ntot, nb, e->partialh.p, e->gr.p);
-  DNSB_CK(ctx, cudaMemsetAsync(x, 0, ntb * sizeof(double), ctx->stream));
   const double *cf = e->gr.p;
   if (e->proj_t) {
     LAUNCH(ctx, k_proj_tri_apply, cdiv((size_t)e->pcnt * nb, 128), 128, 0, (const double *)e->ptri.p,
            (const double *)e->gr.p, e->py.p, e->pcnt, L, nb);
     cf = e->py.p;
   }
-  LAUNCH(ctx, k_gmres_update_x, cdiv(ntb, 256), 256, 0, e->xq.p, ntb, e->pcnt, cf, x,
+  // writes the guess and its copy x0 (imex_push_history measures the new direction from it)
+  LAUNCH(ctx, k_proj_guess, cdiv(ntb, 256), 256, 0, (const double *)e->xq.p, ntb, e->pcnt, cf, x, e->x0.p,
          (size_t)ntot, nb);
-  return 0;
+  return 2;
 }
 
 // inv[m] = 1/sqrt(n2[m]) if n2[m] > eps*ref[m] else 0
@@ -2792,19 +2812,21 @@ static int imex_push_history(dnsb_imex *e, int guess) {
   }
   // ring of raw solutions (for the rebuild)
   const int K = e->pkeep;
-  DNSB_CK(ctx, cudaMemcpyAsync(e->xh.p + (size_t)(e->hist_pos % K) * ntb, e->x.p, ntb * sizeof(double),
-                               cudaMemcpyDeviceToDevice, ctx->stream));
+  double *keep = e->xh.p + (size_t)(e->hist_pos % K) * ntb;
   e->hist_pos++;
   e->hist_cnt++;
-  if (e->pcnt < e->hist_len) {
-    // new direction: the correction x - x0 (or x itself while the space is empty)
+  if (e->pcnt > 0 && e->pcnt < e->hist_len) {
+    // new direction: the correction x - x0, written in the same pass as the ring copy
     double *dir = e->proj_t ? e->xq.p + (size_t)e->pcnt * ntb : e->pd0.p;
-    if (e->pcnt == 0)
-      DNSB_CK(ctx, cudaMemcpyAsync(dir, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    else
-      LAUNCH(ctx, k_axpby, cdiv(ntb, 256), 256, 0, 1.0, (const double *)e->x.p, -1.0,
-             (const double *)e->x0.p, dir, ntb);
-    return proj_add(e, dir, e->pcnt == 0 ? 2 : 1);
+    LAUNCH(ctx, k_proj_dir, cdiv(ntb, 256), 256, 0, (const double *)e->x.p, (const double *)e->x0.p, dir, keep, ntb);
+    return proj_add(e, dir, 1);
+  }
+  DNSB_CK(ctx, cudaMemcpyAsync(keep, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (e->pcnt == 0 && e->pcnt < e->hist_len) {
+    // empty space: the solution itself
+    double *dir = e->proj_t ? e->xq.p : e->pd0.p;
+    DNSB_CK(ctx, cudaMemcpyAsync(dir, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return proj_add(e, dir, 2);
   }
   // space full: rebuild it from the last K raw solutions, oldest first
   e->pcnt = 0;
@@ -3020,7 +3042,7 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
       LAUNCH(ctx, k_axpby, cdiv(npb, 256), 256, 0, -dt, (const double *)e->p.p, 0.0,
              (const double *)nullptr, e->x.p + nvb, npb);
     }
-    if (guess >= 2)
+    if (guess >= 2 && rc != 2)   // rc == 2: imex_guess wrote x0 itself
       DNSB_CK(ctx, cudaMemcpyAsync(e->x0.p, e->x.p, ntb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     rc = solver_solve_dev(e->sl, e->b.p, e->x.p, tol, maxit, false);
     if (rc) return rc;

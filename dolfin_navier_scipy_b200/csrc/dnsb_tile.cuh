@@ -452,7 +452,7 @@ k_cheb_init_p2f(CsrDev A, const double2 *__restrict__ zp, const double2 *__restr
 // flight, sums in CSR order (bit-identical to k_spmm_b2).  They use no shared memory, so they fit next
 // to the ring; a separate tail kernel could neither share the SM with the persistent tile CTA (its
 // staging buffers) nor overlap on a second stream.
-#define TILE_TAIL_WARPS_MAX 12
+#define TILE_TAIL_WARPS_MAX 8
 template <bool HASZ>
 __global__ void __launch_bounds__(TILE_THREADS + 32 * TILE_TAIL_WARPS_MAX, 1)
 k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ x,

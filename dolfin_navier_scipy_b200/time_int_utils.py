@@ -52,31 +52,57 @@ def _union_pattern(mats):
     return acc
 
 
-def lowrank_forcing(fvtd, trange, nv, maxrank=64, tol=1e-13):
+def lowrank_forcing(fvtd, trange, nv, maxrank=64, tol=1e-13, chunk=256):
     """sample ``fvtd(t)`` on ``trange`` and factor it as ``B @ U``
 
     The device loop evaluates ``f(t_n) = sum_k U[k, n] B[:, k]``; separable
     forcings such as ``sin(t)*b`` (`tests/time_dep_nse_bcrob.py:33-34`) have
-    rank 1.  Raises if the sampled forcing has rank > ``maxrank``.
+    rank 1.  The samples are taken ``chunk`` time levels at a time against an
+    orthonormal basis that grows with what the chunk adds, so the memory is
+    ``nv*(rank + chunk)`` whatever the number of steps, and a forcing of rank
+    > ``maxrank`` raises ``NotImplementedError`` at the first chunk that shows
+    it, not after all samples have been evaluated.
     """
-    Fs = np.hstack([np.asarray(fvtd(t), dtype=float).reshape(nv, 1)
-                    for t in trange])
-    nrm = np.linalg.norm(Fs)
-    if nrm == 0.:
-        return np.zeros((nv, 1)), np.zeros((len(trange), 1))
-    rng = np.random.default_rng(0)
-    k = min(maxrank + 8, Fs.shape[1])
-    Q, _ = np.linalg.qr(Fs@rng.standard_normal((Fs.shape[1], k)))
-    U = Q.T@Fs
-    # compress to the numerical rank
+    trange = np.asarray(trange, dtype=float)
+    nt = trange.size
+    Q = np.zeros((nv, 0))
+    coeffs = []            # per chunk: (rank at that time, chunk length)
+    scale = 0.
+    for c0 in range(0, nt, chunk):
+        Fc = np.hstack([np.asarray(fvtd(t), dtype=float).reshape(nv, 1)
+                        for t in trange[c0:c0 + chunk]])
+        scale = max(scale, np.abs(Fc).max() if Fc.size else 0.)
+        C = Q.T@Fc
+        R = Fc - Q@C
+        C2 = Q.T@R                      # second pass: keeps Q orthonormal
+        R -= Q@C2
+        C += C2
+        # what the chunk adds: left singular vectors of the remainder
+        if R.size and np.abs(R).max() > 0.:
+            uu, ss, vv = np.linalg.svd(R, full_matrices=False)
+            ref = max(ss[0], np.linalg.norm(C, 2) if C.size else 0.)
+            r = int(np.sum(ss > tol*ref))
+            if Q.shape[1] + r > maxrank:
+                raise NotImplementedError(
+                    'time dependent forcing of rank > {0} (seen after {1} of '
+                    '{2} time levels)'.format(maxrank, min(nt, c0 + chunk), nt))
+            if r:
+                Q = np.hstack([Q, uu[:, :r]])
+                C = np.vstack([C, ss[:r, None]*vv[:r, :]])
+        coeffs.append(C)
+    if scale == 0.:
+        return np.zeros((nv, 1)), np.zeros((nt, 1))
+    r = Q.shape[1]
+    U = np.zeros((r, nt))
+    c0 = 0
+    for C in coeffs:
+        U[:C.shape[0], c0:c0 + C.shape[1]] = C
+        c0 += C.shape[1]
+    # rotate to the principal directions and drop what is numerically zero
     uu, ss, vv = np.linalg.svd(U, full_matrices=False)
-    r = int(np.sum(ss > tol*ss[0]))
-    B = Q@uu[:, :r]
-    U = (ss[:r, None]*vv[:r, :])
-    if r > maxrank or np.linalg.norm(Fs - B@U) > 1e-12*nrm:
-        raise NotImplementedError('time dependent forcing of rank > {0}'.
-                                  format(maxrank))
-    return B, U.T.copy()
+    keep = int(np.sum(ss > tol*ss[0]))
+    B = Q@uu[:, :keep]
+    return B, (ss[:keep, None]*vv[:keep, :]).T.copy()
 
 
 class DeviceImex(object):

@@ -56,6 +56,34 @@ def test_lowrank_forcing_is_exact_for_separable_inputs():
         assert np.allclose(B@U[k], np.sin(t)*b[:, 0] + t*t*b[:, 1], atol=1e-12)
 
 
+def test_lowrank_forcing_samples_in_chunks_and_fails_early():
+    """round-1 advisor finding: the sampler worked on a dense NV x steps
+    matrix and reported a rank > 64 only after every sample was evaluated.
+    It now grows its basis chunk by chunk: a forcing whose later chunks add
+    directions is still exact, and a full-rank one stops at the first chunks"""
+    rng = np.random.default_rng(1)
+    nv = 300
+    b = rng.standard_normal((3, nv, 1))
+
+    def f(t):
+        return np.sin(t)*b[0] + np.cos(3*t)*b[1] + (t > .5)*b[2]
+    tr = np.linspace(0, 1, 1000)
+    B, U = tiu.lowrank_forcing(f, tr, nv, chunk=64)
+    F = np.hstack([f(t) for t in tr])
+    assert B.shape == (nv, 3) and U.shape == (1000, 3)
+    assert np.linalg.norm(F - B@U.T) < 1e-13*np.linalg.norm(F)
+    B0, U0 = tiu.lowrank_forcing(lambda t: np.zeros((nv, 1)), tr, nv)
+    assert not B0.any() and not U0.any() and U0.shape == (1000, 1)
+    calls = [0]
+
+    def noise(t):
+        calls[0] += 1
+        return rng.standard_normal((nv, 1))
+    with pytest.raises(NotImplementedError):
+        tiu.lowrank_forcing(noise, tr, nv, chunk=64)
+    assert calls[0] <= 128
+
+
 def test_pattern_embedding_keeps_explicit_zeros():
     A = sps.random(20, 20, .3, random_state=1, format='csr') + sps.identity(20)
     M = sps.identity(20, format='csr')
