@@ -139,14 +139,14 @@ struct dnsb_csr {
     TileDevF t;
     t.indptr = indptr.p; t.uptr = t_uptr.p; t.rptr = t_rptr.p; t.runs = t_runs.p; t.pidx = t_pidxf.p; t.pval = t_pvalf.p;
     t.tdesc = t_tdesc.p; t.truns = t_truns.p; t.pdesc = t_pdesc.p; t.rmax = t_rmax;
-    t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap;
+    t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap; t.stages = tile.stages_f;
     return t;
   }
   TileDev tile_view() const {
     TileDev t;
     t.indptr = indptr.p; t.uptr = t_uptr.p; t.rptr = t_rptr.p; t.runs = t_runs.p; t.pidx = t_pidx.p; t.pval = t_pval.p;
     t.tdesc = t_tdesc.p; t.truns = t_truns.p; t.pdesc = t_pdesc.p; t.rmax = t_rmax;
-    t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap;
+    t.ntiles = tile.ntiles; t.npairs = tile.npairs; t.umax = tile.umax; t.cap = tile.cap; t.stages = tile.stages;
     return t;
   }
   // host copies (setup only: assembling the block matrix K, diagonal positions)
@@ -251,6 +251,7 @@ static int g_pkeep = 0;    // raw solutions the projection space is rebuilt from
 static int g_tail_warps = 8;   // warps of k_spmm_tile that serve the unpaired tail rows (0: separate k_spmm_b2 launch)
 static int g_gs_pyth = 1;   // norm of the orthogonalised Arnoldi vector from Pythagoras (batches, columns < 16)
 static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
+static int g_tile_stages = 3, g_tile_stages_f = 3;   // ring depth of the fp64 / fp32 tile kernels (at most what fits)
 static const int TILE_SMEM_OPTIN = 220 * 1024;
 // tiles of TILE_RP row pairs: unique x rows, tile-local gather offsets, pair-interleaved values.
 // Needs the host copies of the matrix (two value arrays, all rows paired).
@@ -303,8 +304,13 @@ static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
   }
   const size_t off_val = (size_t)p.umax * TILE_ROWB;
   p.stage_bytes = (off_val + (size_t)p.cap * 36 + 127) & ~(size_t)127;
-  p.smem = TILE_STAGES * p.stage_bytes;
-  if (p.smem > (size_t)TILE_SMEM_OPTIN) return 0;   // neighbourhoods too large for the ring: row-pair kernels
+  p.stage_bytes_f = ((size_t)p.umax * (TILE_ROWB / 2) + (size_t)p.cap * 20 + 127) & ~(size_t)127;
+  // ring depth: what fits (the kernels are latency bound per tile: more tiles in flight, more bandwidth)
+  p.stages = (int)std::min<size_t>(g_tile_stages, (size_t)TILE_SMEM_OPTIN / p.stage_bytes);
+  p.stages_f = (int)std::min<size_t>(g_tile_stages_f, (size_t)TILE_SMEM_OPTIN / p.stage_bytes_f);
+  if (p.stages < 2 || p.stages_f < 2) return 0;   // neighbourhoods too large for the ring: row-pair kernels
+  p.smem = p.stages * p.stage_bytes;
+  p.smem_f = p.stages_f * p.stage_bytes_f;
   if (runs.empty()) return 0;
   {
     // per-tile descriptors and a fixed-stride copy of the run lists (addresses known without a lookup),
@@ -368,6 +374,7 @@ static int g_schur_tf32 = 0;   // 1: dense Schur inverse applied in 3xTF32 (fp32
 static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur solve
 // 1: dense Schur block on the tcgen05 tensor cores (TF32 operands from an fp32 copy of the inverse,
 // fp32 accumulation in TMEM; dnsb_tc.cuh).  Preconditioner block only: FGMRES stays fp64.
+static int g_schur_l2keep = 1;   // packed inverse read with an L2 evict_last hint (stays resident between applications)
 static int g_schur_tc = 1;
 static const int TC_SMEM_OPTIN = 208 * 1024;
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
@@ -544,6 +551,9 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
+  if (const char *ev = getenv("DNSB_SCHUR_L2KEEP")) g_schur_l2keep = atoi(ev);
+  if (const char *ev = getenv("DNSB_TILE_STAGES")) g_tile_stages = std::max(2, std::min(TILE_MAX_STAGES, atoi(ev)));
+  if (const char *ev = getenv("DNSB_TILE_STAGES_F")) g_tile_stages_f = std::max(2, std::min(TILE_MAX_STAGES, atoi(ev)));
   if (const char *ev = getenv("DNSB_TAIL_WARPS")) g_tail_warps = std::max(0, std::min(TILE_TAIL_WARPS_MAX, atoi(ev)));
   if (const char *ev = getenv("DNSB_PKEEP")) g_pkeep = atoi(ev);
   if (const char *ev = getenv("DNSB_PROJ_T")) g_proj_t = atoi(ev);
@@ -1481,7 +1491,7 @@ static int dense_apply(dnsb_solver *s, MgLevel *L, const double *x,
     while (tmem_cols < p.np_) tmem_cols *= 2;
     LAUNCH(ctx, k_tc_pack_x, dim3(cdiv(p.ldx, 32), cdiv(nb, 32)), 256, 0, x, L->xt.p, n, nb, p.ldx);
     LAUNCH(ctx, k_schur_tc, dim3(p.mtiles, p.splits), TC_THREADS, p.smem, (const float *)L->dinv_f32.p, p.mapB, L->tcpart.p, p.np_,
-           p.kblocks, p.kb_per_split, p.stages, tmem_cols);
+           p.kblocks, p.kb_per_split, p.stages, tmem_cols, g_schur_l2keep);
     LAUNCH(ctx, k_tc_epilogue, cdiv((size_t)n * nb, 256), 256, 0, (const float *)L->tcpart.p, p.splits,
            (size_t)p.mtiles * TC_BM * p.np_, p.np_, x, y, n, nb, alpha, ad, as);
     return 0;
@@ -1555,10 +1565,10 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
       const float c1 = (float)(rho_n * rho), c2 = (float)(2.0 * rho_n / delta);
       const bool first = i == 0, last = i + 2 == k;
 #define CHEB_ARGS_F tv, coef, (const float *)dcf, (const float *)s->cf_dinv.p, s->cf_res.p, dnf, s->cf_z.p, z, c1, c2
-      if (first && last) LAUNCH(ctx, (k_cheb_step_tilef<true, true>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
-      else if (first) LAUNCH(ctx, (k_cheb_step_tilef<true, false>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
-      else if (last) LAUNCH(ctx, (k_cheb_step_tilef<false, true>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
-      else LAUNCH(ctx, (k_cheb_step_tilef<false, false>), grid_, TILE_THREADS, A->tile.smem, CHEB_ARGS_F);
+      if (first && last) LAUNCH(ctx, (k_cheb_step_tilef<true, true>), grid_, TILE_THREADS, A->tile.smem_f, CHEB_ARGS_F);
+      else if (first) LAUNCH(ctx, (k_cheb_step_tilef<true, false>), grid_, TILE_THREADS, A->tile.smem_f, CHEB_ARGS_F);
+      else if (last) LAUNCH(ctx, (k_cheb_step_tilef<false, true>), grid_, TILE_THREADS, A->tile.smem_f, CHEB_ARGS_F);
+      else LAUNCH(ctx, (k_cheb_step_tilef<false, false>), grid_, TILE_THREADS, A->tile.smem_f, CHEB_ARGS_F);
 #undef CHEB_ARGS_F
       std::swap(dcf, dnf);
       rho = rho_n;

@@ -128,7 +128,8 @@ __device__ __forceinline__ void tc_bulk_1d(void *dst, const void *src, uint32_t 
 // Dt: packed tiles [(mtile*kblocks + kb)][128 rows][32 floats], swizzled (k_tc_pack_d)
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_schur_tc(const float *__restrict__ Dt, const __grid_constant__ CUtensorMap mapB,
-           float *__restrict__ part, int NP, int kblocks, int kb_per_split, int stages, int tmem_cols) {
+           float *__restrict__ part, int NP, int kblocks, int kb_per_split, int stages, int tmem_cols,
+           int l2keep) {
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], accum_full;
   __shared__ uint32_t tmem_base_s;

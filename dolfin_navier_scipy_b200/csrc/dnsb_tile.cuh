@@ -38,7 +38,7 @@
 #include "dnsb_batched.cuh"   // spp_acc / spp_dir: the shared, explicitly fused arithmetic
 
 #define TILE_RP 8            // row pairs per tile = consumer warps
-#define TILE_STAGES 3
+#define TILE_MAX_STAGES 8    // ring depth is a plan parameter (TilePlan::stages / stages_f), at most this
 #define TILE_THREADS (TILE_RP * 32 + 32)
 #define TILE_NB 64           // members (a warp = 32 member pairs)
 #define TILE_ROWB (TILE_NB * 8)   // bytes of one vector row
@@ -47,7 +47,9 @@ struct TilePlan {
   int ntiles = 0, npairs = 0;
   int umax = 0;       // most unique x rows of a tile
   int cap = 0;        // most pair-entries of a tile (aligned span, multiple of 4)
-  size_t stage_bytes = 0, smem = 0;
+  size_t stage_bytes = 0, smem = 0;       // fp64 tiles (k_cheb_step_tile, k_spmm_tile)
+  size_t stage_bytes_f = 0, smem_f = 0;   // fp32 tiles (k_cheb_step_tilef)
+  int stages = 0, stages_f = 0;
   bool ok = false;
 };
 
@@ -63,6 +65,7 @@ struct TileDev {
   const int4 *pdesc;        // per row pair: (offset into the staged entries, entries per row, 0, 0)
   int rmax;
   int ntiles, npairs, umax, cap;
+  int stages;               // ring depth
 };
 
 __device__ __forceinline__ uint32_t tl_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -103,14 +106,15 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
                  const double *__restrict__ dinv, double *res, double *__restrict__ dn, double *z,
                  double c1, double c2) {
   extern __shared__ __align__(128) unsigned char tl_raw[];
-  __shared__ __align__(8) uint64_t full[TILE_STAGES], empty[TILE_STAGES];
+  __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
+  const int nst = T.stages;
   // stage: x tile (umax rows) | packed values (cap x 32 B) | gather offsets (cap x 4 B)
   const size_t off_val = (size_t)T.umax * TILE_ROWB;
   const size_t off_idx = off_val + (size_t)T.cap * 32;
   const size_t stage_bytes = (off_idx + (size_t)T.cap * 4 + 127) & ~(size_t)127;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TILE_STAGES; ++s) {
+    for (int s = 0; s < nst; ++s) {
       tl_mbar_init(&full[s], 1);
       tl_mbar_init(&empty[s], TILE_RP);
     }
@@ -137,7 +141,7 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
       }
     }
     for (; t < T.ntiles; t += gridDim.x, ++it) {
-      const int s = it % TILE_STAGES;
+      const int s = it % nst;
       const int tn = t + gridDim.x;
       int4 ndsc = dsc;
       int nrc = 0, nrl = 0, nrs = 0;
@@ -148,8 +152,8 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
           nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
         }
       }
-      if (it >= TILE_STAGES) {
-        if (lane == 0) tl_mbar_wait(&empty[s], ((it / TILE_STAGES) - 1) & 1);
+      if (it >= nst) {
+        if (lane == 0) tl_mbar_wait(&empty[s], ((it / nst) - 1) & 1);
         __syncwarp();
       }
       unsigned char *st = tl_raw + (size_t)s * stage_bytes;
@@ -187,7 +191,7 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
   Ops cur = load_ops(min((int)blockIdx.x, T.ntiles - 1));
   int it = 0;
   for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
-    const int s = it % TILE_STAGES;
+    const int s = it % nst;
     const int p0 = t * TILE_RP;
     const int rp = p0 + warp;
     const bool have = rp < T.npairs;
@@ -196,7 +200,7 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
     const int tn = t + gridDim.x;
     Ops nxt = cur;
     if (tn < T.ntiles) nxt = load_ops(tn);
-    tl_mbar_wait(&full[s], (it / TILE_STAGES) & 1);
+    tl_mbar_wait(&full[s], (it / nst) & 1);
     const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
     if (have) {
       const double2 *sval = reinterpret_cast<const double2 *>(st + off_val) + (size_t)kb * 2;
@@ -267,6 +271,7 @@ struct TileDevF {
   const int4 *pdesc;
   int rmax;
   int ntiles, npairs, umax, cap;
+  int stages;               // ring depth
 };
 
 template <bool FIRST, bool LAST>
@@ -275,12 +280,13 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
                   const float *__restrict__ dinv, float *res, float *__restrict__ dn, float *zf,
                   double *__restrict__ zout, float c1, float c2) {
   extern __shared__ __align__(128) unsigned char tl_raw[];
-  __shared__ __align__(8) uint64_t full[TILE_STAGES], empty[TILE_STAGES];
+  __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
+  const int nst = T.stages;
   const size_t off_val = (size_t)T.umax * TILE_ROWBF;
   const size_t off_idx = off_val + (size_t)T.cap * 16;
   const size_t stage_bytes = (off_idx + (size_t)T.cap * 4 + 127) & ~(size_t)127;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TILE_STAGES; ++s) {
+    for (int s = 0; s < nst; ++s) {
       tl_mbar_init(&full[s], 1);
       tl_mbar_init(&empty[s], TILE_RP);
     }
@@ -307,7 +313,7 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
       }
     }
     for (; t < T.ntiles; t += gridDim.x, ++it) {
-      const int s = it % TILE_STAGES;
+      const int s = it % nst;
       const int tn = t + gridDim.x;
       int4 ndsc = dsc;
       int nrc = 0, nrl = 0, nrs = 0;
@@ -318,8 +324,8 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
           nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
         }
       }
-      if (it >= TILE_STAGES) {
-        if (lane == 0) tl_mbar_wait(&empty[s], ((it / TILE_STAGES) - 1) & 1);
+      if (it >= nst) {
+        if (lane == 0) tl_mbar_wait(&empty[s], ((it / nst) - 1) & 1);
         __syncwarp();
       }
       unsigned char *st = tl_raw + (size_t)s * stage_bytes;
@@ -355,7 +361,7 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
   Ops cur = load_ops(min((int)blockIdx.x, T.ntiles - 1));
   int it = 0;
   for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
-    const int s = it % TILE_STAGES;
+    const int s = it % nst;
     const int p0 = t * TILE_RP;
     const int rp = p0 + warp;
     const bool have = rp < T.npairs;
@@ -364,7 +370,7 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
     const int tn = t + gridDim.x;
     Ops nxt = cur;
     if (tn < T.ntiles) nxt = load_ops(tn);
-    tl_mbar_wait(&full[s], (it / TILE_STAGES) & 1);
+    tl_mbar_wait(&full[s], (it / nst) & 1);
     const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
     if (have) {
       const float4 *sval = reinterpret_cast<const float4 *>(st + off_val) + kb;
@@ -458,12 +464,13 @@ __global__ void __launch_bounds__(TILE_THREADS + 32 * TILE_TAIL_WARPS_MAX, 1)
 k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ x,
             const double *z, double *y, double alpha, double beta, CsrDev A, int row_begin) {
   extern __shared__ __align__(128) unsigned char tl_raw[];
-  __shared__ __align__(8) uint64_t full[TILE_STAGES], empty[TILE_STAGES];
+  __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
+  const int nst = T.stages;
   const size_t off_val = (size_t)T.umax * TILE_ROWB;
   const size_t off_idx = off_val + (size_t)T.cap * 32;
   const size_t stage_bytes = (off_idx + (size_t)T.cap * 4 + 127) & ~(size_t)127;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TILE_STAGES; ++s) {
+    for (int s = 0; s < nst; ++s) {
       tl_mbar_init(&full[s], 1);
       tl_mbar_init(&empty[s], TILE_RP);
     }
@@ -487,7 +494,7 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
       }
     }
     for (; t < T.ntiles; t += gridDim.x, ++it) {
-      const int s = it % TILE_STAGES;
+      const int s = it % nst;
       const int tn = t + gridDim.x;
       int4 ndsc = dsc;
       int nrc = 0, nrl = 0, nrs = 0;
@@ -498,8 +505,8 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
           nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
         }
       }
-      if (it >= TILE_STAGES) {
-        if (lane == 0) tl_mbar_wait(&empty[s], ((it / TILE_STAGES) - 1) & 1);
+      if (it >= nst) {
+        if (lane == 0) tl_mbar_wait(&empty[s], ((it / nst) - 1) & 1);
         __syncwarp();
       }
       unsigned char *st = tl_raw + (size_t)s * stage_bytes;
@@ -574,7 +581,7 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
   Ops cur = load_ops(min((int)blockIdx.x, T.ntiles - 1));
   int it = 0;
   for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
-    const int s = it % TILE_STAGES;
+    const int s = it % nst;
     const int rp = t * TILE_RP + warp;
     const bool have = rp < T.npairs;
     const int kb = cur.pd.x, L = have ? cur.pd.y : 0;
@@ -582,7 +589,7 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
     const int tn = t + gridDim.x;
     Ops nxt = cur;
     if (tn < T.ntiles) nxt = load_ops(tn);
-    tl_mbar_wait(&full[s], (it / TILE_STAGES) & 1);
+    tl_mbar_wait(&full[s], (it / nst) & 1);
     const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
     if (have) {
       const double2 *sval = reinterpret_cast<const double2 *>(st + off_val) + (size_t)kb * 2;

@@ -155,13 +155,23 @@ def solve_steadystate_nse(A=None, J=None, JT=None, M=None,
     hcache = {}
     mdiag = None if M is None else sps.csr_matrix(M).diagonal()
 
+    warm = [None]     # last solution in the solver's sign convention
+
     def _solve(amat, rhsv):
-        return lau.solve_sadpnt_smw(amat=amat, jmat=J, jmatT=JT, rhsv=rhsv,
-                                    rhsp=fp, krylov='gmres',
-                                    vgroups=(np.asarray(invinds)//2,
-                                             np.asarray(invinds) % 2),
-                                    mass_diag=mdiag, cache=hcache,
-                                    krpslvprms=dict(tol=lin_tol, maxiter=2000))
+        # every Picard/Newton system is started from the previous iterate: the
+        # updates shrink from step to step, and so does the work of the
+        # iterative solve (the stopping test is relative to |rhs| either way)
+        prms = dict(tol=lin_tol, maxiter=2000)
+        if warm[0] is not None:
+            prms['x0'] = warm[0]
+        vp = lau.solve_sadpnt_smw(amat=amat, jmat=J, jmatT=JT, rhsv=rhsv,
+                                  rhsp=fp, krylov='gmres',
+                                  vgroups=(np.asarray(invinds)//2,
+                                           np.asarray(invinds) % 2),
+                                  mass_diag=mdiag, cache=hcache,
+                                  krpslvprms=prms)
+        warm[0] = vp.copy()
+        return vp
 
     if vel_start_nwtn is None or only_stokes:
         vp_k = _solve(A, fv)
