@@ -11,6 +11,11 @@
 #include <new>
 
 #include "dnsb_common.cuh"
+#include <cuda.h>
+#ifdef DNSB_NO_NC
+// experiment: no read-only (ld.global.nc) loads -- see DESIGN.md, programmatic dependent launch
+#define __restrict__
+#endif
 #include "dnsb_kernels.cuh"
 #include "dnsb_batched.cuh"
 #include "dnsb_dense.cuh"
@@ -33,7 +38,23 @@
       cudaEventCreate(&pe1_);                                                  \
       cudaEventRecord(pe0_, c_->stream);                                       \
     }                                                                          \
-    kern<<<(grid), (block), (smem), c_->stream>>>(__VA_ARGS__);                \
+    {                                                                          \
+      cudaLaunchConfig_t cfg_ = {};                                            \
+      cfg_.gridDim = dim3(grid);                                               \
+      cfg_.blockDim = dim3(block);                                             \
+      cfg_.dynamicSmemBytes = (smem);                                          \
+      cfg_.stream = c_->stream;                                                \
+      cudaLaunchAttribute at_[1];                                              \
+      at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;          \
+      at_[0].val.programmaticStreamSerializationAllowed = 1;                   \
+      cfg_.attrs = at_;                                                        \
+      cfg_.numAttrs = (c_->pdl && !pr_ && g_pdl_chain_stream == c_->stream && \
+                       (c_->pdl > 1 || (!strstr(#kern, "k_gs_tma") && !strstr(#kern, "k_reduce_partials2"))) && \
+                       (c_->pdl_only.empty() || strstr(#kern, c_->pdl_only.c_str())) && \
+                       (c_->pdl_skip.empty() || !strstr(#kern, c_->pdl_skip.c_str()))) ? 1 : 0; \
+      cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__);                            \
+      g_pdl_chain_stream = pr_ ? nullptr : c_->stream;                         \
+    }                                                                          \
     if (pr_) {                                                                 \
       cudaEventRecord(pe1_, c_->stream);                                       \
       c_->recs.push_back(ProfRec{#kern, pe0_, pe1_, c_->next_work});           \
@@ -374,7 +395,7 @@ static int g_schur_tf32 = 0;   // 1: dense Schur inverse applied in 3xTF32 (fp32
 static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur solve
 // 1: dense Schur block on the tcgen05 tensor cores (TF32 operands from an fp32 copy of the inverse,
 // fp32 accumulation in TMEM; dnsb_tc.cuh).  Preconditioner block only: FGMRES stays fp64.
-static int g_schur_l2keep = 1;   // packed inverse read with an L2 evict_last hint (stays resident between applications)
+static int g_schur_l2keep = 0;   // 1: packed inverse read with an L2 evict_last hint (measured: no effect, the streams of a step flush L2 anyway)
 static int g_schur_tc = 1;
 static const int TC_SMEM_OPTIN = 208 * 1024;
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
@@ -532,6 +553,32 @@ static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7]
   }
 }
 
+// The tuning switches are file-scope variables (read by the launch helpers above), but they BELONG to a
+// context: the DNSB_* environment is read when a context is created and stored with it, and every entry
+// point makes its context's set the current one (dnsb_enter).  Two contexts created under different
+// switches can be used side by side in one process (the parity tests do); contexts are not thread safe.
+#define DNSB_SWITCH_LIST(X) X(g_rows_per_cta) X(g_pair) X(g_tma_min_rows) X(g_gs_tma) X(g_tma_rows) X(g_tma_stages) \
+  X(g_dmma) X(g_schur_tf32) X(g_schur_tc) X(g_tile) X(g_gs_pyth) X(g_schur_l2keep) X(g_tile_stages)             \
+  X(g_tile_stages_f) X(g_tail_warps) X(g_pkeep) X(g_proj_t) X(g_cheb_f32) X(g_conv_colours) X(g_rowpair)         \
+  X(g_graphs) X(g_dense_ctas_per_sm)
+static void switches_store(int *sw) {
+  int k = 0;
+#define X(name) sw[k++] = name;
+  DNSB_SWITCH_LIST(X)
+#undef X
+}
+static void switches_load(const int *sw) {
+  int k = 0;
+#define X(name) name = sw[k++];
+  DNSB_SWITCH_LIST(X)
+#undef X
+}
+static const dnsb_ctx *g_switch_owner = nullptr;
+static inline cudaError_t dnsb_enter(const dnsb_ctx *ctx) {
+  if (g_switch_owner != ctx) { switches_load(ctx->sw); g_switch_owner = ctx; }
+  return cudaSetDevice(ctx->device);
+}
+
 extern "C" int dnsb_version(void) { return DNSB_VERSION; }
 
 extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
@@ -540,6 +587,12 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   dnsb_ctx *ctx = new (std::nothrow) dnsb_ctx();
   if (!ctx) return -3;
   ctx->device = device;
+  {
+    static int defaults[32];
+    static bool have_defaults = false;
+    if (!have_defaults) { switches_store(defaults); have_defaults = true; }
+    switches_load(defaults);   // the environment below is applied to the defaults, not to the last context's set
+  }
   if (const char *ev = getenv("DNSB_ROWS_PER_CTA")) g_rows_per_cta = std::max(1, atoi(ev));
   if (const char *ev = getenv("DNSB_PAIR")) g_pair = atoi(ev);
   if (const char *ev = getenv("DNSB_TMA_MIN_ROWS")) g_tma_min_rows = atoi(ev);
@@ -551,6 +604,9 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
+  if (const char *ev = getenv("DNSB_PDL")) ctx->pdl = atoi(ev);
+  if (const char *ev = getenv("DNSB_PDL_ONLY")) ctx->pdl_only = ev;
+  if (const char *ev = getenv("DNSB_PDL_SKIP")) ctx->pdl_skip = ev;
   if (const char *ev = getenv("DNSB_SCHUR_L2KEEP")) g_schur_l2keep = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE_STAGES")) g_tile_stages = std::max(2, std::min(TILE_MAX_STAGES, atoi(ev)));
   if (const char *ev = getenv("DNSB_TILE_STAGES_F")) g_tile_stages_f = std::max(2, std::min(TILE_MAX_STAGES, atoi(ev)));
@@ -562,6 +618,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_ROWPAIR")) g_rowpair = atoi(ev);
   if (const char *ev = getenv("DNSB_GRAPHS")) g_graphs = atoi(ev);
   if (const char *ev = getenv("DNSB_DENSE_CTAS_PER_SM")) g_dense_ctas_per_sm = std::max(1, atoi(ev));
+  switches_store(ctx->sw);
+  g_switch_owner = ctx;
   *out = ctx;   // returned even on failure so that the message can be read
   DNSB_CK(ctx, cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -609,7 +667,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
 
 extern "C" void dnsb_ctx_destroy(dnsb_ctx *ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  dnsb_enter(ctx);
+  g_switch_owner = nullptr;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   ctx->cn.release(); ctx->geom.release();
   ctx->n2c_ptr.release(); ctx->n2c_idx.release(); ctx->elem.release();
@@ -641,7 +700,7 @@ extern "C" int dnsb_sync(dnsb_ctx *ctx) {
 
 extern "C" int dnsb_profile_begin(dnsb_ctx *ctx, int max_records) {
   if (!ctx) return -2;
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   for (ProfRec &r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   ctx->recs.clear();
   ctx->prof_cap = max_records > 0 ? (size_t)max_records : 0;
@@ -653,7 +712,7 @@ extern "C" int dnsb_profile_begin(dnsb_ctx *ctx, int max_records) {
 // number of bytes needed (incl. the terminating 0) or < 0 on error
 extern "C" int dnsb_profile_end(dnsb_ctx *ctx, char *buf, int buflen) {
   if (!ctx) return -2;
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->prof = false;
   std::vector<std::string> names;
@@ -698,7 +757,7 @@ extern "C" int dnsb_set_mesh(dnsb_ctx *ctx, int ncell, int nnodes,
   if (!ctx) return -2;
   DNSB_REQUIRE(ctx, ncell > 0 && nnodes > 0 && cell_nodes && geom && cell_colour &&
                ncolours > 0, "bad mesh arguments");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   // counting sort of the cells by colour (stable: keeps the mesh order inside
   // a colour); verify the colouring on the way (no shared node per colour)
   std::vector<int> count(ncolours + 1, 0);
@@ -763,7 +822,7 @@ extern "C" int dnsb_set_conv_pattern(dnsb_ctx *ctx, const int32_t *indptr,
   if (!ctx) return -2;
   DNSB_REQUIRE(ctx, ctx->ncell > 0, "set the mesh first");
   DNSB_REQUIRE(ctx, indptr && indices && cell_slots, "null pattern");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const int nrows = 2 * ctx->nnodes;
   const int nnz = indptr[nrows];
   const int ncell = ctx->ncell;
@@ -838,7 +897,7 @@ extern "C" int dnsb_convvec(dnsb_ctx *ctx, const double *u1, const double *u2,
   if (!ctx) return -2;
   DNSB_REQUIRE(ctx, ctx->ncell > 0, "set the mesh first");
   DNSB_REQUIRE(ctx, u1 && out && nb >= 1, "bad arguments");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t nfull = (size_t)2 * ctx->nnodes * nb;
   DNSB_CK(ctx, ctx->stage_a.upload(u1, nfull, ctx->stream));
   if (u2) DNSB_CK(ctx, ctx->stage_b.upload(u2, nfull, ctx->stream));
@@ -911,7 +970,7 @@ extern "C" int dnsb_assemble_stokes(dnsb_ctx *ctx, double nu, int symgrad, int j
   DNSB_REQUIRE(ctx, m_vals && a_vals, "null output");
   DNSB_REQUIRE(ctx, (!j_vals || (jslots && jnnz > 0)) && (!mp_vals || (mpslots && mpnnz > 0)),
                "slot lists of J / MP missing");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const int ncell = ctx->ncell;
   const size_t nnz = ctx->cnnz;
   DBuf<double> ej, emp, dm, da, dj, dmp;
@@ -963,7 +1022,7 @@ extern "C" int dnsb_convmats(dnsb_ctx *ctx, const double *u0, double *n1_data,
   if (!ctx) return -2;
   DNSB_REQUIRE(ctx, ctx->ncell > 0 && ctx->cnnz > 0, "set mesh and pattern first");
   DNSB_REQUIRE(ctx, u0 != nullptr, "null u0");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t nfull = (size_t)2 * ctx->nnodes;
   const size_t nnz = ctx->cnnz;
   DNSB_CK(ctx, ctx->stage_a.upload(u0, nfull, ctx->stream));
@@ -994,12 +1053,12 @@ extern "C" int dnsb_csr_create(dnsb_ctx *ctx, int nrows, int ncols,
                                const double *vals1, const double *vals2,
                                dnsb_csr **out) {
   if (!ctx) return -2;
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   return csr_build(ctx, nrows, ncols, indptr, indices, vals1, vals2, out);
 }
 
 extern "C" void dnsb_csr_destroy(dnsb_csr *mat) {
-  if (mat) cudaSetDevice(mat->ctx->device);
+  if (mat) dnsb_enter(mat->ctx);
   csr_free(mat);
 }
 
@@ -1010,7 +1069,7 @@ extern "C" int dnsb_spmm_dev(dnsb_csr *mat, const double *coef_dev,
   dnsb_ctx *ctx = mat->ctx;
   DNSB_REQUIRE(ctx, x_dev && y_dev && nb >= 1, "bad arguments");
   DNSB_REQUIRE(ctx, !(mat->has2 && coef_dev == nullptr), "matrix has a second value array: coef required");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   spmm_dev(ctx, mat, coef_dev, x_dev, y_dev, y_dev, nb, alpha, beta);
   DNSB_CK(ctx, cudaGetLastError());
   return 0;
@@ -1022,7 +1081,7 @@ extern "C" int dnsb_spmm(dnsb_csr *mat, const double *coef, const double *x,
   dnsb_ctx *ctx = mat->ctx;
   DNSB_REQUIRE(ctx, x && y && nb >= 1, "bad arguments");
   DNSB_REQUIRE(ctx, !(mat->has2 && coef == nullptr), "matrix has a second value array: coef required");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   DNSB_CK(ctx, ctx->stage_a.upload(x, (size_t)mat->ncols * nb, ctx->stream));
   if (beta != 0.0)
     DNSB_CK(ctx, ctx->stage_b.upload(y, (size_t)mat->nrows * nb, ctx->stream));
@@ -1093,6 +1152,7 @@ struct dnsb_solver {
   // CUDA graphs of the Arnoldi steps (one per column j), valid for one tol
   std::vector<cudaGraphExec_t> igraph;
   std::vector<int> igraph_launches;
+  std::vector<int> igraph_seen;   // how often column j ran since the graphs were dropped
   double igraph_tol = -1.0;
   // Pythagorean norm in the Arnoldi step: only for solves that are expected to be SHORT (the
   // previous solve of this solver took <= 8 iterations: the time loop with recycled guesses).
@@ -1130,7 +1190,7 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
   DNSB_REQUIRE(ctx, fmat->ncols == nv && jmat->ncols == nv && jtmat->nrows == nv &&
                jtmat->ncols == np, "inconsistent block shapes");
   DNSB_REQUIRE(ctx, !(fmat->has2 && !coef), "fmat has two value arrays: coef required");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   dnsb_solver *s = new (std::nothrow) dnsb_solver();
   DNSB_REQUIRE(ctx, s != nullptr, "out of host memory");
   s->ctx = ctx; s->nv = nv; s->np = np; s->ntot = nv + np; s->nb = nb;
@@ -1321,7 +1381,7 @@ static void level_free(MgLevel *L) {
 
 extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
+  dnsb_enter(s->ctx);
   cudaStreamSynchronize(s->ctx->stream);
   for (cudaGraphExec_t g : s->igraph) if (g) cudaGraphExecDestroy(g);
   s->igraph.clear();
@@ -1347,7 +1407,7 @@ static int solver_add_level(dnsb_solver *s, int block, dnsb_csr *amat, dnsb_csr 
                             dnsb_csr *rmat, int nsmooth, double lmin, double lmax,
                             const double *dense_inv) {
   dnsb_ctx *ctx = s->ctx;
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   std::vector<MgLevel *> &lv = block == 0 ? s->levels : s->vlevels;
   solver_drop_graphs(s);   // the preconditioner changes: captured launch sequences are stale
   int nexpect;
@@ -1455,7 +1515,7 @@ extern "C" int dnsb_solver_set_schur_mass(dnsb_solver *s, const double *mp_dinv,
   if (!s) return -2;
   dnsb_ctx *ctx = s->ctx;
   DNSB_REQUIRE(ctx, mp_dinv && mp_scale, "null arguments");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   DNSB_CK(ctx, s->mp_dinv.upload(mp_dinv, s->np, ctx->stream));
   DNSB_CK(ctx, s->mp_scale.upload(mp_scale, s->nb, ctx->stream));
   s->has_mass = true;
@@ -1468,7 +1528,7 @@ extern "C" int dnsb_solver_set_schur_lsc(dnsb_solver *s, const double *du_inv) {
   dnsb_ctx *ctx = s->ctx;
   DNSB_REQUIRE(ctx, du_inv != nullptr, "null argument");
   DNSB_REQUIRE(ctx, !s->levels.empty(), "add the levels of L = J Du^-1 JT first");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t nvb = (size_t)s->nv * s->nb, npb = (size_t)s->np * s->nb;
   DNSB_CK(ctx, s->lsc_dinv.upload(du_inv, s->nv, ctx->stream));
   DNSB_CK(ctx, s->lsc_t1.alloc(nvb)); DNSB_CK(ctx, s->lsc_t2.alloc(nvb));
@@ -1683,6 +1743,7 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
 // out[i,m] = alpha*(a[i,m] + b[i,m]*rowscale[i])
 __global__ void k_rowscale_add(const double *a, const double *b, const double *rowscale,
                                double *out, int n, int nb, double alpha) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * nb) return;
   out[t] = alpha * (a[t] + b[t] * rowscale[t / nb]);
@@ -1691,6 +1752,7 @@ __global__ void k_rowscale_add(const double *a, const double *b, const double *r
 // out[i,m] = alpha*a[i,m]*rowscale[i]
 __global__ void k_rowscale_mul(const double *a, const double *rowscale, double *out, int n,
                                int nb, double alpha) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * nb) return;
   out[t] = alpha * a[t] * rowscale[t / nb];
@@ -1853,6 +1915,7 @@ static void solver_drop_graphs(dnsb_solver *s) {
   for (cudaGraphExec_t g : s->igraph) if (g) cudaGraphExecDestroy(g);
   s->igraph.assign(s->mr, nullptr);
   s->igraph_launches.assign(s->mr, 0);
+  s->igraph_seen.assign(s->mr, 0);
 }
 
 static int gmres_iteration(dnsb_solver *s, int j, double tol) {
@@ -1863,6 +1926,9 @@ static int gmres_iteration(dnsb_solver *s, int j, double tol) {
     s->igraph_tol = tol;
     s->igraph_pyth = s->use_pyth;
   }
+  // a column is captured the SECOND time it runs: capture + instantiation cost more than the launches of one
+  // pass, so one-shot solvers (a steady Picard/Newton system, 200 columns used once) stay on plain launches
+  if (!s->igraph[j] && s->igraph_seen[j]++ == 0) return gmres_iteration_launch(s, j, tol);
   if (!s->igraph[j]) {
     const long long l0 = ctx->launches;
     cudaGraph_t graph = nullptr;
@@ -1983,7 +2049,7 @@ extern "C" int dnsb_solver_solve(dnsb_solver *s, const double *rhsv, const doubl
   if (!s) return -2;
   dnsb_ctx *ctx = s->ctx;
   DNSB_REQUIRE(ctx, rhsv && vp && maxit >= 1 && tol > 0, "bad arguments");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const int nb = s->nb;
   const size_t nvb = (size_t)s->nv * nb, npb = (size_t)s->np * nb, ntb = nvb + npb;
   DNSB_CK(ctx, s->sb.alloc(ntb));
@@ -2017,6 +2083,7 @@ extern "C" int dnsb_solver_solve(dnsb_solver *s, const double *rhsv, const doubl
 // F entries first, then the JT entries)
 __global__ void k_copy_f_into_k(CsrDev F, const int *__restrict__ kindptr,
                                 double *__restrict__ kv1) {
+  dnsb_pdl_entry();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= F.nrows) return;
@@ -2033,7 +2100,7 @@ extern "C" int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1) {
   dnsb_ctx *ctx = s->ctx;
   DNSB_REQUIRE(ctx, vals1 != nullptr, "null values");
   DNSB_REQUIRE(ctx, !s->F->has2, "matrices with two value arrays are updated through their coefficients");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   dnsb_csr *F = s->F;
   DNSB_CK(ctx, cudaMemcpyAsync(F->v1.p, vals1, (size_t)F->nnz * sizeof(double), cudaMemcpyHostToDevice,
                                ctx->stream));
@@ -2058,6 +2125,7 @@ extern "C" int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1) {
 __global__ void k_conv_to_pattern(const double *__restrict__ n1, const double *__restrict__ n2,
                                   const int *__restrict__ src, const int *__restrict__ pos,
                                   double *__restrict__ vals, int nconv) {
+  dnsb_pdl_entry();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nconv) return;
   const int sk = src[k];
@@ -2071,6 +2139,7 @@ __global__ void k_conv_rhs(const int *__restrict__ cindptr, const int *__restric
                            const double *__restrict__ ubc, const double *__restrict__ f3,
                            const double *__restrict__ fv, const int *__restrict__ inv,
                            double *__restrict__ out, int nv) {
+  dnsb_pdl_entry();
   const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int i = (int)(tid >> 3), lane = (int)(tid & 7);
   double acc = 0.0;
@@ -2088,6 +2157,7 @@ __global__ void k_conv_rhs(const int *__restrict__ cindptr, const int *__restric
 __global__ void k_vals_combine(const double *__restrict__ a, const double *__restrict__ b,
                                const double *__restrict__ n, double c, double *__restrict__ out,
                                size_t nnz) {
+  dnsb_pdl_entry();
   size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nnz) return;
   out[k] = a[k] + c * (b[k] + n[k]);
@@ -2097,6 +2167,7 @@ __global__ void k_vals_combine(const double *__restrict__ a, const double *__res
 __global__ void k_cn_rhs(double *__restrict__ rhs, const double *__restrict__ fa,
                          const double *__restrict__ fb, const double *__restrict__ y, double c,
                          int n) {
+  dnsb_pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   rhs[i] += c * (fa[i] + fb[i] - y[i]);
@@ -2105,6 +2176,7 @@ __global__ void k_cn_rhs(double *__restrict__ rhs, const double *__restrict__ fa
 // d = v - lin[inv]   (difference to the linearisation point, inner dofs)
 __global__ void k_diff_inner(const double *__restrict__ v, const double *__restrict__ linfull,
                              const int *__restrict__ inv, double *__restrict__ d, int nv) {
+  dnsb_pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nv) return;
   d[i] = v[i] - linfull[inv[i]];
@@ -2145,7 +2217,7 @@ extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double 
     DNSB_REQUIRE(ctx, src[k] >= 0 && src[k] < ctx->cnnz && pos[k] >= 0 && pos[k] < nnz, "convection map out of range");
   for (int i = 0; i < nv; ++i) DNSB_REQUIRE(ctx, invinds[i] >= 0 && invinds[i] < nvf, "invinds out of range");
   for (int i = 0; i < nbc; ++i) DNSB_REQUIRE(ctx, bcinds[i] >= 0 && bcinds[i] < nvf, "bcinds out of range");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   dnsb_cnsweep *w = new (std::nothrow) dnsb_cnsweep();
   DNSB_REQUIRE(ctx, w != nullptr, "out of host memory");
   *out = w;
@@ -2186,7 +2258,7 @@ extern "C" int dnsb_cnsweep_create(dnsb_solver *s, dnsb_csr *mmat, const double 
 
 extern "C" void dnsb_cnsweep_destroy(dnsb_cnsweep *w) {
   if (!w) return;
-  cudaSetDevice(w->ctx->device);
+  dnsb_enter(w->ctx);
   cudaStreamSynchronize(w->ctx->stream);
   csr_free(w->C);
   w->mv.release(); w->av.release(); w->nvn.release(); w->nvc.release();
@@ -2231,7 +2303,7 @@ extern "C" int dnsb_cnsweep_run(dnsb_cnsweep *w, int nsteps, const double *dts, 
   dnsb_ctx *ctx = w->ctx;
   DNSB_REQUIRE(ctx, nsteps >= 1 && dts && linpoint && v0 && vtraj && ptraj, "bad arguments");
   DNSB_REQUIRE(ctx, w->mesh_hash == ctx->mesh_hash, "the mesh of the context is not the one this sweep was created on");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   dnsb_solver *s = w->s;
   const int nv = w->nv, np = w->np, nvf = w->nvf, nnz = s->F->nnz;
   DNSB_CK(ctx, w->lin.upload(linpoint, (size_t)(nsteps + 1) * nvf, ctx->stream));
@@ -2349,7 +2421,7 @@ extern "C" int dnsb_solver_apply_prec(dnsb_solver *s, const double *r, double *z
   if (!s) return -2;
   dnsb_ctx *ctx = s->ctx;
   DNSB_REQUIRE(ctx, r && z, "null arguments");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t ntb = (size_t)s->ntot * s->nb;
   DNSB_CK(ctx, s->sb.alloc(ntb));
   DNSB_CK(ctx, s->sx.alloc(ntb));
@@ -2438,7 +2510,7 @@ extern "C" int dnsb_imex_create(dnsb_ctx *ctx, int scheme, int nb, double dt,
     DNSB_REQUIRE(ctx, invinds[i] >= 0 && invinds[i] < nvf, "invinds out of range");
   for (int i = 0; i < nbc; ++i)
     DNSB_REQUIRE(ctx, bcinds[i] >= 0 && bcinds[i] < nvf, "bcinds out of range");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   dnsb_imex *e = new (std::nothrow) dnsb_imex();
   DNSB_REQUIRE(ctx, e != nullptr, "out of host memory");
   *out = e;
@@ -2486,7 +2558,7 @@ extern "C" int dnsb_imex_create(dnsb_ctx *ctx, int scheme, int nb, double dt,
 
 extern "C" void dnsb_imex_destroy(dnsb_imex *e) {
   if (!e) return;
-  cudaSetDevice(e->ctx->device);
+  dnsb_enter(e->ctx);
   cudaStreamSynchronize(e->ctx->stream);
   csr_free(e->Rm);
   if (e->cstream) { cudaStreamSynchronize(e->cstream); cudaStreamDestroy(e->cstream); }
@@ -2529,7 +2601,7 @@ extern "C" int dnsb_imex_set_forcing(dnsb_imex *e, int nk, const double *bvecs,
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, nk >= 0 && (nk == 0 || (bvecs && useries && ntimes >= 1)), "bad forcing");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   e->nk = nk; e->ntimes = ntimes;
   e->force_t0 = e->have_state ? e->step : 0;   // series starts at the current time level
   if (nk > 0) {
@@ -2543,7 +2615,7 @@ extern "C" int dnsb_imex_set_state(dnsb_imex *e, const double *v0, const double 
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, v0 != nullptr, "null v0");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t nvb = (size_t)e->nv * e->nb, npb = (size_t)e->np * e->nb;
   DNSB_CK(ctx, cudaMemcpyAsync(e->v.p, v0, nvb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (p0)
@@ -2590,6 +2662,7 @@ static void imex_refresh_p(dnsb_imex *e) {
 // out[map[i], m] = x[i, m]  (map == null: identity)
 __global__ void k_scatter_rows(const double *__restrict__ x, const int *__restrict__ map,
                                double *__restrict__ out, int n, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);
@@ -2661,6 +2734,7 @@ static int imex_snapshot(dnsb_imex *e) {
 // y[i] = sum_{j=i..k-1} T[i][j] c[j]
 __global__ void k_proj_tri_apply(const double *__restrict__ T, const double *__restrict__ c,
                                  double *__restrict__ y, int k, int L, int nb) {
+  dnsb_pdl_entry();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= k * nb) return;
   const int i = t / nb, m = t % nb;
@@ -2672,6 +2746,7 @@ __global__ void k_proj_tri_apply(const double *__restrict__ T, const double *__r
 // normalised with inv:  T[i][k] = -inv * sum_{j=i..k-1} T[i][j] g[j],  T[k][k] = inv
 __global__ void k_proj_tri_column(double *__restrict__ T, const double *__restrict__ g,
                                   const double *__restrict__ inv, int k, int L, int nb) {
+  dnsb_pdl_entry();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (k + 1) * nb) return;
   const int i = t / nb, m = t % nb;
@@ -2683,6 +2758,7 @@ __global__ void k_proj_tri_column(double *__restrict__ T, const double *__restri
 // x = x0 = sum_i y[i,m] D_i   (the guess and the copy the new direction is measured from, one pass)
 __global__ void k_proj_guess(const double *__restrict__ D, size_t dstride, int nvec, const double *__restrict__ y,
                              double *__restrict__ x, double *__restrict__ x0, size_t n, int nb) {
+  dnsb_pdl_entry();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * nb) return;
   const int m = (int)(idx % nb);
@@ -2694,6 +2770,7 @@ __global__ void k_proj_guess(const double *__restrict__ D, size_t dstride, int n
 // d = x - x0 and keep = x  (new direction + the ring of raw solutions, one pass)
 __global__ void k_proj_dir(const double *__restrict__ x, const double *__restrict__ x0, double *__restrict__ d,
                            double *__restrict__ keep, size_t n) {
+  dnsb_pdl_entry();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const double v = x[idx];
@@ -2737,6 +2814,7 @@ static int imex_guess(dnsb_imex *e, int guess, double *x) {
 // inv[m] = 1/sqrt(n2[m]) if n2[m] > eps*ref[m] else 0
 __global__ void k_inv_norm(const double *__restrict__ n2, const double *__restrict__ ref,
                            double *__restrict__ inv, int nb, double eps) {
+  dnsb_pdl_entry();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= nb) return;
   const double v = n2[m];
@@ -2878,7 +2956,7 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
                "the mesh of the context is not the one this integrator was created on (dnsb_set_mesh)");
   DNSB_REQUIRE(ctx, e->sl != nullptr, "set the solvers first");
   DNSB_REQUIRE(ctx, nsteps >= 1 && tol > 0 && maxit >= 1 && guess >= 0 && guess <= 64, "bad run arguments");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const int nb = e->nb, nv = e->nv, np = e->np;
   const size_t nvb = (size_t)nv * nb, npb = (size_t)np * nb, ntb = nvb + npb;
   const double dt = e->dt;
@@ -3120,7 +3198,7 @@ extern "C" int dnsb_imex_run(dnsb_imex *e, int nsteps, int snap_stride, double t
 extern "C" int dnsb_imex_get_state(dnsb_imex *e, double *v, double *p) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t nvb = (size_t)e->nv * e->nb, npb = (size_t)e->np * e->nb;
   if (v) DNSB_CK(ctx, cudaMemcpyAsync(v, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (p) DNSB_CK(ctx, cudaMemcpyAsync(p, e->p.p, npb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -3142,7 +3220,7 @@ extern "C" int dnsb_imex_get_snapshots(dnsb_imex *e, double *out) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, out != nullptr, "null output");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const size_t ntb = (size_t)(e->nv + e->np) * e->nb;
   if (e->nsnap == 0) return 0;
   if (e->host_mirror && e->h_snaps && e->nsnap <= e->h_cap) {
@@ -3171,7 +3249,7 @@ extern "C" int dnsb_imex_snapshots_host(dnsb_imex *e, const double **ptr, int *n
 extern "C" int dnsb_imex_set_output_order(dnsb_imex *e, const int32_t *vmap, const int32_t *pmap) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   if (!vmap || !pmap) { e->has_outmap = false; return 0; }
   std::vector<int> mp((size_t)e->nv + e->np);
   std::vector<char> seen(std::max(e->nv, e->np));
@@ -3194,7 +3272,7 @@ extern "C" int dnsb_imex_reserve_snapshots(dnsb_imex *e, int nsnap) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, nsnap >= 0, "bad count");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   return imex_reserve_host(e, nsnap);
 }
 
@@ -3213,6 +3291,7 @@ extern "C" long long dnsb_imex_unconverged(dnsb_imex *e) { return e ? e->run_unc
 __global__ void k_gram_partial(const double *__restrict__ X, size_t xstride,
                                const double *__restrict__ MX,
                                int ns, size_t nvb, double *__restrict__ partial) {
+  dnsb_pdl_entry();
   // block (a, b) pair over blockIdx.y; grid-stride chunks over blockIdx.x
   extern __shared__ double sred[];
   const int pair = blockIdx.y;
@@ -3237,7 +3316,7 @@ extern "C" int dnsb_imex_gram(dnsb_imex *e, double *g) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, g != nullptr && e->nsnap > 0, "no snapshots / null output");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   DBuf<double> gd;
   DNSB_CK(ctx, gd.alloc((size_t)e->nsnap * e->nsnap));
   int rc = imex_gram_impl(e, gd.p);
@@ -3258,7 +3337,7 @@ static int imex_gram_impl(dnsb_imex *e, double *g_dev) {
   if (!e) return -2;
   dnsb_ctx *ctx = e->ctx;
   DNSB_REQUIRE(ctx, g_dev != nullptr && e->nsnap > 0, "no snapshots / null output");
-  DNSB_CK(ctx, cudaSetDevice(ctx->device));
+  DNSB_CK(ctx, dnsb_enter(ctx));
   const int ns = e->nsnap, nb = e->nb;
   const size_t nvb = (size_t)e->nv * nb, ntb = (size_t)(e->nv + e->np) * nb;
   DBuf<double> MX, part;

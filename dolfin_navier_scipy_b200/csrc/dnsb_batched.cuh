@@ -125,6 +125,7 @@ template <bool HAS2>
 __global__ void __launch_bounds__(SPB_THREADS)
 k_spmm_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
          const double *z, double *y, int nb, int gpc, double alpha, double beta) {
+  dnsb_pdl_entry();
   SPB_SMEM(HAS2)
   SPB_FOR_GROUPS() {
     SPB_ROWMAP()
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_init_b(CsrDev A, const double *__restrict__ zp, const double *__restrict__ rv,
               const double *__restrict__ dinv, double *__restrict__ res,
               double *__restrict__ d, int nb, int gpc, double inv_theta) {
+  dnsb_pdl_entry();
   SPB_SMEM(false)
   SPB_FOR_GROUPS() {
     SPB_ROWMAP()
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_step_b(CsrDev A, const double *__restrict__ coef, const double *__restrict__ d,
               const double *__restrict__ dinv, double *res, double *__restrict__ dn,
               double *z, int nb, int gpc, double c1, double c2) {
+  dnsb_pdl_entry();
   SPB_SMEM(HAS2)
   SPB_FOR_GROUPS() {
     SPB_ROWMAP()
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(256)
 k_mdot_b(const double *__restrict__ V, size_t vstride, int nvec,
          const double *__restrict__ w, int n, int nb, int rpb, int rows_per_block,
          double *__restrict__ partial) {
+  dnsb_pdl_entry();
   extern __shared__ double sred[];   // (nvec+1) x blockDim
   const int m = threadIdx.x % nb, rr = threadIdx.x / nb;
   const int r0 = blockIdx.x * rows_per_block;
@@ -268,6 +272,7 @@ k_gs_update_b(const double *__restrict__ V, size_t vstride, int nvec,
               const double *__restrict__ h, const double *__restrict__ w,
               double *__restrict__ vnext, int n, int nb, int rpb, int rows_per_block,
               double *__restrict__ partial2, const double *__restrict__ scale) {
+  dnsb_pdl_entry();
   extern __shared__ double sred[];   // blockDim
   const int m = threadIdx.x % nb, rr = threadIdx.x / nb;
   const int r0 = blockIdx.x * rows_per_block;
@@ -392,6 +397,7 @@ template <bool HAS2>
 __global__ void __launch_bounds__(SPB_THREADS)
 k_spmm_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
           const double2 *z, double2 *y, int nb, int row_begin, double alpha, double beta) {
+  dnsb_pdl_entry();
   // rows [row_begin, nrows): the tail after the paired rows, or everything
   const int nb2 = nb >> 1;
   const long total_ = (long)(A.nrows - row_begin) * nb2;
@@ -417,6 +423,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_init_b2(CsrDev A, const double2 *__restrict__ zp, const double2 *__restrict__ rv,
                const double2 *__restrict__ dinv, double2 *__restrict__ res,
                double2 *__restrict__ d, int nb, double inv_theta) {
+  dnsb_pdl_entry();
   SPB2_ROWMAP()
   SPB_SMEM(false)
   const long te_ = valid ? t_ : 0;
@@ -435,6 +442,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_step_b2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ d,
                const double2 *__restrict__ dinv, double2 *res, double2 *__restrict__ dn,
                double2 *z, int nb, double c1, double c2) {
+  dnsb_pdl_entry();
   SPB2_ROWMAP()
   SPB_SMEM(HAS2)
   const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
@@ -583,6 +591,7 @@ template <bool HAS2>
 __global__ void __launch_bounds__(SPB_THREADS)
 k_spmm_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
           const double2 *z, double2 *y, int nb, int npairs, double alpha, double beta) {
+  dnsb_pdl_entry();
   SPP_MAP(HAS2)
   const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
   const double2 zero = make_double2(0.0, 0.0);
@@ -605,6 +614,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_init_p2(CsrDev A, const double2 *__restrict__ zp, const double2 *__restrict__ rv,
                const double2 *__restrict__ dinv, double2 *__restrict__ res,
                double2 *__restrict__ d, int nb, int npairs, double inv_theta) {
+  dnsb_pdl_entry();
   SPP_MAP(false)
   const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
   const double2 ra = rv[sa_], rb = rv[sb_], da = dinv[sa_], db = dinv[sb_];
@@ -632,6 +642,7 @@ __global__ void __launch_bounds__(SPB_THREADS, SPP_MINB)
 k_cheb_step_p2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ d,
                const double2 *__restrict__ dinv, double2 *res, double2 *__restrict__ dn,
                double2 *z, int nb, int npairs, double c1, double c2) {
+  dnsb_pdl_entry();
   SPP_MAP(HAS2)
   const double2 cm = HAS2 ? reinterpret_cast<const double2 *>(coef)[mp] : make_double2(0.0, 0.0);
   const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
@@ -667,6 +678,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_spmm_k2(CsrDev A, const double *__restrict__ coef, const double2 *__restrict__ x,
           const double2 *z, double2 *y, int nb, int npairs, int tail_blocks,
           double alpha, double beta) {
+  dnsb_pdl_entry();
   const int nb2 = nb >> 1;
   const int lane = threadIdx.x & 31;
   const double2 zero = make_double2(0.0, 0.0);

@@ -13,6 +13,34 @@
 
 struct dnsb_ctx;
 
+// The programmatic launch attribute is only given to a kernel whose predecessor ON ITS STREAM is another
+// kernel of this library: `griddepcontrol.wait` waits for prerequisite GRIDS, and a copy or memset that sits
+// between two kernels is not one (measured: with the attribute on every launch, runs on the large mesh were
+// no longer reproducible bit for bit).  Every other stream operation the library issues breaks the chain.
+static cudaStream_t g_pdl_chain_stream = nullptr;   // stream whose last operation was one of our kernels
+static inline void dnsb_pdl_break() { g_pdl_chain_stream = nullptr; }
+#define cudaMemcpyAsync(...) (dnsb_pdl_break(), cudaMemcpyAsync(__VA_ARGS__))
+#define cudaMemsetAsync(...) (dnsb_pdl_break(), cudaMemsetAsync(__VA_ARGS__))
+#define cudaEventRecord(...) (dnsb_pdl_break(), cudaEventRecord(__VA_ARGS__))
+#define cudaStreamWaitEvent(...) (dnsb_pdl_break(), cudaStreamWaitEvent(__VA_ARGS__))
+#define cudaGraphLaunch(...) (dnsb_pdl_break(), cudaGraphLaunch(__VA_ARGS__))
+#define cudaStreamBeginCapture(...) (dnsb_pdl_break(), cudaStreamBeginCapture(__VA_ARGS__))
+#define cudaStreamEndCapture(...) (dnsb_pdl_break(), cudaStreamEndCapture(__VA_ARGS__))
+#define cudaMemcpyToSymbol(...) (dnsb_pdl_break(), cudaMemcpyToSymbol(__VA_ARGS__))
+
+// Programmatic dependent launch: every kernel of the library starts with this pair.  `launch_dependents`
+// lets the NEXT kernel on the stream be scheduled once all CTAs of this one have started (its CTAs fill
+// the SMs that drain during this kernel's tail, its launch latency is hidden), `wait` holds the kernel
+// until every kernel it depends on has completed and flushed -- nothing is read before it, so the
+// data dependencies are exactly those of plain stream order.  Both are no-ops for kernels launched
+// without the programmatic-serialization attribute (DNSB_PDL=0).
+__device__ __forceinline__ void dnsb_pdl_entry() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 #define DNSB_CK(ctx, call)                                                    \
   do {                                                                        \
     cudaError_t e_ = (call);                                                  \
@@ -82,6 +110,9 @@ struct dnsb_ctx {
   std::string err;
   long long launches = 0;
   long long next_work = 0;   // recorded with the next profiled launch, then reset
+  int pdl = 1;               // launch kernels with programmatic stream serialization (dnsb_pdl_entry)
+  std::string pdl_only, pdl_skip;   // debugging: substring filters on the kernel name
+  int sw[32] = {0};          // this context's tuning switches (DNSB_* environment at creation), see dnsb_enter
 
   // ---- mesh / convection data (cells permuted into colour order) ----------
   int ncell = 0, nnodes = 0, ncolours = 0;

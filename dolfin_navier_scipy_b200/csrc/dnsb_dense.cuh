@@ -36,6 +36,7 @@ template <int TN>
 __global__ void __launch_bounds__(128)
 k_dense_gemm_streamk(const double *__restrict__ D, const double *__restrict__ X,
                      double *__restrict__ part, int n, int nb, DenseSplit sp) {
+  dnsb_pdl_entry();
   __shared__ __align__(16) double sD[2][DGK_TK][DGK_TM + 2];
   __shared__ __align__(16) double sX[2][DGK_TK][TN];
   constexpr int MC = TN / 16;              // member columns per thread
@@ -142,6 +143,7 @@ __global__ void k_dense_epilogue(const double *__restrict__ part, DenseSplit sp,
                                  double alpha,
                                  const double *__restrict__ add_dinv,
                                  const double *__restrict__ add_scale) {
+  dnsb_pdl_entry();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);
@@ -205,6 +207,7 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 __global__ void __launch_bounds__(128)
 k_dense_dmma_streamk(const double *__restrict__ D, const double *__restrict__ X,
                      double *__restrict__ part, int n, int nb, DenseSplit sp) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(16) double dsm[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int m0 = blockIdx.y * 64;
@@ -344,6 +347,7 @@ __device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const unsigned (&a)
 
 __global__ void k_f64_to_f32(const double *__restrict__ src, float *__restrict__ dst, size_t rows,
                              size_t cols, size_t ld) {
+  dnsb_pdl_entry();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rows * ld) return;
   const size_t r = t / ld, c = t - r * ld;
@@ -356,6 +360,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(128)
 k_dense_tf32_streamk(const float *__restrict__ D, int ld, const float *__restrict__ X,
                      double *__restrict__ part, int n, int nb, DenseSplit sp) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(16) float fsm[];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;

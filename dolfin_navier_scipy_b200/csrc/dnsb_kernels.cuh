@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(128)
 k_convvec(int c0, int c1, int ncell, const int *__restrict__ cn,
           const double *__restrict__ geom, const double *__restrict__ u1,
           const double *__restrict__ u2, double *__restrict__ out, int nb) {
+  dnsb_pdl_entry();
   long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   int cell = c0 + (int)(tid / nb);
   int m = (int)(tid % nb);
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(128)
 k_conv_elem(int ncell, const int *__restrict__ cn, const double *__restrict__ geom,
             const double *__restrict__ u1, const double *__restrict__ u2,
             double *__restrict__ E, int nb) {
+  dnsb_pdl_entry();
   long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   int cell = (int)(tid / nb);
   int m = (int)(tid % nb);
@@ -177,6 +179,7 @@ __global__ void k_conv_gather(int nout, const int *__restrict__ dofs,
                               const int *__restrict__ n2c_ptr, const int *__restrict__ n2c_idx,
                               const double *__restrict__ E, double *__restrict__ out, int nb,
                               double sign) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nout * nb) return;
   const int o = (int)(t / nb), m = (int)(t % nb);
@@ -200,6 +203,7 @@ k_convmats(int c0, int c1, int ncell, const int *__restrict__ cn,
            const double *__restrict__ geom, const int *__restrict__ slots,
            const double *__restrict__ u0, double *__restrict__ n1,
            double *__restrict__ n2, double *__restrict__ f3) {
+  dnsb_pdl_entry();
   long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
   int cell = c0 + (int)(tid / 6);
   int n = (int)(tid % 6);
@@ -296,6 +300,7 @@ __global__ void __launch_bounds__(6 * CME_CELLS, 2)
 k_convmats_elem(int ncell, const int *__restrict__ cn, const double *__restrict__ geom,
                 const double *__restrict__ u0, double *__restrict__ EN1,
                 double *__restrict__ EN2) {
+  dnsb_pdl_entry();
   __shared__ __align__(16) double sm[CME_CELLS * CME_LD];
   const int cl = threadIdx.x % CME_CELLS, n = threadIdx.x / CME_CELLS;
   const int cell0 = blockIdx.x * CME_CELLS;
@@ -378,6 +383,7 @@ __global__ void __launch_bounds__(6 * CME_CELLS, 2)
 k_stokes_elem(int ncell, const double *__restrict__ geom, double nu, int symgrad,
               double *__restrict__ EN1, double *__restrict__ EN2, double *__restrict__ EJ,
               double *__restrict__ EMP) {
+  dnsb_pdl_entry();
   __shared__ __align__(16) double sm[CME_CELLS * CME_LD];
   const int cl = threadIdx.x % CME_CELLS, n = threadIdx.x / CME_CELLS;
   const int cell0 = blockIdx.x * CME_CELLS;
@@ -458,6 +464,7 @@ k_stokes_elem(int ncell, const double *__restrict__ geom, double nu, int symgrad
 // out[s] = sum of the element entries listed for slot s (ascending cell order: deterministic)
 __global__ void k_slot_gather(int nslots, const int *__restrict__ sptr, const int *__restrict__ ssrc,
                               const double *__restrict__ E, double *__restrict__ out) {
+  dnsb_pdl_entry();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nslots) return;
   double v = 0.0;
@@ -470,6 +477,7 @@ __global__ void k_convmats_gather(int nnz, int ncell, const int *__restrict__ sp
                                   const int *__restrict__ ssrc, const double *__restrict__ EN1,
                                   const double *__restrict__ EN2, double *__restrict__ n1,
                                   double *__restrict__ n2) {
+  dnsb_pdl_entry();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nnz) return;
   double s1 = 0.0, s2 = 0.0;
@@ -527,6 +535,7 @@ template <int LPR>
 __global__ void
 k_spmm(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x,
        const double *z, double *y, int nb, double alpha, double beta) {
+  dnsb_pdl_entry();
   DNSB_ROWMAP(LPR)
   const double cm = (valid && coef) ? coef[m] : 0.0;
   const double acc = csr_rowdot<LPR>(A, cm, x, nb, row, m, lane, valid);
@@ -546,6 +555,7 @@ k_cheb_init(CsrDev A /*JT*/, const double *__restrict__ zp,
             const double *__restrict__ rv, const double *__restrict__ dinv,
             double *__restrict__ res, double *__restrict__ d, int nb,
             double inv_theta) {
+  dnsb_pdl_entry();
   DNSB_ROWMAP(LPR)
   const double acc = csr_rowdot<LPR>(A, 0.0, zp, nb, row, m, lane, valid);
   if (valid && lane == 0) {
@@ -560,6 +570,7 @@ k_cheb_init(CsrDev A /*JT*/, const double *__restrict__ zp,
 __global__ void k_cheb_init_plain(const double *r, const double *__restrict__ dinv,
                                   double *res, double *__restrict__ d, size_t n,
                                   double inv_theta) {
+  dnsb_pdl_entry();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double rr = r[i];
@@ -575,6 +586,7 @@ k_cheb_step(CsrDev A /*F*/, const double *__restrict__ coef,
             const double *__restrict__ d, const double *__restrict__ dinv,
             double *res, double *__restrict__ dn, double *z, int nb, double c1,
             double c2) {
+  dnsb_pdl_entry();
   DNSB_ROWMAP(LPR)
   const double cm = (valid && coef) ? coef[m] : 0.0;
   const double acc = csr_rowdot<LPR>(A, cm, d, nb, row, m, lane, valid);
@@ -595,6 +607,7 @@ k_cheb_step(CsrDev A /*F*/, const double *__restrict__ coef,
 __global__ void k_diag_inv(CsrDev A, const int *__restrict__ diagpos,
                            const double *__restrict__ coef,
                            double *__restrict__ dinv, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)A.nrows * nb) return;
   const int row = (int)(t / nb), m = (int)(t % nb);
@@ -615,6 +628,7 @@ k_dense_gemv(const double *__restrict__ D, const double *__restrict__ X,
              double *__restrict__ Y, int n, int nb, double alpha,
              const double *__restrict__ add_dinv,
              const double *__restrict__ add_scale) {
+  dnsb_pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
@@ -653,6 +667,7 @@ k_dense_gemv(const double *__restrict__ D, const double *__restrict__ X,
 // partial[b*nb+m] = sum over chunk of x*y  (norms / single dots)
 __global__ void k_dot1(const double *__restrict__ x, const double *__restrict__ y,
                        int n, int nb, int rpb, double *__restrict__ partial) {
+  dnsb_pdl_entry();
   extern __shared__ double sred[];
   const int m = threadIdx.x % nb;
   const int rr = threadIdx.x / nb;
@@ -703,6 +718,7 @@ __device__ __forceinline__ void gmres_track(GmresState &S, int m, double res) {
 
 // members that hit maxit without reaching tol: their last residual counts
 __global__ void k_gmres_track_unconverged(GmresState S, int nb) {
+  dnsb_pdl_entry();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m < nb && !S.done[m]) gmres_track(S, m, S.resid[m]);
 }
@@ -710,6 +726,7 @@ __global__ void k_gmres_track_unconverged(GmresState S, int nb) {
 // start of a cycle: beta = |r| from partials; V0 scale = 1/beta
 __global__ void k_gmres_begin(GmresState S, const double *__restrict__ partial,
                               int nblocks, int nb, double tol, int first_cycle) {
+  dnsb_pdl_entry();
   int m = blockIdx.x * blockDim.x + threadIdx.x;   // single block launch
   if (m < nb) {
     double s = 0.0;
@@ -739,6 +756,7 @@ __global__ void k_gmres_begin(GmresState S, const double *__restrict__ partial,
 // bnorm[m] = |b_m| from partials
 __global__ void k_set_bnorm(GmresState S, const double *__restrict__ partial,
                             int nblocks, int nb) {
+  dnsb_pdl_entry();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= nb) return;
   double s = 0.0;
@@ -754,6 +772,7 @@ __global__ void k_set_bnorm(GmresState S, const double *__restrict__ partial,
 __global__ void __launch_bounds__(1024)
 k_gmres_givens(GmresState S, const double *__restrict__ partial2,
                int nblocks, int nb, int j, double tol, int pyth, int staged) {
+  dnsb_pdl_entry();
   __shared__ double sp[32][33];
   __shared__ double snorm[1024];
   if (pyth) {
@@ -870,6 +889,7 @@ k_gmres_givens(GmresState S, const double *__restrict__ partial2,
 __global__ void __launch_bounds__(1024)
 k_reduce_partials2(const double *__restrict__ partial, int nblocks, int count,
                    double *__restrict__ out) {
+  dnsb_pdl_entry();
   __shared__ double sp[32][33];
   const int cx = threadIdx.x & 31, by = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -910,6 +930,7 @@ k_reduce_partials2(const double *__restrict__ partial, int nblocks, int count,
 
 // y = R^-1 g (per member, using its[m] columns); stored in S.h[i*nb+m]
 __global__ void k_gmres_solve_y(GmresState S, int nb, int jmax) {
+  dnsb_pdl_entry();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= nb) return;
   const int k = S.its[m];
@@ -930,6 +951,7 @@ __global__ void k_gmres_solve_y(GmresState S, int nb, int jmax) {
 __global__ void k_gmres_update_x(const double *__restrict__ Z, size_t zstride,
                                  int nvec, const double *__restrict__ y,
                                  double *__restrict__ x, size_t n, int nb) {
+  dnsb_pdl_entry();
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * nb) return;
   const int m = (int)(idx % nb);
@@ -942,6 +964,7 @@ __global__ void k_gmres_update_x(const double *__restrict__ Z, size_t zstride,
 // out = x * scale[m]
 __global__ void k_scale_member(const double *x, const double *__restrict__ scale,
                                double *out, size_t n, int nb) {
+  dnsb_pdl_entry();
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * nb) return;
   out[idx] = x[idx] * scale[idx % nb];
@@ -953,6 +976,7 @@ __global__ void k_scale_member(const double *x, const double *__restrict__ scale
 // z = a*x + b*y  (y may be null)
 __global__ void k_axpby(double a, const double *x, double b, const double *y,
                         double *z, size_t n) {
+  dnsb_pdl_entry();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   z[i] = y ? a * x[i] + b * y[i] : a * x[i];
@@ -962,6 +986,7 @@ __global__ void k_axpby(double a, const double *x, double b, const double *y,
 __global__ void k_scatter_inner(const double *__restrict__ v,
                                 const int *__restrict__ inv,
                                 double *__restrict__ vfull, int nv, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nv * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);
@@ -973,6 +998,7 @@ __global__ void k_scatter_inner(const double *__restrict__ v,
 __global__ void k_set_bcs(const int *__restrict__ bcinds,
                           const double *__restrict__ bcvals,
                           double *__restrict__ vfull, int nbc, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nbc * nb) return;
   const int k = (int)(t / nb), m = (int)(t % nb);
@@ -983,6 +1009,7 @@ __global__ void k_set_bcs(const int *__restrict__ bcinds,
 __global__ void k_gather_neg(const double *__restrict__ cfull,
                              const int *__restrict__ inv,
                              double *__restrict__ nfc, int nv, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nv * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);
@@ -1000,6 +1027,7 @@ __global__ void k_rhs_combine(double *__restrict__ rhs,
                               const double *__restrict__ ua, double wa,
                               const double *__restrict__ ub, double wb,
                               int nv, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)nv * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);
@@ -1019,6 +1047,7 @@ __global__ void k_rhs_combine(double *__restrict__ rhs,
 // b[(nv+j), m] = fp[j]  (pressure part of the saddle rhs, shared by members)
 __global__ void k_fill_rhsp(double *__restrict__ b, const double *__restrict__ fp,
                             int nv, int np, int nb) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)np * nb) return;
   const int j = (int)(t / nb);
@@ -1028,6 +1057,7 @@ __global__ void k_fill_rhsp(double *__restrict__ b, const double *__restrict__ f
 // p[j,m] = scale * x[(nv+j), m]
 __global__ void k_extract_p(const double *__restrict__ x, double *__restrict__ p,
                             int nv, int np, int nb, double scale) {
+  dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)np * nb) return;
   p[t] = scale * x[(size_t)nv * nb + t];

@@ -85,6 +85,7 @@ template <bool H2, int EPI>
 __global__ void __launch_bounds__(SPT_THREADS)
 k_spmv_tma(CsrDev A, const double *__restrict__ coef, const double *__restrict__ x, SptEpi ep,
            int ntiles, int cap, int stages, int rt) {
+  dnsb_pdl_entry();
   constexpr int NWARP = SPT_CONSUMERS / 32;
   constexpr int UN = 6;
   extern __shared__ __align__(128) unsigned char spt_raw[];
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(288)
 k_gs_tma(const double *__restrict__ V, size_t vstride, int nvec, const double *__restrict__ h,
          const double *__restrict__ w, double *__restrict__ vnext, int n, int nb, int rpb,
          int rows_per_block, double *__restrict__ partial, int stages, const double *__restrict__ scale) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char gst_raw[];
   __shared__ __align__(8) uint64_t full[GST_MAX_STAGES], empty[GST_MAX_STAGES];
   const int nthr = rpb * nb;                 // consumer threads

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_schur_tc(const float *__restrict__ Dt, const __grid_constant__ CUtensorMap mapB,
            float *__restrict__ part, int NP, int kblocks, int kb_per_split, int stages, int tmem_cols,
            int l2keep) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], accum_full;
   __shared__ uint32_t tmem_base_s;
@@ -238,6 +239,7 @@ __device__ __forceinline__ float tc_round_tf32(float v) {
 // column kb*32 + k) at float offset r*32 + (((k >> 2) ^ (r & 7)) << 2) + (k & 3); zero outside n
 __global__ void k_tc_pack_d(const double *__restrict__ src, float *__restrict__ dst, int n, int mtiles,
                             int kblocks) {
+  dnsb_pdl_entry();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)mtiles * kblocks * TC_BM * TC_BK;
   if (t >= total) return;
@@ -251,6 +253,7 @@ __global__ void k_tc_pack_d(const double *__restrict__ src, float *__restrict__ 
 
 // Xt[m*ldx + k] = tf32(x[k*nb + m])  (K-major copy of the right-hand sides; rows m >= nb stay zero)
 __global__ void k_tc_pack_x(const double *__restrict__ x, float *__restrict__ xt, int n, int nb, int ldx) {
+  dnsb_pdl_entry();
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -270,6 +273,7 @@ __global__ void k_tc_epilogue(const float *__restrict__ part, int splits, size_t
                               const double *__restrict__ x, double *__restrict__ y, int n, int nb,
                               double alpha, const double *__restrict__ add_dinv,
                               const double *__restrict__ add_scale) {
+  dnsb_pdl_entry();
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);

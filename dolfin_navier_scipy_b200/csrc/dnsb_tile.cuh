@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1)
 k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ d,
                  const double *__restrict__ dinv, double *res, double *__restrict__ dn, double *z,
                  double c1, double c2) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
   const int nst = T.stages;
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 1)
 k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__restrict__ d,
                   const float *__restrict__ dinv, float *res, float *__restrict__ dn, float *zf,
                   double *__restrict__ zout, float c1, float c2) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
   const int nst = T.stages;
@@ -428,6 +430,7 @@ __global__ void __launch_bounds__(SPB_THREADS)
 k_cheb_init_p2f(CsrDev A, const double2 *__restrict__ zp, const double2 *__restrict__ rv,
                 const float2 *__restrict__ dinv, float2 *__restrict__ res, float2 *__restrict__ d,
                 int nb, int npairs, float inv_theta) {
+  dnsb_pdl_entry();
   SPP_MAP(false)
   const size_t sa_ = valid ? ta_ : 0, sb_ = valid ? tb_ : 0;
   const double2 ra = rv[sa_], rb = rv[sb_];
@@ -463,6 +466,7 @@ template <bool HASZ>
 __global__ void __launch_bounds__(TILE_THREADS + 32 * TILE_TAIL_WARPS_MAX, 1)
 k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ x,
             const double *z, double *y, double alpha, double beta, CsrDev A, int row_begin) {
+  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
   const int nst = T.stages;

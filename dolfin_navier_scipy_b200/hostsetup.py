@@ -368,7 +368,8 @@ def make_saddle_solver(ctx, F1, J, JT=None, F2=None, coef=None, nb=1,
         Fmean = Fext = F1
     if spectrum is None or velocity_amg == 'auto':
         lmin, lmax = jacobi_spectrum(Fext)
-        lmin2, lmax2 = jacobi_spectrum(Fmean)
+        lmin2, lmax2 = (lmin, lmax) if Fmean is Fext else \
+            jacobi_spectrum(Fmean)
         spec = (min(lmin, lmin2), max(lmax, lmax2))
         if velocity_amg == 'auto':
             # mass dominated matrices have cond(D^-1 F) ~ 5; Stokes/Oseen

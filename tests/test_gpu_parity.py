@@ -1295,6 +1295,67 @@ def test_low_rank_update_and_krylovini(cyl1, ctx):
     assert its['upd'] < its['old']
 
 
+def test_switches_belong_to_their_context(cyl1, ctx):
+    """the DNSB_* switches are read when a context is created and stay with
+    it: a context made under DNSB_TILE=0 runs the row-pair kernels, the
+    default context created before it keeps running the tile kernels, also
+    when the two are used alternately in one process (the switch tests above
+    rely on this)"""
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    femp, sm, rhsd = cyl1
+    inv = femp['invinds']
+    other = _ctx_with_env('DNSB_TILE', '0')
+
+    def kernels_of(c):
+        integ = tiu.DeviceImex(sm['M'], sm['A'], sm['J'], femp['V'], inv,
+                               femp['dbcinds'], femp['dbcvals'], 1./512,
+                               nus=np.ones(64), fv=rhsd['fv'], fp=rhsd['fp'],
+                               ctx=c)
+        integ.set_state(np.zeros((sm['M'].shape[0], 1)),
+                        np.zeros((sm['J'].shape[0], 1)))
+        c.profile_begin()
+        integ.run(3, tol=1e-10)
+        names = ' '.join(c.profile_end().keys())
+        integ.close()
+        return names
+    for c, tiled in ((ctx, True), (other, False), (ctx, True), (other, False)):
+        names = kernels_of(c)
+        assert ('k_cheb_step_tile' in names) == tiled, names
+        assert ('k_cheb_step_p2' in names) == (not tiled), names
+
+
+def test_programmatic_launch_is_bitwise_reproducible():
+    """kernels are launched with programmatic stream serialization (every
+    kernel starts with `griddepcontrol.wait`; DNSB_PDL=1, default).  That only
+    changes WHEN a kernel's CTAs become resident, never what it reads: a
+    64-member run on the finest mesh (multi-wave grids, where launching the
+    TMA-streamed Gram-Schmidt kernels this way was measured NOT to be
+    reproducible -- they are excluded) gives the same bits as
+    plain stream order, three times over"""
+    from dolfin_navier_scipy_b200 import problem_setups as dnsps
+    from dolfin_navier_scipy_b200 import time_int_utils as tiu
+    femp, sm, rhsd = dnsps.get_sysmats(
+        problem='cylinderwake', Re=80., scheme='TH', mergerhs=True,
+        meshparams=dict(refinement_level=4))
+    inv = femp['invinds']
+    nus = femp['nu']*np.linspace(.6, 1.6, 64)
+    out = []
+    for flag in ('0', '1', '1', '1'):
+        c = _ctx_with_env('DNSB_PDL', flag)
+        integ = tiu.DeviceImex(sm['M'], sm['A']/femp['nu'], sm['J'], femp['V'],
+                               inv, femp['dbcinds'], femp['dbcvals'], 1./1024,
+                               nus=nus, fv=rhsd['fv'], fp=rhsd['fp'], ctx=c)
+        integ.set_state(np.zeros((sm['M'].shape[0], 1)),
+                        np.zeros((sm['J'].shape[0], 1)))
+        integ.run(30, tol=1e-12, guess=24)
+        out.append(integ.state() + (integ.stats()['iters'],))
+        integ.close()
+    for v, p, its in out[1:]:
+        assert its == out[0][2]
+        assert np.array_equal(v, out[0][0])
+        assert np.array_equal(p, out[0][1])
+
+
 def test_projection_space_forms_agree_across_rebuilds(cyl1, ctx):
     """the recycled-solution space in its implicit form (raw directions + a
     triangular factor per member, DNSB_PROJ_T=1, default) against the explicit
@@ -1335,7 +1396,8 @@ def test_projection_space_forms_agree_across_rebuilds(cyl1, ctx):
                                     'DNSB_ROWPAIR=0', 'DNSB_GS_TMA=0',
                                     'DNSB_TILE=0', 'DNSB_SCHUR_TC=0',
                                     'DNSB_GS_PYTH=0', 'DNSB_CHEB_F32=0',
-                                    'DNSB_PROJ_T=0', 'DNSB_TAIL_WARPS=0'])
+                                    'DNSB_PROJ_T=0', 'DNSB_TAIL_WARPS=0',
+                                    'DNSB_PDL=0'])
 def test_every_tuning_switch_gives_the_same_trajectory(cyl1, ctx, switch):
     """the environment switches select kernel VARIANTS of the same arithmetic
     (coloured scatter vs gather assembly -- the form `north_star` names --,

@@ -33,6 +33,14 @@ def main():
         t0 = time.perf_counter()
         v, p = snu.solve_steadystate_nse(return_vp=True, verbose=False, **sd)
         out['device_s_call%d' % rep] = time.perf_counter() - t0
+    if '--profile' in sys.argv:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        snu.solve_steadystate_nse(return_vp=True, verbose=False, **sd)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
     if '--oracle' in sys.argv:
         from oracle import snu as osnu
         t0 = time.perf_counter()
