@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 k_schur_tc(const float *__restrict__ Dt, const __grid_constant__ CUtensorMap mapB,
            float *__restrict__ part, int NP, int kblocks, int kb_per_split, int stages, int tmem_cols,
            int l2keep) {
-  dnsb_pdl_entry();
   extern __shared__ __align__(1024) unsigned char tc_raw[];
   __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], empty[TC_MAX_STAGES], accum_full;
   __shared__ uint32_t tmem_base_s;
@@ -163,6 +162,7 @@ k_schur_tc(const float *__restrict__ Dt, const __grid_constant__ CUtensorMap map
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  dnsb_pdl_entry();   // barriers and the TMEM allocation above do not depend on the previous kernel
 
   if (warp == 0) {
     // ---- TMA producer ----

@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 1)
 k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ d,
                  const double *__restrict__ dinv, double *res, double *__restrict__ dn, double *z,
                  double c1, double c2) {
-  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
   const int nst = T.stages;
@@ -125,6 +124,8 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // barrier set-up and the first (static) tile descriptor are taken before the programmatic-launch wait
+  if (warp != TILE_RP) dnsb_pdl_entry();
   if (warp == TILE_RP) {
     // ---- producer warp: the descriptor and the runs of the NEXT tile are loaded (one independent
     // round trip each, fixed addresses) while the copies of the current one are issued -- the loop
@@ -141,6 +142,7 @@ k_cheb_step_tile(TileDev T, const double *__restrict__ coef, const double *__res
         rc = rr[0]; rl = rr[1]; rs = rr[2];
       }
     }
+    dnsb_pdl_entry();
     for (; t < T.ntiles; t += gridDim.x, ++it) {
       const int s = it % nst;
       const int tn = t + gridDim.x;
@@ -280,7 +282,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 1)
 k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__restrict__ d,
                   const float *__restrict__ dinv, float *res, float *__restrict__ dn, float *zf,
                   double *__restrict__ zout, float c1, float c2) {
-  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
   const int nst = T.stages;
@@ -298,6 +299,8 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // barrier set-up and the first (static) tile descriptor are taken before the programmatic-launch wait
+  if (warp != TILE_RP) dnsb_pdl_entry();
   if (warp == TILE_RP) {
     // ---- producer warp: the descriptor and the runs of the NEXT tile are loaded (one independent
     // round trip each, fixed addresses) while the copies of the current one are issued -- the loop
@@ -314,6 +317,7 @@ k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__re
         rc = rr[0]; rl = rr[1]; rs = rr[2];
       }
     }
+    dnsb_pdl_entry();
     for (; t < T.ntiles; t += gridDim.x, ++it) {
       const int s = it % nst;
       const int tn = t + gridDim.x;
@@ -466,7 +470,6 @@ template <bool HASZ>
 __global__ void __launch_bounds__(TILE_THREADS + 32 * TILE_TAIL_WARPS_MAX, 1)
 k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict__ x,
             const double *z, double *y, double alpha, double beta, CsrDev A, int row_begin) {
-  dnsb_pdl_entry();
   extern __shared__ __align__(128) unsigned char tl_raw[];
   __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
   const int nst = T.stages;
@@ -485,6 +488,8 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double *d = x;   // the producer below streams rows of `d`
 
+  // barrier set-up and the first (static) tile descriptor are taken before the programmatic-launch wait
+  if (warp != TILE_RP) dnsb_pdl_entry();
   if (warp == TILE_RP) {
     int it = 0;
     int t = blockIdx.x;
@@ -497,6 +502,7 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
         rc = rr[0]; rl = rr[1]; rs = rr[2];
       }
     }
+    dnsb_pdl_entry();
     for (; t < T.ntiles; t += gridDim.x, ++it) {
       const int s = it % nst;
       const int tn = t + gridDim.x;
