@@ -57,6 +57,8 @@ SIGNATURES = {
                                c_int_p, c_dbl_p]),
     'dnsb_solver_update_fvalues': (_i, [_vp, c_dbl_p]),
     'dnsb_solver_apply_prec': (_i, [_vp, c_dbl_p, c_dbl_p]),
+    'dnsb_solver_set_prec_mode': (_i, [_vp, _i]),
+    'dnsb_solver_apply_k': (_i, [_vp, c_dbl_p, c_dbl_p]),
     'dnsb_cnsweep_create': (_i, [_vp, _vp, c_dbl_p, c_dbl_p, _i, c_int_p, c_int_p,
                                  c_int_p, _i, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p,
                                  c_void_pp]),
@@ -462,6 +464,17 @@ class SaddleSolver(object):
         self.ctx.check(self.ctx.lib.dnsb_solver_apply_prec(self.h, _dp(r),
                                                            _dp(z)))
         return z
+
+    def set_prec_mode(self, block_diagonal):
+        self.ctx.check(self.ctx.lib.dnsb_solver_set_prec_mode(
+            self.h, int(bool(block_diagonal))))
+
+    def apply_k(self, x):
+        """``K @ x`` for ``K = [[F, JT], [J, 0]]`` on the device"""
+        x = _f64(x).reshape(self.nv + self.np_, self.nb)
+        y = np.empty_like(x)
+        self.ctx.check(self.ctx.lib.dnsb_solver_apply_k(self.h, _dp(x), _dp(y)))
+        return y
 
     def update_fvalues(self, vals1):
         vals1 = _f64(vals1)

@@ -1153,6 +1153,8 @@ struct dnsb_solver {
   std::vector<cudaGraphExec_t> igraph;
   std::vector<int> igraph_launches;
   std::vector<int> igraph_seen;   // how often column j ran since the graphs were dropped
+  int prec_diag = 0;   // 1: block-DIAGONAL, symmetric positive definite form of the preconditioner (MINRES)
+  DBuf<double> zero_p;
   double igraph_tol = -1.0;
   // Pythagorean norm in the Arnoldi step: only for solves that are expected to be SHORT (the
   // previous solve of this solver took <= 8 iterations: the time loop with recycled guesses).
@@ -1395,6 +1397,7 @@ extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   s->ginvh.release(); s->gbnorm.release(); s->gresid.release(); s->grelmax.release();
   s->gdone.release(); s->gits.release(); s->gittot.release(); s->gflags.release();
   s->mp_dinv.release(); s->mp_scale.release(); s->sb.release(); s->sx.release();
+  s->zero_p.release();
   s->lsc_dinv.release(); s->lsc_t1.release(); s->lsc_t2.release(); s->lsc_p1.release(); s->lsc_p2.release();
   for (MgLevel *L : s->levels) level_free(L);
   for (MgLevel *L : s->vlevels) level_free(L);
@@ -1812,6 +1815,19 @@ static int apply_prec(dnsb_solver *s, const double *r, double *z) {
   const double *rv = r, *rp = r + nvb;
   double *zv = z, *zp = z + nvb;
   DNSB_REQUIRE(ctx, !s->levels.empty() || s->has_mass, "no Schur approximation set");
+  if (s->prec_diag) {
+    // diag(Fh^-1, +Sh^-1): no gradient coupling, positive Schur block -- the symmetric positive definite
+    // preconditioner MINRES needs (Chebyshev polynomial of the symmetric F, dense inverse of J Z JT)
+    DNSB_REQUIRE(ctx, !s->has_lsc && !s->levels.empty() && s->levels[0]->kind == MG_DENSE &&
+                          s->vlevels[0]->kind == MG_SMOOTH,
+                 "block-diagonal preconditioner: Chebyshev velocity block + dense Schur block only");
+    DNSB_CK(ctx, s->zero_p.alloc(npb));
+    DNSB_CK(ctx, s->zero_p.zero(ctx->stream));
+    dense_apply(s, s->levels[0], rp, zp, 1.0, s->has_mass);
+    cheb_run(s, s->F, s->has_coef ? s->coef.p : nullptr, s->dinv.p, s->JT, s->zero_p.p, rv, zv, s->cres.p,
+             s->cd0.p, s->cd1.p, s->kF, s->lmin, s->lmax);
+    return 0;
+  }
   // ---- zp = -Sh^-1 rp ------------------------------------------------------
   if (s->has_lsc) {
     // least-squares commutator (Elman et al. 2006):
@@ -2429,6 +2445,30 @@ extern "C" int dnsb_solver_apply_prec(dnsb_solver *s, const double *r, double *z
   DNSB_CK(ctx, cudaMemsetAsync(s->sx.p, 0, ntb * sizeof(double), ctx->stream));
   if (apply_prec(s, s->sb.p, s->sx.p)) return -1;
   DNSB_CK(ctx, cudaMemcpyAsync(z, s->sx.p, ntb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
+  DNSB_CK(ctx, cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dnsb_solver_set_prec_mode(dnsb_solver *s, int block_diagonal) {
+  if (!s) return -2;
+  s->prec_diag = block_diagonal ? 1 : 0;
+  solver_drop_graphs(s);
+  return 0;
+}
+
+// y = K x for the solver's saddle-point matrix, host vectors (ntot x nb)
+extern "C" int dnsb_solver_apply_k(dnsb_solver *s, const double *x, double *y) {
+  if (!s) return -2;
+  dnsb_ctx *ctx = s->ctx;
+  DNSB_REQUIRE(ctx, x && y, "null arguments");
+  DNSB_CK(ctx, dnsb_enter(ctx));
+  const size_t ntb = (size_t)s->ntot * s->nb;
+  DNSB_CK(ctx, s->sb.alloc(ntb));
+  DNSB_CK(ctx, s->sx.alloc(ntb));
+  DNSB_CK(ctx, cudaMemcpyAsync(s->sb.p, x, ntb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  spmm_dev(ctx, s->K, s->has_coef ? s->coef.p : nullptr, s->sb.p, nullptr, s->sx.p, s->nb, 1.0, 0.0);
+  DNSB_CK(ctx, cudaMemcpyAsync(y, s->sx.p, ntb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DNSB_CK(ctx, cudaStreamSynchronize(ctx->stream));
   DNSB_CK(ctx, cudaGetLastError());
   return 0;

@@ -75,6 +75,67 @@ class SadpntOperator(object):
                                   float('nan')))
         return vp
 
+    def solve_minres(self, rhsv, rhsp=None, x0=None, tol=1e-12, maxit=800):
+        """MINRES for a SYMMETRIC saddle-point matrix (the Stokes / IMEX
+        systems of `cylinderwake`; `north_star` K3, the reference's own
+        experiment is the unpreconditioned `scipy` call at `snu:879-890`).
+
+        The recurrence (`scipy.sparse.linalg.minres`) runs on the host; every
+        product with ``K`` and every application of the preconditioner --
+        ``diag(Fh^-1, Sh^-1)``, the symmetric positive definite form of the
+        device's block preconditioner -- runs on the device
+        (`dnsb_solver_apply_k`, `dnsb_solver_apply_prec`).  MINRES stops on
+        the preconditioned residual; the true relative residual is checked
+        afterwards and the iteration is continued from the iterate until it
+        meets ``tol``.  Single right-hand side.  Against the device FGMRES
+        (block triangular preconditioner, device resident) it needs about
+        twice the iterations and a host round trip each: it is here for
+        symmetric problems where a short recurrence is wanted, not for speed
+        (DESIGN.md section 8)."""
+        import scipy.sparse.linalg as spsla
+        if self.ncols != 1:
+            raise NotImplementedError('MINRES: one right-hand side at a time')
+        n = self.NV + self.NP
+        b = np.zeros(n)
+        b[:self.NV] = np.asarray(rhsv, dtype=float).ravel()
+        if rhsp is not None:
+            b[self.NV:] = np.asarray(rhsp, dtype=float).ravel()
+        kop = spsla.LinearOperator(
+            (n, n), matvec=lambda x: self.solver.apply_k(x).ravel(),
+            dtype=float)
+        pop = spsla.LinearOperator(
+            (n, n), matvec=lambda r: self.solver.apply_prec(r).ravel(),
+            dtype=float)
+        count = [0]
+
+        def cb(xk):
+            count[0] += 1
+        bn = np.linalg.norm(b)
+        x = np.zeros(n) if x0 is None else np.asarray(x0, float).ravel().copy()
+        self.solver.set_prec_mode(True)
+        try:
+            rel, rtol = np.inf, tol
+            for attempt in range(6):
+                left = maxit - count[0]
+                if left <= 0:
+                    break
+                x, _ = spsla.minres(kop, b, x0=x, rtol=rtol, maxiter=left,
+                                    M=pop, callback=cb)
+                rel = np.linalg.norm(b - kop.matvec(x))/bn if bn > 0 else 0.
+                if rel <= tol:
+                    break
+                rtol = max(1e-3*rtol, 1e-16)
+        finally:
+            self.solver.set_prec_mode(False)
+        self.last_iters = np.array([count[0]])
+        self.last_relres = np.array([rel])
+        self.last_vp = x.reshape(-1, 1)
+        if not rel <= tol:
+            raise _lib.NotConverged(
+                'MINRES stopped after {0} iterations at a relative residual '
+                'of {1:.3e} (tol {2:.1e})'.format(count[0], rel, tol))
+        return x.reshape(-1, 1)
+
     def update_values(self, vals):
         """new values of ``amat`` on the pattern given at construction"""
         self.solver.update_fvalues(vals)
@@ -147,6 +208,7 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
     if decouplevp:
         raise NotImplementedError('decoupled v/p solves')
     NP, NV = jmat.shape
+    amat = sps.csr_matrix(amat)
     rhsv = np.asarray(rhsv, dtype=float).reshape(NV, -1)
     k = rhsv.shape[1]
     op = sadlu if sadlu is not None else \
@@ -156,7 +218,12 @@ def solve_sadpnt_smw(amat=None, jmat=None, rhsv=None, jmatT=None,
     tol = krpslvprms.get('tol', 1e-12) if krylov is not None else 1e-12
     maxit = krpslvprms.get('maxiter', 800) if krylov is not None else 800
     x0 = krpslvprms.get('x0', None) if krylov is not None else None
-    vp = op.solve(rhsv, rhsp, x0=x0, tol=tol, maxit=maxit)
+    if krylov is not None and str(krylov).lower() == 'minres':
+        if abs(amat - amat.T).max() > 1e-12*abs(amat).max():
+            raise ValueError('MINRES needs a symmetric velocity block')
+        vp = op.solve_minres(rhsv, rhsp, x0=x0, tol=tol, maxit=maxit)
+    else:
+        vp = op.solve(rhsv, rhsp, x0=x0, tol=tol, maxit=maxit)
     if 'convstatsl' in krpslvprms:
         krpslvprms['convstatsl'].append(int(op.last_iters.max()))
     if return_alu:

@@ -166,6 +166,13 @@ int dnsb_solver_update_fvalues(dnsb_solver *s, const double *vals1);
  * vectors ((nv+np)*nb); used by the tests to check the multigrid / Schur
  * pieces against a numpy restatement */
 int dnsb_solver_apply_prec(dnsb_solver *s, const double *r, double *z);
+/* block_diagonal = 1: the preconditioner is applied as diag(Fh^-1, +Sh^-1) (symmetric positive definite, what
+ * MINRES needs; Chebyshev velocity block + dense Schur block only); 0 (default): block triangular (FGMRES).
+ * Replaces nothing in the reference: its MINRES experiment (`stokes_navier_utils.py:879-890`) is unpreconditioned. */
+int dnsb_solver_set_prec_mode(dnsb_solver *s, int block_diagonal);
+/* y = K x with K = [[F, JT], [J, 0]] of the solver, host vectors of (nv + np) x nb doubles (operator for host-driven
+ * Krylov methods: `lin_alg_utils.solve_sadpnt_smw(krylov='minres')`) */
+int dnsb_solver_apply_k(dnsb_solver *s, const double *x, double *y);
 
 /* ---- device-resident IMEX time stepping ----------------------------------
  * CNAB (time_int_utils.py:23-145), SBDF2 (:260-355) incl. the Heun start

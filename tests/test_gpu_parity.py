@@ -1295,6 +1295,45 @@ def test_low_rank_update_and_krylovini(cyl1, ctx):
     assert its['upd'] < its['old']
 
 
+def test_minres_on_the_symmetric_imex_matrix_matches_lu(cyl1, ctx):
+    """`north_star` K3: MINRES for the symmetric saddle-point matrix of the IMEX
+    schemes, with the device's preconditioner in its symmetric positive
+    definite (block diagonal) form; products with K and the preconditioner
+    run on the device, the three-term recurrence on the host.  Parity against
+    the sparse LU (`oracle.lau`, what the reference calls) at 1e-9; a
+    nonsymmetric block is refused"""
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    from oracle import lau as olau
+    femp, sm, rhsd = cyl1
+    dt = 1./512
+    F = (sm['M'] + .5*dt*sm['A']).tocsr()
+    rng = np.random.default_rng(3)
+    rhsv = sm['M']@rng.standard_normal((F.shape[0], 1)) + dt*rhsd['fv']
+    rhsp = rhsd['fp']
+    ref = olau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'],
+                                rhsv=rhsv, rhsp=rhsp)
+    st = []
+    vp = lau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=rhsv,
+                              rhsp=rhsp, krylov='minres',
+                              krpslvprms=dict(tol=1e-11, maxiter=600,
+                                              convstatsl=st))
+    nv = F.shape[0]
+    assert _rel(vp[:nv], ref[:nv]) < 1e-9
+    assert _rel(vp[nv:], ref[nv:]) < 1e-8
+    assert 0 < st[0] < 300
+    # the same system by the device FGMRES: fewer iterations (block triangular form)
+    st2 = []
+    lau.solve_sadpnt_smw(amat=F, jmat=sm['J'], jmatT=sm['JT'], rhsv=rhsv,
+                         rhsp=rhsp, krylov='gmres',
+                         krpslvprms=dict(tol=1e-11, maxiter=600,
+                                         convstatsl=st2))
+    assert st2[0] < st[0]
+    with pytest.raises(ValueError):
+        N1 = sps.random(nv, nv, 1e-3, random_state=1, format='csr')
+        lau.solve_sadpnt_smw(amat=F + N1, jmat=sm['J'], jmatT=sm['JT'],
+                             rhsv=rhsv, rhsp=rhsp, krylov='minres')
+
+
 def test_switches_belong_to_their_context(cyl1, ctx):
     """the DNSB_* switches are read when a context is created and stay with
     it: a context made under DNSB_TILE=0 runs the row-pair kernels, the
