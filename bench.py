@@ -52,8 +52,9 @@ def parse():
                     help='untimed steps before the W warm-up steps: the solver recycles the last 16 '
                          'solutions for its initial guesses; a run reaches that operating point after 16 steps')
     ap.add_argument('--schur-precision', default='tc', choices=['f64', 'tf32x3', 'tf32x2', 'tf32', 'tc'],
-                    help='dense Schur block of the preconditioner: fp64 (default) or 3xTF32 '
-                         '(fp32 copy of the inverse; FGMRES residuals stay fp64)')
+                    help='dense Schur block of the preconditioner: tc = tcgen05 TF32 with TMEM accumulators '
+                         '(default), f64 = fp64 DMMA, tf32* = legacy mma.sync variants; FGMRES '
+                         'bases, residuals and stopping test stay fp64 in every case')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-seconds', type=float, default=12.)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -62,6 +63,8 @@ def parse():
                     help='skip the secondary records (configs 1, 3, 4, dt = 1/512)')
     ap.add_argument('--no-strong', action='store_true',
                     help='N > 1: skip the strong-scaling record (64 members split over the GPUs)')
+    ap.add_argument('--no-bind', action='store_true',
+                    help='do not pin the ranks of a multi-GPU run to the cores next to their GPU')
     ap.add_argument('--no-parity', action='store_true',
                     help='skip the CPU-oracle check of the measured trajectory')
     return ap.parse_args()
@@ -928,6 +931,10 @@ def _main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         return run_reference(args, rank, world)
+    if world > 1 and not args.no_bind:
+        # NUMA-local pinned snapshot mirrors (see ensemble.bind_to_gpu_cpus)
+        from dolfin_navier_scipy_b200 import ensemble as _ens
+        _ens.bind_to_gpu_cpus(local_rank)
     import torch
     import torch.distributed as dist
     if world > 1:

@@ -35,6 +35,38 @@ __global__ void __launch_bounds__(1024) kB(const int *slots, int nslots, int it,
     if (slots[i] != it) atomicAdd(bad, 1);
 }
 
+// mode 5: the chain of one Arnoldi column:  A (586 x 288, 110 KB, writes slots) -> R (few CTAs of 1024 threads:
+// sums the slots into h) -> G (ONE CTA of 1024 threads with dynamic shared memory: h -> h2) ->
+// U (586 x 288, 110 KB: every CTA checks h2).  All four launched with the attribute, wait first, then trigger.
+__global__ void __launch_bounds__(1024) kR(const int *slots, int nslots, int *h, int it) {
+  pdl_wait(); pdl_trigger();
+  __shared__ int sp[1024];
+  int s = 0;
+  for (int i = threadIdx.x; i < nslots; i += blockDim.x) s += (slots[i] == it) ? 1 : 0;
+  sp[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int q = 0; q < 1024; ++q) t += sp[q];
+    h[blockIdx.x] = t * 1000 + it % 1000;   // nslots*1000 + it%1000 when every slot was current
+  }
+}
+__global__ void __launch_bounds__(1024) kG(const int *h, int nh, int *h2) {
+  extern __shared__ unsigned char smem[];
+  pdl_wait(); pdl_trigger();
+  if ((int)threadIdx.x < nh) h2[threadIdx.x] = h[threadIdx.x];
+  if (threadIdx.x == 0) smem[0] = 1;
+}
+__global__ void __launch_bounds__(288) kU(const int *h2, int nh, int expect, long long spin, int *bad, float *sink) {
+  extern __shared__ unsigned char smem[];
+  pdl_wait(); pdl_trigger();
+  if ((int)threadIdx.x < nh && h2[threadIdx.x] != expect) atomicAdd(bad, 1);
+  const long long t0 = clock64();
+  float acc = 0.f;
+  while (clock64() - t0 < spin) acc += 1e-9f;
+  if (threadIdx.x == 0) { smem[0] = 1; if (acc == 12345.f) *sink = acc; }
+}
+
 template <class... Args>
 static void launch(void (*k)(Args...), dim3 g, dim3 b, size_t smem, cudaStream_t s, bool attr, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -89,6 +121,27 @@ int main(int argc, char **argv) {
       cudaMemcpy(&h, bad, sizeof(int), cudaMemcpyDeviceToHost); cudaMemcpy(&h2, bad2, sizeof(int), cudaMemcpyDeviceToHost);
       printf("mode 4 spin %lld: stale slots seen behind a D2D copy: %d, stale entries IN the copy: %d   (%s)\n", spin, h, h2,
              cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  {
+    const int nh = 14;
+    int *h, *h2; cudaMalloc(&h, nh * sizeof(int)); cudaMalloc(&h2, nh * sizeof(int));
+    cudaFuncSetAttribute(kU, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    cudaFuncSetAttribute(kG, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    for (long long spin : {2000LL, 20000LL}) {
+      cudaMemset(slots, 0xff, nblocks * sizeof(int)); cudaMemset(bad, 0, sizeof(int));
+      cudaMemset(h, 0, nh * sizeof(int)); cudaMemset(h2, 0, nh * sizeof(int));
+      cudaDeviceSynchronize();
+      for (int it = 0; it < iters; ++it) {
+        launch(kA, dim3(nblocks), dim3(288), (size_t)110 * 1024, s, it > 0, slots, it, 2, spin, sink);
+        launch(kR, dim3(nh), dim3(1024), (size_t)0, s, true, (const int *)slots, nblocks, h, it);
+        launch(kG, dim3(1), dim3(1024), (size_t)50 * 1024, s, true, (const int *)h, nh, h2);
+        launch(kU, dim3(nblocks), dim3(288), (size_t)110 * 1024, s, true, (const int *)h2, nh, nblocks * 1000 + it % 1000, spin, bad, sink);
+      }
+      cudaStreamSynchronize(s);
+      int hb = -1; cudaMemcpy(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost);
+      printf("mode 5 spin %lld: wrong values seen at the end of the chain A -> R -> G -> U over %d iterations: %d   (%s)\n", spin,
+             iters, hb, cudaGetErrorString(cudaGetLastError()));
     }
   }
   return 0;
