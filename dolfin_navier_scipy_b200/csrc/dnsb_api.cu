@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 
 #include "dnsb_common.cuh"
@@ -1384,12 +1385,20 @@ static void level_free(MgLevel *L) {
 extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   if (!s) return;
   dnsb_enter(s->ctx);
+  const bool trace = getenv("DNSB_TRACE_DESTROY") != nullptr;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  double t0 = now();
+  auto lap = [&](const char *what) { if (trace) { double t = now(); fprintf(stderr, "[destroy] %-12s %.2f ms\n", what, 1e3 * (t - t0)); t0 = t; } };
   cudaStreamSynchronize(s->ctx->stream);
+  lap("sync");
   for (cudaGraphExec_t g : s->igraph) if (g) cudaGraphExecDestroy(g);
   s->igraph.clear();
+  lap("graphs");
   csr_free(s->K);
+  lap("K");
   s->coef.release(); s->dinv.release(); s->diagpos.release();
   s->Vb.release(); s->Zb.release(); s->w.release();
+  lap("bases");
   s->cf_res.release(); s->cf_d0.release(); s->cf_d1.release(); s->cf_z.release(); s->cf_dinv.release();
   s->cres.release(); s->cd0.release(); s->cd1.release();
   s->partial.release(); s->partial2.release(); s->red.release();
@@ -1399,9 +1408,13 @@ extern "C" void dnsb_solver_destroy(dnsb_solver *s) {
   s->mp_dinv.release(); s->mp_scale.release(); s->sb.release(); s->sx.release();
   s->zero_p.release();
   s->lsc_dinv.release(); s->lsc_t1.release(); s->lsc_t2.release(); s->lsc_p1.release(); s->lsc_p2.release();
+  lap("small");
   for (MgLevel *L : s->levels) level_free(L);
+  lap("levels");
   for (MgLevel *L : s->vlevels) level_free(L);
+  lap("vlevels");
   if (s->h_flags) cudaFreeHost(s->h_flags);
+  lap("pinned");
   delete s;
 }
 
