@@ -273,6 +273,7 @@ static int g_pkeep = 0;    // raw solutions the projection space is rebuilt from
 static int g_tail_warps = 8;   // warps of k_spmm_tile that serve the unpaired tail rows (0: separate k_spmm_b2 launch)
 static int g_gs_pyth = 1;   // norm of the orthogonalised Arnoldi vector from Pythagoras (batches, columns < 16)
 static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
+static int g_tilef_ctas = 2;   // resident CTAs per SM of the fp32 tile kernel (its ring is small enough for two)
 static int g_tile_stages = 3, g_tile_stages_f = 3;   // ring depth of the fp64 / fp32 tile kernels (at most what fits)
 static const int TILE_SMEM_OPTIN = 220 * 1024;
 // tiles of TILE_RP row pairs: unique x rows, tile-local gather offsets, pair-interleaved values.
@@ -397,6 +398,7 @@ static int g_dmma = 1;   // fp64 tensor-core (DMMA) variant of the dense Schur s
 // 1: dense Schur block on the tcgen05 tensor cores (TF32 operands from an fp32 copy of the inverse,
 // fp32 accumulation in TMEM; dnsb_tc.cuh).  Preconditioner block only: FGMRES stays fp64.
 static int g_schur_l2keep = 0;   // 1: packed inverse read with an L2 evict_last hint (measured: no effect, the streams of a step flush L2 anyway)
+static int g_tc_ctas = 1;   // CTAs per SM of k_schur_tc (2: more K splits on all SMs, half the ring depth each)
 static int g_schur_tc = 1;
 static const int TC_SMEM_OPTIN = 208 * 1024;
 static int g_conv_colours = 0;   // 1: coloured scatter instead of the gather formulation of K1a
@@ -561,7 +563,7 @@ static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7]
 #define DNSB_SWITCH_LIST(X) X(g_rows_per_cta) X(g_pair) X(g_tma_min_rows) X(g_gs_tma) X(g_tma_rows) X(g_tma_stages) \
   X(g_dmma) X(g_schur_tf32) X(g_schur_tc) X(g_tile) X(g_gs_pyth) X(g_schur_l2keep) X(g_tile_stages)             \
   X(g_tile_stages_f) X(g_tail_warps) X(g_pkeep) X(g_proj_t) X(g_cheb_f32) X(g_conv_colours) X(g_rowpair)         \
-  X(g_graphs) X(g_dense_ctas_per_sm)
+  X(g_graphs) X(g_dense_ctas_per_sm) X(g_tilef_ctas) X(g_tc_ctas)
 static void switches_store(int *sw) {
   int k = 0;
 #define X(name) sw[k++] = name;
@@ -605,6 +607,8 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
+  if (const char *ev = getenv("DNSB_TC_CTAS")) g_tc_ctas = atoi(ev);
+  if (const char *ev = getenv("DNSB_TILEF_CTAS")) g_tilef_ctas = atoi(ev);
   if (const char *ev = getenv("DNSB_PDL")) ctx->pdl = atoi(ev);
   if (const char *ev = getenv("DNSB_PDL_ONLY")) ctx->pdl_only = ev;
   if (const char *ev = getenv("DNSB_PDL_SKIP")) ctx->pdl_skip = ev;
@@ -1354,12 +1358,13 @@ static cudaError_t tc_setup(dnsb_ctx *ctx, MgLevel *L, int n, int nb) {
   p.np_ = (nb + 15) & ~15;
   p.kblocks = (n + TC_BK - 1) / TC_BK;
   p.mtiles = (n + TC_BM - 1) / TC_BM;
-  p.splits = std::max(1, std::min(p.kblocks, ctx->sm_count / p.mtiles));
+  const int per_sm = std::max(1, std::min(2, g_tc_ctas));   // resident CTAs per SM the split-K grid is sized for
+  p.splits = std::max(1, std::min(p.kblocks, per_sm * ctx->sm_count / p.mtiles));
   p.kb_per_split = (p.kblocks + p.splits - 1) / p.splits;
   p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
   const size_t a_bytes = (size_t)TC_BM * TC_BK * 4;
   const size_t b_bytes = (((size_t)p.np_ * TC_BK * 4) + 1023) & ~(size_t)1023;
-  p.stages = (int)std::min<size_t>(TC_MAX_STAGES, ((size_t)TC_SMEM_OPTIN - 1024) / (a_bytes + b_bytes));
+  p.stages = (int)std::min<size_t>(TC_MAX_STAGES, ((size_t)TC_SMEM_OPTIN / per_sm - 1024) / (a_bytes + b_bytes));
   if (p.stages < 2) return cudaSuccess;
   p.smem = (size_t)p.stages * (a_bytes + b_bytes) + 1024;
   p.ldx = (n + 3) & ~3;
@@ -1634,7 +1639,8 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
     LAUNCH(ctx, k_cheb_init_p2f, spp_grid(n / 2, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
            (const float2 *)s->cf_dinv.p, (float2 *)s->cf_res.p, (float2 *)s->cf_d0.p, nb, n / 2, (float)(1.0 / theta));
     float *dcf = s->cf_d0.p, *dnf = s->cf_d1.p;
-    const unsigned grid_ = std::min(A->tile.ntiles, ctx->sm_count);
+    const int per_sm_ = (g_tilef_ctas >= 2 && 2 * (A->tile.smem_f + 2048) <= (size_t)227 * 1024) ? 2 : 1;
+    const unsigned grid_ = std::min(A->tile.ntiles, per_sm_ * ctx->sm_count);
     const TileDevF tv = A->tile_view_f();
     for (int i = 0; i + 1 < k; ++i) {
       const double rho_n = 1.0 / (2.0 * sigma - rho);

@@ -278,7 +278,7 @@ struct TileDevF {
 };
 
 template <bool FIRST, bool LAST>
-__global__ void __launch_bounds__(TILE_THREADS, 1)
+__global__ void __launch_bounds__(TILE_THREADS, 2)   // two CTAs per SM fit (registers, fp32 ring): see g_tilef_ctas
 k_cheb_step_tilef(TileDevF T, const double *__restrict__ coef, const float *__restrict__ d,
                   const float *__restrict__ dinv, float *res, float *__restrict__ dn, float *zf,
                   double *__restrict__ zout, float c1, float c2) {
