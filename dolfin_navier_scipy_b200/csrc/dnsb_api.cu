@@ -2596,6 +2596,8 @@ extern "C" int dnsb_imex_create(dnsb_ctx *ctx, int scheme, int nb, double dt,
     int rc = csr_build(ctx, nv, nv, mmat->h_indptr.data(), mmat->h_indices.data(), r1.data(),
                        amat->h_v2.data(), &e->Rm);
     if (rc) return rc;
+    // the right-hand side product R v of every step through the staged tile kernel as well (bit-identical)
+    if (nb == TILE_NB) { rc = tile_setup(ctx, e->Rm); if (rc) return rc; }
   }
   const size_t nvb = (size_t)nv * nb, npb = (size_t)e->np * nb, nfb = (size_t)nvf * nb;
   DNSB_CK(ctx, e->v.alloc(nvb)); DNSB_CK(ctx, e->vprev.alloc(nvb));
