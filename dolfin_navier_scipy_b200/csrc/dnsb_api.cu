@@ -273,16 +273,18 @@ static int g_pkeep = 0;    // raw solutions the projection space is rebuilt from
 static int g_tail_warps = 8;   // warps of k_spmm_tile that serve the unpaired tail rows (0: separate k_spmm_b2 launch)
 static int g_gs_pyth = 1;   // norm of the orthogonalised Arnoldi vector from Pythagoras (batches, columns < 16)
 static int g_tile = 1;   // fully TMA-staged batched Chebyshev step (dnsb_tile.cuh)
+static int g_init_tile = 1;    // Chebyshev start of the fp32 smoother as a tile kernel (k_cheb_init_tilef)
 static int g_tilef_ctas = 2;   // resident CTAs per SM of the fp32 tile kernel (its ring is small enough for two)
 static int g_tile_stages = 3, g_tile_stages_f = 3;   // ring depth of the fp64 / fp32 tile kernels (at most what fits)
 static const int TILE_SMEM_OPTIN = 220 * 1024;
 // tiles of TILE_RP row pairs: unique x rows, tile-local gather offsets, pair-interleaved values.
 // Needs the host copies of the matrix (two value arrays, all rows paired).
-static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
+// `single`: a matrix with one value array (the gradient block JT): the second coefficient of an entry is zero.
+static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m, bool single = false) {
   TilePlan &p = m->tile;
   p.ok = false;
-  if (!g_tile || !m->has2 || m->npair_rows < 2 || m->h_indptr.empty() || m->h_v2.empty() || ctx->cc < 100)
-    return 0;
+  if (!g_tile || m->npair_rows < 2 || m->h_indptr.empty() || ctx->cc < 100) return 0;
+  if (single ? m->has2 : (!m->has2 || m->h_v2.empty())) return 0;
   const int np = m->npair_rows / 2;   // leading paired rows (all of F; the velocity rows of K)
   const std::vector<int> &ip = m->h_indptr, &ix = m->h_indices;
   p.npairs = np;
@@ -314,8 +316,8 @@ static int tile_setup(dnsb_ctx *ctx, dnsb_csr *m) {
       for (int k = 0; k < L; ++k) {
         const int ka = ip[2 * q] + k, kb = ka + L;
         pidx[e0 + k] = slot[ix[ka]] * TILE_ROWB;
-        pval[(e0 + k) * 4 + 0] = m->h_v1[ka]; pval[(e0 + k) * 4 + 1] = m->h_v2[ka];
-        pval[(e0 + k) * 4 + 2] = m->h_v1[kb]; pval[(e0 + k) * 4 + 3] = m->h_v2[kb];
+        pval[(e0 + k) * 4 + 0] = m->h_v1[ka]; pval[(e0 + k) * 4 + 1] = single ? 0.0 : m->h_v2[ka];
+        pval[(e0 + k) * 4 + 2] = m->h_v1[kb]; pval[(e0 + k) * 4 + 3] = single ? 0.0 : m->h_v2[kb];
       }
     }
     for (size_t u = 0; u < ucols.size(); ++u) slot[ucols[u]] = -1;
@@ -563,7 +565,7 @@ static void fill_tabulation(double phi[7][6], double dphi[7][6][3], double qw[7]
 #define DNSB_SWITCH_LIST(X) X(g_rows_per_cta) X(g_pair) X(g_tma_min_rows) X(g_gs_tma) X(g_tma_rows) X(g_tma_stages) \
   X(g_dmma) X(g_schur_tf32) X(g_schur_tc) X(g_tile) X(g_gs_pyth) X(g_schur_l2keep) X(g_tile_stages)             \
   X(g_tile_stages_f) X(g_tail_warps) X(g_pkeep) X(g_proj_t) X(g_cheb_f32) X(g_conv_colours) X(g_rowpair)         \
-  X(g_graphs) X(g_dense_ctas_per_sm) X(g_tilef_ctas) X(g_tc_ctas)
+  X(g_graphs) X(g_dense_ctas_per_sm) X(g_tilef_ctas) X(g_tc_ctas) X(g_init_tile)
 static void switches_store(int *sw) {
   int k = 0;
 #define X(name) sw[k++] = name;
@@ -607,6 +609,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   if (const char *ev = getenv("DNSB_SCHUR_TC")) g_schur_tc = atoi(ev);
   if (const char *ev = getenv("DNSB_TILE")) g_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_GS_PYTH")) g_gs_pyth = atoi(ev);
+  if (const char *ev = getenv("DNSB_INIT_TILE")) g_init_tile = atoi(ev);
   if (const char *ev = getenv("DNSB_TC_CTAS")) g_tc_ctas = atoi(ev);
   if (const char *ev = getenv("DNSB_TILEF_CTAS")) g_tilef_ctas = atoi(ev);
   if (const char *ev = getenv("DNSB_PDL")) ctx->pdl = atoi(ev);
@@ -663,6 +666,7 @@ extern "C" int dnsb_ctx_create(int device, dnsb_ctx **out) {
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_spmm_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_spmm_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
+  DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_init_tilef, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
   DNSB_CK(ctx, cudaFuncSetAttribute(k_cheb_step_tilef<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_OPTIN));
@@ -1247,6 +1251,7 @@ extern "C" int dnsb_solver_create(dnsb_ctx *ctx, dnsb_csr *fmat, dnsb_csr *jmat,
   }
   if (nb == TILE_NB && coef && !fmat->tile.ok) { int rc = tile_setup(ctx, fmat); if (rc) return rc; }
   const bool want_f32 = g_cheb_f32 && nb == TILE_NB && coef && fmat->tile.ok;
+  if (want_f32 && g_init_tile && !jtmat->tile.ok) { int rc = tile_setup(ctx, jtmat, true); if (rc) return rc; }
   std::vector<int> dp;
   { int rc = find_diagpos(ctx, fmat, dp); if (rc) return rc; }
   DNSB_CK(ctx, s->diagpos.upload(dp.data(), dp.size(), ctx->stream));
@@ -1636,8 +1641,15 @@ static void cheb_run(dnsb_solver *s, const dnsb_csr *A, const double *coef,
   if (g_cheb_f32 && C && A == s->F && s->cf_res.p && rowpair && has2 && nb == TILE_NB && A->tile.ok && k >= 2 &&
       rowpairs_of(C, nb) * 2 == n) {
     // fp32 smoother (dnsb_tile.cuh): fp64 in (r, zc), fp64 out (z), work vectors and matrix values fp32
-    LAUNCH(ctx, k_cheb_init_p2f, spp_grid(n / 2, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
-           (const float2 *)s->cf_dinv.p, (float2 *)s->cf_res.p, (float2 *)s->cf_d0.p, nb, n / 2, (float)(1.0 / theta));
+    if (g_init_tile && C->tile.ok && C->tile.npairs == n / 2) {
+      const TilePlan &cp = C->tile;
+      const int per_sm_i = 2 * (cp.smem + 2048) <= (size_t)227 * 1024 ? 2 : 1;
+      LAUNCH(ctx, k_cheb_init_tilef, std::min(cp.ntiles, per_sm_i * ctx->sm_count), TILE_THREADS, cp.smem, C->tile_view(), zc,
+             D2C(r), (const float2 *)s->cf_dinv.p, (float2 *)s->cf_res.p, (float2 *)s->cf_d0.p, (float)(1.0 / theta));
+    } else {
+      LAUNCH(ctx, k_cheb_init_p2f, spp_grid(n / 2, nb), SPB_THREADS, 0, C->view(), D2C(zc), D2C(r),
+             (const float2 *)s->cf_dinv.p, (float2 *)s->cf_res.p, (float2 *)s->cf_d0.p, nb, n / 2, (float)(1.0 / theta));
+    }
     float *dcf = s->cf_d0.p, *dnf = s->cf_d1.p;
     const int per_sm_ = (g_tilef_ctas >= 2 && 2 * (A->tile.smem_f + 2048) <= (size_t)227 * 1024) ? 2 : 1;
     const unsigned grid_ = std::min(A->tile.ntiles, per_sm_ * ctx->sm_count);

@@ -639,3 +639,138 @@ k_spmm_tile(TileDev T, const double *__restrict__ coef, const double *__restrict
     cur = nxt;
   }
 }
+
+// ---------------------------------------------------------------------------
+// Chebyshev start of the fp32 smoother with the same staging:  res = rv - JT*zp ;  d = dinv*res/theta
+// (k_cheb_init_p2f: 15 us for 26 MB, bound by the dependent loads of its gather).  `T` is the tile plan
+// of the gradient block JT (one value array: the second coefficient of a packed entry is zero), `x` =
+// zp; sums in CSR order.  The stages are small (a tile touches ~20 pressure rows): two CTAs per SM.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+k_cheb_init_tilef(TileDev T, const double *__restrict__ x, const double2 *__restrict__ rv,
+                  const float2 *__restrict__ dinv, float2 *__restrict__ res, float2 *__restrict__ dout,
+                  float inv_theta) {
+  extern __shared__ __align__(128) unsigned char tl_raw[];
+  __shared__ __align__(8) uint64_t full[TILE_MAX_STAGES], empty[TILE_MAX_STAGES];
+  const int nst = T.stages;
+  const size_t off_val = (size_t)T.umax * TILE_ROWB;
+  const size_t off_idx = off_val + (size_t)T.cap * 32;
+  const size_t stage_bytes = (off_idx + (size_t)T.cap * 4 + 127) & ~(size_t)127;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nst; ++s) {
+      tl_mbar_init(&full[s], 1);
+      tl_mbar_init(&empty[s], TILE_RP);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double *d = x;   // the producer below streams rows of `d`
+
+  // barrier set-up and the first (static) tile descriptor are taken before the programmatic-launch wait
+  if (warp != TILE_RP) dnsb_pdl_entry();
+  if (warp == TILE_RP) {
+    int it = 0;
+    int t = blockIdx.x;
+    int4 dsc = make_int4(0, 0, 0, 0);
+    int rc = 0, rl = 0, rs = 0;
+    if (t < T.ntiles) {
+      dsc = T.tdesc[t];
+      if (lane < T.rmax) {
+        const int *rr = T.truns + ((size_t)t * T.rmax + lane) * 3;
+        rc = rr[0]; rl = rr[1]; rs = rr[2];
+      }
+    }
+    dnsb_pdl_entry();
+    for (; t < T.ntiles; t += gridDim.x, ++it) {
+      const int s = it % nst;
+      const int tn = t + gridDim.x;
+      int4 ndsc = dsc;
+      int nrc = 0, nrl = 0, nrs = 0;
+      if (tn < T.ntiles) {
+        ndsc = T.tdesc[tn];
+        if (lane < T.rmax) {
+          const int *rr = T.truns + ((size_t)tn * T.rmax + lane) * 3;
+          nrc = rr[0]; nrl = rr[1]; nrs = rr[2];
+        }
+      }
+      if (it >= nst) {
+        if (lane == 0) tl_mbar_wait(&empty[s], ((it / nst) - 1) & 1);
+        __syncwarp();
+      }
+      unsigned char *st = tl_raw + (size_t)s * stage_bytes;
+      if (lane == 0) {
+        tl_mbar_expect(&full[s], (uint32_t)dsc.z * TILE_ROWB + (uint32_t)dsc.y * 36);
+        tl_bulk(st + off_val, T.pval + (size_t)dsc.x * 4, (uint32_t)dsc.y * 32, &full[s]);
+        tl_bulk(st + off_idx, T.pidx + dsc.x, (uint32_t)dsc.y * 4, &full[s]);
+      }
+      __syncwarp();
+      if (lane < dsc.w)
+        tl_bulk(st + (size_t)rs * TILE_ROWB, d + (size_t)rc * TILE_NB, (uint32_t)rl * TILE_ROWB, &full[s]);
+      dsc = ndsc; rc = nrc; rl = nrl; rs = nrs;
+    }
+    return;
+  }
+
+  const double2 zero = make_double2(0.0, 0.0);
+  struct Ops { double2 ra, rb; float2 da, db; int4 pd; };
+  auto load_ops = [&](int tile) {
+    Ops o;
+    const int q = min(tile * TILE_RP + warp, T.npairs - 1);
+    o.pd = T.pdesc[q];
+    const size_t ia = (size_t)(2 * q) * (TILE_NB / 2) + lane, ib = ia + TILE_NB / 2;
+    o.ra = rv[ia]; o.rb = rv[ib];
+    o.da = dinv[ia]; o.db = dinv[ib];
+    return o;
+  };
+  Ops cur = load_ops(min((int)blockIdx.x, T.ntiles - 1));
+  int it = 0;
+  for (int t = blockIdx.x; t < T.ntiles; t += gridDim.x, ++it) {
+    const int s = it % nst;
+    const int rp = t * TILE_RP + warp;
+    const bool have = rp < T.npairs;
+    const int kb = cur.pd.x, L = have ? cur.pd.y : 0;
+    const size_t ta = (size_t)(2 * (have ? rp : 0)) * (TILE_NB / 2) + lane, tb = ta + TILE_NB / 2;
+    const int tn = t + gridDim.x;
+    Ops nxt = cur;
+    if (tn < T.ntiles) nxt = load_ops(tn);
+    tl_mbar_wait(&full[s], (it / nst) & 1);
+    const unsigned char *st = tl_raw + (size_t)s * stage_bytes;
+    if (have) {
+      const double2 *sval = reinterpret_cast<const double2 *>(st + off_val) + (size_t)kb * 2;
+      const int *sidx = reinterpret_cast<const int *>(st + off_idx) + kb;
+      const unsigned char *xt = st + (size_t)lane * 16;
+      double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+      int k = 0;
+      for (; k + 2 <= L; k += 2) {
+        const int o0 = sidx[k], o1 = sidx[k + 1];
+        const double2 x0 = *reinterpret_cast<const double2 *>(xt + o0);
+        const double2 x1 = *reinterpret_cast<const double2 *>(xt + o1);
+        const double2 a0 = sval[2 * k], b0 = sval[2 * k + 1], a1 = sval[2 * k + 2], b1 = sval[2 * k + 3];
+        ax = __fma_rn(a0.x, x0.x, ax);  ay = __fma_rn(a0.x, x0.y, ay);
+        bx = __fma_rn(b0.x, x0.x, bx);  by = __fma_rn(b0.x, x0.y, by);
+        ax = __fma_rn(a1.x, x1.x, ax);  ay = __fma_rn(a1.x, x1.y, ay);
+        bx = __fma_rn(b1.x, x1.x, bx);  by = __fma_rn(b1.x, x1.y, by);
+      }
+      for (; k < L; ++k) {
+        const double2 xv = *reinterpret_cast<const double2 *>(xt + sidx[k]);
+        const double2 a = sval[2 * k], b = sval[2 * k + 1];
+        ax = __fma_rn(a.x, xv.x, ax);  ay = __fma_rn(a.x, xv.y, ay);
+        bx = __fma_rn(b.x, xv.x, bx);  by = __fma_rn(b.x, xv.y, by);
+      }
+      __syncwarp();
+      if (lane == 0) tl_mbar_arrive(&empty[s]);
+      const float rax = (float)(cur.ra.x - ax), ray = (float)(cur.ra.y - ay);
+      const float rbx = (float)(cur.rb.x - bx), rby = (float)(cur.rb.y - by);
+      res[ta] = make_float2(rax, ray);
+      res[tb] = make_float2(rbx, rby);
+      dout[ta] = make_float2(cur.da.x * rax * inv_theta, cur.da.y * ray * inv_theta);
+      dout[tb] = make_float2(cur.db.x * rbx * inv_theta, cur.db.y * rby * inv_theta);
+    } else {
+      __syncwarp();
+      if (lane == 0) tl_mbar_arrive(&empty[s]);
+    }
+    cur = nxt;
+  }
+}
