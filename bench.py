@@ -798,7 +798,7 @@ def kernel_bytes(name, info, integ, mean_work=0.):
         return 8.*(n + npp)*nb*(mean_work + 1.)           # basis vectors + w
     if name.startswith('k_gs_tma<true>') or name.startswith('k_gs_update_b'):
         return 8.*(n + npp)*nb*(mean_work + 2.)           # basis vectors + w in, vnext out
-    if name.startswith('k_cheb_init_p2f'):
+    if name.startswith(('k_cheb_init_p2f', 'k_cheb_init_tilef')):
         # JT entries, zp and rv (fp64) in, dinv (fp32) in, res and d (fp32) out
         return 12.*J.nnz + 4.*(n + 1) + 8.*npp*nb + 20.*n*nb
     if name.startswith('k_cheb_init'):
