@@ -84,6 +84,81 @@ def test_lowrank_forcing_samples_in_chunks_and_fails_early():
     assert calls[0] <= 128
 
 
+class _FakeDeviceSolver(object):
+    """what `SadpntOperator.solve_minres` needs from `_lib.Solver`, in scipy:
+    the product with K and the block-diagonal preconditioner"""
+
+    def __init__(self, F, J, exact_schur=True):
+        import scipy.sparse.linalg as spsla
+        self.nv, self.np_, self.nb = F.shape[0], J.shape[0], 1
+        self.K = sps.bmat([[F, J.T], [J, None]], format='csr')
+        self.Finv = spsla.factorized(sps.csc_matrix(F))
+        S = (J@sps.diags(1./F.diagonal())@J.T).toarray()
+        self.Sinv = np.linalg.inv(S)
+        self.mode = []
+
+    def set_prec_mode(self, flag):
+        self.mode.append(bool(flag))
+
+    def apply_k(self, x):
+        return self.K@np.asarray(x).reshape(-1, 1)
+
+    def apply_prec(self, r):
+        assert self.mode and self.mode[-1], 'MINRES must ask for the SPD form'
+        r = np.asarray(r).ravel()
+        return np.concatenate([self.Finv(r[:self.nv]), self.Sinv@r[self.nv:]])
+
+
+def _minres_operator(F, J):
+    from dolfin_navier_scipy_b200 import lin_alg_utils as lau
+    op = lau.SadpntOperator.__new__(lau.SadpntOperator)
+    op.NP, op.NV = J.shape
+    op.ncols = 1
+    op.solver = _FakeDeviceSolver(F, J)
+    return op
+
+
+def test_minres_host_recurrence_checks_the_true_residual(cyl1):
+    """the host side of `krylov='minres'`: scipy's recurrence over the device's
+    operators (here replaced by scipy ones), the SPD preconditioner mode
+    switched on for the solve and off again afterwards, the TRUE relative
+    residual checked against the tolerance, `NotConverged` when the iteration
+    budget does not reach it"""
+    from dolfin_navier_scipy_b200 import _lib
+    from oracle import lau as olau
+    femp, sm, rhsd = cyl1
+    F = (sm['M'] + .5/512*sm['A']).tocsr()
+    J = sm['J'].tocsr()
+    rng = np.random.default_rng(5)
+    rhsv = rng.standard_normal((F.shape[0], 1))
+    op = _minres_operator(F, J)
+    vp = op.solve_minres(rhsv, rhsd['fp'], tol=1e-10, maxit=400)
+    ref = olau.solve_sadpnt_smw(amat=F, jmat=J, jmatT=J.T, rhsv=rhsv,
+                                rhsp=rhsd['fp'])
+    assert np.linalg.norm(vp - ref) < 1e-8*np.linalg.norm(ref)
+    assert op.last_relres[0] <= 1e-10 and 0 < op.last_iters[0] <= 400
+    assert op.solver.mode[0] is True and op.solver.mode[-1] is False
+    op2 = _minres_operator(F, J)
+    with pytest.raises(_lib.NotConverged):
+        op2.solve_minres(rhsv, rhsd['fp'], tol=1e-12, maxit=3)
+    assert op2.solver.mode[-1] is False          # switched back on the error path too
+    op3 = _minres_operator(F, J)
+    op3.ncols = 2
+    with pytest.raises(NotImplementedError):
+        op3.solve_minres(np.hstack([rhsv, rhsv]))
+
+
+def test_cpu_binding_helper_never_raises():
+    """`ensemble.bind_to_gpu_cpus` pins a rank next to its GPU when NVML can
+    say where that is, and is a no-op (None) everywhere else -- e.g. here"""
+    import os
+    from dolfin_navier_scipy_b200 import ensemble
+    before = os.sched_getaffinity(0)
+    got = ensemble.bind_to_gpu_cpus(0)
+    assert got is None or set(got) <= before
+    os.sched_setaffinity(0, before)
+
+
 def test_pattern_embedding_keeps_explicit_zeros():
     A = sps.random(20, 20, .3, random_state=1, format='csr') + sps.identity(20)
     M = sps.identity(20, format='csr')
