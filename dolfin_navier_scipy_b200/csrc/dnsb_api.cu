@@ -2733,14 +2733,17 @@ static void imex_refresh_p(dnsb_imex *e) {
 }
 
 // out[map[i], m] = x[i, m]  (map == null: identity)
+// copy != null: copy[t] = x[t] as well (the device-side trajectory store, same pass)
 __global__ void k_scatter_rows(const double *__restrict__ x, const int *__restrict__ map,
-                               double *__restrict__ out, int n, int nb) {
+                               double *__restrict__ out, int n, int nb, double *__restrict__ copy) {
   dnsb_pdl_entry();
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)n * nb) return;
   const int i = (int)(t / nb), m = (int)(t % nb);
   const int o = map ? map[i] : i;
-  out[(size_t)o * nb + m] = x[t];
+  const double v = x[t];
+  out[(size_t)o * nb + m] = v;
+  if (copy) copy[t] = v;
 }
 
 // pinned host mirror with room for `cap` snapshots (contents are kept)
@@ -2768,15 +2771,19 @@ static int imex_snapshot(dnsb_imex *e) {
   const size_t nvb = (size_t)e->nv * e->nb, npb = (size_t)e->np * e->nb, ntb = nvb + npb;
   imex_refresh_p(e);
   double *dst = e->snaps.p + (size_t)e->nsnap * ntb;
-  DNSB_CK(ctx, cudaMemcpyAsync(dst, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  DNSB_CK(ctx, cudaMemcpyAsync(dst + nvb, e->p.p, npb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (e->host_mirror && e->nsnap < e->h_cap) {
+  const bool mirror = e->host_mirror && e->nsnap < e->h_cap;
+  if (!mirror) {
+    DNSB_CK(ctx, cudaMemcpyAsync(dst, e->v.p, nvb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    DNSB_CK(ctx, cudaMemcpyAsync(dst + nvb, e->p.p, npb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  if (mirror) {   // the un-permuting kernels below fill the device-side store in the same pass
     const int q = e->nsnap % dnsb_imex::NSTAGE;
     if (e->stage_busy[q]) DNSB_CK(ctx, cudaStreamWaitEvent(ctx->stream, e->ev_free[q], 0));
     const int *mv = e->has_outmap ? e->outmap.p : nullptr;
     const int *mp = e->has_outmap ? e->outmap.p + e->nv : nullptr;
-    LAUNCH(ctx, k_scatter_rows, cdiv(nvb, 256), 256, 0, (const double *)e->v.p, mv, e->stage[q].p, e->nv, e->nb);
-    LAUNCH(ctx, k_scatter_rows, cdiv(npb, 256), 256, 0, (const double *)e->p.p, mp, e->stage[q].p + nvb, e->np, e->nb);
+    LAUNCH(ctx, k_scatter_rows, cdiv(nvb, 256), 256, 0, (const double *)e->v.p, mv, e->stage[q].p, e->nv, e->nb, dst);
+    LAUNCH(ctx, k_scatter_rows, cdiv(npb, 256), 256, 0, (const double *)e->p.p, mp, e->stage[q].p + nvb, e->np, e->nb,
+           dst + nvb);
     DNSB_CK(ctx, cudaEventRecord(e->ev_ready[q], ctx->stream));
     DNSB_CK(ctx, cudaStreamWaitEvent(e->cstream, e->ev_ready[q], 0));
     DNSB_CK(ctx, cudaMemcpyAsync(e->h_snaps + (size_t)e->nsnap * ntb, e->stage[q].p, ntb * sizeof(double),
