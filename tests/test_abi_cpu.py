@@ -3,6 +3,7 @@ symbol `include/dnsb.h` declares; host-side setup logic."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -272,6 +273,39 @@ def test_stokes_slot_patterns_reproduce_the_host_assembly():
                           (Q.dim(), V.dim()))
     got = _lib._csr_from_keys(jk, Q.dim(), V.dim(), vals)
     assert abs(got - ref).max() < 1e-14
+
+
+def test_bench_byte_formulas_cover_the_kernels_of_a_step(cyl1):
+    """`bench.kernel_bytes` (the ALGORITHMIC bytes behind `roofline`): every
+    HBM-class kernel that the committed bench line of the final state lists
+    has a formula, the fp32 variants count fewer bytes than the fp64 ones
+    they replace, and the Gram-Schmidt count grows with the vectors read"""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    femp, sm, rhsd = cyl1
+
+    class _Integ(object):
+        nb = 64
+        _host = dict(M=sm['M'].tocsr(), J=sm['J'].tocsr())
+    with open(os.path.join(root, 'profiles', 'r2f_bench.json')) as fh:
+        line = json.loads([ln for ln in fh if ln.startswith('{')][-1])
+    names = [k.strip('()') for k in line['kernels']]
+    assert any(n.startswith('k_gs_tma') for n in names)
+    by = {n: bench.kernel_bytes(n, None, _Integ, 8.) for n in names}
+    for n, b in by.items():
+        if n.startswith(('k_gs_tma', 'k_cheb_step_tilef', 'k_cheb_init', 'k_spmm',
+                         'k_schur_tc', 'k_scale_member')):
+            assert b is not None and b > 0, n
+    f64 = bench.kernel_bytes('k_cheb_step_tile<false, false>', None, _Integ)
+    f32 = bench.kernel_bytes('k_cheb_step_tilef<false, false>', None, _Integ)
+    assert f32 < f64 < bench.kernel_bytes('k_cheb_step_p2<true, false, false>', None, _Integ)
+    assert bench.kernel_bytes('k_cheb_init_tilef', None, _Integ) == \
+        bench.kernel_bytes('k_cheb_init_p2f', None, _Integ) < \
+        bench.kernel_bytes('k_cheb_init_p2', None, _Integ)
+    assert bench.kernel_bytes('k_gs_tma<false>', None, _Integ, 20.) > \
+        2*bench.kernel_bytes('k_gs_tma<false>', None, _Integ, 8.)
 
 
 def test_bench_reference_arm_prints_one_contract_line():
